@@ -1,0 +1,91 @@
+/*
+ * mq_oracle.h -- CPU restatement of most-queue's simulation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library, and only as the checker or as
+ * the timed CPU baseline.  The product path (most_queue_b200/) never links,
+ * imports or calls it.
+ *
+ * Parity pin: the replay entry points are checked bit-for-bit against the
+ * reference's own QsSim / PriorityQueueSimulator / NetworkSimulator (run in the
+ * build container with pre-generated arrays injected through .generate())
+ * via the fixtures in tests/golden/ (generator: tests/golden/make_golden.py).
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * the reference checkout, most_queue/...).
+ */
+#ifndef MQ_ORACLE_H
+#define MQ_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* distribution kinds (most_queue/random/utils/create.py:19-80) */
+enum {
+    MQO_M = 0,      /* exponential, params[0] = mu                         */
+    MQO_H2 = 1,     /* hyper-exponential, params = {p1, mu1, mu2}          */
+    MQO_E = 2,      /* Erlang, params = {r, mu}                            */
+    MQO_GAMMA = 3,  /* Gamma, params = {mu, alpha}                         */
+    MQO_PA = 4,     /* Pareto, params = {alpha, K}                         */
+    MQO_D = 5,      /* deterministic, params[0] = b                        */
+    MQO_C2 = 6,     /* Cox-2, params = {p1, mu1, mu2}                      */
+    MQO_UNIFORM = 7,/* uniform, params = {mean, half_interval}             */
+    MQO_NORM = 8,   /* normal, params = {mean, std_dev}                    */
+    MQO_WEIBULL = 9 /* Weibull (reference formula), params = {k, W}        */
+};
+
+typedef struct {
+    int kind;
+    double p[4];
+} mqo_dist;
+
+/* results of one FIFO replication */
+typedef struct {
+    double w_sum[4];   /* sum of w^k, k=1..4, accumulated in the reference's sample order */
+    double v_sum[4];   /* sum of v^k, same                                                 */
+    double w_run[4];   /* the reference's running-mean moments (stats_update.py:6-22)     */
+    double v_run[4];
+    double busy_run[3];/* busy-period running moments (base.py:276-281)                   */
+    int64_t busy_n;
+    int64_t arrived, taked, served, dropped, in_sys, queued;
+    double ttek;       /* clock at stop                                                   */
+    double p_over;     /* time spent in states >= p_bins                                  */
+    int64_t a_used, s_used; /* how many interarrival / service variates were consumed     */
+} mqo_fifo_out;
+
+/* QsSim.run() with pre-generated variates (sim/base.py:488-528).
+ * A[0] is the draw made by set_sources (base.py:112); S[j] is the j-th service draw
+ * (servers.py:88).  buffer < 0 means infinite (base.py:204).  p has p_bins entries
+ * (time-in-state sums, NOT normalised).  w_samples / v_samples may be NULL; when given
+ * they receive up to cap samples in the reference's sample order.
+ * Returns 0, or -1 when the arrays ran out before total_served departures. */
+int mqo_fifo_replay(int c, int64_t buffer, const double *A, int64_t nA, int64_t strideA,
+                    const double *S, int64_t nS, int64_t strideS, int64_t total_served,
+                    double *p, int64_t p_bins, mqo_fifo_out *out,
+                    double *w_samples, int64_t w_cap, double *v_samples, int64_t v_cap);
+
+/* Same event loop driven by the counter-based generator spec of DESIGN.md
+ * (Philox2x32-10 keyed by seed, counter = (arrival index, replication id)),
+ * evaluated in fp64 with libm.  One call simulates replications [rep0, rep0+reps)
+ * with `threads` OpenMP threads; outputs are arrays of `reps` records, p is
+ * [reps][p_bins]. */
+int mqo_fifo_generate(int c, int64_t buffer, const mqo_dist *src, const mqo_dist *srv,
+                      int64_t total_served, uint32_t seed, int64_t rep0, int64_t reps,
+                      double *p, int64_t p_bins, mqo_fifo_out *out, int threads);
+
+/* generator building blocks, exported so that tests can pin them */
+void mqo_philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[2]);
+void mqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* variate of `d` for arrival index i of replication rep; which = 0 source, 1 server */
+double mqo_variate(const mqo_dist *d, uint32_t seed, uint32_t rep, uint32_t i, int which);
+
+const char *mqo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

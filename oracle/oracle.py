@@ -1,0 +1,211 @@
+"""ctypes wrapper around the CPU oracle (oracle/libmqoracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(most_queue_b200) never imports this module.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmqoracle.so")
+
+KINDS = {"M": 0, "H": 1, "E": 2, "Gamma": 3, "Pa": 4, "D": 5, "C": 6, "Uniform": 7, "Norm": 8, "Weibull": 9}
+
+
+class MqoDist(C.Structure):
+    _fields_ = [("kind", C.c_int), ("p", C.c_double * 4)]
+
+
+class MqoFifoOut(C.Structure):
+    _fields_ = [
+        ("w_sum", C.c_double * 4),
+        ("v_sum", C.c_double * 4),
+        ("w_run", C.c_double * 4),
+        ("v_run", C.c_double * 4),
+        ("busy_run", C.c_double * 3),
+        ("busy_n", C.c_int64),
+        ("arrived", C.c_int64),
+        ("taked", C.c_int64),
+        ("served", C.c_int64),
+        ("dropped", C.c_int64),
+        ("in_sys", C.c_int64),
+        ("queued", C.c_int64),
+        ("ttek", C.c_double),
+        ("p_over", C.c_double),
+        ("a_used", C.c_int64),
+        ("s_used", C.c_int64),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s", "CC=gcc"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        L.mqo_fifo_replay.restype = C.c_int
+        L.mqo_fifo_replay.argtypes = [
+            C.c_int, C.c_int64, dp, C.c_int64, C.c_int64, dp, C.c_int64, C.c_int64, C.c_int64,
+            dp, C.c_int64, C.POINTER(MqoFifoOut), dp, C.c_int64, dp, C.c_int64,
+        ]
+        L.mqo_fifo_generate.restype = C.c_int
+        L.mqo_fifo_generate.argtypes = [
+            C.c_int, C.c_int64, C.POINTER(MqoDist), C.POINTER(MqoDist), C.c_int64, C.c_uint32,
+            C.c_int64, C.c_int64, dp, C.c_int64, C.POINTER(MqoFifoOut), C.c_int,
+        ]
+        L.mqo_philox2x32_10.restype = None
+        L.mqo_philox2x32_10.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.mqo_philox4x32_10.restype = None
+        L.mqo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        L.mqo_variate.restype = C.c_double
+        L.mqo_variate.argtypes = [C.POINTER(MqoDist), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.mqo_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_dist(kind: str, params) -> MqoDist:
+    """(kendall code, reference-style params) -> oracle struct.
+
+    Param order follows most_queue/random/utils/params.py: H2Params(mu1, mu2, p1) etc.
+    """
+    d = MqoDist()
+    d.kind = KINDS[kind]
+    if kind in ("M", "D"):
+        vals = [float(params)]
+    elif kind in ("H", "C"):
+        vals = [float(params.p1), float(params.mu1), float(params.mu2)]
+    elif kind == "E":
+        vals = [float(params.r), float(params.mu)]
+    elif kind == "Gamma":
+        vals = [float(params.mu), float(params.alpha)]
+    elif kind == "Pa":
+        vals = [float(params.alpha), float(params.K)]
+    elif kind == "Uniform":
+        vals = [float(params.mean), float(params.half_interval)]
+    elif kind == "Norm":
+        vals = [float(params.mean), float(params.std_dev)]
+    elif kind == "Weibull":
+        vals = [float(params.k), float(params.W)]
+    else:
+        raise ValueError(kind)
+    for i, v in enumerate(vals):
+        d.p[i] = v
+    return d
+
+
+@dataclass
+class FifoResult:
+    w_sum: np.ndarray
+    v_sum: np.ndarray
+    w: np.ndarray  # reference running-mean moments
+    v: np.ndarray
+    busy: np.ndarray
+    busy_n: int
+    arrived: int
+    taked: int
+    served: int
+    dropped: int
+    in_sys: int
+    queued: int
+    ttek: float
+    p_time: np.ndarray  # time-in-state sums
+    p_over: float
+    a_used: int
+    s_used: int
+    w_samples: np.ndarray | None = None
+    v_samples: np.ndarray | None = None
+
+    @property
+    def p(self) -> np.ndarray:
+        return self.p_time / self.ttek
+
+
+def _unpack(o: MqoFifoOut, p: np.ndarray, ws=None, vs=None) -> FifoResult:
+    return FifoResult(
+        w_sum=np.array(o.w_sum[:]), v_sum=np.array(o.v_sum[:]),
+        w=np.array(o.w_run[:]), v=np.array(o.v_run[:]), busy=np.array(o.busy_run[:]),
+        busy_n=o.busy_n, arrived=o.arrived, taked=o.taked, served=o.served, dropped=o.dropped,
+        in_sys=o.in_sys, queued=o.queued, ttek=o.ttek, p_time=p, p_over=o.p_over,
+        a_used=o.a_used, s_used=o.s_used, w_samples=ws, v_samples=vs,
+    )
+
+
+def fifo_replay(c: int, buffer, A: np.ndarray, S: np.ndarray, total_served: int,
+                p_bins: int = 64, samples: bool = False) -> FifoResult:
+    """QsSim.run() on pre-generated interarrival (A) and service (S) arrays."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    p = np.zeros(p_bins)
+    out = MqoFifoOut()
+    ws = np.zeros(len(S)) if samples else None
+    vs = np.zeros(int(total_served)) if samples else None
+    rc = lib().mqo_fifo_replay(
+        c, -1 if buffer is None else int(buffer), _dp(A), len(A), 1, _dp(S), len(S), 1,
+        int(total_served), _dp(p), p_bins, C.byref(out),
+        _dp(ws) if samples else None, len(ws) if samples else 0,
+        _dp(vs) if samples else None, len(vs) if samples else 0,
+    )
+    if rc != 0:
+        raise RuntimeError(f"oracle fifo_replay failed rc={rc} (input arrays too short?)")
+    if samples:
+        ws = ws[: out.taked]
+        vs = vs[: out.served]
+    return _unpack(out, p, ws, vs)
+
+
+def fifo_generate(c: int, buffer, src, srv, total_served: int, seed: int, rep0: int, reps: int,
+                  p_bins: int = 64, threads: int = 1) -> list[FifoResult]:
+    """Generator-mode oracle: src/srv are (kendall code, params) tuples."""
+    ds, dv = make_dist(*src), make_dist(*srv)
+    p = np.zeros((reps, p_bins))
+    outs = (MqoFifoOut * reps)()
+    rc = lib().mqo_fifo_generate(
+        c, -1 if buffer is None else int(buffer), C.byref(ds), C.byref(dv), int(total_served),
+        C.c_uint32(seed & 0xFFFFFFFF), int(rep0), int(reps), _dp(p), p_bins, outs, int(threads),
+    )
+    if rc != 0:
+        raise RuntimeError(f"oracle fifo_generate failed rc={rc}")
+    return [_unpack(outs[r], p[r]) for r in range(reps)]
+
+
+def philox2x32(c0: int, c1: int, key: int) -> tuple[int, int]:
+    out = (C.c_uint32 * 2)()
+    lib().mqo_philox2x32_10(c0, c1, key, out)
+    return int(out[0]), int(out[1])
+
+
+def philox4x32(ctr, key) -> tuple[int, ...]:
+    out = (C.c_uint32 * 4)()
+    lib().mqo_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    return tuple(int(x) for x in out)
+
+
+def variate(src_or_srv, seed: int, rep: int, i: int, which: int) -> float:
+    d = make_dist(*src_or_srv)
+    return float(lib().mqo_variate(C.byref(d), seed & 0xFFFFFFFF, rep, i, which))

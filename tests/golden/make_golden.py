@@ -1,0 +1,207 @@
+"""Generate golden fixtures by running the UNMODIFIED reference in the build container.
+
+Run from the repo root (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports most_queue from /root/reference (with an in-memory stub for the missing
+`colorama` package, which the reference only uses for ANSI colours), feeds QsSim /
+PriorityQueueSimulator / NetworkSimulator pre-generated variate arrays through objects
+whose .generate() pops from an array (the reference only ever calls .generate():
+sim/base.py:112,236, sim/utils/servers.py:88), and records inputs + outputs as .npz
+under tests/golden/.  The committed fixtures are what the tests read; this script is
+the provenance.
+"""
+
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("MQ_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _install_stub_colorama():
+    if "colorama" in sys.modules:
+        return
+    m = types.ModuleType("colorama")
+
+    class _Blank:
+        def __getattr__(self, _):
+            return ""
+
+    m.Fore = m.Style = m.Back = _Blank()
+    m.init = lambda *a, **k: None
+    sys.modules["colorama"] = m
+
+
+def import_reference():
+    _install_stub_colorama()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import most_queue  # noqa: F401
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        yield
+
+
+class ReplayDist:
+    """Pops pre-generated variates; stands in for any most_queue.random distribution."""
+
+    def __init__(self, arr, counter):
+        self.arr = arr
+        self.counter = counter  # shared [index] so that all servers consume one stream
+
+    def generate(self):
+        i = self.counter[0]
+        self.counter[0] = i + 1
+        return float(self.arr[i])
+
+
+# --------------------------------------------------------------------------- FIFO
+def fifo_case(name, c, buffer, A, S, total_served, nprobs=256):
+    from most_queue.sim.base import QsSim
+
+    qs = QsSim(c, buffer=buffer)
+    qs.set_sources(1.0, "M")
+    qs.set_servers(1.0, "M")
+    ia, isv = [0], [0]
+    qs.source = ReplayDist(A, ia)
+    for s in qs.servers:
+        s.dist = ReplayDist(S, isv)
+    qs.arrival_time = qs.source.generate()  # the draw set_sources makes (base.py:112)
+
+    ws, vs = [], []
+    ow, ov = qs.refresh_w_stat, qs.refresh_v_stat
+
+    def rw(x, count=None):
+        ws.append(x)
+        ow(x, count)
+
+    def rv(x, count=None):
+        vs.append(x)
+        ov(x, count)
+
+    qs.refresh_w_stat, qs.refresh_v_stat = rw, rv
+    with quiet():
+        while qs.served < total_served:  # run() minus tqdm and calc_load (base.py:505-506)
+            qs.run_one_step()
+    p = np.array(qs.p[:nprobs], dtype=np.float64)  # time-in-state sums (base.py:340)
+    np.savez_compressed(
+        os.path.join(OUT, f"fifo_{name}.npz"),
+        c=c, buffer=-1 if buffer is None else buffer, total_served=total_served,
+        A=np.asarray(A), S=np.asarray(S),
+        w=np.array(qs.w, dtype=np.float64), v=np.array(qs.v, dtype=np.float64),
+        busy=np.array(qs.busy, dtype=np.float64), busy_n=qs.busy_moments,
+        p_time=p, ttek=float(qs.ttek), arrived=qs.arrived, taked=qs.taked, served=qs.served,
+        dropped=qs.dropped, in_sys=qs.in_sys, queued=qs.queue.size(),
+        a_used=ia[0], s_used=isv[0],
+        w_samples=np.array(ws, dtype=np.float64), v_samples=np.array(vs, dtype=np.float64),
+    )
+    print(f"fifo_{name}: taked={qs.taked} served={qs.served} dropped={qs.dropped} w1={qs.w[0]:.6g}")
+
+
+def make_fifo():
+    rng = np.random.default_rng(20260101)
+    n = 3000
+    # M/M/3 rho=0.667 (README quick start), infinite buffer
+    fifo_case("mm3_inf", 3, None, rng.exponential(0.5, n + 200), rng.exponential(1.0, n + 200), n)
+    # M/M/3/30 at the load of tests/test_qs_sim.py:46-55 (l=1, mu=1/2.1)
+    fifo_case("mm3_r30", 3, 30, rng.exponential(1.0, n + 400), rng.exponential(2.1, n + 400), n)
+    # tight buffer with many drops
+    fifo_case("mg3_r4", 3, 4, rng.exponential(0.4, 2 * n), rng.gamma(2.0, 0.7, 2 * n), n)
+    # pure loss system (tests/test_erlang.py:48)
+    fifo_case("mm3_r0", 3, 0, rng.exponential(0.5, 3 * n), rng.exponential(1.2, 3 * n), n)
+    # cfg2 shape: M/H2/8 rho=0.7 cv=1.5
+    p1, mu1, mu2 = 0.447586, 0.0950716, 0.619214
+    br = rng.random(n + 300) < p1
+    S = rng.exponential(1.0, n + 300) / np.where(br, mu1, mu2)
+    fifo_case("mh2_8_inf", 8, None, rng.exponential(1.0, n + 300), S, n)
+    # cfg3 shape: Gamma/Pareto/1
+    A = rng.gamma(3.18878, 1.0 / 3.18878, n + 300)
+    S = 0.395878 * rng.random(n + 300) ** (-1.0 / 2.30171)
+    fifo_case("gpa_1_inf", 1, None, A, S, n)
+    # deterministic service with exact ties (D/D-like lattice times)
+    A = rng.integers(1, 4, 2 * n).astype(np.float64) * 0.5
+    S = np.full(2 * n, 2.0)
+    fifo_case("lattice_3_r3", 3, 3, A, S, n)
+    # heavy load, long queue (exercises queue growth)
+    fifo_case("mm2_heavy", 2, None, rng.exponential(0.52, n + 1200), rng.exponential(1.0, n + 1200), n)
+    # tiny run
+    fifo_case("tiny", 2, None, rng.exponential(1.0, 40), rng.exponential(1.5, 40), 5)
+
+
+# --------------------------------------------------------------------------- theory
+def make_theory():
+    """Analytical values used by the generator-mode (statistical) tests."""
+    from most_queue.random.distributions import GammaDistribution, H2Distribution, ParetoDistribution
+    from most_queue.random.utils.params import H2Params
+    from most_queue.theory.fifo.mgn_takahasi import MGnCalc
+    from most_queue.theory.fifo.mmnr import MMnrCalc
+
+    out = {}
+    with quiet():
+        c = MMnrCalc(n=3, r=100)
+        c.set_sources(2.0)
+        c.set_servers(1.0)
+        r = c.run()
+    out["mm3_r100"] = {"l": 2.0, "mu": 1.0, "n": 3, "r": 100, "w": list(map(float, r.w)),
+                       "v": list(map(float, r.v)), "p": list(map(float, r.p[:32]))}
+    with quiet():
+        c = MMnrCalc(n=3, r=30)
+        c.set_sources(1.0)
+        c.set_servers(1.0 / 2.1)
+        r = c.run()
+    out["mm3_r30"] = {"l": 1.0, "mu": 1.0 / 2.1, "n": 3, "r": 30, "w": list(map(float, r.w)),
+                      "v": list(map(float, r.v)), "p": list(map(float, r.p[:32]))}
+    with quiet():
+        c = MMnrCalc(n=3, r=0)
+        c.set_sources(2.0)
+        c.set_servers(1.0)
+        r = c.run()
+    out["mm3_r0"] = {"l": 2.0, "mu": 1.0, "n": 3, "r": 0, "p": list(map(float, r.p[:4]))}
+
+    h2 = H2Distribution.get_params_by_mean_and_cv(5.6, 1.5)
+    with quiet():
+        c = MGnCalc(n=8)
+        c.set_sources(1.0)
+        c.set_servers(H2Params(p1=h2.p1, mu1=h2.mu1, mu2=h2.mu2))
+        r = c.run()
+    out["mh2_8"] = {"l": 1.0, "n": 8, "h2": {"p1": float(h2.p1), "mu1": float(h2.mu1), "mu2": float(h2.mu2)},
+                    "w": list(map(float, np.real(r.w))), "v": list(map(float, np.real(r.v))),
+                    "p": list(map(float, np.real(r.p[:32])))}
+
+    # fitter pins (host-side parameter helpers re-implemented in most_queue_b200.random)
+    fits = {}
+    for mean, cv in [(5.6, 1.5), (1.0, 1.2), (2.0, 1.05), (0.7, 3.0)]:
+        h = H2Distribution.get_params_by_mean_and_cv(mean, cv)
+        fits[f"h2_{mean}_{cv}"] = [float(h.p1), float(h.mu1), float(h.mu2)]
+    for mean, cv in [(1.0, 0.56), (2.0, 1.2), (4.0, 1.2), (0.3, 2.0)]:
+        g = GammaDistribution.get_params_by_mean_and_cv(mean, cv)
+        fits[f"gamma_{mean}_{cv}"] = [float(g.mu), float(g.alpha)]
+    for mean, cv in [(0.7, 1.2), (1.0, 0.8)]:
+        pa = ParetoDistribution.get_params_by_mean_and_cv(mean, cv)
+        fits[f"pareto_{mean}_{cv}"] = [float(pa.alpha), float(pa.K)]
+    out["fits"] = fits
+    with open(os.path.join(OUT, "theory.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("theory.json written")
+
+
+if __name__ == "__main__":
+    import_reference()
+    which = sys.argv[1:] or ["fifo", "theory"]
+    if "fifo" in which:
+        make_fifo()
+    if "theory" in which:
+        make_theory()
