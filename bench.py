@@ -1,0 +1,350 @@
+"""Benchmark of the hot path: simulated jobs/sec of M/H2/8 FIFO (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels via the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the reference algorithm on
+                                                              # the host cores (oracle port, all threads)
+
+One "step" = one pass of QsSim.run(): `replications` independent M/H2/8 replications of
+`total_served` jobs each, per GPU (weak scaling: every rank simulates the full configuration with
+its own global replication ids).  Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# cfg2 of BASELINE.json: M/H2/8, rho = 0.7, CV = 1.5 (H2 fitted to mean 5.6, cv 1.5)
+H2 = {"p1": 0.447586, "mu1": 0.0950716, "mu2": 0.619214}
+C_SERVERS = 8
+ARRIVAL_RATE = 1.0
+I_ALG = 160.0  # planning lane-instructions per job for cfg2: the issue roofline's work unit
+METRIC = "simulated jobs/sec (M/H2/8 FIFO)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(seconds_target: float, jobs: int, threads: int | None = None):
+    """Times the oracle port (CPU restatement of QsSim.run, fp64, libm) on a bounded sample of the
+    same workload: `reps` replications of `jobs` jobs spread over all host threads."""
+    from oracle import oracle
+
+    threads = threads or os.cpu_count() or 1
+
+    class Prm:
+        p1, mu1, mu2 = H2["p1"], H2["mu1"], H2["mu2"]
+
+    src, srv = ("M", ARRIVAL_RATE), ("H", Prm)
+    # calibrate with one replication per thread, then size the sample for ~seconds_target
+    t0 = time.perf_counter()
+    oracle.fifo_generate(C_SERVERS, None, src, srv, jobs, 12345, 0, threads, p_bins=32, threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-3)
+    rounds = max(1, int(seconds_target / dt))
+    reps = threads * rounds
+    t0 = time.perf_counter()
+    res = oracle.fifo_generate(C_SERVERS, None, src, srv, jobs, 12345, threads, reps, p_bins=32, threads=threads)
+    dt = time.perf_counter() - t0
+    served = sum(r.served for r in res)
+    return {"value": served / dt, "unit": "jobs/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} replications x {jobs} jobs of the same M/H2/8 workload, {dt:.1f} s, "
+                      f"oracle/mq_oracle.c (fp64, libm) on {threads} threads",
+            "seconds": dt, "w1": float(np.mean([r.w_sum[0] / r.taked for r in res]))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    jobs = args.jobs
+    base = None
+    vals = []
+    for i in range(args.warmup + args.steps):
+        b = cpu_baseline(args.ref_seconds, jobs)
+        if i >= args.warmup:
+            vals.append(b)
+        base = b
+    total_jobs = sum(b["value"] * b["seconds"] for b in vals)
+    total_s = sum(b["seconds"] for b in vals)
+    value = total_jobs / total_s
+    base = dict(base, value=value)
+    base.pop("seconds", None)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "jobs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(len(vals), 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"M/H2/{C_SERVERS} FIFO rho=0.7 CV=1.5, {jobs} jobs per replication (cfg2), "
+                               "bounded sample per step", "generator": "Philox2x32-10"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "jobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as tdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from most_queue_b200 import _lib
+    from most_queue_b200.random.utils.params import H2Params
+    from most_queue_b200.sim.base import QsSim
+
+    peaks, peak_src = _peaks()
+    reps, jobs = args.reps, args.jobs
+    p_bins = 128
+    h2 = H2Params(**H2)
+    ctx = _lib.default_context(local_rank)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    src, srv = _lib.make_dist("M", ARRIVAL_RATE), _lib.make_dist("H", h2)
+
+    # ---- device-resident throughput: the C-ABI call, timed with CUDA events on its stream ----
+    def step(i):
+        # every rank simulates `reps` replications with its own global ids (weak scaling)
+        agg, _ = ctx.sim_fifo(C_SERVERS, None, src, srv, jobs, reps, rank * reps, 20260101 + i, p_bins=p_bins)
+        return agg, ctx.last_timing()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    dev_ms, sim_ms, launches = 0.0, 0.0, 0
+    served = 0.0
+    agg_sum = None
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            agg, tm = step(args.warmup + i)
+            dev_ms += tm["sim_ms"] + tm["reduce_ms"]
+            sim_ms += tm["sim_ms"]
+            launches += tm["launches"]
+            served += agg[_lib.A_SERVED]
+            agg_sum = agg if agg_sum is None else agg_sum + agg
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = clk.summary()
+    dev_ms = maxreduce(dev_ms)
+    wall_ms = maxreduce(wall_ms)
+    sim_ms_max = maxreduce(sim_ms)
+    jobs_all = float(served)
+    if world > 1:
+        t = torch.tensor([jobs_all], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t)
+        jobs_all = float(t.item())
+    value = jobs_all / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API (QsSim.run with replications=), host in / host out ----
+    def api_step(i):
+        qs = QsSim(C_SERVERS, seed=777 + i, p_bins=p_bins)
+        qs.set_sources(ARRIVAL_RATE, "M")
+        qs.set_servers(h2, "H")
+        # under torchrun QsSim shards `replications` over the ranks and allreduces the aggregate
+        res = qs.run(jobs, replications=reps * world)
+        return qs, res
+
+    api_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_served = 0
+    for i in range(args.steps):
+        qs, res = api_step(1 + i)
+        e2e_served += qs.total_served_all
+    barrier()
+    e2e_s = maxreduce(time.perf_counter() - t0)
+    e2e_value = e2e_served / e2e_s
+    h2d = int(__import__("ctypes").sizeof(_lib.MqFifoCfg))
+    d2h = 8 * _lib.agg_len(p_bins)
+
+    # ---- moments against theory (Takahashi-Takami, tests/golden/theory.json) ----
+    moment_err = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "theory.json")) as f:
+            th = json.load(f)["mh2_8"]
+        R = agg_sum[_lib.A_REPS]
+        w1 = agg_sum[_lib.A_W] / R
+        v1 = agg_sum[_lib.A_V] / R
+        sd_w = np.sqrt(max(agg_sum[_lib.A_W2] / R - w1 * w1, 0.0) / R)
+        sd_v = np.sqrt(max(agg_sum[_lib.A_V2] / R - v1 * v1, 0.0) / R)
+        moment_err = {"w1": w1, "w1_theory": th["w"][0], "w1_ci99": 2.5758 * sd_w,
+                      "v1": v1, "v1_theory": th["v"][0], "v1_ci99": 2.5758 * sd_v,
+                      "note": "QsSim starts empty and keeps all jobs: O(1/N) start-up bias is part of the estimator"}
+    except Exception:
+        pass
+
+    if rank == 0:
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        peak_issue = sms * 128 * sm_max * 1e6 / 1e9  # G lane-instructions / s
+        per_gpu_jobs_s = (jobs_all / world) / (sim_ms_max * 1e-3)
+        achieved = per_gpu_jobs_s * I_ALG / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "jobs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"M/H2/{C_SERVERS} FIFO rho=0.7 CV=1.5 (BASELINE cfg2): {reps} replications x "
+                                   f"{jobs} jobs per GPU", "replications_per_gpu": reps, "jobs_per_replication": jobs,
+                       "p_bins": p_bins, "generator": "Philox2x32-10, counter=(arrival index, global replication id)",
+                       "cache": "generator mode has no input arrays; per-replication records "
+                                f"({8 * _lib.rec_rows(p_bins) * reps / 1e6:.0f} MB) exceed L2",
+                       "parallelism": f"replications sharded over {world} GPU(s), one allreduce of {d2h} B"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "jobs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "QsSim(8).set_sources/set_servers/run(total_served, replications=)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "issue", "achieved": achieved, "peak": peak_issue, "unit": "Glane-instr/s",
+                         "frac": achieved / peak_issue, "traffic": None,
+                         "kernel": "k2_fifo_gen<8,M,H2,infinite>",
+                         "note": f"achieved = jobs/s/GPU x {I_ALG:.0f} algorithmic lane-instructions per job "
+                                 f"(SURVEY 8d); peak = {sms} SMs x 128 lanes x {sm_max:.0f} MHz ({peak_src} clock); "
+                                 "HBM traffic is ~1 KB per replication, not the bound"},
+            "moments": moment_err,
+        }
+        if world == 1 and not args.no_cpu:
+            base = cpu_baseline(args.cpu_seconds, jobs)
+            base.pop("seconds", None)
+            line["cpu_baseline"] = base
+        if world == 1 and not args.no_replay:
+            try:
+                line["replay"] = replay_leg(ctx, peaks, peak_src)
+            except Exception as e:  # the headline must not be lost to the secondary measurement
+                line["replay"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def replay_leg(ctx, peaks, peak_src, reps=65536, rows=4096, steps=3):
+    """cfg 2r: K1 on HBM-resident fp64 arrays (16 B/job), timed with CUDA events; HBM roofline."""
+    import torch
+
+    from most_queue_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = -torch.log(1.0 - torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64))
+    br = torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64) < H2["p1"]
+    S = -torch.log(1.0 - torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64))
+    S = S / torch.where(br, H2["mu1"], H2["mu2"])
+    del br
+    n = int(rows * 0.9)  # departures per replication; leaves slack in the arrays
+    rec = torch.empty((_lib.replay_rows(64), reps), device="cuda", dtype=torch.float64)
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(steps + 1):
+        agg = ctx.replay_fifo_device(C_SERVERS, None, A.data_ptr(), S.data_ptr(), rows, rows, reps, n,
+                                     rec.data_ptr(), p_bins=64)
+        if i:
+            ms.append(ctx.last_timing()["sim_ms"])
+    jobs = float(agg[_lib.A_SERVED])
+    used = float((rec[_lib.rec_rows(64) + _lib.RF_AUSED].sum() + rec[_lib.rec_rows(64) + _lib.RF_SUSED].sum()).item())
+    t = float(np.mean(ms)) * 1e-3
+    achieved = 8.0 * used / t / 1e9
+    return {"kernel": "k1_fifo_replay<8,infinite>", "jobs_per_s": jobs / t, "ms": t * 1e3,
+            "workload": f"{reps} replications x {n} jobs, fp64 A,S resident in HBM ([draw][replication])",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": float(peaks.get("hbm_gbs", 6650.0)),
+                         "unit": "GB/s", "frac": achieved / float(peaks.get("hbm_gbs", 6650.0)), "traffic": None,
+                         "note": f"algorithmic bytes = 8 B x variates consumed (16 B/job); peak {peak_src}"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reps", type=int, default=1_000_000, help="replications per GPU (cfg2: 1e6)")
+    ap.add_argument("--jobs", type=int, default=100_000, help="jobs per replication (cfg2: 1e5)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=8.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-replay", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

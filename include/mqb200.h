@@ -1,0 +1,170 @@
+/*
+ * mqb200.h -- C ABI of libmqb200.so, the B200-native batched discrete-event simulation
+ * engine that stands in for most-queue's pure-Python simulation loops.
+ *
+ * The reference has no FFI: its hot path sits behind Python objects
+ * (QsSim / PriorityQueueSimulator / NetworkSimulator).  The entry points below are what a
+ * ctypes binding of those objects' run() methods binds (INTEGRATION.md shows the stub);
+ * each one names the reference interface it replaces (paths relative to most_queue/).
+ *
+ * Conventions: plain C types only, return 0 on success and a negative MQ_E_* code on
+ * failure (mq_last_error() holds the message, thread-local); the library never keeps a
+ * caller pointer after a call returns; every output buffer is allocated by the caller.
+ * One mq_ctx drives one GPU and is not re-entrant; use one context (one process) per GPU.
+ */
+#ifndef MQB200_H
+#define MQB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQ_ABI_VERSION 1
+
+/* error codes */
+#define MQ_OK 0
+#define MQ_E_INVALID (-1)     /* bad argument (the Python layer raises ValueError)        */
+#define MQ_E_CUDA (-2)        /* CUDA runtime error                                       */
+#define MQ_E_NODEVICE (-3)    /* no usable CUDA device                                    */
+#define MQ_E_INPUT_SHORT (-4) /* replay arrays ran out before total_served departures     */
+#define MQ_E_UNSUPPORTED (-5) /* configuration outside what the kernels cover             */
+#define MQ_E_OVERFLOW (-6)    /* a bounded per-lane structure overflowed                  */
+
+/* distribution kinds == Kendall codes of random/utils/create.py:19-80 */
+#define MQ_M 0       /* "M"       p = {mu}                  distributions.py:887-914 */
+#define MQ_H2 1      /* "H"       p = {p1, mu1, mu2}        distributions.py:407-429 */
+#define MQ_E 2       /* "E"       p = {r, mu}               distributions.py:807-820 */
+#define MQ_GAMMA 3   /* "Gamma"   p = {mu, alpha}           distributions.py:996-1003 */
+#define MQ_PA 4      /* "Pa"      p = {alpha, K}            distributions.py:749-761 */
+#define MQ_D 5       /* "D"       p = {b}                   distributions.py:614-626 */
+#define MQ_C2 6      /* "C"       p = {p1, mu1, mu2}        distributions.py:542-560 */
+#define MQ_UNIFORM 7 /* "Uniform" p = {mean, half_interval} distributions.py:298-309 */
+#define MQ_NORM 8    /* "Norm"    p = {mean, std_dev}       distributions.py:209-216 */
+#define MQ_WEIBULL 9 /* "Weibull" p = {k, W}                distributions.py:94-102  */
+
+typedef struct {
+    int32_t kind;
+    int32_t reserved;
+    double p[4];
+} mq_dist;
+
+typedef struct mq_ctx mq_ctx;
+
+/* ---- per-replication record: one fp64 row per field, replication-minor ([field][rep]) ---- */
+#define MQ_F_W 0        /* 4 rows: sum of w^k, k=1..4 over jobs that started service       */
+#define MQ_F_V 4        /* 4 rows: sum of v^k over served jobs                             */
+#define MQ_F_ARRIVED 8  /* QsSim.arrived  (base.py:222)                                    */
+#define MQ_F_TAKED 9    /* QsSim.taked    (base.py:172,300) = number of w samples          */
+#define MQ_F_SERVED 10  /* QsSim.served   (base.py:269)     = number of v samples          */
+#define MQ_F_DROPPED 11 /* QsSim.dropped  (base.py:211)                                    */
+#define MQ_F_TTEK 12    /* QsSim.ttek at stop                                              */
+#define MQ_F_FLAGS 13   /* non-zero: replication hit a library limit (see MQ_FLAG_*)       */
+#define MQ_F_POVER 14   /* time spent in states >= p_bins                                  */
+#define MQ_F_RESERVED 15
+#define MQ_F_P 16       /* p_bins rows: time spent with exactly j jobs in the system       */
+#define MQ_REC_ROWS(p_bins) (16 + (p_bins))
+
+#define MQ_FLAG_QUEUE_OVERFLOW 1
+
+/* ---- aggregate over replications (fp64 vector, what the multi-GPU allreduce sums) ---- */
+#define MQ_A_REPS 0      /* number of replications summed                                  */
+#define MQ_A_W 1         /* 4: sum over reps of the per-rep moment estimate  sum(w^k)/taked */
+#define MQ_A_W2 5        /* 4: sum over reps of that estimate squared (for CIs)            */
+#define MQ_A_V 9         /* 4 */
+#define MQ_A_V2 13       /* 4 */
+#define MQ_A_ARRIVED 17
+#define MQ_A_TAKED 18
+#define MQ_A_SERVED 19
+#define MQ_A_DROPPED 20
+#define MQ_A_TTEK 21
+#define MQ_A_WPOOL 22    /* 4: sum over reps of sum(w^k) (pooled moments)                  */
+#define MQ_A_VPOOL 26    /* 4 */
+#define MQ_A_FLAGGED 30  /* replications with a non-zero flag                              */
+#define MQ_A_POVER 31    /* sum over reps of p_over/ttek                                   */
+#define MQ_A_P 32        /* p_bins: sum over reps of p_time[j]/ttek, then p_bins squares   */
+#define MQ_AGG_LEN(p_bins) (32 + 2 * (p_bins))
+
+/* GI/G/c/r FIFO, generator mode.  Replaces QsSim.set_sources/set_servers/run
+ * (sim/base.py:95,114,488) for `replications` independent runs. */
+typedef struct {
+    int32_t c;            /* num_of_channels                               base.py:29   */
+    int32_t p_bins;       /* state-probability bins reported (1..MQ_MAX_PBINS)          */
+    int64_t buffer;       /* waiting places, -1 = infinite                 base.py:204  */
+    mq_dist src;          /* set_sources(params, kendall_notation)         base.py:95   */
+    mq_dist srv;          /* set_servers(params, kendall_notation)         base.py:114  */
+    int64_t total_served; /* run(total_served): departures per replication base.py:505  */
+    int64_t replications; /* replications simulated by THIS call (this rank's shard)    */
+    int64_t rep0;         /* global id of the first one: Philox counter word            */
+    uint64_t seed;        /* QsSim(seed=...) -> Philox key                 base_core.py:23 */
+    int32_t flags;        /* reserved, 0                                                */
+    int32_t reserved;
+} mq_fifo_cfg;
+
+#define MQ_MAX_PBINS 1024
+#define MQ_MAX_CHANNELS 32
+
+/* GI/G/c/r FIFO, replay mode: variates come from caller arrays instead of the generator.
+ * A[i * replications + r] is the i-th interarrival draw of replication r (A[0][r] is the
+ * draw set_sources makes, base.py:112); S[j * replications + r] the j-th service draw
+ * (servers.py:88).  fp64 throughout, bit-exact with the reference for the same arrays. */
+typedef struct {
+    int32_t c;
+    int32_t p_bins;
+    int64_t buffer;
+    int64_t total_served;
+    int64_t replications;
+    int64_t n_a;          /* rows of A */
+    int64_t n_s;          /* rows of S */
+    int32_t device_ptrs;  /* 1: A, S (and rep_out when given) are device pointers       */
+    int32_t flags;
+} mq_replay_cfg;
+
+/* extra rows appended to the replay record after MQ_REC_ROWS(p_bins): the reference's own
+ * running-mean moments (stats_update.py:6-22), bit-exact */
+#define MQ_RF_WRUN 0    /* 4 */
+#define MQ_RF_VRUN 4    /* 4 */
+#define MQ_RF_BUSYRUN 8 /* 3: QsSim.busy (base.py:276-281)                              */
+#define MQ_RF_BUSYN 11
+#define MQ_RF_INSYS 12
+#define MQ_RF_QUEUED 13
+#define MQ_RF_AUSED 14
+#define MQ_RF_SUSED 15
+#define MQ_REPLAY_EXTRA 16
+#define MQ_REPLAY_ROWS(p_bins) (MQ_REC_ROWS(p_bins) + MQ_REPLAY_EXTRA)
+
+int mq_version(void);
+int mq_device_count(void);
+const char *mq_last_error(void);
+
+int mq_create(mq_ctx **out, int device_id);
+int mq_destroy(mq_ctx *ctx);
+
+/* agg: MQ_AGG_LEN(p_bins) doubles (host).  rep_out: NULL, or MQ_REC_ROWS(p_bins) *
+ * replications doubles (host), [field][rep]. */
+int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_out);
+
+/* rep_out: MQ_REPLAY_ROWS(p_bins) * replications doubles, [field][rep] (host, or device
+ * when cfg->device_ptrs).  agg may be NULL. */
+int mq_replay_fifo(mq_ctx *ctx, const mq_replay_cfg *cfg, const double *A, const double *S,
+                   double *agg, double *rep_out);
+
+/* device time of the kernels of the last call on this context, in milliseconds
+ * (CUDA events on the context's stream): simulation kernel(s), reduction kernel, and the
+ * whole call including copies. */
+int mq_last_timing(mq_ctx *ctx, double *sim_ms, double *reduce_ms, double *total_ms);
+/* number of kernels the last call launched */
+int mq_last_launches(mq_ctx *ctx);
+
+/* generator building blocks, exported for the known-answer tests */
+int mq_debug_philox2x32(mq_ctx *ctx, uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[2]);
+/* n variates of `d` for arrival indices 0..n-1 of replication `rep` (which: 0 source word,
+ * 1 server word), evaluated by the device sampler */
+int mq_debug_variates(mq_ctx *ctx, const mq_dist *d, uint64_t seed, uint32_t rep, int which,
+                      int64_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

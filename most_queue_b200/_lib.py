@@ -1,0 +1,273 @@
+"""ctypes binding of libmqb200.so (the C ABI in include/mqb200.h).
+
+The library is the only compute path.  If it is missing the import of any simulator fails
+loudly with instructions to build it; there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmqb200.so")
+
+# distribution kinds (mqb200.h MQ_M ...)
+KINDS = {"M": 0, "H": 1, "E": 2, "Gamma": 3, "Pa": 4, "D": 5, "C": 6, "Uniform": 7, "Norm": 8, "Weibull": 9}
+
+# error codes
+MQ_E_INVALID, MQ_E_CUDA, MQ_E_NODEVICE, MQ_E_INPUT_SHORT, MQ_E_UNSUPPORTED, MQ_E_OVERFLOW = -1, -2, -3, -4, -5, -6
+
+# record rows / aggregate layout (mqb200.h)
+F_W, F_V, F_ARRIVED, F_TAKED, F_SERVED, F_DROPPED, F_TTEK, F_FLAGS, F_POVER, F_P = 0, 4, 8, 9, 10, 11, 12, 13, 14, 16
+A_REPS, A_W, A_W2, A_V, A_V2 = 0, 1, 5, 9, 13
+A_ARRIVED, A_TAKED, A_SERVED, A_DROPPED, A_TTEK, A_WPOOL, A_VPOOL, A_FLAGGED, A_POVER, A_P = 17, 18, 19, 20, 21, 22, 26, 30, 31, 32
+RF_WRUN, RF_VRUN, RF_BUSYRUN, RF_BUSYN, RF_INSYS, RF_QUEUED, RF_AUSED, RF_SUSED, REPLAY_EXTRA = 0, 4, 8, 11, 12, 13, 14, 15, 16
+MAX_PBINS = 1024
+
+
+def rec_rows(p_bins: int) -> int:
+    return 16 + p_bins
+
+
+def agg_len(p_bins: int) -> int:
+    return 32 + 2 * p_bins
+
+
+def replay_rows(p_bins: int) -> int:
+    return rec_rows(p_bins) + REPLAY_EXTRA
+
+
+class MqDist(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 4)]
+
+
+class MqFifoCfg(C.Structure):
+    _fields_ = [
+        ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64),
+        ("src", MqDist), ("srv", MqDist),
+        ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64),
+        ("seed", C.c_uint64), ("flags", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class MqReplayCfg(C.Structure):
+    _fields_ = [
+        ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("total_served", C.c_int64),
+        ("replications", C.c_int64), ("n_a", C.c_int64), ("n_s", C.c_int64),
+        ("device_ptrs", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+class MqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmqb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libmqb200.so; raise if it has not been built (no fallback path exists)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing. Build it with `python -m most_queue_b200.build` "
+                "(needs nvcc; the CUDA library is the only compute path, there is no CPU fallback)."
+            )
+        L = C.CDLL(LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        vp = C.c_void_p
+        L.mq_version.restype = C.c_int
+        L.mq_device_count.restype = C.c_int
+        L.mq_last_error.restype = C.c_char_p
+        L.mq_create.restype = C.c_int
+        L.mq_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.mq_destroy.restype = C.c_int
+        L.mq_destroy.argtypes = [vp]
+        L.mq_sim_fifo.restype = C.c_int
+        L.mq_sim_fifo.argtypes = [vp, C.POINTER(MqFifoCfg), dp, dp]
+        L.mq_replay_fifo.restype = C.c_int
+        L.mq_replay_fifo.argtypes = [vp, C.POINTER(MqReplayCfg), vp, vp, dp, vp]
+        L.mq_last_timing.restype = C.c_int
+        L.mq_last_timing.argtypes = [vp, dp, dp, dp]
+        L.mq_last_launches.restype = C.c_int
+        L.mq_last_launches.argtypes = [vp]
+        L.mq_debug_philox2x32.restype = C.c_int
+        L.mq_debug_philox2x32.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.mq_debug_variates.restype = C.c_int
+        L.mq_debug_variates.argtypes = [vp, C.POINTER(MqDist), C.c_uint64, C.c_uint32, C.c_int, C.c_int64,
+                                        C.POINTER(C.c_float)]
+        _lib = L
+        return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().mq_last_error().decode("utf-8", "replace")
+        if rc == MQ_E_INVALID:
+            raise ValueError(msg)
+        raise MqError(rc, msg)
+
+
+def _get(params, name):
+    if isinstance(params, dict):
+        return params[name]
+    return getattr(params, name)
+
+
+def make_dist(kendall_notation: str, params) -> MqDist:
+    """(Kendall code, reference-style params) -> mq_dist.
+
+    Unknown codes raise ValueError exactly like create_distribution (random/utils/create.py:76).
+    """
+    if kendall_notation not in KINDS or kendall_notation == "Weibull":
+        raise ValueError(
+            "Incorrect distribution type specified. Supported: M, H, E, Gamma, C, Pa, Uniform, Norm, D"
+        )
+    d = MqDist()
+    d.kind = KINDS[kendall_notation]
+    k = kendall_notation
+    if k in ("M", "D"):
+        vals = [float(params)]
+    elif k in ("H", "C"):
+        p1, m1, m2 = _get(params, "p1"), _get(params, "mu1"), _get(params, "mu2")
+        if any(isinstance(x, complex) and abs(x.imag) > 0 for x in (p1, m1, m2)):
+            raise ValueError("complex H2/Cox parameters cannot be sampled")
+        vals = [float(getattr(p1, "real", p1)), float(getattr(m1, "real", m1)), float(getattr(m2, "real", m2))]
+    elif k == "E":
+        vals = [float(_get(params, "r")), float(_get(params, "mu"))]
+    elif k == "Gamma":
+        vals = [float(_get(params, "mu")), float(_get(params, "alpha"))]
+    elif k == "Pa":
+        vals = [float(_get(params, "alpha")), float(_get(params, "K"))]
+    elif k == "Uniform":
+        vals = [float(_get(params, "mean")), float(_get(params, "half_interval"))]
+    elif k == "Norm":
+        vals = [float(_get(params, "mean")), float(_get(params, "std_dev"))]
+    else:  # pragma: no cover
+        raise ValueError(k)
+    for i, v in enumerate(vals):
+        d.p[i] = v
+    return d
+
+
+class Context:
+    """One mq_ctx: one GPU, one stream.  Not re-entrant."""
+
+    def __init__(self, device: int | None = None):
+        self._L = load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+            n = self._L.mq_device_count()
+            if n > 0:
+                device %= n
+        self.device = device
+        self._h = C.c_void_p()
+        check(self._L.mq_create(C.byref(self._h), int(device)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.mq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- K2 ----
+    def sim_fifo(self, c, buffer, src: MqDist, srv: MqDist, total_served, replications, rep0, seed,
+                 p_bins=128, per_replication=False):
+        cfg = MqFifoCfg()
+        cfg.c, cfg.p_bins = int(c), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        cfg.src, cfg.srv = src, srv
+        cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        agg = np.zeros(agg_len(p_bins))
+        rec = np.empty((rec_rows(p_bins), int(replications))) if per_replication else None
+        check(self._L.mq_sim_fifo(
+            self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+            rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    # ---- K1 ----
+    def replay_fifo(self, c, buffer, A: np.ndarray, S: np.ndarray, total_served, p_bins=128, want_agg=True):
+        """A: [n_a, R], S: [n_s, R] float64 host arrays (replication-minor)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        if A.ndim != 2 or S.ndim != 2 or A.shape[1] != S.shape[1]:
+            raise ValueError("A and S must be 2-D [draw][replication] with equal replication counts")
+        R = A.shape[1]
+        cfg = MqReplayCfg()
+        cfg.c, cfg.p_bins = int(c), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        cfg.total_served, cfg.replications = int(total_served), R
+        cfg.n_a, cfg.n_s, cfg.device_ptrs = A.shape[0], S.shape[0], 0
+        rec = np.empty((replay_rows(p_bins), R))
+        agg = np.zeros(agg_len(p_bins)) if want_agg else None
+        check(self._L.mq_replay_fifo(
+            self._h, C.byref(cfg), A.ctypes.data, S.ctypes.data,
+            agg.ctypes.data_as(C.POINTER(C.c_double)) if want_agg else None, rec.ctypes.data))
+        return agg, rec
+
+    def replay_fifo_device(self, c, buffer, a_ptr: int, s_ptr: int, n_a, n_s, replications, total_served,
+                           rec_ptr: int, p_bins=128):
+        """Device-pointer form (inputs already resident in HBM); rec_ptr: replay_rows x R doubles."""
+        cfg = MqReplayCfg()
+        cfg.c, cfg.p_bins = int(c), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        cfg.total_served, cfg.replications = int(total_served), int(replications)
+        cfg.n_a, cfg.n_s, cfg.device_ptrs = int(n_a), int(n_s), 1
+        agg = np.zeros(agg_len(p_bins))
+        check(self._L.mq_replay_fifo(self._h, C.byref(cfg), a_ptr, s_ptr,
+                                     agg.ctypes.data_as(C.POINTER(C.c_double)), rec_ptr))
+        return agg
+
+    def last_timing(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(self._L.mq_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sim_ms": a.value, "reduce_ms": b.value, "total_ms": c.value,
+                "launches": self._L.mq_last_launches(self._h)}
+
+    # ---- debug / known-answer ----
+    def philox2x32(self, c0, c1, key):
+        out = (C.c_uint32 * 2)()
+        check(self._L.mq_debug_philox2x32(self._h, c0, c1, key, out))
+        return int(out[0]), int(out[1])
+
+    def variates(self, dist: MqDist, seed, rep, which, n):
+        out = np.empty(int(n), dtype=np.float32)
+        check(self._L.mq_debug_variates(self._h, C.byref(dist), int(seed) & 0xFFFFFFFFFFFFFFFF, int(rep),
+                                        int(which), int(n), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    key = -1 if device is None else int(device)
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(device)
+    return _default_ctx[key]
+
+
+def seed_to_key(seed: int) -> int:
+    """64-bit seed -> 32-bit Philox key (splitmix64 finaliser; mirrors mq_api.cu seed_to_key)."""
+    m = 0xFFFFFFFFFFFFFFFF
+    s = (int(seed) + 0x9E3779B97F4A7C15) & m
+    s = ((s ^ (s >> 30)) * 0xBF58476D1CE4E5B9) & m
+    s = ((s ^ (s >> 27)) * 0x94D049BB133111EB) & m
+    s ^= s >> 31
+    return (s ^ (s >> 32)) & 0xFFFFFFFF

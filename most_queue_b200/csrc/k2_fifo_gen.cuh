@@ -1,0 +1,361 @@
+// k2_fifo_gen.cuh -- K2: generate-and-simulate GI/G/c/r FIFO kernel.
+//
+// One lane = one independent replication of QsSim.run() (most_queue/sim/base.py:488-528).
+// The lane walks the same event sequence as the reference (arrival wins ties, base.py:442-454;
+// stop right after the total_served-th departure, base.py:505) and produces the same sample
+// sets: w for every job that starts service (base.py:172-173,301-305), v for every served job
+// (base.py:269-272), p[j] = time with j jobs in the system (base.py:327-340), finite-buffer
+// drops (base.py:204-212).
+//
+// Layout of one lane's state (all on chip):
+//   * clock, next arrival, c completion times: fp32 registers, RELATIVE to an epoch that is
+//     re-based every MQ_EV events so magnitudes stay small; the elapsed epochs are summed in
+//     fp64.  The c completion times are kept sorted; the low TB bits of each key carry the id of
+//     the server slot (keys are therefore all distinct and the slot survives the sorting
+//     network); free servers are large finite sentinels carrying their slot id.
+//   * v of the job in service on each slot: shared memory [slot][lane] (bank = lane, conflict
+//     free).  v is accumulated when service STARTS and the <= c jobs still in service at the
+//     stop are subtracted at the end, which yields exactly the reference's sample set.
+//   * time-in-state histogram: first MQ_BF states in shared memory [state][lane] (fp32, flushed
+//     to the fp64 per-replication record every MQ_FLUSH epochs); higher states go straight to
+//     the fp64 record in HBM (rare).
+//   * infinite buffer: the queue is NOT stored.  A lagging Philox cursor regenerates the
+//     arrival time and service time of the job at the head of the queue (same words, same
+//     summation), so the queue is unbounded with O(1) state.
+//   * finite buffer r: (gap to previous queued arrival, service time) per waiting job in a ring
+//     of r entries per lane in HBM scratch [slot][lane].
+#pragma once
+
+#include "mq_device.cuh"
+
+namespace mq {
+
+constexpr int MQ_BLOCK = 128;    // lanes per CTA
+constexpr int MQ_BF = 32;        // histogram states kept in shared memory
+constexpr int MQ_EV = 32;        // events between epoch re-bases
+constexpr int MQ_FLUSH = 64;     // re-bases between fp32 -> fp64 flushes
+constexpr uint32_t MQ_SENT_FREE = 0x7f000000u;  // 1.7e38: free server (plus slot id)
+constexpr uint32_t MQ_SENT_OFF = 0x7e800000u;   // 8.5e37: slot not used (c < CT)
+
+struct K2Params {
+    int c;
+    int p_bins;
+    long long buffer;  // -1 infinite
+    long long jobs;
+    long long reps;
+    uint32_t rep0;
+    uint32_t key0;
+    DistF src, srv;
+    double *rec;      // [MQ_REC_ROWS(p_bins)][reps], zeroed by the caller
+    float2 *ring;     // finite buffer: [buffer][total lanes]
+    long long lanes;  // gridDim.x * MQ_BLOCK
+};
+
+template <int CT>
+struct Tag {
+    static constexpr int TB = CT <= 1 ? 0 : CT <= 2 ? 1 : CT <= 4 ? 2 : CT <= 8 ? 3 : CT <= 16 ? 4 : 5;
+    static constexpr uint32_t MASK = (1u << TB) - 1u;
+    static constexpr uint32_t HALF = TB ? (1u << (TB - 1)) : 0u;
+};
+
+// round the key to the tag grid (nearest) and stamp the slot id into its low bits
+template <int CT>
+__device__ __forceinline__ float stamp(float x, uint32_t tag)
+{
+    if (Tag<CT>::TB == 0) return x;
+    uint32_t b = __float_as_uint(x);
+    return __uint_as_float(((b + Tag<CT>::HALF) & ~Tag<CT>::MASK) | tag);
+}
+
+// L[0..CT-1] sorted ascending.  new L = sorted(L[0..CT-2] + {y}); the old maximum is dropped.
+template <int CT>
+__device__ __forceinline__ void insert_drop_last(float (&L)[CT], float y)
+{
+    float prev = L[0];
+    L[0] = fminf(prev, y);
+#pragma unroll
+    for (int j = 1; j < CT; ++j) {
+        float cur = L[j];
+        float up = fmaxf(prev, y);
+        L[j] = (j == CT - 1) ? up : fminf(cur, up);
+        prev = cur;
+    }
+    if (CT == 1) L[0] = y;
+}
+
+// new L = sorted(L[1..CT-1] + {y}); the old minimum is dropped.
+template <int CT>
+__device__ __forceinline__ void insert_drop_first(float (&L)[CT], float y)
+{
+    if (CT == 1) {
+        L[0] = y;
+        return;
+    }
+    float prev = L[1];
+    L[0] = fminf(prev, y);
+#pragma unroll
+    for (int j = 1; j < CT - 1; ++j) {
+        float cur = L[j + 1];
+        L[j] = fminf(cur, fmaxf(prev, y));
+        prev = cur;
+    }
+    L[CT - 1] = fmaxf(prev, y);
+}
+
+// After a re-base two keys can land on the same grid point and then differ only by their slot
+// ids, which may invert an adjacent pair.  Restore strict order (odd-even transposition until
+// clean; almost always the check alone).
+template <int CT>
+__device__ __forceinline__ void restore_order(float (&L)[CT])
+{
+    if (CT == 1) return;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j + 1 < CT; ++j) bad |= L[j] > L[j + 1];
+    while (bad) {
+        bad = false;
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+#pragma unroll
+            for (int j = par; j + 1 < CT; j += 2) {
+                const float lo = fminf(L[j], L[j + 1]), hi = fmaxf(L[j], L[j + 1]);
+                bad |= lo != L[j];
+                L[j] = lo;
+                L[j + 1] = hi;
+            }
+        }
+    }
+}
+
+template <int CT, int SRCK, int SRVK, bool FINITE>
+__global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
+{
+    extern __shared__ float smem[];
+    float *hist = smem;                       // [MQ_BF][MQ_BLOCK]
+    float *vslot = smem + MQ_BF * MQ_BLOCK;   // [CT][MQ_BLOCK]
+    const int tid = threadIdx.x;
+    const long long gtid = (long long)blockIdx.x * MQ_BLOCK + tid;
+    const int c = P.c;
+    const uint32_t key0 = P.key0;
+    const long long R = P.reps;
+    const uint32_t N = (uint32_t)P.jobs;
+    const uint32_t cap = FINITE ? (uint32_t)P.buffer : 0u;
+
+    for (long long rl = gtid; rl < R; rl += P.lanes) {
+        const uint32_t rep = P.rep0 + (uint32_t)rl;
+        double *rec = P.rec + rl;
+
+        // ---- state ----
+        float L[CT];
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+            // ascending: unused slots (OFF) first, then the c free servers with ids 0..c-1
+            int nfree_first = CT - c;
+            L[j] = __uint_as_float(j < nfree_first ? (MQ_SENT_OFF | (uint32_t)(c + j))
+                                                   : (MQ_SENT_FREE | (uint32_t)(j - nfree_first)));
+        }
+#pragma unroll
+        for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK + tid] = 0.0f;
+
+        float t = 0.0f;
+        double tbase = 0.0;
+        float sw[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t arrived = 0, taked = 0, served = 0, dropped = 0;
+        int n = 0, nbusy = 0;
+        uint32_t q = 0;
+        // infinite buffer: lagging cursor = head of the queue
+        uint32_t h = 0;
+        float a_h = 0.0f, S_h = 0.0f;
+        // finite buffer: ring bookkeeping
+        uint32_t head = 0;
+        float a_anchor = 0.0f, a_lastq = 0.0f;
+        uint32_t flags = 0;
+
+        // first arrival: the draw set_sources makes (base.py:112)
+        float tA, S_pend;
+        {
+            uint2 w = philox2x32_10(0u, rep, key0);
+            tA = sample<SRCK>(P.src, w.x, 0u, rep, key0, 0);
+            S_pend = sample<SRVK>(P.srv, w.y, 0u, rep, key0, 1);
+        }
+
+        int epoch = 0;
+        bool done = (N == 0);
+        while (!done) {
+#pragma unroll 1
+            for (int ev = 0; ev < MQ_EV; ++ev) {
+                const float d0 = L[0];
+                const bool is_arr = tA <= d0;  // arrival wins ties (base.py:442-454)
+                const float te = is_arr ? tA : d0;
+                const float dt = te - t;
+                // _update_state_probs (base.py:327-340)
+                if (n < MQ_BF) {
+                    hist[n * MQ_BLOCK + tid] += dt;
+                } else if (n < P.p_bins) {
+                    rec[(long long)(MQ_F_P + n) * R] += (double)dt;
+                } else {
+                    rec[(long long)MQ_F_POVER * R] += (double)dt;
+                }
+                t = te;
+
+                // one generator site per event: the next arrival (lead cursor) or, on a
+                // departure that leaves jobs waiting, the next queue head (lag cursor)
+                uint32_t ridx = arrived + 1u;
+                bool need = is_arr;
+                if (!FINITE && !is_arr) {
+                    ridx = h + 1u;
+                    need = q > 1u;
+                }
+                float gx = 0.0f, sx = 0.0f;
+                if (need) {
+                    uint2 w = philox2x32_10(ridx, rep, key0);
+                    gx = sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
+                    sx = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
+                }
+
+                if (is_arr) {
+                    // arrival() base.py:214-247
+                    const uint32_t idx = arrived;
+                    arrived++;
+                    const float S_i = S_pend;
+                    tA = t + gx;
+                    S_pend = sx;
+                    if (nbusy < c) {
+                        // send_task_to_channel base.py:155-184: a free slot sits at the top
+                        const uint32_t tag = __float_as_uint(L[CT - 1]) & Tag<CT>::MASK;
+                        insert_drop_last<CT>(L, stamp<CT>(t + S_i, tag));
+                        vslot[tag * MQ_BLOCK + tid] = S_i;
+                        taked++;
+                        nbusy++;
+                        n++;
+                        acc4(sv, S_i);  // w = 0 adds nothing to the w sums
+                    } else if (!FINITE || q < cap) {
+                        // send_task_to_queue base.py:186-212
+                        n++;
+                        if (!FINITE) {
+                            if (q == 0u) {
+                                h = idx;
+                                a_h = t;
+                                S_h = S_i;
+                            }
+                        } else {
+                            float gap = 0.0f;
+                            if (q == 0u) a_anchor = t; else gap = t - a_lastq;
+                            a_lastq = t;
+                            uint32_t slot = head + q;
+                            if (slot >= cap) slot -= cap;
+                            P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_i);
+                        }
+                        q++;
+                    } else {
+                        dropped++;  // base.py:211-212
+                    }
+                } else {
+                    // serving() base.py:249-286
+                    served++;
+                    n--;
+                    const uint32_t tag = __float_as_uint(d0) & Tag<CT>::MASK;
+                    if (q > 0u) {
+                        // send_head_of_queue_to_channel base.py:288-310
+                        float a, S;
+                        if (!FINITE) {
+                            a = a_h;
+                            S = S_h;
+                            if (q > 1u) {
+                                h++;
+                                a_h += gx;
+                                S_h = sx;
+                            }
+                        } else {
+                            float2 e = P.ring[(long long)head * P.lanes + gtid];
+                            a = a_anchor + e.x;
+                            a_anchor = a;
+                            S = e.y;
+                            head++;
+                            if (head >= cap) head = 0u;
+                        }
+                        q--;
+                        const float w = fmaxf(t - a, 0.0f);
+                        const float vv = w + S;
+                        insert_drop_first<CT>(L, stamp<CT>(t + S, tag));
+                        vslot[tag * MQ_BLOCK + tid] = vv;
+                        taked++;
+                        acc4(sw, w);
+                        acc4(sv, vv);
+                    } else {
+                        insert_drop_first<CT>(L, __uint_as_float(MQ_SENT_FREE | tag));
+                        nbusy--;
+                    }
+                    if (served >= N) {
+                        done = true;
+                        break;
+                    }
+                }
+            }
+
+            // ---- re-base the epoch ----
+            const float base = t;
+            tbase += (double)base;
+            t = 0.0f;
+            tA -= base;
+            a_h -= base;
+            a_anchor -= base;
+            a_lastq -= base;
+#pragma unroll
+            for (int j = 0; j < CT; ++j) {
+                const uint32_t b = __float_as_uint(L[j]);
+                const float moved = stamp<CT>(L[j] - base, b & Tag<CT>::MASK);
+                L[j] = (b < MQ_SENT_OFF) ? moved : L[j];
+            }
+            restore_order<CT>(L);
+            ++epoch;
+            if (done || (epoch % MQ_FLUSH) == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    rec[(long long)(MQ_F_W + k) * R] += (double)sw[k];
+                    rec[(long long)(MQ_F_V + k) * R] += (double)sv[k];
+                    sw[k] = 0.0f;
+                    sv[k] = 0.0f;
+                }
+                const int nb = P.p_bins < MQ_BF ? P.p_bins : MQ_BF;
+                for (int b = 0; b < nb; ++b) {
+                    rec[(long long)(MQ_F_P + b) * R] += (double)hist[b * MQ_BLOCK + tid];
+                    hist[b * MQ_BLOCK + tid] = 0.0f;
+                }
+                if (P.p_bins < MQ_BF) {
+                    double over = 0.0;
+                    for (int b = P.p_bins; b < MQ_BF; ++b) {
+                        over += (double)hist[b * MQ_BLOCK + tid];
+                        hist[b * MQ_BLOCK + tid] = 0.0f;
+                    }
+                    rec[(long long)MQ_F_POVER * R] += over;
+                }
+            }
+        }
+
+        // ---- jobs still in service at the stop were counted at start: take them out ----
+        double vfix[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+            const uint32_t b = __float_as_uint(L[j]);
+            if (b < MQ_SENT_OFF) {
+                const double x = (double)vslot[(b & Tag<CT>::MASK) * MQ_BLOCK + tid];
+                const double x2 = x * x;
+                vfix[0] += x;
+                vfix[1] += x2;
+                vfix[2] += x2 * x;
+                vfix[3] += x2 * x2;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rec[(long long)(MQ_F_V + k) * R] -= vfix[k];
+        rec[(long long)MQ_F_ARRIVED * R] = (double)arrived;
+        rec[(long long)MQ_F_TAKED * R] = (double)taked;
+        rec[(long long)MQ_F_SERVED * R] = (double)served;
+        rec[(long long)MQ_F_DROPPED * R] = (double)dropped;
+        rec[(long long)MQ_F_TTEK * R] = tbase + (double)t;
+        rec[(long long)MQ_F_FLAGS * R] = (double)flags;
+    }
+}
+
+}  // namespace mq

@@ -1,0 +1,184 @@
+// mq_device.cuh -- device-side building blocks shared by the simulation kernels:
+// Philox2x32-10, word -> variate samplers (fp32, MUFU log/exp), small helpers.
+//
+// Generator spec (DESIGN.md "Generator streams"): arrival index i of replication r makes
+// one primary call philox2x32_10(c0 = i, c1 = r, key0); word 0 drives the interarrival
+// gap before arrival i, word 1 the service time of arrival i.  Distributions that need
+// more than one word take them from extension calls with key0 + STRIDE * (2n + which),
+// n = 1, 2, ...  The samplers follow most_queue/random/distributions.py (formulas cited at
+// each case) but evaluate in fp32 with MUFU.LG2 / MUFU.EX2.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mqb200.h"
+
+#define MQ_PHILOX_M 0xD256D193u
+#define MQ_PHILOX_W 0x9E3779B9u
+#define MQ_KEY_STRIDE 0xB5297A4Du
+
+namespace mq {
+
+// fp32 device form of an mq_dist, prepared on the host (see make_distf in mq_api.cu)
+struct DistF {
+    int kind;
+    int r;       // Erlang order; Gamma: 1 when alpha < 1
+    uint32_t T;  // H2 / Cox branch threshold on the raw 32-bit word
+    float a, b, c, d;
+};
+
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi = __umulhi(MQ_PHILOX_M, c0);
+        uint32_t lo = MQ_PHILOX_M * c0;
+        c0 = hi ^ (key + (uint32_t)r * MQ_PHILOX_W) ^ c1;
+        c1 = lo;
+    }
+    return make_uint2(c0, c1);
+}
+
+__device__ __forceinline__ float fast_lg2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float fast_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// (w + 0.5) * 2^-32, in (0, 1]
+__device__ __forceinline__ float u01(uint32_t w)
+{
+    return fmaf(__uint2float_rn(w), 0x1p-32f, 0x1p-33f);
+}
+
+// extension words of one variate: call n >= 1 of stream `which`
+__device__ __forceinline__ uint2 ext_words(uint32_t idx, uint32_t rep, uint32_t key0, int which, uint32_t n)
+{
+    return philox2x32_10(idx, rep, key0 + MQ_KEY_STRIDE * (2u * n + (uint32_t)which));
+}
+
+// -------------------------------------------------------------------------------------
+// samplers.  KIND >= 0 compiles exactly one of them; KIND < 0 switches on d.kind at run
+// time (uniform across the grid, so the branch does not diverge).
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ float sample_m(const DistF &d, uint32_t w0)
+{
+    // distributions.py:906 -> :807-820 with r = 1: -log(U)/mu ; d.a = -ln2/mu
+    return fast_lg2(u01(w0)) * d.a;
+}
+
+__device__ __forceinline__ float sample_h2(const DistF &d, uint32_t w0)
+{
+    // distributions.py:407-429.  One word: the branch test "r < p1" is done on the raw word
+    // against T = floor(p1 * 2^32); given the branch, the word is uniform on its side of
+    // T and is reused as the exponential's uniform.  d.a = 1/T, d.b = 1/(2^32-T),
+    // d.c = -ln2/mu1, d.d = -ln2/mu2
+    bool first = w0 < d.T;
+    uint32_t off = first ? w0 : w0 - d.T;
+    float inv = first ? d.a : d.b;
+    float sc = first ? d.c : d.d;
+    float u = fmaf(__uint2float_rn(off), inv, 0.5f * inv);
+    return fast_lg2(u) * sc;
+}
+
+__device__ __forceinline__ float sample_pa(const DistF &d, uint32_t w0)
+{
+    // distributions.py:749-761: K * U^(-1/alpha); d.a = -1/alpha, d.b = K
+    return d.b * fast_ex2(fast_lg2(u01(w0)) * d.a);
+}
+
+static __device__ __noinline__ float sample_erlang(const DistF &d, uint32_t w0, uint32_t idx, uint32_t rep,
+                                            uint32_t key0, int which)
+{
+    // distributions.py:807-820: -log(prod U)/mu, as a sum of logs; d.a = -ln2/mu
+    float acc = fast_lg2(u01(w0));
+    uint2 e = make_uint2(0u, 0u);
+    for (int k = 1; k < d.r; ++k) {
+        if (k & 1) e = ext_words(idx, rep, key0, which, (uint32_t)(k + 1) >> 1);
+        acc += fast_lg2(u01((k & 1) ? e.x : e.y));
+    }
+    return acc * d.a;
+}
+
+static __device__ __noinline__ float sample_gamma(const DistF &d, uint32_t w0, uint32_t idx, uint32_t rep,
+                                           uint32_t key0, int which)
+{
+    // distributions.py:996-1003 (Generator.gamma(alpha, 1/mu)) restated as Marsaglia-Tsang
+    // with Box-Muller normals.  d.a = dd, d.b = cc, d.c = 1/mu, d.d = 1/alpha, d.r = alpha<1
+    const float dd = d.a, cc = d.b;
+    float x = dd;
+    for (uint32_t t = 0; t < 15; ++t) {
+        uint2 e0 = ext_words(idx, rep, key0, which, 2 * t + 1);
+        uint2 e1 = ext_words(idx, rep, key0, which, 2 * t + 2);
+        float rad = sqrtf(-1.3862943611198906f * fast_lg2(u01(e0.x)));  // sqrt(-2 ln u)
+        float z = rad * cospif(2.0f * u01(e0.y));
+        float v = fmaf(cc, z, 1.0f);
+        if (v <= 0.0f) continue;
+        v = v * v * v;
+        x = dd * v;
+        float lhs = 0.6931471805599453f * fast_lg2(u01(e1.x));
+        float rhs = 0.5f * z * z + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
+        if (lhs < rhs) break;
+    }
+    if (d.r) x *= fast_ex2(fast_lg2(u01(w0)) * d.d);
+    return x * d.c;
+}
+
+template <int KIND>
+__device__ __forceinline__ float sample(const DistF &d, uint32_t w0, uint32_t idx, uint32_t rep,
+                                        uint32_t key0, int which)
+{
+    const int kind = KIND >= 0 ? KIND : d.kind;
+    switch (kind) {
+    case MQ_M:
+        return sample_m(d, w0);
+    case MQ_H2:
+        return sample_h2(d, w0);
+    case MQ_E:
+        return sample_erlang(d, w0, idx, rep, key0, which);
+    case MQ_GAMMA:
+        return sample_gamma(d, w0, idx, rep, key0, which);
+    case MQ_PA:
+        return sample_pa(d, w0);
+    case MQ_D:  // distributions.py:614-626
+        return d.a;
+    case MQ_C2: {  // distributions.py:542-560; d.a = -ln2/mu1, d.b = -ln2/mu2
+        uint2 e = ext_words(idx, rep, key0, which, 1);
+        float res = fast_lg2(u01(w0)) * d.a;
+        if (e.x < d.T) res += fast_lg2(u01(e.y)) * d.b;
+        return res;
+    }
+    case MQ_UNIFORM:  // distributions.py:298-309; d.a = mean - half, d.b = 2 half
+        return fmaf(d.b, u01(w0), d.a);
+    case MQ_NORM: {  // distributions.py:209-216 (Box-Muller); d.a = mean, d.b = std
+        uint2 e = ext_words(idx, rep, key0, which, 1);
+        float rad = sqrtf(-1.3862943611198906f * fast_lg2(u01(w0)));
+        return fmaf(d.b * rad, cospif(2.0f * u01(e.x)), d.a);
+    }
+    case MQ_WEIBULL:  // distributions.py:94-102: pow(-log(p) * W, -1/k); d.a = W, d.b = -1/k
+        return fast_ex2(fast_lg2(-0.6931471805599453f * fast_lg2(u01(w0)) * d.a) * d.b);
+    default:
+        return 0.0f;
+    }
+}
+
+// sum of x^k, k = 1..4 (5 issue slots)
+__device__ __forceinline__ void acc4(float (&s)[4], float x)
+{
+    float x2 = x * x;
+    s[0] += x;
+    s[1] += x2;
+    s[2] = fmaf(x2, x, s[2]);
+    s[3] = fmaf(x2, x2, s[3]);
+}
+
+}  // namespace mq

@@ -91,6 +91,13 @@ static inline void ws_ext(const word_src *s, uint32_t n, uint32_t out[2])
 
 static inline double u01(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
 
+/* "r < p1" on the raw word: T = floor(p1 * 2^32) */
+static inline uint32_t branch_threshold(double p1)
+{
+    double t = floor(p1 * 0x1p32);
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+}
+
 static double variate_from(const mqo_dist *d, const word_src *s)
 {
     const double *p = d->p;
@@ -99,8 +106,7 @@ static double variate_from(const mqo_dist *d, const word_src *s)
         return -log(u01(s->w0)) / p[0];
     case MQO_H2: { /* distributions.py:407-429; the branch word is reused as the
                       conditional uniform of the chosen phase */
-        double t = floor(p[0] * 0x1p32);
-        uint32_t T = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+        uint32_t T = branch_threshold(p[0]);
         if (s->w0 < T)
             return -log(((double)s->w0 + 0.5) / (double)T) / p[1];
         return -log(((double)(s->w0 - T) + 0.5) / (4294967296.0 - (double)T)) / p[2];
@@ -143,7 +149,7 @@ static double variate_from(const mqo_dist *d, const word_src *s)
         uint32_t e[2];
         ws_ext(s, 1, e);
         double res = -log(u01(s->w0)) / p[1];
-        if (u01(e[0]) < p[0]) res += -log(u01(e[1])) / p[2];
+        if (e[0] < branch_threshold(p[0])) res += -log(u01(e[1])) / p[2];
         return res;
     }
     case MQO_UNIFORM: /* distributions.py:298-309 */
