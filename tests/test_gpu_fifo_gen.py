@@ -123,16 +123,18 @@ def _theory():
         return json.load(f)
 
 
-def _check_vs_theory(res, th, nw=3, npr=8, bias_rel=0.0):
+def _check_vs_theory(res, th, nw=3, npr=8, bias_rel=0.0, bias_p=0.0):
     """|mean - theory| within the 99 % CI half-width plus an allowance for the O(1/N) start-up
-    bias every QsSim replication carries (system starts empty, no warm-up: SURVEY section 7)."""
+    bias every QsSim replication carries (system starts empty, no warm-up: SURVEY section 7);
+    bias_p is the absolute allowance on state probabilities (a few time units of the initial
+    transient divided by the run length)."""
     for k in range(nw):
         tol = res.ci["w"][k] + bias_rel * abs(th["w"][k]) + 1e-12
         assert abs(res.w[k] - th["w"][k]) <= tol, ("w", k, res.w[k], th["w"][k], tol)
         tol = res.ci["v"][k] + bias_rel * abs(th["v"][k])
         assert abs(res.v[k] - th["v"][k]) <= tol, ("v", k, res.v[k], th["v"][k], tol)
     for j in range(npr):
-        tol = res.ci["p"][j] + bias_rel * th["p"][j] + 1e-9
+        tol = res.ci["p"][j] + bias_rel * th["p"][j] + bias_p + 1e-9
         assert abs(res.p[j] - th["p"][j]) <= tol, ("p", j, res.p[j], th["p"][j], tol)
 
 
@@ -146,7 +148,7 @@ def test_mm3_r100_against_mmnr_theory():
     qs.set_servers(1.0, "M")
     res = qs.run(20000)
     assert res.replications == 4096 and abs(res.utilization - 2.0 / 3.0) < 1e-12
-    _check_vs_theory(res, th, bias_rel=2e-3)
+    _check_vs_theory(res, th, bias_rel=2e-3, bias_p=5.0 / 20000)
     # single replication with the README's seed: the reference's own tolerance (tests/test_qs_sim.py:81-84)
     one = QsSim(3, buffer=100, seed=1234)
     one.set_sources(2.0, "M")
@@ -182,4 +184,4 @@ def test_mh2_8_against_takahashi_takami():
     qs.set_sources(1.0, "M")
     qs.set_servers(H2Params(**th["h2"]), "H")
     res = qs.run(20000)
-    _check_vs_theory(res, th, bias_rel=4e-3)
+    _check_vs_theory(res, th, bias_rel=4e-3, bias_p=10.0 / 20000)
