@@ -166,6 +166,15 @@ static double variate_from(const mqo_dist *d, const word_src *s)
     }
 }
 
+double mqo_variate_sid(const mqo_dist *d, uint32_t seed, uint32_t sid, uint32_t rep, uint32_t i, int which)
+{
+    word_src s = {seed, sid, rep, i, which, 0u};
+    uint32_t w[2];
+    mqo_philox2x32_10(i, rep, ws_key(&s, 0), w);
+    s.w0 = w[which];
+    return variate_from(d, &s);
+}
+
 double mqo_variate(const mqo_dist *d, uint32_t seed, uint32_t rep, uint32_t i, int which)
 {
     word_src s = {seed, 0u, rep, i, which, 0u};

@@ -83,6 +83,46 @@ void mqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 /* variate of `d` for arrival index i of replication rep; which = 0 source, 1 server */
 double mqo_variate(const mqo_dist *d, uint32_t seed, uint32_t rep, uint32_t i, int which);
 
+/* same for stream `sid` (priority class / network node): key = seed + STRIDE * 64 * sid */
+double mqo_variate_sid(const mqo_dist *d, uint32_t seed, uint32_t sid, uint32_t rep, uint32_t i, int which);
+
+/* ---------------------------------------------------------------------------------------
+ * A variate source: either a caller array (replay) or the counter-based generator, which is
+ * by definition the replay of the virtual array  x[i] = variate(word `which` of the primary
+ * call (i, rep) of stream sid).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    int generate;          /* 0: replay arr, 1: generator                                 */
+    const double *arr;     /* replay: values, element i at arr[i * stride]                */
+    int64_t n, stride;
+    mqo_dist dist;         /* generator                                                    */
+    uint32_t seed, sid, rep;
+    int which;
+    int64_t pos;           /* next index to hand out (in/out: number consumed)            */
+} mqo_src;
+
+/* ---- multi-class priority queue: PriorityQueueSimulator.run (sim/priority.py:622-657) ---- */
+enum { MQO_NP = 0, MQO_PR = 1, MQO_RS = 2, MQO_RW = 3 };
+
+typedef struct {
+    double w_run[4], v_run[4]; /* running-mean moments, priority.py:676-690 */
+    double w_sum[4], v_sum[4];
+    int64_t arrived, taked, served, dropped, in_sys, queued;
+    double t_old;
+    double p_over;
+} mqo_prio_class_out;
+
+/* arrivals[k], services[k]: per-class sources (sources consumed in the reference's draw order:
+ * arrival_time[k] draws at set_sources and at each class-k arrival, priority.py:130,300;
+ * service draws at ServerPriority.start_service for non-resumed jobs, servers.py:241, and for
+ * RS at the pre-emption, priority.py:425, from the ARRIVING class's stream).
+ * p: [K][p_bins] time-in-state sums of in_sys[k] (priority.py:304,472).  Free server = lowest
+ * index; pre-emption victim = first server in index order serving a weaker class
+ * (priority.py:401-407).  buffer <= 0 means infinite (priority.py:373,437). */
+int mqo_prio_run(int c, int K, int prty_type, int64_t buffer, mqo_src *arrivals, mqo_src *services,
+                 int64_t total_served, double *p, int64_t p_bins, mqo_prio_class_out *out,
+                 double *ttek_out);
+
 const char *mqo_version(void);
 
 #ifdef __cplusplus
