@@ -134,6 +134,68 @@ typedef struct {
 #define MQ_REPLAY_EXTRA 16
 #define MQ_REPLAY_ROWS(p_bins) (MQ_REC_ROWS(p_bins) + MQ_REPLAY_EXTRA)
 
+/* ---- multi-class priority queue.  Replaces PriorityQueueSimulator(num_of_channels,
+ * num_of_classes, prty_type, buffer).set_sources/set_servers/run (sim/priority.py:28,111,134,622) */
+#define MQ_MAX_CLASSES 8
+#define MQ_PRIO_MAX_CHANNELS 16
+#define MQ_PRTY_NP 0 /* "NP" non-preemptive                       */
+#define MQ_PRTY_PR 1 /* "PR" preemptive resume                    */
+#define MQ_PRTY_RS 2 /* "RS" preemptive repeat with resampling    */
+#define MQ_PRTY_RW 3 /* "RW" preemptive repeat without resampling */
+
+typedef struct {
+    int32_t c;             /* num_of_channels                                   priority.py:28 */
+    int32_t K;             /* num_of_classes                                                   */
+    int32_t prty_type;     /* MQ_PRTY_*                                                        */
+    int32_t p_bins;        /* per-class state bins                                             */
+    int64_t buffer;        /* total waiting places, <= 0 infinite         priority.py:373,437  */
+    int64_t total_served;  /* run(total_served): departures of all classes priority.py:636     */
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+    int32_t queue_cap;     /* per-class waiting-line capacity of the engine (0: default 512);  */
+                           /* a replication that exceeds it is flagged, never silently wrong   */
+    int32_t flags;
+    mq_dist src[MQ_MAX_CLASSES]; /* set_sources([{"type","params"}]*K)          priority.py:111 */
+    mq_dist srv[MQ_MAX_CLASSES]; /* set_servers([{"type","params"}]*K)          priority.py:134 */
+} mq_prio_cfg;
+
+/* per-replication record: 2 global rows, then for each class MQ_PRIO_ROWS(p_bins) rows */
+#define MQ_PG_TTEK 0
+#define MQ_PG_FLAGS 1
+#define MQ_PG_ROWS 2
+#define MQ_PF_WSUM 0   /* 4: sum of w^k over served jobs of the class (priority.py:480)          */
+#define MQ_PF_VSUM 4   /* 4 */
+#define MQ_PF_WRUN 8   /* 4: the reference's running-mean moments, exact in replay mode          */
+#define MQ_PF_VRUN 12  /* 4 */
+#define MQ_PF_ARRIVED 16
+#define MQ_PF_TAKED 17
+#define MQ_PF_SERVED 18
+#define MQ_PF_DROPPED 19
+#define MQ_PF_INSYS 20
+#define MQ_PF_QUEUED 21
+#define MQ_PF_TOLD 22
+#define MQ_PF_POVER 23
+#define MQ_PF_AUSED 24
+#define MQ_PF_SUSED 25
+#define MQ_PF_P 26     /* p_bins: time with exactly j class-k jobs in the system (priority.py:304,472) */
+#define MQ_PRIO_ROWS(p_bins) (26 + (p_bins))
+#define MQ_PRIO_REC_ROWS(K, p_bins) (2 + (K) * MQ_PRIO_ROWS(p_bins))
+
+/* aggregate: [0] replications, [1] sum ttek, [2] flagged replications, [3] reserved, then per class
+ * MQ_PRIO_AGG(p_bins) entries: w[4] (sum over reps of sum(w^k)/served), w2[4] (squares), v[4], v2[4],
+ * arrived, taked, served, dropped, 4 reserved, p[p_bins] (sum of p_time/ttek), p2[p_bins] */
+#define MQ_PRIO_AGG(p_bins) (24 + 2 * (p_bins))
+#define MQ_PRIO_AGG_LEN(K, p_bins) (4 + (K) * MQ_PRIO_AGG(p_bins))
+
+int mq_sim_prio(mq_ctx *ctx, const mq_prio_cfg *cfg, double *agg, double *rep_out);
+
+/* replay form: A[k] / S[k] are class k's gap / service rows, [n][replications] fp64 host arrays
+ * (A[k][0] is the draw set_sources makes, priority.py:130; S[k][j] the j-th draw from class k's
+ * service stream in the reference's draw order).  src/srv of cfg are ignored. */
+int mq_replay_prio(mq_ctx *ctx, const mq_prio_cfg *cfg, const double *const *A, const int64_t *n_a,
+                   const double *const *S, const int64_t *n_s, double *agg, double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

@@ -62,6 +62,39 @@ class MqReplayCfg(C.Structure):
     ]
 
 
+MAX_CLASSES = 8
+PRTY = {"NP": 0, "PR": 1, "RS": 2, "RW": 3}
+PG_TTEK, PG_FLAGS, PG_ROWS = 0, 1, 2
+PF_WSUM, PF_VSUM, PF_WRUN, PF_VRUN = 0, 4, 8, 12
+PF_ARRIVED, PF_TAKED, PF_SERVED, PF_DROPPED, PF_INSYS, PF_QUEUED, PF_TOLD, PF_POVER, PF_AUSED, PF_SUSED, PF_P = (
+    16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26)
+
+
+def prio_rows(p_bins: int) -> int:
+    return 26 + p_bins
+
+
+def prio_rec_rows(K: int, p_bins: int) -> int:
+    return 2 + K * prio_rows(p_bins)
+
+
+def prio_agg(p_bins: int) -> int:
+    return 24 + 2 * p_bins
+
+
+def prio_agg_len(K: int, p_bins: int) -> int:
+    return 4 + K * prio_agg(p_bins)
+
+
+class MqPrioCfg(C.Structure):
+    _fields_ = [
+        ("c", C.c_int32), ("K", C.c_int32), ("prty_type", C.c_int32), ("p_bins", C.c_int32),
+        ("buffer", C.c_int64), ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64),
+        ("seed", C.c_uint64), ("queue_cap", C.c_int32), ("flags", C.c_int32),
+        ("src", MqDist * MAX_CLASSES), ("srv", MqDist * MAX_CLASSES),
+    ]
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -97,6 +130,11 @@ def load():
         L.mq_sim_fifo.argtypes = [vp, C.POINTER(MqFifoCfg), dp, dp]
         L.mq_replay_fifo.restype = C.c_int
         L.mq_replay_fifo.argtypes = [vp, C.POINTER(MqReplayCfg), vp, vp, dp, vp]
+        L.mq_sim_prio.restype = C.c_int
+        L.mq_sim_prio.argtypes = [vp, C.POINTER(MqPrioCfg), dp, dp]
+        L.mq_replay_prio.restype = C.c_int
+        L.mq_replay_prio.argtypes = [vp, C.POINTER(MqPrioCfg), C.POINTER(vp), C.POINTER(C.c_int64),
+                                     C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -233,6 +271,46 @@ class Context:
         check(self._L.mq_replay_fifo(self._h, C.byref(cfg), a_ptr, s_ptr,
                                      agg.ctypes.data_as(C.POINTER(C.c_double)), rec_ptr))
         return agg
+
+    # ---- K4 ----
+    def _prio_cfg(self, c, K, prty, buffer, total_served, replications, rep0, seed, p_bins, queue_cap):
+        if prty not in PRTY:
+            raise ValueError(f"prty_type {prty!r} is not supported by the GPU engine (supported: NP, PR, RS, RW)")
+        cfg = MqPrioCfg()
+        cfg.c, cfg.K, cfg.prty_type, cfg.p_bins = int(c), int(K), PRTY[prty], int(p_bins)
+        cfg.buffer = 0 if not buffer else int(buffer)  # priority.py:373: None or 0 -> infinite
+        cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.queue_cap = int(queue_cap)
+        return cfg
+
+    def sim_prio(self, c, K, prty, buffer, src, srv, total_served, replications, rep0, seed, p_bins=64,
+                 queue_cap=0, per_replication=False):
+        cfg = self._prio_cfg(c, K, prty, buffer, total_served, replications, rep0, seed, p_bins, queue_cap)
+        for k in range(K):
+            cfg.src[k], cfg.srv[k] = src[k], srv[k]
+        agg = np.zeros(prio_agg_len(K, p_bins))
+        rec = np.empty((prio_rec_rows(K, p_bins), int(replications))) if per_replication else None
+        check(self._L.mq_sim_prio(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                  rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_prio(self, c, K, prty, buffer, A, S, total_served, p_bins=64, queue_cap=0):
+        """A[k], S[k]: per-class [n, R] float64 host arrays."""
+        A = [np.ascontiguousarray(a, dtype=np.float64) for a in A]
+        S = [np.ascontiguousarray(x, dtype=np.float64) for x in S]
+        R = A[0].shape[1]
+        cfg = self._prio_cfg(c, K, prty, buffer, total_served, R, 0, 0, p_bins, queue_cap)
+        pa = (C.c_void_p * K)(*[a.ctypes.data for a in A])
+        ps = (C.c_void_p * K)(*[x.ctypes.data for x in S])
+        na = (C.c_int64 * K)(*[a.shape[0] for a in A])
+        ns = (C.c_int64 * K)(*[x.shape[0] for x in S])
+        agg = np.zeros(prio_agg_len(K, p_bins))
+        rec = np.empty((prio_rec_rows(K, p_bins), R))
+        check(self._L.mq_replay_prio(self._h, C.byref(cfg), pa, na, ps, ns,
+                                     agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                     rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
 
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -1,15 +1,9 @@
 // mq_api.cu -- the C ABI of libmqb200.so (include/mqb200.h): context, argument checking,
 // scratch management, kernel dispatch, timing.  No CPU fallback exists: every entry point
 // that computes launches CUDA kernels and fails with MQ_E_NODEVICE / MQ_E_CUDA otherwise.
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <new>
-
+#include "mq_host.cuh"
 #include "k1_fifo_replay.cuh"
 #include "k2_fifo_gen.cuh"
-#include "reduce.cuh"
 
 namespace mq {
 
@@ -21,56 +15,7 @@ MQ_DECL_K2(8) MQ_DECL_K2(16) MQ_DECL_K2(32)
 MQ_DECL_K1(1) MQ_DECL_K1(2) MQ_DECL_K1(3) MQ_DECL_K1(4) MQ_DECL_K1(5) MQ_DECL_K1(6) MQ_DECL_K1(7)
 MQ_DECL_K1(8) MQ_DECL_K1(16) MQ_DECL_K1(32)
 
-static thread_local char g_err[512] = "";
-
-static int fail(int code, const char *fmt, ...)
-{
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define CU(expr)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (expr);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(MQ_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
-                        __LINE__);                                                            \
-    } while (0)
-
-struct Buf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
-}  // namespace mq
-
-struct mq_ctx {
-    int device = 0;
-    int sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, sim done, reduce done, end
-    mq::Buf rec, agg, ring, in_a, in_s;
-    double *h_agg = nullptr;  // pinned staging
-    size_t h_agg_cap = 0;
-    double sim_ms = 0, reduce_ms = 0, total_ms = 0;
-    int launches = 0;
-};
-
-namespace mq {
-
-static int ensure(Buf &b, size_t bytes)
-{
-    if (bytes <= b.cap) return MQ_OK;
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr;
-    b.cap = 0;
-    CU(cudaMalloc(&b.p, bytes));
-    b.cap = bytes;
-    return MQ_OK;
-}
+thread_local char g_err[512] = "";
 
 static int ct_for(int c)
 {
@@ -80,7 +25,7 @@ static int ct_for(int c)
     return 0;
 }
 
-static int check_dist(const mq_dist &d, const char *what)
+int check_dist(const mq_dist &d, const char *what)
 {
     const double *p = d.p;
     auto pos = [](double x) { return std::isfinite(x) && x > 0.0; };
@@ -128,7 +73,7 @@ static uint32_t branch_threshold(double p1)
     return t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
 }
 
-static DistF make_distf(const mq_dist &d)
+DistF make_distf(const mq_dist &d)
 {
     const double LN2 = 0.6931471805599453;
     DistF f;
@@ -189,7 +134,7 @@ static DistF make_distf(const mq_dist &d)
 }
 
 // 64-bit user seed -> 32-bit Philox key (splitmix64 finaliser)
-static uint32_t seed_to_key(uint64_t s)
+uint32_t seed_to_key(uint64_t s)
 {
     s += 0x9E3779B97F4A7C15ull;
     s = (s ^ (s >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -225,18 +170,6 @@ static cudaError_t k1_dispatch(int ct, const K1Params &P, bool fin, cudaStream_t
     default:
         return cudaErrorInvalidValue;
     }
-}
-
-static int finish_timing(mq_ctx *ctx)
-{
-    float a = 0, b = 0, c = 0;
-    CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
-    CU(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
-    CU(cudaEventElapsedTime(&c, ctx->ev[0], ctx->ev[3]));
-    ctx->sim_ms = a;
-    ctx->reduce_ms = b;
-    ctx->total_ms = c;
-    return MQ_OK;
 }
 
 __global__ void debug_philox_kernel(uint32_t c0, uint32_t c1, uint32_t key, uint32_t *out)
@@ -301,7 +234,7 @@ int mq_destroy(mq_ctx *ctx)
 {
     if (!ctx) return MQ_OK;
     cudaSetDevice(ctx->device);
-    for (Buf *b : {&ctx->rec, &ctx->agg, &ctx->ring, &ctx->in_a, &ctx->in_s})
+    for (Buf *b : {&ctx->rec, &ctx->agg, &ctx->ring, &ctx->in_a, &ctx->in_s, &ctx->desc})
         if (b->p) cudaFree(b->p);
     if (ctx->h_agg) cudaFreeHost(ctx->h_agg);
     for (auto &e : ctx->ev)
@@ -313,16 +246,7 @@ int mq_destroy(mq_ctx *ctx)
 
 static int stage_agg(mq_ctx *ctx, int p_bins)
 {
-    const size_t bytes = sizeof(double) * MQ_AGG_LEN(p_bins);
-    if (ensure(ctx->agg, bytes)) return MQ_E_CUDA;
-    if (ctx->h_agg_cap < bytes) {
-        if (ctx->h_agg) cudaFreeHost(ctx->h_agg);
-        ctx->h_agg = nullptr;
-        ctx->h_agg_cap = 0;
-        CU(cudaMallocHost(&ctx->h_agg, bytes));
-        ctx->h_agg_cap = bytes;
-    }
-    return MQ_OK;
+    return ensure_host_agg(ctx, sizeof(double) * MQ_AGG_LEN(p_bins));
 }
 
 int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_out)
@@ -387,9 +311,7 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     CU(k2_dispatch(ct, P, pc, finite, (int)grid, smem, ctx->stream, nullptr));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    reduce_records<<<MQ_AGG_LEN(cfg->p_bins), MQ_RED_BLOCK, 0, ctx->stream>>>(
-        (const double *)ctx->rec.p, R, cfg->p_bins, (double *)ctx->agg.p);
-    CU(cudaGetLastError());
+    CU(launch_reduce_records((const double *)ctx->rec.p, R, cfg->p_bins, (double *)ctx->agg.p, ctx->stream));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_agg, ctx->agg.p, sizeof(double) * MQ_AGG_LEN(cfg->p_bins),
@@ -461,9 +383,7 @@ int mq_replay_fifo(mq_ctx *ctx, const mq_replay_cfg *cfg, const double *A, const
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (agg) {
-        reduce_records<<<MQ_AGG_LEN(cfg->p_bins), MQ_RED_BLOCK, 0, ctx->stream>>>(
-            (const double *)ctx->rec.p, R, cfg->p_bins, (double *)ctx->agg.p);
-        CU(cudaGetLastError());
+        CU(launch_reduce_records((const double *)ctx->rec.p, R, cfg->p_bins, (double *)ctx->agg.p, ctx->stream));
         ctx->launches++;
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -1,10 +1,8 @@
-// reduce.cuh -- deterministic reduction of the per-replication records to the aggregate
+// reduce.cu -- deterministic reduction of the per-replication records to the aggregate
 // vector (MQ_A_* layout of include/mqb200.h).  One CTA per aggregate entry, fixed-order tree,
 // so the result does not depend on scheduling.  The aggregate is what a multi-GPU run sums
 // with one allreduce.
-#pragma once
-
-#include "mq_device.cuh"
+#include "mq_host.cuh"
 
 namespace mq {
 
@@ -59,6 +57,53 @@ __global__ void __launch_bounds__(MQ_RED_BLOCK) reduce_records(const double *rec
         __syncthreads();
     }
     if (threadIdx.x == 0) agg[qi] = part[0];
+}
+
+// generic form used by the priority and network kernels: entry q is the sum over replications of
+// x = rec[num][r] / rec[den][r] (den < 0: x = rec[num][r]) and, in out[nq + q], of x^2.
+__global__ void __launch_bounds__(MQ_RED_BLOCK) reduce_ratio(const double *rec, long long R, const RatioDesc *desc,
+                                                             int nq, double *out)
+{
+    __shared__ double part[MQ_RED_BLOCK], part2[MQ_RED_BLOCK];
+    const int qi = blockIdx.x;
+    const RatioDesc d = desc[qi];
+    double acc = 0.0, acc2 = 0.0;
+    for (long long r = threadIdx.x; r < R; r += MQ_RED_BLOCK) {
+        double x = rec[(long long)d.num * R + r];
+        if (d.den >= 0) {
+            const double dn = rec[(long long)d.den * R + r];
+            x = dn != 0.0 ? x / dn : 0.0;
+        }
+        acc += x;
+        acc2 += x * x;
+    }
+    part[threadIdx.x] = acc;
+    part2[threadIdx.x] = acc2;
+    __syncthreads();
+    for (int s = MQ_RED_BLOCK / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            part[threadIdx.x] += part[threadIdx.x + s];
+            part2[threadIdx.x] += part2[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[qi] = part[0];
+        out[nq + qi] = part2[0];
+    }
+}
+
+cudaError_t launch_reduce_records(const double *rec, long long R, int p_bins, double *agg, cudaStream_t st)
+{
+    reduce_records<<<MQ_AGG_LEN(p_bins), MQ_RED_BLOCK, 0, st>>>(rec, R, p_bins, agg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_ratio(const double *rec, long long R, const RatioDesc *desc, int nq, double *out,
+                                cudaStream_t st)
+{
+    reduce_ratio<<<nq, MQ_RED_BLOCK, 0, st>>>(rec, R, desc, nq, out);
+    return cudaGetLastError();
 }
 
 }  // namespace mq

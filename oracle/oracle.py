@@ -45,6 +45,25 @@ class MqoFifoOut(C.Structure):
     ]
 
 
+class MqoSrc(C.Structure):
+    _fields_ = [
+        ("generate", C.c_int), ("arr", C.POINTER(C.c_double)), ("n", C.c_int64), ("stride", C.c_int64),
+        ("dist", MqoDist), ("seed", C.c_uint32), ("sid", C.c_uint32), ("rep", C.c_uint32),
+        ("which", C.c_int), ("pos", C.c_int64),
+    ]
+
+
+class MqoPrioClassOut(C.Structure):
+    _fields_ = [
+        ("w_run", C.c_double * 4), ("v_run", C.c_double * 4), ("w_sum", C.c_double * 4), ("v_sum", C.c_double * 4),
+        ("arrived", C.c_int64), ("taked", C.c_int64), ("served", C.c_int64), ("dropped", C.c_int64),
+        ("in_sys", C.c_int64), ("queued", C.c_int64), ("t_old", C.c_double), ("p_over", C.c_double),
+    ]
+
+
+PRTY = {"NP": 0, "PR": 1, "RS": 2, "RW": 3}
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
@@ -80,6 +99,11 @@ def lib():
         L.mqo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.mqo_variate.restype = C.c_double
         L.mqo_variate.argtypes = [C.POINTER(MqoDist), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.mqo_variate_sid.restype = C.c_double
+        L.mqo_variate_sid.argtypes = [C.POINTER(MqoDist), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.mqo_prio_run.restype = C.c_int
+        L.mqo_prio_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(MqoSrc), C.POINTER(MqoSrc),
+                                   C.c_int64, dp, C.c_int64, C.POINTER(MqoPrioClassOut), dp]
         L.mqo_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -209,3 +233,72 @@ def philox4x32(ctr, key) -> tuple[int, ...]:
 def variate(src_or_srv, seed: int, rep: int, i: int, which: int) -> float:
     d = make_dist(*src_or_srv)
     return float(lib().mqo_variate(C.byref(d), seed & 0xFFFFFFFF, rep, i, which))
+
+
+# --------------------------------------------------------------------------- priority
+def _replay_src(arr: np.ndarray) -> MqoSrc:
+    s = MqoSrc()
+    s.generate = 0
+    s.arr = _dp(arr)
+    s.n, s.stride, s.pos = len(arr), 1, 0
+    return s
+
+
+def _gen_src(dist, seed: int, sid: int, rep: int, which: int) -> MqoSrc:
+    s = MqoSrc()
+    s.generate = 1
+    s.dist = make_dist(*dist)
+    s.seed, s.sid, s.rep, s.which, s.pos = seed & 0xFFFFFFFF, sid, rep, which, 0
+    return s
+
+
+@dataclass
+class PrioResult:
+    w: np.ndarray  # [K][4] running-mean moments
+    v: np.ndarray
+    w_sum: np.ndarray
+    v_sum: np.ndarray
+    arrived: np.ndarray
+    taked: np.ndarray
+    served: np.ndarray
+    dropped: np.ndarray
+    in_sys: np.ndarray
+    queued: np.ndarray
+    t_old: np.ndarray
+    p_time: np.ndarray  # [K][p_bins]
+    p_over: np.ndarray
+    ttek: float
+    a_used: np.ndarray
+    s_used: np.ndarray
+
+
+def _prio_run(c, K, prty, buffer, arrivals, services, total_served, p_bins) -> PrioResult:
+    A = (MqoSrc * K)(*arrivals)
+    S = (MqoSrc * K)(*services)
+    p = np.zeros((K, p_bins))
+    outs = (MqoPrioClassOut * K)()
+    ttek = C.c_double()
+    rc = lib().mqo_prio_run(c, K, PRTY[prty], -1 if buffer is None else int(buffer), A, S, int(total_served),
+                            _dp(p), p_bins, outs, C.byref(ttek))
+    if rc != 0:
+        raise RuntimeError(f"oracle prio run failed rc={rc}")
+    f = lambda name: np.array([getattr(outs[k], name) for k in range(K)])
+    g = lambda name: np.array([list(getattr(outs[k], name)) for k in range(K)])
+    return PrioResult(w=g("w_run"), v=g("v_run"), w_sum=g("w_sum"), v_sum=g("v_sum"), arrived=f("arrived"),
+                      taked=f("taked"), served=f("served"), dropped=f("dropped"), in_sys=f("in_sys"),
+                      queued=f("queued"), t_old=f("t_old"), p_time=p, p_over=f("p_over"), ttek=ttek.value,
+                      a_used=np.array([A[k].pos for k in range(K)]), s_used=np.array([S[k].pos for k in range(K)]))
+
+
+def prio_replay(c, K, prty, A, S, total_served, buffer=None, p_bins=64) -> PrioResult:
+    """PriorityQueueSimulator.run() on per-class pre-generated arrays A[k], S[k]."""
+    A = [np.ascontiguousarray(a, dtype=np.float64) for a in A]
+    S = [np.ascontiguousarray(x, dtype=np.float64) for x in S]
+    return _prio_run(c, K, prty, buffer, [_replay_src(a) for a in A], [_replay_src(x) for x in S],
+                     total_served, p_bins)
+
+
+def prio_generate(c, K, prty, sources, servers, total_served, seed, rep, buffer=None, p_bins=64) -> PrioResult:
+    """Generator mode: class k draws gaps from word 0 and services from word 1 of stream sid=k."""
+    return _prio_run(c, K, prty, buffer, [_gen_src(sources[k], seed, k, rep, 0) for k in range(K)],
+                     [_gen_src(servers[k], seed, k, rep, 1) for k in range(K)], total_served, p_bins)

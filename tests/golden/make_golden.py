@@ -141,6 +141,71 @@ def make_fifo():
     fifo_case("tiny", 2, None, rng.exponential(1.0, 40), rng.exponential(1.5, 40), 5)
 
 
+# --------------------------------------------------------------------------- priority
+class LowestFirstSet(set):
+    """The reference picks a free server with next(iter(self._free_servers)) (priority.py:355):
+    CPython set order, which depends on the removal history.  For pre-emptive disciplines the
+    server index decides who is pre-empted (priority.py:401-407), so the fixtures pin that choice
+    to "lowest free index" -- the rule the oracle and the kernels use."""
+
+    def __iter__(self):
+        return iter(sorted(set.__iter__(self)))
+
+
+def prio_case(name, c, K, prty, A, S, total_served, nprobs=64):
+    from most_queue.sim.priority import PriorityQueueSimulator
+
+    qs = PriorityQueueSimulator(c, K, prty)
+    qs.set_sources([{"type": "M", "params": 1.0} for _ in range(K)])
+    qs.set_servers([{"type": "M", "params": 1.0} for _ in range(K)])
+    ia = [[0] for _ in range(K)]
+    isv = [[0] for _ in range(K)]
+    for k in range(K):
+        qs.sources[k] = ReplayDist(A[k], ia[k])
+        qs.arrival_time[k] = qs.sources[k].generate()  # the draw set_sources makes (priority.py:130)
+    for srv in qs.servers:
+        srv.dist = [ReplayDist(S[k], isv[k]) for k in range(K)]
+    qs._free_servers = LowestFirstSet(range(c))
+    with quiet():
+        while sum(qs.served) < total_served:  # run() minus tqdm (priority.py:636-637)
+            qs.run_one_step()
+    out = dict(c=c, K=K, prty=prty, total_served=total_served, ttek=float(qs.ttek))
+    for k in range(K):
+        out[f"A{k}"] = np.asarray(A[k])
+        out[f"S{k}"] = np.asarray(S[k])
+    np.savez_compressed(
+        os.path.join(OUT, f"prio_{name}.npz"), **out,
+        w=np.array(qs.w, dtype=np.float64), v=np.array(qs.v, dtype=np.float64),
+        p_time=np.array([qs.p[k][:nprobs] for k in range(K)], dtype=np.float64),
+        arrived=np.array(qs.arrived), served=np.array(qs.served), taked=np.array(qs.taked),
+        dropped=np.array(qs.dropped), in_sys=np.array(qs.in_sys), t_old=np.array(qs.t_old, dtype=np.float64),
+        a_used=np.array([x[0] for x in ia]), s_used=np.array([x[0] for x in isv]),
+    )
+    print(f"prio_{name}: served={qs.served} v1={[round(float(x[0]), 4) for x in qs.v]}")
+
+
+def make_prio():
+    rng = np.random.default_rng(20260202)
+    n = 3000
+    # cfg4 shape: c=4, two classes, M arrivals l=[0.3,0.5], Gamma service means [2,4] cv 1.2
+    def gam(mean, cv, size):
+        shape = 1.0 / cv**2
+        return rng.gamma(shape, mean / shape, size)
+
+    for prty in ("NP", "PR", "RS", "RW"):
+        A = [rng.exponential(1 / 0.3, n), rng.exponential(1 / 0.5, n)]
+        S = [gam(2.0, 1.2, 2 * n), gam(4.0, 1.2, 2 * n)]
+        prio_case(f"c4k2_{prty}", 4, 2, prty, A, S, n)
+    # three classes, heavier load, single and two servers
+    for prty in ("NP", "PR"):
+        A = [rng.exponential(4.0, n), rng.exponential(3.0, n), rng.exponential(2.5, n)]
+        S = [rng.exponential(1.0, 2 * n), gam(1.5, 0.7, 2 * n), rng.exponential(1.2, 2 * n)]
+        prio_case(f"c2k3_{prty}", 2, 3, prty, A, S, n)
+        A = [rng.exponential(5.0, n), rng.exponential(4.0, n), rng.exponential(3.0, n)]
+        S = [rng.exponential(0.8, 2 * n), rng.exponential(1.0, 2 * n), rng.exponential(0.9, 2 * n)]
+        prio_case(f"c1k3_{prty}", 1, 3, prty, A, S, n)
+
+
 # --------------------------------------------------------------------------- theory
 def make_theory():
     """Analytical values used by the generator-mode (statistical) tests."""
@@ -200,8 +265,12 @@ def make_theory():
 
 if __name__ == "__main__":
     import_reference()
-    which = sys.argv[1:] or ["fifo", "theory"]
+    which = sys.argv[1:] or ["fifo", "prio", "net", "theory"]
     if "fifo" in which:
         make_fifo()
+    if "prio" in which:
+        make_prio()
+    if "net" in which and "make_net" in globals():
+        make_net()
     if "theory" in which:
         make_theory()
