@@ -196,6 +196,69 @@ int mq_sim_prio(mq_ctx *ctx, const mq_prio_cfg *cfg, double *agg, double *rep_ou
 int mq_replay_prio(mq_ctx *ctx, const mq_prio_cfg *cfg, const double *const *A, const int64_t *n_a,
                    const double *const *S, const int64_t *n_s, double *agg, double *rep_out);
 
+/* ---- open network of FIFO multi-server nodes with Markov routing.  Replaces
+ * NetworkSimulator().set_sources(arrival_rate, R, source_kendall, source_params) /
+ * set_nodes(serv_params, n) / run(job_served)  (sim/networks/network.py:53,82,196) */
+#define MQ_NET_MAX_NODES 16
+#define MQ_NET_MAX_SERVERS 64 /* sum of channels over all nodes */
+
+typedef struct {
+    int32_t m;                               /* number of nodes                     network.py:93 */
+    int32_t flags;
+    int32_t channels[MQ_NET_MAX_NODES];      /* n[i]                                network.py:82 */
+    double R[(MQ_NET_MAX_NODES + 1) * (MQ_NET_MAX_NODES + 1)]; /* (m+1)x(m+1), row-major, packed   */
+                                             /* with stride m+1: row 0 = source, row i+1 = node i, */
+                                             /* column m = leave                    network.py:57-66 */
+    mq_dist src;                             /* external flow ("M" arrival_rate)    network.py:72-76 */
+    mq_dist srv[MQ_NET_MAX_NODES];           /* serv_params[i]                      network.py:95-97 */
+    int64_t job_served;                      /* run(job_served)                     network.py:211 */
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+    int32_t queue_cap;                       /* per-node waiting-line capacity (0: default 512)    */
+    int32_t reserved;
+} mq_net_cfg;
+
+/* per-replication record rows */
+#define MQ_NG_TTEK 0
+#define MQ_NG_FLAGS 1
+#define MQ_NG_SERVED 2
+#define MQ_NG_ARRIVED 3
+#define MQ_NG_INSYS 4
+#define MQ_NG_AUSED 5
+#define MQ_NG_UUSED 6
+#define MQ_NG_VSUM 8   /* 3: sum of (network sojourn)^k over served jobs  network.py:188 */
+#define MQ_NG_WSUM 11  /* 3: sum of (network wait)^k                      network.py:189 */
+#define MQ_NG_VRUN 14  /* 3: v_network running moments (network.py:116-124)             */
+#define MQ_NG_WRUN 17  /* 3 */
+#define MQ_NG_ROWS 20
+#define MQ_NN_VSUM 0   /* 4: node-level sojourn power sums (qs[i].v)                    */
+#define MQ_NN_WSUM 4   /* 4 */
+#define MQ_NN_VRUN 8   /* 4: qs[i].v running moments, exact in replay mode              */
+#define MQ_NN_WRUN 12  /* 4 */
+#define MQ_NN_ARRIVED 16
+#define MQ_NN_TAKED 17
+#define MQ_NN_SERVED 18
+#define MQ_NN_SUSED 19
+#define MQ_NN_INSYS 20
+#define MQ_NN_QUEUED 21
+#define MQ_NN_ROWS 22
+#define MQ_NET_REC_ROWS(m) (MQ_NG_ROWS + (m) * MQ_NN_ROWS)
+
+/* aggregate: [0] replications, [1] sum ttek, [2] flagged, [3] sum served, [4] sum arrived,
+ * [5..7] sum over reps of v_sum[k]/served, [8..10] squares, [11..13] same for w, [14..16] squares,
+ * then per node 16 entries: v[4] (v_sum/served), w[4] (w_sum/taked), served, taked, arrived,
+ * v1 squared, w1 squared, 3 reserved */
+#define MQ_NET_AGG_LEN(m) (20 + 16 * (m))
+
+int mq_sim_net(mq_ctx *ctx, const mq_net_cfg *cfg, double *agg, double *rep_out);
+
+/* replay form: A = external gaps [n_a][replications] (A[0] is the draw set_sources makes,
+ * network.py:76), U = routing uniforms [n_u][replications] in the order choose_next_node consumes
+ * them (network.py:109), S[i] = node i's service draws [n_s[i]][replications] (servers.py:88). */
+int mq_replay_net(mq_ctx *ctx, const mq_net_cfg *cfg, const double *A, int64_t n_a, const double *U,
+                  int64_t n_u, const double *const *S, const int64_t *n_s, double *agg, double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

@@ -95,6 +95,31 @@ class MqPrioCfg(C.Structure):
     ]
 
 
+NET_MAX_NODES = 16
+NG_TTEK, NG_FLAGS, NG_SERVED, NG_ARRIVED, NG_INSYS, NG_AUSED, NG_UUSED = 0, 1, 2, 3, 4, 5, 6
+NG_VSUM, NG_WSUM, NG_VRUN, NG_WRUN, NG_ROWS = 8, 11, 14, 17, 20
+NN_VSUM, NN_WSUM, NN_VRUN, NN_WRUN, NN_ARRIVED, NN_TAKED, NN_SERVED, NN_SUSED, NN_INSYS, NN_QUEUED, NN_ROWS = (
+    0, 4, 8, 12, 16, 17, 18, 19, 20, 21, 22)
+
+
+def net_rec_rows(m: int) -> int:
+    return NG_ROWS + m * NN_ROWS
+
+
+def net_agg_len(m: int) -> int:
+    return 20 + 16 * m
+
+
+class MqNetCfg(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32), ("flags", C.c_int32), ("channels", C.c_int32 * NET_MAX_NODES),
+        ("R", C.c_double * ((NET_MAX_NODES + 1) * (NET_MAX_NODES + 1))),
+        ("src", MqDist), ("srv", MqDist * NET_MAX_NODES),
+        ("job_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
+        ("queue_cap", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -135,6 +160,11 @@ def load():
         L.mq_replay_prio.restype = C.c_int
         L.mq_replay_prio.argtypes = [vp, C.POINTER(MqPrioCfg), C.POINTER(vp), C.POINTER(C.c_int64),
                                      C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
+        L.mq_sim_net.restype = C.c_int
+        L.mq_sim_net.argtypes = [vp, C.POINTER(MqNetCfg), dp, dp]
+        L.mq_replay_net.restype = C.c_int
+        L.mq_replay_net.argtypes = [vp, C.POINTER(MqNetCfg), vp, C.c_int64, vp, C.c_int64, C.POINTER(vp),
+                                    C.POINTER(C.c_int64), dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -310,6 +340,56 @@ class Context:
         check(self._L.mq_replay_prio(self._h, C.byref(cfg), pa, na, ps, ns,
                                      agg.ctypes.data_as(C.POINTER(C.c_double)),
                                      rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
+
+    # ---- K5 ----
+    def _net_cfg(self, R, channels, job_served, replications, rep0, seed, queue_cap):
+        m = len(channels)
+        Rm = np.asarray(R, dtype=np.float64)
+        if Rm.shape != (m + 1, m + 1):
+            raise ValueError(f"routing matrix must be {(m + 1)} x {(m + 1)} for {m} nodes")
+        if m > NET_MAX_NODES:
+            raise MqError(MQ_E_UNSUPPORTED, f"at most {NET_MAX_NODES} nodes")
+        cfg = MqNetCfg()
+        cfg.m = m
+        for i, c in enumerate(channels):
+            cfg.channels[i] = int(c)
+        flat = Rm.reshape(-1)
+        for i in range(flat.size):
+            cfg.R[i] = float(flat[i])
+        cfg.job_served, cfg.replications, cfg.rep0 = int(job_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.queue_cap = int(queue_cap)
+        return cfg
+
+    def sim_net(self, R, channels, src, srv, job_served, replications, rep0, seed, queue_cap=0,
+                per_replication=False):
+        cfg = self._net_cfg(R, channels, job_served, replications, rep0, seed, queue_cap)
+        cfg.src = src
+        for i, d in enumerate(srv):
+            cfg.srv[i] = d
+        m = len(channels)
+        agg = np.zeros(net_agg_len(m))
+        rec = np.empty((net_rec_rows(m), int(replications))) if per_replication else None
+        check(self._L.mq_sim_net(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                 rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_net(self, R, channels, A, U, S, job_served, queue_cap=0):
+        """A: [n_a, reps] external gaps, U: [n_u, reps] routing uniforms, S[i]: [n, reps] node services."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        S = [np.ascontiguousarray(x, dtype=np.float64) for x in S]
+        reps = A.shape[1]
+        m = len(channels)
+        cfg = self._net_cfg(R, channels, job_served, reps, 0, 0, queue_cap)
+        ps = (C.c_void_p * m)(*[x.ctypes.data for x in S])
+        ns = (C.c_int64 * m)(*[x.shape[0] for x in S])
+        agg = np.zeros(net_agg_len(m))
+        rec = np.empty((net_rec_rows(m), reps))
+        check(self._L.mq_replay_net(self._h, C.byref(cfg), A.ctypes.data, A.shape[0], U.ctypes.data, U.shape[0],
+                                    ps, ns, agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                    rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec
 
     def last_timing(self):

@@ -123,6 +123,31 @@ int mqo_prio_run(int c, int K, int prty_type, int64_t buffer, mqo_src *arrivals,
                  int64_t total_served, double *p, int64_t p_bins, mqo_prio_class_out *out,
                  double *ttek_out);
 
+double mqo_src_next(mqo_src *s, int *err);
+
+/* ---- open network of FIFO nodes: NetworkSimulator.run (sim/networks/network.py:196-229) ---- */
+#define MQO_NET_MAX_NODES 16
+typedef struct {
+    double v_run[4], w_run[4]; /* node-level running moments (QsSim.v / .w of qs[m]) */
+    double v_sum[4], w_sum[4];
+    int64_t arrived, taked, served, in_sys, queued;
+} mqo_net_node_out;
+
+typedef struct {
+    double v_run[3], w_run[3]; /* v_network / w_network, network.py:116-135 (math.pow powers) */
+    double v_sum[3], w_sum[3]; /* plain power sums (repeated multiplication) */
+    int64_t served, arrived, in_sys;
+    double ttek;
+} mqo_net_out;
+
+/* R: (m+1) x (m+1) row-major routing matrix (network.py:57-66): row 0 = source, row i+1 = node i,
+ * column j < m = to node j, column m = leave.  arrivals: external gaps; routing: uniforms in the
+ * order choose_next_node consumes them (network.py:109); services[i]: node i's service draws.
+ * v_samples / w_samples (may be NULL): network sojourn / wait of each served job, in order. */
+int mqo_net_run(int m, const int *channels, const double *R, mqo_src *arrivals, mqo_src *routing,
+                mqo_src *services, int64_t job_served, mqo_net_out *out, mqo_net_node_out *nodes,
+                double *v_samples, double *w_samples, int64_t cap);
+
 const char *mqo_version(void);
 
 #ifdef __cplusplus

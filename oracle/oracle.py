@@ -64,6 +64,18 @@ class MqoPrioClassOut(C.Structure):
 PRTY = {"NP": 0, "PR": 1, "RS": 2, "RW": 3}
 
 
+class MqoNetNodeOut(C.Structure):
+    _fields_ = [("v_run", C.c_double * 4), ("w_run", C.c_double * 4), ("v_sum", C.c_double * 4),
+                ("w_sum", C.c_double * 4), ("arrived", C.c_int64), ("taked", C.c_int64), ("served", C.c_int64),
+                ("in_sys", C.c_int64), ("queued", C.c_int64)]
+
+
+class MqoNetOut(C.Structure):
+    _fields_ = [("v_run", C.c_double * 3), ("w_run", C.c_double * 3), ("v_sum", C.c_double * 3),
+                ("w_sum", C.c_double * 3), ("served", C.c_int64), ("arrived", C.c_int64), ("in_sys", C.c_int64),
+                ("ttek", C.c_double)]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
@@ -104,6 +116,10 @@ def lib():
         L.mqo_prio_run.restype = C.c_int
         L.mqo_prio_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(MqoSrc), C.POINTER(MqoSrc),
                                    C.c_int64, dp, C.c_int64, C.POINTER(MqoPrioClassOut), dp]
+        L.mqo_net_run.restype = C.c_int
+        L.mqo_net_run.argtypes = [C.c_int, C.POINTER(C.c_int), dp, C.POINTER(MqoSrc), C.POINTER(MqoSrc),
+                                  C.POINTER(MqoSrc), C.c_int64, C.POINTER(MqoNetOut), C.POINTER(MqoNetNodeOut),
+                                  dp, dp, C.c_int64]
         L.mqo_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -302,3 +318,73 @@ def prio_generate(c, K, prty, sources, servers, total_served, seed, rep, buffer=
     """Generator mode: class k draws gaps from word 0 and services from word 1 of stream sid=k."""
     return _prio_run(c, K, prty, buffer, [_gen_src(sources[k], seed, k, rep, 0) for k in range(K)],
                      [_gen_src(servers[k], seed, k, rep, 1) for k in range(K)], total_served, p_bins)
+
+
+# --------------------------------------------------------------------------- network
+@dataclass
+class NetResult:
+    v: np.ndarray  # v_network running moments (3)
+    w: np.ndarray
+    v_sum: np.ndarray
+    w_sum: np.ndarray
+    served: int
+    arrived: int
+    in_sys: int
+    ttek: float
+    node_v: np.ndarray  # [m][4]
+    node_w: np.ndarray
+    node_v_sum: np.ndarray
+    node_w_sum: np.ndarray
+    node_served: np.ndarray
+    node_taked: np.ndarray
+    node_arrived: np.ndarray
+    a_used: int
+    u_used: int
+    s_used: np.ndarray
+    v_samples: np.ndarray | None = None
+    w_samples: np.ndarray | None = None
+
+
+def _net_run(R, channels, arrivals, routing, services, job_served, samples) -> NetResult:
+    m = len(channels)
+    Rm = np.ascontiguousarray(np.asarray(R, dtype=np.float64))
+    assert Rm.shape == (m + 1, m + 1)
+    ch = (C.c_int * m)(*[int(x) for x in channels])
+    S = (MqoSrc * m)(*services)
+    out = MqoNetOut()
+    nodes = (MqoNetNodeOut * m)()
+    vs = np.zeros(int(job_served)) if samples else None
+    ws = np.zeros(int(job_served)) if samples else None
+    rc = lib().mqo_net_run(m, ch, _dp(Rm), C.byref(arrivals), C.byref(routing), S, int(job_served),
+                           C.byref(out), nodes, _dp(vs) if samples else None, _dp(ws) if samples else None,
+                           int(job_served) if samples else 0)
+    if rc != 0:
+        raise RuntimeError(f"oracle net run failed rc={rc}")
+    g = lambda name: np.array([list(getattr(nodes[i], name)) for i in range(m)])
+    f = lambda name: np.array([getattr(nodes[i], name) for i in range(m)])
+    return NetResult(v=np.array(out.v_run[:]), w=np.array(out.w_run[:]), v_sum=np.array(out.v_sum[:]),
+                     w_sum=np.array(out.w_sum[:]), served=out.served, arrived=out.arrived, in_sys=out.in_sys,
+                     ttek=out.ttek, node_v=g("v_run"), node_w=g("w_run"), node_v_sum=g("v_sum"),
+                     node_w_sum=g("w_sum"), node_served=f("served"), node_taked=f("taked"),
+                     node_arrived=f("arrived"), a_used=arrivals.pos, u_used=routing.pos,
+                     s_used=np.array([S[i].pos for i in range(m)]), v_samples=vs, w_samples=ws)
+
+
+def net_replay(R, channels, A, U, S, job_served, samples=False) -> NetResult:
+    """NetworkSimulator.run() on pre-generated external gaps A, routing uniforms U, node services S[i]."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    S = [np.ascontiguousarray(x, dtype=np.float64) for x in S]
+    return _net_run(R, channels, _replay_src(A), _replay_src(U), [_replay_src(x) for x in S], job_served, samples)
+
+
+def net_generate(R, channels, source, servers, job_served, seed, rep) -> NetResult:
+    """Generator mode: node i's services = word 1 of stream sid=i; external gaps = word 0 of stream
+    sid=m; routing uniforms = word 1 of stream sid=m mapped by ("Uniform", mean .5, half .5)."""
+    m = len(channels)
+
+    class U01:
+        mean, half_interval = 0.5, 0.5
+
+    return _net_run(R, channels, _gen_src(source, seed, m, rep, 0), _gen_src(("Uniform", U01), seed, m, rep, 1),
+                    [_gen_src(servers[i], seed, i, rep, 1) for i in range(m)], job_served, False)

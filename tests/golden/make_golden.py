@@ -206,6 +206,93 @@ def make_prio():
         prio_case(f"c1k3_{prty}", 1, 3, prty, A, S, n)
 
 
+# --------------------------------------------------------------------------- network
+NET_R = [
+    [1, 0, 0, 0, 0, 0],
+    [0, 0.4, 0.6, 0, 0, 0],
+    [0, 0, 0.2, 0.4, 0.4, 0],
+    [0, 0, 0, 0, 1, 0],
+    [0, 0, 0, 0, 1, 0],
+    [0, 0, 0, 0, 0, 1],
+]  # tests/test_network_no_prty.py:37-46
+NET_CH = [3, 2, 3, 4, 3]
+
+
+def net_case(name, R, channels, A, U, S, job_served):
+    import numpy
+
+    from most_queue.sim.networks.network import NetworkSimulator
+
+    m = len(channels)
+    qn = NetworkSimulator()
+    qn.set_sources(arrival_rate=1.0, R=np.matrix(R))
+    qn.set_nodes(serv_params=[{"type": "M", "params": 1.0} for _ in range(m)], n=channels)
+    ia, iu = [0], [0]
+    isv = [[0] for _ in range(m)]
+    qn.source = ReplayDist(A, ia)
+    qn.arrival_time = qn.source.generate()  # the draw set_sources makes (network.py:76)
+    for i in range(m):
+        for srv in qn.qs[i].servers:
+            srv.dist = ReplayDist(S[i], isv[i])
+        qn.qs[i]._free_servers = LowestFirstSet(range(channels[i]))
+    ureplay = ReplayDist(U, iu)
+    vs, ws = [], []
+    ov, ow = qn.refresh_v_stat, qn.refresh_w_stat
+
+    def rv(x):
+        vs.append(x)
+        ov(x)
+
+    def rw(x):
+        ws.append(x)
+        ow(x)
+
+    qn.refresh_v_stat, qn.refresh_w_stat = rv, rw
+    orig = numpy.random.rand
+    numpy.random.rand = ureplay.generate  # choose_next_node draws its uniform here (network.py:109)
+    try:
+        with quiet():
+            while qn.served < job_served:  # run() minus tqdm (network.py:211-212)
+                qn.run_one_step()
+    finally:
+        numpy.random.rand = orig
+    out = dict(R=np.array(R, dtype=np.float64), channels=np.array(channels), job_served=job_served,
+               A=np.asarray(A), U=np.asarray(U), ttek=float(qn.ttek), served=qn.served, arrived=qn.arrived,
+               in_sys=qn.in_sys, v=np.array(qn.v_network, dtype=np.float64), w=np.array(qn.w_network, dtype=np.float64),
+               v_samples=np.array(vs, dtype=np.float64), w_samples=np.array(ws, dtype=np.float64),
+               a_used=ia[0], u_used=iu[0], s_used=np.array([x[0] for x in isv]),
+               node_v=np.array([q.v for q in qn.qs], dtype=np.float64),
+               node_w=np.array([q.w for q in qn.qs], dtype=np.float64),
+               node_served=np.array([q.served for q in qn.qs]), node_taked=np.array([q.taked for q in qn.qs]),
+               node_arrived=np.array([q.arrived for q in qn.qs]))
+    for i in range(m):
+        out[f"S{i}"] = np.asarray(S[i])
+    np.savez_compressed(os.path.join(OUT, f"net_{name}.npz"), **out)
+    print(f"net_{name}: served={qn.served} arrived={qn.arrived} v1={qn.v_network[0]:.5f} u_used={iu[0]}")
+
+
+def make_net():
+    rng = np.random.default_rng(20260303)
+    n = 2500
+    # cfg5 shape: test_network_no_prty topology, node service H2-like mixtures, rho = 0.7 per node
+    S = []
+    for i, c in enumerate(NET_CH):
+        mean = 0.7 * c / 1.0
+        mix = rng.random(8 * n) < 0.3
+        S.append(rng.exponential(1.0, 8 * n) * np.where(mix, 2.2 * mean, 0.486 * mean))
+    net_case("cfg5_h2", NET_R, NET_CH, rng.exponential(1.0, 2 * n), rng.random(16 * n), S, n)
+    # Jackson sub-case (tests/test_jackson_network.py:29-31): exponential service
+    S = [rng.exponential(0.7 * c / 1.3, 8 * n) for c in NET_CH]
+    net_case("jackson", NET_R, NET_CH, rng.exponential(1.0, 2 * n), rng.random(16 * n), S, n)
+    # two-node tandem with feedback, single servers
+    R2 = [[1, 0, 0], [0, 0.8, 0.2], [0.3, 0, 0.7]]
+    S = [rng.gamma(2.0, 0.25, 8 * n), rng.gamma(0.8, 0.6, 8 * n)]
+    net_case("tandem2_fb", R2, [1, 1], rng.exponential(1.0, 2 * n), rng.random(8 * n), S, n)
+    # one node == M/M/3 (tests/test_jackson_network.py::test_single_node_reduces_to_mmn)
+    net_case("single", [[1, 0], [0, 1]], [3], rng.exponential(0.5, 2 * n), rng.random(4 * n),
+             [rng.exponential(1.0, 3 * n)], n)
+
+
 # --------------------------------------------------------------------------- theory
 def make_theory():
     """Analytical values used by the generator-mode (statistical) tests."""
