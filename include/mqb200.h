@@ -259,6 +259,45 @@ int mq_sim_net(mq_ctx *ctx, const mq_net_cfg *cfg, double *agg, double *rep_out)
 int mq_replay_net(mq_ctx *ctx, const mq_net_cfg *cfg, const double *A, int64_t n_a, const double *U,
                   int64_t n_u, const double *const *S, const int64_t *n_s, double *agg, double *rep_out);
 
+/* ---- one very long GI/G/1 FIFO chain: max-plus Lindley scan.  Replaces QsSim(1).run(N)
+ * (sim/base.py:488 with num_of_channels = 1, buffer = None) for N far beyond what a sequential
+ * walk can do.  Jobs n = 0..N-1, A[n] = gap before arrival n, S[n] = service of job n. */
+typedef struct {
+    mq_dist src;          /* generator form: set_sources                        base.py:95   */
+    mq_dist srv;          /*                 set_servers                        base.py:114  */
+    int64_t jobs;         /* jobs of THIS range                                              */
+    int64_t job0;         /* global index of its first job (Philox counter; 0 on one GPU)    */
+    uint64_t seed;
+    uint32_t chain;       /* chain id (generator stream)                                     */
+    int32_t device_ptrs;  /* replay form: A, S (and W) are device pointers                   */
+    int32_t last_range;   /* 1: this range ends the chain (apply the stop rule, base.py:505) */
+    int32_t flags;
+} mq_scan_cfg;
+
+#define MQ_S_W 0       /* 4: sum of W^k over the jobs of the range (+ job N when last_range and it  */
+                       /*    was already waiting at the N-th departure, base.py:300-305)            */
+#define MQ_S_V 4       /* 4: sum of (W + S)^k                                                       */
+#define MQ_S_SUMA 8    /* sum of the range's gaps                                                   */
+#define MQ_S_SUMS 9    /* sum of the range's service times (= busy time of the single server)       */
+#define MQ_S_TAKED 10  /* number of w samples                                                        */
+#define MQ_S_SERVED 11 /* number of v samples                                                        */
+#define MQ_S_A 12      /* max-plus summary of the range: W_out = max(a, W_in + b)                    */
+#define MQ_S_B 13
+#define MQ_S_WIN 14
+#define MQ_S_WOUT 15   /* carry into the next range                                                  */
+#define MQ_S_TAILRAW 16 /* W[n-1] + x[n-1] before clamping                                           */
+#define MQ_S_TAILV 17  /* W[n-1] + S[n-1]: clock at the last departure minus the last arrival time   */
+#define MQ_SCAN_LEN 20
+
+/* A, S == NULL: generator form.  Replay form: A has jobs + 1 entries (x[n] uses A[n+1]), S has jobs.
+ * summary: ab[2] = (a, b) of the range.  apply: walks the range from carry w_in; stats has
+ * MQ_SCAN_LEN doubles; W (optional, may be NULL) receives the per-job waits.
+ * mq_scan_gg1 = summary + apply with w_in = 0 for a chain held by one GPU. */
+int mq_scan_gg1_summary(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double ab[2]);
+int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double w_in,
+                      double *stats, double *W);
+int mq_scan_gg1(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double *stats, double *W);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

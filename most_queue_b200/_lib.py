@@ -120,6 +120,17 @@ class MqNetCfg(C.Structure):
     ]
 
 
+S_W, S_V, S_SUMA, S_SUMS, S_TAKED, S_SERVED, S_A, S_B, S_WIN, S_WOUT, S_TAILRAW, S_TAILV, SCAN_LEN = (
+    0, 4, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20)
+
+
+class MqScanCfg(C.Structure):
+    _fields_ = [
+        ("src", MqDist), ("srv", MqDist), ("jobs", C.c_int64), ("job0", C.c_int64), ("seed", C.c_uint64),
+        ("chain", C.c_uint32), ("device_ptrs", C.c_int32), ("last_range", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -165,6 +176,12 @@ def load():
         L.mq_replay_net.restype = C.c_int
         L.mq_replay_net.argtypes = [vp, C.POINTER(MqNetCfg), vp, C.c_int64, vp, C.c_int64, C.POINTER(vp),
                                     C.POINTER(C.c_int64), dp, dp]
+        L.mq_scan_gg1_summary.restype = C.c_int
+        L.mq_scan_gg1_summary.argtypes = [vp, C.POINTER(MqScanCfg), vp, vp, dp]
+        L.mq_scan_gg1_apply.restype = C.c_int
+        L.mq_scan_gg1_apply.argtypes = [vp, C.POINTER(MqScanCfg), vp, vp, C.c_double, dp, vp]
+        L.mq_scan_gg1.restype = C.c_int
+        L.mq_scan_gg1.argtypes = [vp, C.POINTER(MqScanCfg), vp, vp, dp, vp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -392,6 +409,35 @@ class Context:
                                     rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec
 
+    # ---- K3 ----
+    def _scan_cfg(self, src, srv, jobs, job0, seed, chain, device_ptrs, last_range):
+        cfg = MqScanCfg()
+        if src is not None:
+            cfg.src, cfg.srv = src, srv
+        cfg.jobs, cfg.job0 = int(jobs), int(job0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.chain, cfg.device_ptrs, cfg.last_range = int(chain), int(device_ptrs), int(last_range)
+        return cfg
+
+    def scan_summary(self, jobs, job0=0, src=None, srv=None, seed=0, chain=0, A=None, S=None, device_ptrs=False):
+        """(a, b) of the range: W_out = max(a, W_in + b).  A, S: numpy arrays or device pointers (ints)."""
+        cfg = self._scan_cfg(src, srv, jobs, job0, seed, chain, device_ptrs, 0)
+        pa, ps, _keep = _scan_ptrs(A, S, jobs, device_ptrs)
+        ab = (C.c_double * 2)()
+        check(self._L.mq_scan_gg1_summary(self._h, C.byref(cfg), pa, ps, ab))
+        return float(ab[0]), float(ab[1])
+
+    def scan_apply(self, jobs, w_in, job0=0, src=None, srv=None, seed=0, chain=0, A=None, S=None,
+                   device_ptrs=False, last_range=True, want_w=False):
+        cfg = self._scan_cfg(src, srv, jobs, job0, seed, chain, device_ptrs, last_range)
+        pa, ps, _keep = _scan_ptrs(A, S, jobs, device_ptrs)
+        stats = np.zeros(SCAN_LEN)
+        W = np.empty(int(jobs)) if want_w else None
+        check(self._L.mq_scan_gg1_apply(self._h, C.byref(cfg), pa, ps, float(w_in),
+                                        stats.ctypes.data_as(C.POINTER(C.c_double)),
+                                        W.ctypes.data if W is not None else None))
+        return stats, W
+
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         check(self._L.mq_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
@@ -409,6 +455,18 @@ class Context:
         check(self._L.mq_debug_variates(self._h, C.byref(dist), int(seed) & 0xFFFFFFFFFFFFFFFF, int(rep),
                                         int(which), int(n), out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+
+def _scan_ptrs(A, S, jobs, device_ptrs):
+    if A is None and S is None:
+        return None, None, None
+    if device_ptrs:
+        return int(A), int(S), None
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    if A.shape[0] < jobs + 1 or S.shape[0] < jobs:
+        raise ValueError("replay form needs jobs + 1 gaps and jobs service times")
+    return A.ctypes.data, S.ctypes.data, (A, S)
 
 
 _default_ctx: dict[int, Context] = {}

@@ -1,0 +1,254 @@
+// k3_lindley.cu -- K3: max-plus Lindley parallel scan for ONE very long GI/G/1 FIFO chain.
+//
+// With one channel and an infinite buffer QsSim.run() (most_queue/sim/base.py:488-528) is the
+// Lindley recursion  W[n+1] = max(0, W[n] + x[n]),  x[n] = S[n] - A[n+1]  (wait = start - arrival,
+// base.py:302; the start of job n+1 is the departure of job n), v[n] = W[n] + S[n] (base.py:272).
+// The reference can only walk it sequentially (base.py:505).  Each step is the map
+// w -> max(a, w + b) with (a, b) = (0, x[n]); maps compose associatively in max-plus algebra:
+//   later o earlier = (max(a2, a1 + b2), b1 + b2),
+// so the chain is cut into segments of K3_L jobs (one thread each), segment summaries are scanned
+// with a FIXED association tree (Kogge-Stone over the 32 lanes of a warp, sequential over the 8 warps
+// of a tile, then the tile level: 1024 chunks folded sequentially, Kogge-Stone over 32, sequential over
+// 32), and every segment is then walked sequentially from its carry.  fp64 '+' is not associative,
+// so the tree is part of the specification: oracle/mq_oracle_scan.c evaluates the same tree and the
+// per-job waits agree bit for bit.
+//
+// Three launches: (1) tile summaries, (2) tile-level scan (one CTA), (3) walk + moment sums.  The
+// replay form reads A and S twice (32 B/job); the generator form regenerates the variates with the
+// counter-based generator (counter = global job index, so any range can be evaluated anywhere).
+#include "k3_lindley.cuh"
+
+namespace mq {
+
+__device__ __forceinline__ MP mp_id() { return MP{-INFINITY, 0.0}; }
+
+__device__ __forceinline__ MP mp_then(MP earlier, MP later)
+{
+    return MP{fmax(later.a, __dadd_rn(earlier.a, later.b)), __dadd_rn(earlier.b, later.b)};
+}
+
+__device__ __forceinline__ MP mp_step(MP f, double x)
+{
+    return MP{fmax(0.0, __dadd_rn(f.a, x)), __dadd_rn(f.b, x)};
+}
+
+__device__ __forceinline__ double mp_apply(MP f, double w) { return fmax(f.a, __dadd_rn(w, f.b)); }
+
+__device__ __forceinline__ MP mp_shfl_up(MP v, int d)
+{
+    return MP{__shfl_up_sync(0xffffffffu, v.a, d), __shfl_up_sync(0xffffffffu, v.b, d)};
+}
+
+// exclusive prefix of `mine` over the CTA (groups of 32 lanes: Kogge-Stone; groups: sequential).
+// Returns the exclusive prefix; *total receives the fold of all values (valid in every thread).
+template <int NT>
+__device__ __forceinline__ MP cta_scan(MP mine, MP *smem, MP *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MP inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        MP up = mp_shfl_up(inc, d);
+        if (lane >= d) inc = mp_then(up, inc);
+    }
+    MP within = mp_shfl_up(inc, 1);
+    if (lane == 0) within = mp_id();
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    MP carry = mp_id(), tot = mp_id();
+    for (int g = 0; g < NT / 32; ++g) {
+        if (g == warp) carry = tot;
+        tot = mp_then(tot, smem[g]);
+    }
+    __syncthreads();
+    *total = tot;
+    return mp_then(carry, within);
+}
+
+// x[j] = S[n] - A[n+1] and S[j] for the K3_L jobs of this thread's segment
+template <bool REPLAY>
+__device__ __forceinline__ void load_segment(const K3Params &P, long long n0, double (&x)[K3_L], double (&s)[K3_L],
+                                             double (&a)[K3_L])
+{
+    if (REPLAY) {
+#pragma unroll
+        for (int j = 0; j < K3_L; ++j) {
+            const long long n = n0 + j;
+            const bool ok = n < P.n;
+            s[j] = ok ? __ldg(P.S + n) : 0.0;
+            a[j] = ok ? __ldg(P.A + n) : 0.0;
+            const double an = ok ? __ldg(P.A + n + 1) : 0.0;
+            x[j] = __dsub_rn(s[j], an);
+        }
+    } else {
+        // word 0 of call n = gap before job n, word 1 of call n = service of job n
+        unsigned long long g = (unsigned long long)(P.job0 + n0);
+        uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+        double gap = (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+#pragma unroll
+        for (int j = 0; j < K3_L; ++j) {
+            const long long n = n0 + j;
+            const bool ok = n < P.n;
+            const double sv = (double)sample<-1>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
+            ++g;
+            w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+            const double gnext = (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+            s[j] = ok ? sv : 0.0;
+            a[j] = ok ? gap : 0.0;
+            x[j] = ok ? __dsub_rn(sv, gnext) : 0.0;
+            gap = gnext;
+        }
+    }
+}
+
+__device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, const double (&x)[K3_L])
+{
+    MP f = mp_id();
+#pragma unroll
+    for (int j = 0; j < K3_L; ++j)
+        if (n0 + j < P.n) f = mp_step(f, x[j]);
+    return f;
+}
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
+{
+    __shared__ MP smem[K3_THREADS / 32];
+    for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+        const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
+        double x[K3_L], s[K3_L], a[K3_L];
+        load_segment<REPLAY>(P, n0, x, s, a);
+        MP total;
+        cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);
+        if (threadIdx.x == 0) P.tile_sum[t] = total;
+    }
+}
+
+__global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
+{
+    __shared__ MP smem[K3_TOP / 32];
+    const long long chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
+    const long long lo = (long long)threadIdx.x * chunk;
+    MP f = mp_id();
+    for (long long t = lo; t < lo + chunk && t < P.ntiles; ++t) f = mp_then(f, P.tile_sum[t]);
+    MP total;
+    MP ex = cta_scan<K3_TOP>(f, smem, &total);
+    for (long long t = lo; t < lo + chunk && t < P.ntiles; ++t) {
+        P.tile_ex[t] = ex;
+        ex = mp_then(ex, P.tile_sum[t]);
+    }
+    if (threadIdx.x == 0) *P.total = total;
+}
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
+{
+    __shared__ MP smem[K3_THREADS / 32];
+    __shared__ double red[K3_THREADS / 32][K3_NSTAT];
+    double acc[K3_NSTAT];
+#pragma unroll
+    for (int i = 0; i < K3_NSTAT; ++i) acc[i] = 0.0;
+
+    for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+        const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
+        double x[K3_L], s[K3_L], a[K3_L];
+        load_segment<REPLAY>(P, n0, x, s, a);
+        MP total;
+        const MP ex = cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);
+        const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
+        double w = mp_apply(ex, w_tile);
+#pragma unroll
+        for (int j = 0; j < K3_L; ++j) {
+            const long long n = n0 + j;
+            if (n < P.n) {
+                if (P.W) P.W[n] = w;
+                const double v = __dadd_rn(w, s[j]);
+                const double w2 = w * w, v2 = v * v;
+                acc[0] += w;
+                acc[1] += w2;
+                acc[2] += w2 * w;
+                acc[3] += w2 * w2;
+                acc[4] += v;
+                acc[5] += v2;
+                acc[6] += v2 * v;
+                acc[7] += v2 * v2;
+                acc[8] += a[j];
+                acc[9] += s[j];
+                const double raw = __dadd_rn(w, x[j]);
+                if (n == P.n - 1) {
+                    P.tail[0] = raw;
+                    P.tail[1] = v;
+                }
+                w = fmax(0.0, raw);
+            }
+        }
+    }
+    // fixed-order CTA reduction of the partial sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < K3_NSTAT; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < K3_NSTAT) {
+        double v = 0.0;
+        for (int wv = 0; wv < K3_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        P.partial[(long long)blockIdx.x * K3_NSTAT + threadIdx.x] = v;
+    }
+}
+
+__global__ void k3_final(const double *partial, int grid, double *stats)
+{
+    const int i = threadIdx.x;
+    if (i >= K3_NSTAT) return;
+    double v = 0.0;
+    for (int b = 0; b < grid; ++b) v += partial[(long long)b * K3_NSTAT + i];
+    stats[i] = v;
+}
+
+cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
+{
+    if (P.replay)
+        k3_summary<true><<<grid, K3_THREADS, 0, st>>>(P);
+    else
+        k3_summary<false><<<grid, K3_THREADS, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st)
+{
+    k3_top<<<1, K3_TOP, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st)
+{
+    if (P.replay)
+        k3_walk<true><<<grid, K3_THREADS, 0, st>>>(P);
+    else
+        k3_walk<false><<<grid, K3_THREADS, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_launch_final(const double *partial, int grid, double *stats, cudaStream_t st)
+{
+    k3_final<<<1, 32, 0, st>>>(partial, grid, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_occupancy(int *summary_blocks, int *walk_blocks)
+{
+    int a = 0, b = 0, c = 0, d = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_summary<false>, K3_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k3_walk<true>, K3_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k3_walk<false>, K3_THREADS, 0);
+    *summary_blocks = a < b ? a : b;
+    *walk_blocks = c < d ? c : d;
+    return e;
+}
+
+}  // namespace mq

@@ -1,0 +1,41 @@
+// k3_lindley.cuh -- parameters of the max-plus Lindley scan kernels (k3_lindley.cu).
+#pragma once
+
+#include "mq_device.cuh"
+
+namespace mq {
+
+constexpr int K3_THREADS = 256;   // segments per tile
+constexpr int K3_L = 16;          // jobs per segment (one 128-byte line of fp64 per array per thread)
+constexpr int K3_TOP = 1024;      // threads of the tile-level scan
+constexpr int K3_NSTAT = 16;      // per-block partial sums
+
+struct MP {
+    double a, b;  // the map w -> max(a, w + b)
+};
+
+struct K3Params {
+    long long n;        // jobs in this range
+    long long job0;     // global index of the first one (Philox counter)
+    int replay;
+    uint32_t key;       // key0 + STRIDE * 64 * chain
+    DistF src, srv;
+    const double *A;    // replay: A[0] = gap before job job0; n + 1 entries
+    const double *S;    // replay: n entries
+    MP *tile_sum;       // [ntiles]
+    MP *tile_ex;        // [ntiles]
+    MP *total;          // [1]
+    double w_in;
+    double *partial;    // [grid][K3_NSTAT]
+    double *tail;       // [2]: W[n-1] + x[n-1] (before clamping), W[n-1] + S[n-1]
+    double *W;          // optional per-job waits
+    long long ntiles;
+};
+
+cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
+cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
+cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);
+cudaError_t k3_launch_final(const double *partial, int grid, double *stats, cudaStream_t st);
+cudaError_t k3_occupancy(int *summary_blocks, int *walk_blocks);
+
+}  // namespace mq

@@ -1,0 +1,183 @@
+// mq_api_scan.cu -- C ABI entry points of the Lindley scan (mq_scan_gg1*).
+#include "k3_lindley.cuh"
+#include "mq_host.cuh"
+
+using namespace mq;
+
+namespace {
+
+struct ScanRun {
+    K3Params P;
+    int grid_sum = 0, grid_walk = 0;
+    bool staged_inputs = false;
+};
+
+int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, ScanRun &run, const char *who)
+{
+    if (!ctx || !cfg) return fail(MQ_E_INVALID, "%s: NULL argument", who);
+    if (cfg->jobs < 1 || cfg->job0 < 0) return fail(MQ_E_INVALID, "%s: jobs must be >= 1 and job0 >= 0", who);
+    const bool replay = A != nullptr || S != nullptr;
+    if (replay && (!A || !S)) return fail(MQ_E_INVALID, "%s: both A and S are needed in replay form", who);
+    if (!replay) {
+        if (int rc = check_dist(cfg->src, "set_sources")) return rc;
+        if (int rc = check_dist(cfg->srv, "set_servers")) return rc;
+    }
+    CU(cudaSetDevice(ctx->device));
+    K3Params &P = run.P;
+    std::memset(&P, 0, sizeof(P));
+    P.n = cfg->jobs;
+    P.job0 = cfg->job0;
+    P.replay = replay ? 1 : 0;
+    P.key = seed_to_key(cfg->seed) + MQ_KEY_STRIDE * (64u * cfg->chain);
+    const long long tile = (long long)K3_THREADS * K3_L;
+    P.ntiles = (P.n + tile - 1) / tile;
+
+    int occ_s = 0, occ_w = 0;
+    CU(k3_occupancy(&occ_s, &occ_w));
+    if (occ_s < 1 || occ_w < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
+    run.grid_sum = (int)std::min<long long>(P.ntiles, (long long)occ_s * ctx->sms);
+    run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
+
+    // scratch: tile_sum, tile_ex, total, tail, partial, stats
+    const size_t bytes = sizeof(MP) * (2 * (size_t)P.ntiles + 1) + sizeof(double) * (2 + (size_t)run.grid_walk * K3_NSTAT + K3_NSTAT);
+    if (int rc = ensure(ctx->rec, bytes)) return rc;
+    char *base = (char *)ctx->rec.p;
+    P.tile_sum = (MP *)base;
+    P.tile_ex = P.tile_sum + P.ntiles;
+    P.total = P.tile_ex + P.ntiles;
+    P.tail = (double *)(P.total + 1);
+    P.partial = P.tail + 2;
+    if (int rc = ensure_host_agg(ctx, sizeof(double) * 64)) return rc;
+
+    if (replay) {
+        if (cfg->device_ptrs) {
+            P.A = A;
+            P.S = S;
+        } else {
+            if (int rc = ensure(ctx->in_a, sizeof(double) * (size_t)(P.n + 1))) return rc;
+            if (int rc = ensure(ctx->in_s, sizeof(double) * (size_t)P.n)) return rc;
+            CU(cudaMemcpyAsync(ctx->in_a.p, A, sizeof(double) * (size_t)(P.n + 1), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->in_s.p, S, sizeof(double) * (size_t)P.n, cudaMemcpyHostToDevice, ctx->stream));
+            P.A = (const double *)ctx->in_a.p;
+            P.S = (const double *)ctx->in_s.p;
+        }
+    } else {
+        P.src = make_distf(cfg->src);
+        P.srv = make_distf(cfg->srv);
+    }
+    return MQ_OK;
+}
+
+int scan_summary(mq_ctx *ctx, ScanRun &run)
+{
+    CU(k3_launch_summary(run.P, run.grid_sum, ctx->stream));
+    CU(k3_launch_top(run.P, ctx->stream));
+    ctx->launches += 2;
+    return MQ_OK;
+}
+
+int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, double *stats, double *W)
+{
+    K3Params &P = run.P;
+    P.w_in = w_in;
+    double *dW = nullptr;
+    if (W) {
+        if (cfg->device_ptrs) {
+            dW = W;
+        } else {
+            if (int rc = ensure(ctx->ring, sizeof(double) * (size_t)P.n)) return rc;
+            dW = (double *)ctx->ring.p;
+        }
+    }
+    P.W = dW;
+    double *d_stats = P.partial + (size_t)run.grid_walk * K3_NSTAT;
+    CU(k3_launch_walk(P, run.grid_walk, ctx->stream));
+    CU(k3_launch_final(P.partial, run.grid_walk, d_stats, ctx->stream));
+    ctx->launches += 2;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    double *h = ctx->h_agg;
+    CU(cudaMemcpyAsync(h, d_stats, sizeof(double) * K3_NSTAT, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h + 32, P.total, sizeof(MP), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h + 34, P.tail, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (W && !cfg->device_ptrs)
+        CU(cudaMemcpyAsync(W, dW, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+
+    for (int i = 0; i < MQ_SCAN_LEN; ++i) stats[i] = 0.0;
+    for (int k = 0; k < 4; ++k) {
+        stats[MQ_S_W + k] = h[k];
+        stats[MQ_S_V + k] = h[4 + k];
+    }
+    stats[MQ_S_SUMA] = h[8];
+    stats[MQ_S_SUMS] = h[9];
+    stats[MQ_S_TAKED] = (double)P.n;
+    stats[MQ_S_SERVED] = (double)P.n;
+    stats[MQ_S_A] = h[32];
+    stats[MQ_S_B] = h[33];
+    stats[MQ_S_WIN] = w_in;
+    stats[MQ_S_WOUT] = std::fmax(h[32], w_in + h[33]);
+    stats[MQ_S_TAILRAW] = h[34];
+    stats[MQ_S_TAILV] = h[35];
+    if (cfg->last_range && h[34] >= 0.0) {
+        // job N arrived by the N-th departure: popped there and sampled (base.py:300-305)
+        double pw = h[34];
+        for (int k = 0; k < 4; ++k) {
+            stats[MQ_S_W + k] += pw;
+            pw *= h[34];
+        }
+        stats[MQ_S_TAKED] += 1.0;
+    }
+    return finish_timing(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mq_scan_gg1_summary(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double ab[2])
+{
+    if (!ab) return fail(MQ_E_INVALID, "mq_scan_gg1_summary: NULL output");
+    ScanRun run;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_summary")) return rc;
+    ctx->launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (int rc = scan_summary(ctx, run)) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_agg, run.P.total, sizeof(MP), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ab[0] = ctx->h_agg[0];
+    ab[1] = ctx->h_agg[1];
+    return finish_timing(ctx);
+}
+
+int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double w_in,
+                      double *stats, double *W)
+{
+    if (!stats) return fail(MQ_E_INVALID, "mq_scan_gg1_apply: NULL output");
+    ScanRun run;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_apply")) return rc;
+    ctx->launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // the tile prefixes are a function of the range only; recompute them (scratch is not kept between calls)
+    if (int rc = scan_summary(ctx, run)) return rc;
+    return scan_apply(ctx, cfg, run, w_in, stats, W);
+}
+
+int mq_scan_gg1(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double *stats, double *W)
+{
+    if (!stats) return fail(MQ_E_INVALID, "mq_scan_gg1: NULL output");
+    ScanRun run;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1")) return rc;
+    ctx->launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (int rc = scan_summary(ctx, run)) return rc;
+    mq_scan_cfg c2 = *cfg;
+    c2.last_range = 1;
+    return scan_apply(ctx, &c2, run, 0.0, stats, W);
+}
+
+}  // extern "C"

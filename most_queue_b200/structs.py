@@ -19,6 +19,7 @@ class QueueResults:
     # additive: replication statistics
     replications: int = 1
     ci: dict | None = None  # 99 % confidence half-widths across replications: {"w": [...], "v": [...], "p": [...]}
+    timing: dict | None = None  # device time of the kernels of the run (ms)
 
 
 @dataclass

@@ -148,6 +148,28 @@ int mqo_net_run(int m, const int *channels, const double *R, mqo_src *arrivals, 
                 mqo_src *services, int64_t job_served, mqo_net_out *out, mqo_net_node_out *nodes,
                 double *v_samples, double *w_samples, int64_t cap);
 
+/* ---- single long GI/G/1 FIFO chain: max-plus Lindley scan (DESIGN.md "K3") -------------------
+ * Jobs n = 0..N-1; A[n] = gap before arrival n (A[0] = first arrival, sim/base.py:112), S[n] =
+ * service of job n (servers.py:88).  With c = 1, infinite buffer, QsSim.run(N) is the Lindley
+ * recursion  W[0] = 0,  W[n+1] = max(0, W[n] + x[n]),  x[n] = S[n] - A[n+1]  (wait = start - arrival,
+ * base.py:302; start of job n+1 = departure of job n), v[n] = W[n] + S[n].
+ * mqo_lindley_seq walks it sequentially; mqo_lindley_tree evaluates it with the kernel's fixed
+ * association tree (segments of L jobs folded sequentially, Kogge-Stone over the 32 segments of a
+ * warp, sequential over the warps of a 256-thread tile, then the tile level: 1024 chunks folded
+ * sequentially, Kogge-Stone over 32 chunks, sequential over 32 groups), so that its W[] equals the
+ * kernel's bit for bit.  A needs N+1 entries (x[N-1] uses A[N]).  w_in is the carry into job 0. */
+typedef struct {
+    double w_sum[4], v_sum[4];
+    int64_t taked, served;
+    double sum_a, sum_s; /* sum A[0..N-1], sum S[0..N-1] */
+    double w_last_raw;   /* W[N-1] + x[N-1] before clamping: >= 0 iff job N was already waiting */
+    double a, b;         /* max-plus summary of the whole range: W_out = max(a, W_in + b) */
+} mqo_lindley_out;
+
+int mqo_lindley_seq(const double *A, const double *S, int64_t N, double w_in, double *W, mqo_lindley_out *out);
+int mqo_lindley_tree(const double *A, const double *S, int64_t N, double w_in, int L, double *W,
+                     mqo_lindley_out *out);
+
 const char *mqo_version(void);
 
 #ifdef __cplusplus

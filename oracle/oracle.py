@@ -76,6 +76,12 @@ class MqoNetOut(C.Structure):
                 ("ttek", C.c_double)]
 
 
+class MqoLindleyOut(C.Structure):
+    _fields_ = [("w_sum", C.c_double * 4), ("v_sum", C.c_double * 4), ("taked", C.c_int64), ("served", C.c_int64),
+                ("sum_a", C.c_double), ("sum_s", C.c_double), ("w_last_raw", C.c_double), ("a", C.c_double),
+                ("b", C.c_double)]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
@@ -120,6 +126,10 @@ def lib():
         L.mqo_net_run.argtypes = [C.c_int, C.POINTER(C.c_int), dp, C.POINTER(MqoSrc), C.POINTER(MqoSrc),
                                   C.POINTER(MqoSrc), C.c_int64, C.POINTER(MqoNetOut), C.POINTER(MqoNetNodeOut),
                                   dp, dp, C.c_int64]
+        L.mqo_lindley_seq.restype = C.c_int
+        L.mqo_lindley_seq.argtypes = [dp, dp, C.c_int64, C.c_double, dp, C.POINTER(MqoLindleyOut)]
+        L.mqo_lindley_tree.restype = C.c_int
+        L.mqo_lindley_tree.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_int, dp, C.POINTER(MqoLindleyOut)]
         L.mqo_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -388,3 +398,22 @@ def net_generate(R, channels, source, servers, job_served, seed, rep) -> NetResu
 
     return _net_run(R, channels, _gen_src(source, seed, m, rep, 0), _gen_src(("Uniform", U01), seed, m, rep, 1),
                     [_gen_src(servers[i], seed, i, rep, 1) for i in range(m)], job_served, False)
+
+
+# --------------------------------------------------------------------------- Lindley chain
+def lindley(A, S, N=None, w_in=0.0, tree=True, L=16):
+    """W[0..N) of the GI/G/1 chain: sequentially (tree=False) or with the scan kernel's association
+    tree (tree=True).  Returns (W, MqoLindleyOut)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    N = int(len(S) if N is None else N)
+    assert len(A) >= N + 1
+    W = np.zeros(N)
+    out = MqoLindleyOut()
+    if tree:
+        rc = lib().mqo_lindley_tree(_dp(A), _dp(S), N, float(w_in), int(L), _dp(W), C.byref(out))
+    else:
+        rc = lib().mqo_lindley_seq(_dp(A), _dp(S), N, float(w_in), _dp(W), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle lindley failed rc={rc}")
+    return W, out

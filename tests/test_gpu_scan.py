@@ -1,0 +1,89 @@
+"""K3 (max-plus Lindley scan) through the C ABI: per-job waits bit-exact against the oracle's
+evaluation of the same association tree, carries across ranges, generator form against K2."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class P:
+    def __init__(self, **k):
+        self.__dict__.update(k)
+
+
+GAMMA = P(mu=3.18878, alpha=3.18878)      # mean 1.0, cv 0.56  (cfg3 source)
+PARETO = P(alpha=2.30171, K=0.395878)     # mean 0.7, cv 1.2   (cfg3 server)
+
+
+@pytest.mark.parametrize("N", [1, 15, 16, 17, 255 * 16 + 3, 4096, 4097, 100_003, 1_300_000])
+def test_replay_waits_bitwise_vs_oracle_tree(N):
+    from most_queue_b200.sim.lindley import replay_chain
+    from oracle import oracle
+
+    rng = np.random.default_rng(N)
+    A = rng.gamma(3.18878, 1 / 3.18878, N + 1)
+    S = 0.395878 * rng.random(N) ** (-1 / 2.30171)
+    out, W = replay_chain(A, S, N)
+    Wt, ot = oracle.lindley(A, S, N, tree=True)
+    assert np.array_equal(W, Wt)                      # bit for bit, same association tree
+    Ws, os_ = oracle.lindley(A, S, N, tree=False)
+    np.testing.assert_allclose(W, Ws, rtol=0, atol=1e-9)   # and equal to the sequential walk to rounding
+    assert (out["taked"], out["served"]) == (ot.taked, ot.served)
+    assert out["pairs"][0] == (ot.a, ot.b)
+    np.testing.assert_allclose(out["w_sum"], ot.w_sum, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(out["v_sum"], ot.v_sum, rtol=1e-12)
+    np.testing.assert_allclose([out["sum_a"], out["sum_s"]], [ot.sum_a, ot.sum_s], rtol=1e-12)
+    assert out["tail_raw"] == ot.w_last_raw
+
+
+def test_ranges_with_carries_equal_oracle_per_range():
+    """The multi-GPU path on one GPU: 5 contiguous ranges, summaries folded into carries; every range's
+    waits equal the oracle's tree evaluation of that range from the same carry, bit for bit."""
+    from most_queue_b200.sim.lindley import replay_chain
+    from oracle import oracle
+
+    rng = np.random.default_rng(42)
+    N = 300_000
+    A = rng.exponential(1.0, N + 1)
+    S = rng.exponential(0.93, N)   # heavy load: carries are large and matter
+    out, W = replay_chain(A, S, N, ranges=5)
+    bounds = [N * g // 5 for g in range(6)]
+    for g in range(5):
+        lo, hi = bounds[g], bounds[g + 1]
+        Wt, ot = oracle.lindley(A[lo:], S[lo:], hi - lo, w_in=out["carries"][g], tree=True)
+        assert np.array_equal(W[lo:hi], Wt)
+        assert out["pairs"][g] == (ot.a, ot.b)
+    Ws, _ = oracle.lindley(A, S, N, tree=False)
+    np.testing.assert_allclose(W, Ws, rtol=0, atol=1e-8)
+    assert max(out["carries"]) > 1.0
+
+
+def test_generator_chain_matches_k2_single_channel():
+    """A short chain simulated by the scan and by the event-loop kernel (c=1, replication 0) consumes
+    the same Philox words: the moments agree to fp32 accuracy."""
+    from most_queue_b200.sim.base import QsSim
+    from most_queue_b200.sim.lindley import run_chain
+
+    N, seed = 200_000, 31
+    res = run_chain(("Gamma", GAMMA), ("Pa", PARETO), N, seed=seed)
+    qs = QsSim(1, seed=seed)
+    qs.set_sources(GAMMA, "Gamma")
+    qs.set_servers(PARETO, "Pa")
+    ev = qs.run(N)
+    assert res.served == N and abs(res.taked - qs.taked) <= 1
+    np.testing.assert_allclose(res.w[0], ev.w[0], rtol=2e-3)
+    np.testing.assert_allclose(res.v[:2], ev.v[:2], rtol=2e-3)
+    np.testing.assert_allclose(res.p[0], ev.p[0], rtol=2e-3)
+    np.testing.assert_allclose(res.ttek, qs.ttek, rtol=1e-4)
+    assert abs(res.utilization - 0.7) < 1e-4
+
+
+def test_long_generator_chain_mg1_theory():
+    """M/M/1 sanity on 2e8 jobs: E[W] = rho / (mu - lambda), utilisation = rho."""
+    from most_queue_b200.sim.lindley import run_chain
+
+    res = run_chain(("M", 1.0), ("M", 1.0 / 0.7), 200_000_000, seed=7)
+    assert abs(res.w[0] - 0.7 * 0.7 / 0.3) < 0.01
+    assert abs(res.measured_utilization - 0.7) < 2e-4
+    assert abs(res.v[0] - (0.7 * 0.7 / 0.3 + 0.7)) < 0.01
