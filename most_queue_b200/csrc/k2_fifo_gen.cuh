@@ -51,6 +51,18 @@ struct K2Params {
     long long lanes;  // gridDim.x * MQ_BLOCK
 };
 
+__device__ __forceinline__ float ld_shared(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void st_shared(uint32_t addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 template <int CT>
 struct Tag {
     static constexpr int TB = CT <= 1 ? 0 : CT <= 2 ? 1 : CT <= 4 ? 2 : CT <= 8 ? 3 : CT <= 16 ? 4 : 5;
@@ -102,6 +114,24 @@ __device__ __forceinline__ void insert_drop_first(float (&L)[CT], float y)
     L[CT - 1] = fmaxf(prev, y);
 }
 
+// One wiring for both event kinds: an arrival keeps L[0..CT-2] (the old maximum -- a free slot, or
+// y itself when nothing starts -- is dropped), a departure drops L[0]; y is inserted in order.
+template <int CT>
+__device__ __forceinline__ void unified_insert(float (&L)[CT], float y, bool is_arr)
+{
+    if (CT == 1) {
+        L[0] = y;
+        return;
+    }
+    float M[CT > 1 ? CT - 1 : 1];
+#pragma unroll
+    for (int j = 0; j < CT - 1; ++j) M[j] = is_arr ? L[j] : L[j + 1];
+    L[0] = fminf(M[0], y);
+#pragma unroll
+    for (int j = 1; j < CT - 1; ++j) L[j] = fminf(M[j], fmaxf(M[j - 1], y));
+    L[CT - 1] = fmaxf(M[CT - 2], y);
+}
+
 // After a re-base two keys can land on the same grid point and then differ only by their slot
 // ids, which may invert an adjacent pair.  Restore strict order (odd-even transposition until
 // clean; almost always the check alone).
@@ -131,9 +161,12 @@ template <int CT, int SRCK, int SRVK, bool FINITE>
 __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
 {
     extern __shared__ float smem[];
-    float *hist = smem;                       // [MQ_BF][MQ_BLOCK]
-    float *vslot = smem + MQ_BF * MQ_BLOCK;   // [CT][MQ_BLOCK]
     const int tid = threadIdx.x;
+    float *hist = smem + tid;                           // [MQ_BF][MQ_BLOCK], this lane's column
+    float *vslot = smem + MQ_BF * MQ_BLOCK + tid;       // [CT][MQ_BLOCK]
+    // 32-bit shared-window addresses of this lane's columns (keeps the address math out of the loop)
+    const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
+    const uint32_t vslot_sa = (uint32_t)__cvta_generic_to_shared(vslot);
     const long long gtid = (long long)blockIdx.x * MQ_BLOCK + tid;
     const int c = P.c;
     const uint32_t key0 = P.key0;
@@ -155,17 +188,17 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
                                                    : (MQ_SENT_FREE | (uint32_t)(j - nfree_first)));
         }
 #pragma unroll
-        for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK + tid] = 0.0f;
+        for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
 
         float t = 0.0f;
         double tbase = 0.0;
         float sw[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t arrived = 0, taked = 0, served = 0, dropped = 0;
-        int n = 0, nbusy = 0;
-        uint32_t q = 0;
-        // infinite buffer: lagging cursor = head of the queue
-        uint32_t h = 0;
-        float a_h = 0.0f, S_h = 0.0f;
+        // nxt = index of the arrival scheduled at tA (= number of arrivals so far); n = jobs in the
+        // system: n < c <=> a server is free, q = n - c jobs wait when n > c.  Infinite buffer: the
+        // waiting jobs are the last q arrivals, so the head of the queue is job nxt - q.
+        uint32_t nxt = 0, served = 0, dropped = 0;
+        int n = 0;
+        float a_h = 0.0f, S_h = 0.0f;  // infinite buffer: arrival time and service time of the queue head
         // finite buffer: ring bookkeeping
         uint32_t head = 0;
         float a_anchor = 0.0f, a_lastq = 0.0f;
@@ -186,11 +219,12 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
             for (int ev = 0; ev < MQ_EV; ++ev) {
                 const float d0 = L[0];
                 const bool is_arr = tA <= d0;  // arrival wins ties (base.py:442-454)
-                const float te = is_arr ? tA : d0;
+                const float te = fminf(tA, d0);
                 const float dt = te - t;
                 // _update_state_probs (base.py:327-340)
                 if (n < MQ_BF) {
-                    hist[n * MQ_BLOCK + tid] += dt;
+                    const uint32_t ha = hist_sa + (uint32_t)n * (MQ_BLOCK * 4u);
+                    st_shared(ha, ld_shared(ha) + dt);
                 } else if (n < P.p_bins) {
                     rec[(long long)(MQ_F_P + n) * R] += (double)dt;
                 } else {
@@ -198,98 +232,75 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
                 }
                 t = te;
 
-                // one generator site per event: the next arrival (lead cursor) or, on a
-                // departure that leaves jobs waiting, the next queue head (lag cursor)
-                uint32_t ridx = arrived + 1u;
-                bool need = is_arr;
-                if (!FINITE && !is_arr) {
-                    ridx = h + 1u;
-                    need = q > 1u;
-                }
+                const int q = n - c;              // waiting jobs when positive
+                const bool free_srv = q < 0;
+                const bool has_q = q > 0;
+                // one generator site per event: the arrival after this one (lead cursor) or, on a
+                // departure that leaves jobs waiting, the next head of the queue (lag cursor)
+                const bool pop_more = !FINITE && !is_arr && q > 1;
                 float gx = 0.0f, sx = 0.0f;
-                if (need) {
+                if (is_arr || pop_more) {
+                    const uint32_t ridx = (is_arr ? nxt : nxt - (uint32_t)q) + 1u;
                     uint2 w = philox2x32_10(ridx, rep, key0);
                     gx = sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
                     sx = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
                 }
 
-                if (is_arr) {
-                    // arrival() base.py:214-247
-                    const uint32_t idx = arrived;
-                    arrived++;
-                    const float S_i = S_pend;
-                    tA = t + gx;
-                    S_pend = sx;
-                    if (nbusy < c) {
-                        // send_task_to_channel base.py:155-184: a free slot sits at the top
-                        const uint32_t tag = __float_as_uint(L[CT - 1]) & Tag<CT>::MASK;
-                        insert_drop_last<CT>(L, stamp<CT>(t + S_i, tag));
-                        vslot[tag * MQ_BLOCK + tid] = S_i;
-                        taked++;
-                        nbusy++;
-                        n++;
-                        acc4(sv, S_i);  // w = 0 adds nothing to the w sums
-                    } else if (!FINITE || q < cap) {
-                        // send_task_to_queue base.py:186-212
-                        n++;
-                        if (!FINITE) {
-                            if (q == 0u) {
-                                h = idx;
-                                a_h = t;
-                                S_h = S_i;
-                            }
-                        } else {
-                            float gap = 0.0f;
-                            if (q == 0u) a_anchor = t; else gap = t - a_lastq;
-                            a_lastq = t;
-                            uint32_t slot = head + q;
-                            if (slot >= cap) slot -= cap;
-                            P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_i);
-                        }
-                        q++;
-                    } else {
-                        dropped++;  // base.py:211-212
+                // ---- one predicated body for both event kinds (arrival() base.py:214-247,
+                // serving() base.py:249-286) ----
+                const bool start = is_arr ? free_srv : has_q;  // a job starts service in this event
+                float a_q = a_h, S_q = S_h;
+                if (FINITE) {
+                    a_q = 0.0f;
+                    S_q = 0.0f;
+                    if (!is_arr && has_q) {
+                        const float2 e = P.ring[(long long)head * P.lanes + gtid];
+                        a_q = a_anchor + e.x;
+                        S_q = e.y;
+                        a_anchor = a_q;
+                        head++;
+                        if (head >= cap) head = 0u;
+                    }
+                }
+                // the job that starts: the arriving one (send_task_to_channel base.py:155-184) or the
+                // head of the queue (send_head_of_queue_to_channel base.py:288-310)
+                const float S_st = is_arr ? S_pend : S_q;
+                const float w = is_arr ? 0.0f : fmaxf(t - a_q, 0.0f);
+                const float vv = w + S_st;
+                const float top = L[CT - 1];
+                const uint32_t tag = __float_as_uint(is_arr ? top : d0) & Tag<CT>::MASK;
+                const float y_idle = is_arr ? top : __uint_as_float(MQ_SENT_FREE | tag);
+                const float y = start ? stamp<CT>(t + S_st, tag) : y_idle;
+                unified_insert<CT>(L, y, is_arr);
+                if (start) st_shared(vslot_sa + tag * (MQ_BLOCK * 4u), vv);
+                acc4(sw, start ? w : 0.0f);
+                acc4(sv, start ? vv : 0.0f);
+
+                // ---- state ----
+                const bool accept = !FINITE || free_srv || (uint32_t)q < cap;  // base.py:204-212
+                if (FINITE) {
+                    if (is_arr && !free_srv && accept) {
+                        float gap = 0.0f;
+                        if (q == 0) a_anchor = t; else gap = t - a_lastq;
+                        a_lastq = t;
+                        uint32_t slot = head + (uint32_t)q;
+                        if (slot >= cap) slot -= cap;
+                        P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_pend);
                     }
                 } else {
-                    // serving() base.py:249-286
-                    served++;
-                    n--;
-                    const uint32_t tag = __float_as_uint(d0) & Tag<CT>::MASK;
-                    if (q > 0u) {
-                        // send_head_of_queue_to_channel base.py:288-310
-                        float a, S;
-                        if (!FINITE) {
-                            a = a_h;
-                            S = S_h;
-                            if (q > 1u) {
-                                h++;
-                                a_h += gx;
-                                S_h = sx;
-                            }
-                        } else {
-                            float2 e = P.ring[(long long)head * P.lanes + gtid];
-                            a = a_anchor + e.x;
-                            a_anchor = a;
-                            S = e.y;
-                            head++;
-                            if (head >= cap) head = 0u;
-                        }
-                        q--;
-                        const float w = fmaxf(t - a, 0.0f);
-                        const float vv = w + S;
-                        insert_drop_first<CT>(L, stamp<CT>(t + S, tag));
-                        vslot[tag * MQ_BLOCK + tid] = vv;
-                        taked++;
-                        acc4(sw, w);
-                        acc4(sv, vv);
-                    } else {
-                        insert_drop_first<CT>(L, __uint_as_float(MQ_SENT_FREE | tag));
-                        nbusy--;
-                    }
-                    if (served >= N) {
-                        done = true;
-                        break;
-                    }
+                    const bool enq_first = is_arr && q == 0;  // the arriving job becomes the head
+                    a_h = enq_first ? t : (pop_more ? a_h + gx : a_h);
+                    S_h = enq_first ? S_pend : (pop_more ? sx : S_h);
+                }
+                tA = is_arr ? t + gx : tA;
+                S_pend = is_arr ? sx : S_pend;
+                nxt += is_arr ? 1u : 0u;
+                dropped += (is_arr && !accept) ? 1u : 0u;
+                n += is_arr ? (accept ? 1 : 0) : -1;
+                served += is_arr ? 0u : 1u;
+                if (served >= N) {
+                    done = true;
+                    break;
                 }
             }
 
@@ -319,14 +330,14 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
                 }
                 const int nb = P.p_bins < MQ_BF ? P.p_bins : MQ_BF;
                 for (int b = 0; b < nb; ++b) {
-                    rec[(long long)(MQ_F_P + b) * R] += (double)hist[b * MQ_BLOCK + tid];
-                    hist[b * MQ_BLOCK + tid] = 0.0f;
+                    rec[(long long)(MQ_F_P + b) * R] += (double)hist[b * MQ_BLOCK];
+                    hist[b * MQ_BLOCK] = 0.0f;
                 }
                 if (P.p_bins < MQ_BF) {
                     double over = 0.0;
                     for (int b = P.p_bins; b < MQ_BF; ++b) {
-                        over += (double)hist[b * MQ_BLOCK + tid];
-                        hist[b * MQ_BLOCK + tid] = 0.0f;
+                        over += (double)hist[b * MQ_BLOCK];
+                        hist[b * MQ_BLOCK] = 0.0f;
                     }
                     rec[(long long)MQ_F_POVER * R] += over;
                 }
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
         for (int j = 0; j < CT; ++j) {
             const uint32_t b = __float_as_uint(L[j]);
             if (b < MQ_SENT_OFF) {
-                const double x = (double)vslot[(b & Tag<CT>::MASK) * MQ_BLOCK + tid];
+                const double x = (double)vslot[(b & Tag<CT>::MASK) * MQ_BLOCK];
                 const double x2 = x * x;
                 vfix[0] += x;
                 vfix[1] += x2;
@@ -349,8 +360,10 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) rec[(long long)(MQ_F_V + k) * R] -= vfix[k];
-        rec[(long long)MQ_F_ARRIVED * R] = (double)arrived;
-        rec[(long long)MQ_F_TAKED * R] = (double)taked;
+        // every accepted arrival that is not waiting any more has started service (base.py:172,300)
+        const uint32_t waiting = n > c ? (uint32_t)(n - c) : 0u;
+        rec[(long long)MQ_F_ARRIVED * R] = (double)nxt;
+        rec[(long long)MQ_F_TAKED * R] = (double)(nxt - dropped - waiting);
         rec[(long long)MQ_F_SERVED * R] = (double)served;
         rec[(long long)MQ_F_DROPPED * R] = (double)dropped;
         rec[(long long)MQ_F_TTEK * R] = tbase + (double)t;
