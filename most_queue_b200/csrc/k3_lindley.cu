@@ -65,20 +65,49 @@ __device__ __forceinline__ MP cta_scan(MP mine, MP *smem, MP *total)
     return mp_then(carry, within);
 }
 
-// x[j] = S[n] - A[n+1] and S[j] for the K3_L jobs of this thread's segment
-template <bool REPLAY>
-__device__ __forceinline__ void load_segment(const K3Params &P, long long n0, double (&x)[K3_L], double (&s)[K3_L],
-                                             double (&a)[K3_L])
+// Replay form: the CTA stages the tile's S[0..4096) and A[0..4096] in shared memory with coalesced
+// streaming loads (a warp reads 256 contiguous bytes per instruction) and each thread then reads its own
+// 16-job segment.  One pad word per 16 entries (index e + e/16) makes the strided per-thread reads
+// conflict free (two wavefronts per 64-bit warp access, the minimum).
+constexpr int K3_TILE = K3_THREADS * K3_L;
+constexpr int K3_PADDED = K3_TILE + K3_TILE / 16 + 2;
+constexpr size_t K3_STAGE_BYTES = sizeof(double) * 2 * K3_PADDED;
+
+__device__ __forceinline__ int k3_pad(int e) { return e + (e >> 4); }
+
+__device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_base, double *smS, double *smA)
 {
+#pragma unroll
+    for (int k = 0; k < K3_L; ++k) {
+        const int e = k * K3_THREADS + threadIdx.x;
+        const long long n = tile_base + e;
+        smS[k3_pad(e)] = n < P.n ? __ldcs(P.S + n) : 0.0;
+        smA[k3_pad(e)] = n <= P.n ? __ldcs(P.A + n) : 0.0;
+    }
+    if (threadIdx.x == 0) {
+        const long long n = tile_base + K3_TILE;
+        smA[k3_pad(K3_TILE)] = n <= P.n ? __ldcs(P.A + n) : 0.0;
+    }
+    __syncthreads();
+}
+
+// x[j] = S[n] - A[n+1] and S[j] for the K3_L jobs of this thread's segment; returns the sum of the
+// segment's gaps A[n]
+template <bool REPLAY>
+__device__ __forceinline__ double load_segment(const K3Params &P, long long n0, double (&x)[K3_L], double (&s)[K3_L],
+                                               const double *smS, const double *smA)
+{
+    double sum_a = 0.0;
     if (REPLAY) {
+        const int e0 = threadIdx.x * K3_L;
+        double an = smA[k3_pad(e0)];
 #pragma unroll
         for (int j = 0; j < K3_L; ++j) {
-            const long long n = n0 + j;
-            const bool ok = n < P.n;
-            s[j] = ok ? __ldg(P.S + n) : 0.0;
-            a[j] = ok ? __ldg(P.A + n) : 0.0;
-            const double an = ok ? __ldg(P.A + n + 1) : 0.0;
-            x[j] = __dsub_rn(s[j], an);
+            const bool ok = n0 + j < P.n;
+            s[j] = smS[k3_pad(e0 + j)];
+            sum_a += ok ? an : 0.0;
+            an = smA[k3_pad(e0 + j + 1)];
+            x[j] = ok ? __dsub_rn(s[j], an) : 0.0;
         }
     } else {
         // word 0 of call n = gap before job n, word 1 of call n = service of job n
@@ -94,11 +123,12 @@ __device__ __forceinline__ void load_segment(const K3Params &P, long long n0, do
             w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
             const double gnext = (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
             s[j] = ok ? sv : 0.0;
-            a[j] = ok ? gap : 0.0;
+            sum_a += ok ? gap : 0.0;
             x[j] = ok ? __dsub_rn(sv, gnext) : 0.0;
             gap = gnext;
         }
     }
+    return sum_a;
 }
 
 __device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, const double (&x)[K3_L])
@@ -114,12 +144,15 @@ template <bool REPLAY>
 __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
+    extern __shared__ double stage[];
+    double *smS = stage, *smA = stage + K3_PADDED;
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
-        double x[K3_L], s[K3_L], a[K3_L];
-        load_segment<REPLAY>(P, n0, x, s, a);
+        double x[K3_L], s[K3_L];
+        if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
+        load_segment<REPLAY>(P, n0, x, s, smS, smA);
         MP total;
-        cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);
+        cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);  // its barriers also fence the stage reuse
         if (threadIdx.x == 0) P.tile_sum[t] = total;
     }
 }
@@ -149,10 +182,13 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
 #pragma unroll
     for (int i = 0; i < K3_NSTAT; ++i) acc[i] = 0.0;
 
+    extern __shared__ double stage[];
+    double *smS = stage, *smA = stage + K3_PADDED;
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
-        double x[K3_L], s[K3_L], a[K3_L];
-        load_segment<REPLAY>(P, n0, x, s, a);
+        double x[K3_L], s[K3_L];
+        if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
+        acc[8] += load_segment<REPLAY>(P, n0, x, s, smS, smA);
         MP total;
         const MP ex = cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);
         const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
@@ -172,7 +208,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
                 acc[5] += v2;
                 acc[6] += v2 * v;
                 acc[7] += v2 * v2;
-                acc[8] += a[j];
                 acc[9] += s[j];
                 const double raw = __dadd_rn(w, x[j]);
                 if (n == P.n - 1) {
@@ -211,10 +246,14 @@ __global__ void k3_final(const double *partial, int grid, double *stats)
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
 {
-    if (P.replay)
-        k3_summary<true><<<grid, K3_THREADS, 0, st>>>(P);
-    else
+    if (P.replay) {
+        cudaError_t e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)K3_STAGE_BYTES);
+        if (e != cudaSuccess) return e;
+        k3_summary<true><<<grid, K3_THREADS, K3_STAGE_BYTES, st>>>(P);
+    } else {
         k3_summary<false><<<grid, K3_THREADS, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
 
@@ -226,10 +265,14 @@ cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st)
 
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st)
 {
-    if (P.replay)
-        k3_walk<true><<<grid, K3_THREADS, 0, st>>>(P);
-    else
+    if (P.replay) {
+        cudaError_t e = cudaFuncSetAttribute(k3_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)K3_STAGE_BYTES);
+        if (e != cudaSuccess) return e;
+        k3_walk<true><<<grid, K3_THREADS, K3_STAGE_BYTES, st>>>(P);
+    } else {
         k3_walk<false><<<grid, K3_THREADS, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
 
@@ -239,15 +282,24 @@ cudaError_t k3_launch_final(const double *partial, int grid, double *stats, cuda
     return cudaGetLastError();
 }
 
-cudaError_t k3_occupancy(int *summary_blocks, int *walk_blocks)
+cudaError_t k3_occupancy(bool replay, int *summary_blocks, int *walk_blocks)
 {
-    int a = 0, b = 0, c = 0, d = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_summary<false>, K3_THREADS, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k3_walk<true>, K3_THREADS, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k3_walk<false>, K3_THREADS, 0);
-    *summary_blocks = a < b ? a : b;
-    *walk_blocks = c < d ? c : d;
+    int a = 0, b = 0;
+    cudaError_t e;
+    if (replay) {
+        e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k3_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<true>, K3_THREADS, K3_STAGE_BYTES);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false>, K3_THREADS, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<false>, K3_THREADS, 0);
+    }
+    *summary_blocks = a;
+    *walk_blocks = b;
     return e;
 }
 

@@ -36,6 +36,6 @@ cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_final(const double *partial, int grid, double *stats, cudaStream_t st);
-cudaError_t k3_occupancy(int *summary_blocks, int *walk_blocks);
+cudaError_t k3_occupancy(bool replay, int *summary_blocks, int *walk_blocks);
 
 }  // namespace mq

@@ -33,7 +33,7 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     P.ntiles = (P.n + tile - 1) / tile;
 
     int occ_s = 0, occ_w = 0;
-    CU(k3_occupancy(&occ_s, &occ_w));
+    CU(k3_occupancy(replay, &occ_s, &occ_w));
     if (occ_s < 1 || occ_w < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     run.grid_sum = (int)std::min<long long>(P.ntiles, (long long)occ_s * ctx->sms);
     run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
