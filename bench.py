@@ -274,11 +274,15 @@ def run_ours(args):
                     "api": "QsSim(8).set_sources/set_servers/run(total_served, replications=)"},
             "gpu_launches": launches,
             "roofline": {"bound": "issue", "achieved": achieved, "peak": peak_issue, "unit": "Glane-instr/s",
-                         "frac": achieved / peak_issue, "traffic": None,
+                         "frac": achieved / peak_issue,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch
+                         # (profiles/r01_ncu_k2_v2_full.txt); valid for the default 1e6 x 1e5 configuration
+                         "traffic": 5.057e9 if (reps, jobs) == (1_000_000, 100_000) else None,
                          "kernel": "k2_fifo_gen<8,M,H2,infinite>",
                          "note": f"achieved = jobs/s/GPU x {I_ALG:.0f} algorithmic lane-instructions per job "
                                  f"(SURVEY 8d); peak = {sms} SMs x 128 lanes x {sm_max:.0f} MHz ({peak_src} clock); "
-                                 "HBM traffic is ~1 KB per replication, not the bound"},
+                                 "traffic in bytes per launch (fp64 per-replication records, ~5 KB per replication incl. "
+                                 "flushes): HBM is idle, the kernel is issue bound"},
             "moments": moment_err,
         }
         if world == 1 and not args.no_cpu:
