@@ -38,15 +38,24 @@ struct K1Params {
     const double *S;  // [n_s][reps]
     double *rec;      // [MQ_REPLAY_ROWS(p_bins)][reps], zeroed by the caller
     double *ring;     // finite buffer: [buffer][reps]
+    const double2 *inv;  // inv[k] = {1/k, 1 - 1/k} (round-to-nearest), k = 0..n_inv-1; shared by all lanes
+    long long n_inv;
 };
 
 // refresh_moments_stat, stats_update.py:6-22, op for op
 template <int NM>
-__device__ __forceinline__ void refresh_moments(double (&m)[NM], double x, long long count)
+__device__ __forceinline__ void refresh_moments(double (&m)[NM], double x, long long count, const K1Params &P)
 {
     double power = x;
-    const double inv_count = __ddiv_rn(1.0, (double)count);
-    const double one_minus = __dsub_rn(1.0, inv_count);
+    double inv_count, one_minus;
+    if (count < P.n_inv) {  // 1/count and 1 - 1/count from the shared table (same roundings)
+        const double2 t = __ldg(P.inv + count);
+        inv_count = t.x;
+        one_minus = t.y;
+    } else {
+        inv_count = __ddiv_rn(1.0, (double)count);
+        one_minus = __dsub_rn(1.0, inv_count);
+    }
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         m[i] = __dadd_rn(__dmul_rn(m[i], one_minus), __dmul_rn(power, inv_count));
@@ -108,6 +117,9 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
 
     double arrival_time = P.n_a > 0 ? A[0] : 0.0;  // base.py:112
     if (P.n_a < 1) status = MQ_E_INPUT_SHORT;
+    // the next draw of each stream is loaded one event ahead of its use (hides the HBM latency)
+    double a_next = P.n_a > 1 ? A[R] : 0.0;  // default caching: the lag cursor re-reads these rows from L2
+    double s_next = P.n_s > 0 ? __ldcs(S) : 0.0;
 
     while (served < N && status == 0) {
         // _get_min_server_time base.py:312-325
@@ -140,8 +152,9 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
                 status = MQ_E_INPUT_SHORT;
                 break;
             }
-            arrival_time = __dadd_rn(ttek, A[ia * R]);
+            arrival_time = __dadd_rn(ttek, a_next);
             ia++;
+            a_next = ia < P.n_a ? A[ia * R] : 0.0;
             in_sys++;
             if (free_channels == 0) {
                 // send_task_to_queue base.py:186-212
@@ -164,14 +177,15 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
                 // send_task_to_channel base.py:155-184 (lowest free slot)
                 const int j = __ffs(~busy & ((c >= 32) ? 0xffffffffu : ((1u << c) - 1u))) - 1;
                 taked++;
-                refresh_moments<4>(w_run, 0.0, taked);
+                refresh_moments<4>(w_run, 0.0, taked, P);
                 add_powers(w_sum, 0.0);
                 if (is >= P.n_s) {
                     status = MQ_E_INPUT_SHORT;
                     break;
                 }
-                const double e = __dadd_rn(ttek, S[is * R]);  // servers.py:88
+                const double e = __dadd_rn(ttek, s_next);  // servers.py:88
                 is++;
+                s_next = is < P.n_s ? __ldcs(S + is * R) : 0.0;
 #pragma unroll
                 for (int k = 0; k < CT; ++k) {
                     if (k == j) {
@@ -209,12 +223,12 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
             served++;
             free_channels++;
             const double v = __dsub_rn(ttek, a_dep);
-            refresh_moments<4>(v_run, v, served);
+            refresh_moments<4>(v_run, v, served, P);
             add_powers(v_sum, v);
             in_sys--;
             if (q == 0 && free_channels == 1 && in_sys == c - 1) {
                 busy_n++;
-                refresh_moments<3>(busy_run, __dsub_rn(ttek, start_busy), busy_n);
+                refresh_moments<3>(busy_run, __dsub_rn(ttek, start_busy), busy_n, P);
             }
             if (q != 0) {
                 // send_head_of_queue_to_channel base.py:288-310
@@ -234,14 +248,15 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
                 if (free_channels == 1) start_busy = ttek;
                 taked++;
                 const double w = __dadd_rn(0.0, __dsub_rn(ttek, a));
-                refresh_moments<4>(w_run, w, taked);
+                refresh_moments<4>(w_run, w, taked, P);
                 add_powers(w_sum, w);
                 if (is >= P.n_s) {
                     status = MQ_E_INPUT_SHORT;
                     break;
                 }
-                const double e = __dadd_rn(ttek, S[is * R]);
+                const double e = __dadd_rn(ttek, s_next);
                 is++;
+                s_next = is < P.n_s ? __ldcs(S + is * R) : 0.0;
 #pragma unroll
                 for (int k = 0; k < CT; ++k) {
                     if (k == midx) {
