@@ -9,19 +9,26 @@
 //
 // Layout of one lane's state (all on chip):
 //   * clock, next arrival, c completion times: fp32 registers, RELATIVE to an epoch that is
-//     re-based every MQ_EV events so magnitudes stay small; the elapsed epochs are summed in
-//     fp64.  The c completion times are kept sorted; the low TB bits of each key carry the id of
-//     the server slot (keys are therefore all distinct and the slot survives the sorting
-//     network); free servers are large finite sentinels carrying their slot id.
-//   * v of the job in service on each slot: shared memory [slot][lane] (bank = lane, conflict
-//     free).  v is accumulated when service STARTS and the <= c jobs still in service at the
-//     stop are subtracted at the end, which yields exactly the reference's sample set.
-//   * time-in-state histogram: first MQ_BF states in shared memory [state][lane] (fp32, flushed
-//     to the fp64 per-replication record every MQ_FLUSH epochs); higher states go straight to
-//     the fp64 record in HBM (rare).
-//   * infinite buffer: the queue is NOT stored.  A lagging Philox cursor regenerates the
-//     arrival time and service time of the job at the head of the queue (same words, same
-//     summation), so the queue is unbounded with O(1) state.
+//     re-based every MQ_EV events so magnitudes stay small; the elapsed epochs are summed in fp64.
+//   * the c completion times are kept sorted (min/max insertion network) in Kiefer-Wolfowitz style:
+//     a key <= now means "this server is free since then".  The low TB bits of each key carry the
+//     id of the server slot, so keys are all distinct and the slot survives sorting.
+//   * LAZY DEPARTURES: while nobody waits (q = 0) a departure changes nothing but the number in the
+//     system, so it is not an event: at the next arrival the time-in-state of the interval is settled
+//     for all servers at once from the sorted keys (state c-j lasts from key j-1 to key j, clamped
+//     to the interval; c+1 register accumulators with static indices).  Only while jobs wait (q > 0)
+//     are departures events (they start the head of the queue).  That is ~1 + P(wait) iterations per
+//     job instead of 2.  From the total_served-th START on, an exact one-event-at-a-time end game
+//     applies the reference's stop rule (stop right after the total_served-th departure).
+//   * v of the job in service on each slot: shared memory [slot][lane] (bank = lane, conflict free).
+//     v is accumulated when service STARTS and the <= c jobs still in service at the stop are
+//     subtracted at the end, which yields exactly the reference's sample set.
+//   * time-in-state: states 0..c in registers (see above), states c+1..c+MQ_BF in shared memory
+//     [state][lane] (fp32, flushed to the fp64 per-replication record every MQ_FLUSH epochs), higher
+//     states go straight to the fp64 record in HBM (rare).
+//   * infinite buffer: the queue is NOT stored.  A lagging Philox cursor regenerates the arrival
+//     time and service time of the job at the head of the queue (same words, same summation), so the
+//     queue is unbounded with O(1) state.
 //   * finite buffer r: (gap to previous queued arrival, service time) per waiting job in a ring
 //     of r entries per lane in HBM scratch [slot][lane].
 #pragma once
@@ -34,8 +41,9 @@ constexpr int MQ_BLOCK = 128;    // lanes per CTA
 constexpr int MQ_BF = 32;        // histogram states kept in shared memory
 constexpr int MQ_EV = 32;        // events between epoch re-bases
 constexpr int MQ_FLUSH = 64;     // re-bases between fp32 -> fp64 flushes
-constexpr uint32_t MQ_SENT_FREE = 0x7f000000u;  // 1.7e38: free server (plus slot id)
-constexpr uint32_t MQ_SENT_OFF = 0x7e800000u;   // 8.5e37: slot not used (c < CT)
+constexpr uint32_t MQ_KEY_GONE = 0xfe800000u;  // -8.5e37: server free "since ever" (plus slot id)
+constexpr uint32_t MQ_KEY_OFF = 0x7e800000u;   // +8.5e37: slot not used (c < CT): always busy, never departs
+constexpr float MQ_KEY_LIM = 1.0e30f;          // |key| below this is a real time
 
 struct K2Params {
     int c;
@@ -158,11 +166,11 @@ __device__ __forceinline__ void restore_order(float (&L)[CT])
 }
 
 template <int CT, int SRCK, int SRVK, bool FINITE>
-__global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
+__global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const K2Params P)
 {
     extern __shared__ float smem[];
     const int tid = threadIdx.x;
-    float *hist = smem + tid;                           // [MQ_BF][MQ_BLOCK], this lane's column
+    float *hist = smem + tid;                           // [MQ_BF][MQ_BLOCK]: states c+1 .. c+MQ_BF
     float *vslot = smem + MQ_BF * MQ_BLOCK + tid;       // [CT][MQ_BLOCK]
     // 32-bit shared-window addresses of this lane's columns (keeps the address math out of the loop)
     const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
@@ -173,6 +181,7 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
     const long long R = P.reps;
     const uint32_t N = (uint32_t)P.jobs;
     const uint32_t cap = FINITE ? (uint32_t)P.buffer : 0u;
+    const int off = CT - c;  // register hs[m] holds state m - off
 
     for (long long rl = gtid; rl < R; rl += P.lanes) {
         const uint32_t rep = P.rep0 + (uint32_t)rl;
@@ -182,25 +191,23 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
         float L[CT];
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
-            // ascending: unused slots (OFF) first, then the c free servers with ids 0..c-1
-            int nfree_first = CT - c;
-            L[j] = __uint_as_float(j < nfree_first ? (MQ_SENT_OFF | (uint32_t)(c + j))
-                                                   : (MQ_SENT_FREE | (uint32_t)(j - nfree_first)));
+            // ascending: the c real slots, free since ever (more negative = larger slot id), then unused
+            L[j] = __uint_as_float(j < c ? (MQ_KEY_GONE | (uint32_t)(c - 1 - j)) : (MQ_KEY_OFF | (uint32_t)j));
         }
+        float hs[CT + 1];
+#pragma unroll
+        for (int m = 0; m <= CT; ++m) hs[m] = 0.0f;
 #pragma unroll
         for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
 
         float t = 0.0f;
         double tbase = 0.0;
         float sw[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
-        // nxt = index of the arrival scheduled at tA (= number of arrivals so far); n = jobs in the
-        // system: n < c <=> a server is free, q = n - c jobs wait when n > c.  Infinite buffer: the
-        // waiting jobs are the last q arrivals, so the head of the queue is job nxt - q.
-        uint32_t nxt = 0, served = 0, dropped = 0;
-        int n = 0;
+        // nxt = index of the arrival scheduled at tA (= number of arrivals so far); q = waiting jobs.
+        // Infinite buffer: the waiting jobs are the last q arrivals, so the head of the queue is nxt - q.
+        uint32_t nxt = 0, taked = 0, dropped = 0, q = 0;
         float a_h = 0.0f, S_h = 0.0f;  // infinite buffer: arrival time and service time of the queue head
-        // finite buffer: ring bookkeeping
-        uint32_t head = 0;
+        uint32_t head = 0;             // finite buffer: ring bookkeeping
         float a_anchor = 0.0f, a_lastq = 0.0f;
         uint32_t flags = 0;
 
@@ -212,99 +219,29 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
             S_pend = sample<SRVK>(P.srv, w.y, 0u, rep, key0, 1);
         }
 
-        int epoch = 0;
-        bool done = (N == 0);
-        while (!done) {
-#pragma unroll 1
-            for (int ev = 0; ev < MQ_EV; ++ev) {
-                const float d0 = L[0];
-                const bool is_arr = tA <= d0;  // arrival wins ties (base.py:442-454)
-                const float te = fminf(tA, d0);
-                const float dt = te - t;
-                // _update_state_probs (base.py:327-340)
-                if (n < MQ_BF) {
-                    const uint32_t ha = hist_sa + (uint32_t)n * (MQ_BLOCK * 4u);
-                    st_shared(ha, ld_shared(ha) + dt);
-                } else if (n < P.p_bins) {
-                    rec[(long long)(MQ_F_P + n) * R] += (double)dt;
-                } else {
-                    rec[(long long)MQ_F_POVER * R] += (double)dt;
-                }
-                t = te;
-
-                const int q = n - c;              // waiting jobs when positive
-                const bool free_srv = q < 0;
-                const bool has_q = q > 0;
-                // one generator site per event: the arrival after this one (lead cursor) or, on a
-                // departure that leaves jobs waiting, the next head of the queue (lag cursor)
-                const bool pop_more = !FINITE && !is_arr && q > 1;
-                float gx = 0.0f, sx = 0.0f;
-                if (is_arr || pop_more) {
-                    const uint32_t ridx = (is_arr ? nxt : nxt - (uint32_t)q) + 1u;
-                    uint2 w = philox2x32_10(ridx, rep, key0);
-                    gx = sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
-                    sx = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
-                }
-
-                // ---- one predicated body for both event kinds (arrival() base.py:214-247,
-                // serving() base.py:249-286) ----
-                const bool start = is_arr ? free_srv : has_q;  // a job starts service in this event
-                float a_q = a_h, S_q = S_h;
-                if (FINITE) {
-                    a_q = 0.0f;
-                    S_q = 0.0f;
-                    if (!is_arr && has_q) {
-                        const float2 e = P.ring[(long long)head * P.lanes + gtid];
-                        a_q = a_anchor + e.x;
-                        S_q = e.y;
-                        a_anchor = a_q;
-                        head++;
-                        if (head >= cap) head = 0u;
-                    }
-                }
-                // the job that starts: the arriving one (send_task_to_channel base.py:155-184) or the
-                // head of the queue (send_head_of_queue_to_channel base.py:288-310)
-                const float S_st = is_arr ? S_pend : S_q;
-                const float w = is_arr ? 0.0f : fmaxf(t - a_q, 0.0f);
-                const float vv = w + S_st;
-                const float top = L[CT - 1];
-                const uint32_t tag = __float_as_uint(is_arr ? top : d0) & Tag<CT>::MASK;
-                const float y_idle = is_arr ? top : __uint_as_float(MQ_SENT_FREE | tag);
-                const float y = start ? stamp<CT>(t + S_st, tag) : y_idle;
-                unified_insert<CT>(L, y, is_arr);
-                if (start) st_shared(vslot_sa + tag * (MQ_BLOCK * 4u), vv);
-                acc4(sw, start ? w : 0.0f);
-                acc4(sv, start ? vv : 0.0f);
-
-                // ---- state ----
-                const bool accept = !FINITE || free_srv || (uint32_t)q < cap;  // base.py:204-212
-                if (FINITE) {
-                    if (is_arr && !free_srv && accept) {
-                        float gap = 0.0f;
-                        if (q == 0) a_anchor = t; else gap = t - a_lastq;
-                        a_lastq = t;
-                        uint32_t slot = head + (uint32_t)q;
-                        if (slot >= cap) slot -= cap;
-                        P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_pend);
-                    }
-                } else {
-                    const bool enq_first = is_arr && q == 0;  // the arriving job becomes the head
-                    a_h = enq_first ? t : (pop_more ? a_h + gx : a_h);
-                    S_h = enq_first ? S_pend : (pop_more ? sx : S_h);
-                }
-                tA = is_arr ? t + gx : tA;
-                S_pend = is_arr ? sx : S_pend;
-                nxt += is_arr ? 1u : 0u;
-                dropped += (is_arr && !accept) ? 1u : 0u;
-                n += is_arr ? (accept ? 1 : 0) : -1;
-                served += is_arr ? 0u : 1u;
-                if (served >= N) {
-                    done = true;
-                    break;
+        auto flush = [&]() {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                rec[(long long)(MQ_F_W + k) * R] += (double)sw[k];
+                rec[(long long)(MQ_F_V + k) * R] += (double)sv[k];
+                sw[k] = 0.0f;
+                sv[k] = 0.0f;
+            }
+#pragma unroll
+            for (int m = 0; m <= CT; ++m) {
+                const int k = m - off;
+                if (k >= 0) {
+                    rec[(long long)(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)hs[m];
+                    hs[m] = 0.0f;
                 }
             }
-
-            // ---- re-base the epoch ----
+            for (int b = 0; b < MQ_BF; ++b) {
+                const int k = c + 1 + b;
+                rec[(long long)(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)hist[b * MQ_BLOCK];
+                hist[b * MQ_BLOCK] = 0.0f;
+            }
+        };
+        auto rebase = [&]() {
             const float base = t;
             tbase += (double)base;
             t = 0.0f;
@@ -314,43 +251,233 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
             a_lastq -= base;
 #pragma unroll
             for (int j = 0; j < CT; ++j) {
-                const uint32_t b = __float_as_uint(L[j]);
-                const float moved = stamp<CT>(L[j] - base, b & Tag<CT>::MASK);
-                L[j] = (b < MQ_SENT_OFF) ? moved : L[j];
+                const float moved = stamp<CT>(L[j] - base, __float_as_uint(L[j]) & Tag<CT>::MASK);
+                L[j] = fabsf(L[j]) < MQ_KEY_LIM ? moved : L[j];
             }
             restore_order<CT>(L);
-            ++epoch;
-            if (done || (epoch % MQ_FLUSH) == 0) {
+        };
+        // time with c + qq jobs in the system, qq >= 1
+        auto add_q_state = [&](uint32_t qq, float dt) {
+            if (qq <= (uint32_t)MQ_BF) {
+                const uint32_t ha = hist_sa + (qq - 1u) * (MQ_BLOCK * 4u);
+                st_shared(ha, ld_shared(ha) + dt);
+            } else {
+                const long long k = (long long)c + qq;
+                rec[(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)dt;
+            }
+        };
+
+        // ================= main phase: until the N-th job has STARTED service =================
+        int epoch = 0;
+        while (taked < N) {
+#pragma unroll 1
+            for (int ev = 0; ev < MQ_EV; ++ev) {
+                const float d0 = L[0];
+                const bool q0 = q == 0u;
+                // nobody waits: the next event is the arrival (departures are settled lazily);
+                // otherwise arrival or departure, arrival wins ties (base.py:442-454)
+                const bool is_arr = q0 || tA <= d0;
+                const float te = is_arr ? tA : d0;
+                // _update_state_probs (base.py:327-340)
+                if (q0) {
+                    // between t and te the c servers finish in key order: state (c - j) lasts until key j
+                    float prev = t;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    rec[(long long)(MQ_F_W + k) * R] += (double)sw[k];
-                    rec[(long long)(MQ_F_V + k) * R] += (double)sv[k];
-                    sw[k] = 0.0f;
-                    sv[k] = 0.0f;
-                }
-                const int nb = P.p_bins < MQ_BF ? P.p_bins : MQ_BF;
-                for (int b = 0; b < nb; ++b) {
-                    rec[(long long)(MQ_F_P + b) * R] += (double)hist[b * MQ_BLOCK];
-                    hist[b * MQ_BLOCK] = 0.0f;
-                }
-                if (P.p_bins < MQ_BF) {
-                    double over = 0.0;
-                    for (int b = P.p_bins; b < MQ_BF; ++b) {
-                        over += (double)hist[b * MQ_BLOCK];
-                        hist[b * MQ_BLOCK] = 0.0f;
+                    for (int j = 0; j < CT; ++j) {
+                        const float e = fminf(fmaxf(L[j], t), te);
+                        hs[CT - j] += e - prev;
+                        prev = e;
                     }
-                    rec[(long long)MQ_F_POVER * R] += over;
+                    hs[0] += te - prev;
+                } else {
+                    add_q_state(q, te - t);
+                }
+                t = te;
+
+                // one generator site per event: the arrival after this one (lead cursor) or, on a
+                // departure that leaves jobs waiting, the next head of the queue (lag cursor)
+                const bool pop_more = !FINITE && !is_arr && q > 1u;
+                float gx = 0.0f, sx = 0.0f;
+                if (is_arr || pop_more) {
+                    const uint32_t ridx = (is_arr ? nxt : nxt - q) + 1u;
+                    uint2 w = philox2x32_10(ridx, rep, key0);
+                    gx = sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
+                    sx = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
+                }
+
+                // a job starts service: the arriving one if a server is free (send_task_to_channel
+                // base.py:155-184), or the head of the queue on a departure (base.py:288-310)
+                const bool start = is_arr ? (q0 && d0 <= te) : true;
+                float a_q = a_h, S_q = S_h;
+                if (FINITE) {
+                    a_q = 0.0f;
+                    S_q = 0.0f;
+                    if (!is_arr) {
+                        const float2 e = P.ring[(long long)head * P.lanes + gtid];
+                        a_q = a_anchor + e.x;
+                        S_q = e.y;
+                        a_anchor = a_q;
+                        head++;
+                        if (head >= cap) head = 0u;
+                    }
+                }
+                const float S_st = is_arr ? S_pend : S_q;
+                const float w = is_arr ? 0.0f : fmaxf(t - a_q, 0.0f);
+                const float vv = w + S_st;
+                const uint32_t tag = __float_as_uint(d0) & Tag<CT>::MASK;
+                const float y = start ? stamp<CT>(t + S_st, tag) : d0;  // d0 back in = no change
+                insert_drop_first<CT>(L, y);
+                if (start) st_shared(vslot_sa + tag * (MQ_BLOCK * 4u), vv);
+                acc4(sw, start ? w : 0.0f);
+                acc4(sv, start ? vv : 0.0f);
+                taked += start ? 1u : 0u;
+
+                // ---- queue ----
+                const bool accept = start || !FINITE || q < cap;  // base.py:204-212
+                const bool enq = is_arr && !start && accept;
+                if (FINITE) {
+                    if (enq) {
+                        float gap = 0.0f;
+                        if (q0) a_anchor = t; else gap = t - a_lastq;
+                        a_lastq = t;
+                        uint32_t slot = head + q;
+                        if (slot >= cap) slot -= cap;
+                        P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_pend);
+                    }
+                } else {
+                    const bool enq_first = enq && q0;  // the arriving job becomes the head
+                    a_h = enq_first ? t : (pop_more ? a_h + gx : a_h);
+                    S_h = enq_first ? S_pend : (pop_more ? sx : S_h);
+                }
+                tA = is_arr ? t + gx : tA;
+                S_pend = is_arr ? sx : S_pend;
+                nxt += is_arr ? 1u : 0u;
+                dropped += (is_arr && !accept) ? 1u : 0u;
+                q += (enq ? 1u : 0u) - (is_arr ? 0u : 1u);
+                if (taked >= N) break;
+            }
+            rebase();
+            if ((++epoch % MQ_FLUSH) == 0) flush();
+        }
+
+        // ================= end game: one event at a time until the N-th departure =================
+        // (base.py:505: the loop stops right after served == total_served)
+        if (N > 0u) {
+            int busy = 0;
+#pragma unroll
+            for (int j = 0; j < CT; ++j) {
+                const uint32_t tg = __float_as_uint(L[j]) & Tag<CT>::MASK;
+                const bool real = L[j] < MQ_KEY_LIM;     // not an unused slot
+                const bool gone = L[j] <= t;             // departed (settled lazily) or never used
+                L[j] = (real && gone) ? __uint_as_float(MQ_KEY_GONE | tg) : L[j];
+                busy += (real && !gone) ? 1 : 0;
+            }
+            uint32_t served = taked - (uint32_t)busy;
+            while (served < N) {
+                float dmin = 3.0e38f;
+#pragma unroll
+                for (int j = 0; j < CT; ++j) dmin = L[j] > -MQ_KEY_LIM ? fminf(dmin, L[j]) : dmin;
+                const bool is_arr = busy == 0 || tA <= dmin;
+                const float te = is_arr ? tA : dmin;
+                {
+                    const long long k = (long long)busy + q;
+                    rec[(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)(te - t);
+                }
+                t = te;
+                if (is_arr) {
+                    const uint32_t idx1 = nxt + 1u;
+                    nxt++;
+                    uint2 w = philox2x32_10(idx1, rep, key0);
+                    const float gx = sample<SRCK>(P.src, w.x, idx1, rep, key0, 0);
+                    const float sx = sample<SRVK>(P.srv, w.y, idx1, rep, key0, 1);
+                    const float S_i = S_pend;
+                    tA = t + gx;
+                    S_pend = sx;
+                    if (busy < c) {
+                        bool placed = false;
+#pragma unroll
+                        for (int j = 0; j < CT; ++j) {
+                            if (!placed && L[j] < -MQ_KEY_LIM) {
+                                const uint32_t tg = __float_as_uint(L[j]) & Tag<CT>::MASK;
+                                L[j] = stamp<CT>(t + S_i, tg);
+                                st_shared(vslot_sa + tg * (MQ_BLOCK * 4u), S_i);
+                                placed = true;
+                            }
+                        }
+                        busy++;
+                        taked++;
+                        acc4(sv, S_i);
+                    } else if (!FINITE || q < cap) {
+                        if (!FINITE) {
+                            if (q == 0u) {
+                                a_h = t;
+                                S_h = S_i;
+                            }
+                        } else {
+                            float gap = 0.0f;
+                            if (q == 0u) a_anchor = t; else gap = t - a_lastq;
+                            a_lastq = t;
+                            uint32_t slot = head + q;
+                            if (slot >= cap) slot -= cap;
+                            P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_i);
+                        }
+                        q++;
+                    } else {
+                        dropped++;
+                    }
+                } else {
+                    served++;
+                    float a = 0.0f, S = 0.0f;
+                    const bool pop = q > 0u;
+                    if (pop) {
+                        if (!FINITE) {
+                            a = a_h;
+                            S = S_h;
+                            if (q > 1u) {
+                                const uint32_t ridx = nxt - q + 1u;
+                                uint2 w = philox2x32_10(ridx, rep, key0);
+                                a_h += sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
+                                S_h = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
+                            }
+                        } else {
+                            const float2 e = P.ring[(long long)head * P.lanes + gtid];
+                            a = a_anchor + e.x;
+                            a_anchor = a;
+                            S = e.y;
+                            head++;
+                            if (head >= cap) head = 0u;
+                        }
+                        q--;
+                        taked++;
+                    } else {
+                        busy--;
+                    }
+                    const float w = fmaxf(t - a, 0.0f);
+                    const float vv = w + S;
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) {
+                        if (L[j] == dmin) {
+                            const uint32_t tg = __float_as_uint(L[j]) & Tag<CT>::MASK;
+                            L[j] = pop ? stamp<CT>(t + S, tg) : __uint_as_float(MQ_KEY_GONE | tg);
+                            if (pop) st_shared(vslot_sa + tg * (MQ_BLOCK * 4u), vv);
+                        }
+                    }
+                    if (pop) {
+                        acc4(sw, w);
+                        acc4(sv, vv);
+                    }
                 }
             }
         }
+        tbase += (double)t;
+        flush();
 
         // ---- jobs still in service at the stop were counted at start: take them out ----
         double vfix[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
-            const uint32_t b = __float_as_uint(L[j]);
-            if (b < MQ_SENT_OFF) {
-                const double x = (double)vslot[(b & Tag<CT>::MASK) * MQ_BLOCK];
+            if (fabsf(L[j]) < MQ_KEY_LIM) {
+                const double x = (double)vslot[(__float_as_uint(L[j]) & Tag<CT>::MASK) * MQ_BLOCK];
                 const double x2 = x * x;
                 vfix[0] += x;
                 vfix[1] += x2;
@@ -360,13 +487,11 @@ __global__ void __launch_bounds__(MQ_BLOCK) k2_fifo_gen(const K2Params P)
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) rec[(long long)(MQ_F_V + k) * R] -= vfix[k];
-        // every accepted arrival that is not waiting any more has started service (base.py:172,300)
-        const uint32_t waiting = n > c ? (uint32_t)(n - c) : 0u;
         rec[(long long)MQ_F_ARRIVED * R] = (double)nxt;
-        rec[(long long)MQ_F_TAKED * R] = (double)(nxt - dropped - waiting);
-        rec[(long long)MQ_F_SERVED * R] = (double)served;
+        rec[(long long)MQ_F_TAKED * R] = (double)taked;
+        rec[(long long)MQ_F_SERVED * R] = (double)N;
         rec[(long long)MQ_F_DROPPED * R] = (double)dropped;
-        rec[(long long)MQ_F_TTEK * R] = tbase + (double)t;
+        rec[(long long)MQ_F_TTEK * R] = tbase;
         rec[(long long)MQ_F_FLAGS * R] = (double)flags;
     }
 }
