@@ -298,6 +298,50 @@ int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, cons
                       double *stats, double *W);
 int mq_scan_gg1(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, double *stats, double *W);
 
+/* ---- tandem line of single-server nodes with finite buffers and blocking after service.
+ * Replaces TandemBlockingSim(seed).set_sources(arrival_rate, kendall) / set_nodes(serv_params,
+ * capacity) / run(total_served, warmup_fraction)  (sim/networks/tandem_blocking.py:32,38,50) */
+typedef struct {
+    int32_t m;                              /* number of nodes                                    */
+    int32_t flags;
+    int64_t capacity[MQ_NET_MAX_NODES];     /* K_i: max jobs at node i incl. the one in service,  */
+                                            /* < 0 = unlimited (None)          tandem_blocking.py:45 */
+    mq_dist src;                            /* external flow into node 1        tandem_blocking.py:35 */
+    mq_dist srv[MQ_NET_MAX_NODES];          /* per-node service                 tandem_blocking.py:44 */
+    int64_t total_served;                   /* departures from the last node AFTER warm-up   :52   */
+    double warmup_fraction;                 /* default 0.05 in the reference                 :50   */
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+} mq_tandem_cfg;
+
+/* per-replication record rows */
+#define MQ_TG_ELAPSED 0   /* t - t0 (tandem_blocking.py:130)                                        */
+#define MQ_TG_FLAGS 1
+#define MQ_TG_ARRIVED 2   /* counted after warm-up                                                  */
+#define MQ_TG_LOST 3
+#define MQ_TG_DEPARTURES 4
+#define MQ_TG_SERVED 5    /* including warm-up                                                      */
+#define MQ_TG_AREASUM 6   /* sum over nodes of area_l[i]  (v[0] = this / departures)                */
+#define MQ_TG_TEND 7
+#define MQ_TG_T0 8
+#define MQ_TG_AUSED 9
+#define MQ_TG_ROWS 10
+#define MQ_TN_AREA 0      /* area_l[i] = integral of jobs[i] dt after warm-up                       */
+#define MQ_TN_SUSED 1
+#define MQ_TN_ROWS 2
+#define MQ_TANDEM_REC_ROWS(m) (MQ_TG_ROWS + (m) * MQ_TN_ROWS)
+
+/* aggregate: [0] replications, [1] flagged, [2],[3] sum and sum of squares over replications of the
+ * throughput departures/elapsed, [4],[5] of the loss probability lost/arrived, [6],[7] of
+ * v[0] = sum(mean_jobs)/throughput, then per node [8+2i],[9+2i] of mean_jobs[i] = area/elapsed */
+#define MQ_TANDEM_AGG_LEN(m) (8 + 2 * (m))
+
+int mq_sim_tandem(mq_ctx *ctx, const mq_tandem_cfg *cfg, double *agg, double *rep_out);
+/* replay form: A = external gaps [n_a][replications], S[i] = node i's draws in start_service order */
+int mq_replay_tandem(mq_ctx *ctx, const mq_tandem_cfg *cfg, const double *A, int64_t n_a, const double *const *S,
+                     const int64_t *n_s, double *agg, double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

@@ -131,6 +131,28 @@ class MqScanCfg(C.Structure):
     ]
 
 
+TG_ELAPSED, TG_FLAGS, TG_ARRIVED, TG_LOST, TG_DEPARTURES, TG_SERVED, TG_AREASUM, TG_TEND, TG_T0, TG_AUSED, TG_ROWS = (
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10)
+TN_AREA, TN_SUSED, TN_ROWS = 0, 1, 2
+
+
+def tandem_rec_rows(m: int) -> int:
+    return TG_ROWS + m * TN_ROWS
+
+
+def tandem_agg_len(m: int) -> int:
+    return 8 + 2 * m
+
+
+class MqTandemCfg(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32), ("flags", C.c_int32), ("capacity", C.c_int64 * NET_MAX_NODES),
+        ("src", MqDist), ("srv", MqDist * NET_MAX_NODES),
+        ("total_served", C.c_int64), ("warmup_fraction", C.c_double),
+        ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
+    ]
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -182,6 +204,11 @@ def load():
         L.mq_scan_gg1_apply.argtypes = [vp, C.POINTER(MqScanCfg), vp, vp, C.c_double, dp, vp]
         L.mq_scan_gg1.restype = C.c_int
         L.mq_scan_gg1.argtypes = [vp, C.POINTER(MqScanCfg), vp, vp, dp, vp]
+        L.mq_sim_tandem.restype = C.c_int
+        L.mq_sim_tandem.argtypes = [vp, C.POINTER(MqTandemCfg), dp, dp]
+        L.mq_replay_tandem.restype = C.c_int
+        L.mq_replay_tandem.argtypes = [vp, C.POINTER(MqTandemCfg), vp, C.c_int64, C.POINTER(vp),
+                                       C.POINTER(C.c_int64), dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -437,6 +464,47 @@ class Context:
                                         stats.ctypes.data_as(C.POINTER(C.c_double)),
                                         W.ctypes.data if W is not None else None))
         return stats, W
+
+    # ---- K6 ----
+    def _tandem_cfg(self, capacity, total_served, warmup_fraction, replications, rep0, seed):
+        m = len(capacity)
+        if m > NET_MAX_NODES:
+            raise MqError(MQ_E_UNSUPPORTED, f"at most {NET_MAX_NODES} nodes")
+        cfg = MqTandemCfg()
+        cfg.m = m
+        for i, k in enumerate(capacity):
+            cfg.capacity[i] = -1 if (k is None or k == float("inf")) else int(k)
+        cfg.total_served, cfg.warmup_fraction = int(total_served), float(warmup_fraction)
+        cfg.replications, cfg.rep0 = int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        return cfg
+
+    def sim_tandem(self, capacity, src, srv, total_served, warmup_fraction, replications, rep0, seed,
+                   per_replication=False):
+        cfg = self._tandem_cfg(capacity, total_served, warmup_fraction, replications, rep0, seed)
+        cfg.src = src
+        for i, d in enumerate(srv):
+            cfg.srv[i] = d
+        m = len(capacity)
+        agg = np.zeros(tandem_agg_len(m))
+        rec = np.empty((tandem_rec_rows(m), int(replications))) if per_replication else None
+        check(self._L.mq_sim_tandem(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                    rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_tandem(self, capacity, A, S, total_served, warmup_fraction=0.05):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        S = [np.ascontiguousarray(x, dtype=np.float64) for x in S]
+        reps, m = A.shape[1], len(capacity)
+        cfg = self._tandem_cfg(capacity, total_served, warmup_fraction, reps, 0, 0)
+        ps = (C.c_void_p * m)(*[x.ctypes.data for x in S])
+        ns = (C.c_int64 * m)(*[x.shape[0] for x in S])
+        agg = np.zeros(tandem_agg_len(m))
+        rec = np.empty((tandem_rec_rows(m), reps))
+        check(self._L.mq_replay_tandem(self._h, C.byref(cfg), A.ctypes.data, A.shape[0], ps, ns,
+                                       agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                       rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
 
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

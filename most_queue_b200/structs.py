@@ -51,3 +51,12 @@ class NetworkResults:
     w: list | None = None  # additive: network waiting-time moments (reference keeps them on the object)
     replications: int = 1
     ci: dict | None = field(default=None)
+
+
+@dataclass
+class NetworkMeansResults(NetworkResults):
+    """Mean-value results for open networks (structs.py:102-113 of the reference)."""
+
+    mean_jobs: list | None = None  # L_i: mean number of jobs at each node
+    v_node: list | None = None
+    negative_intensities: list | None = None

@@ -170,6 +170,20 @@ int mqo_lindley_seq(const double *A, const double *S, int64_t N, double w_in, do
 int mqo_lindley_tree(const double *A, const double *S, int64_t N, double w_in, int L, double *W,
                      mqo_lindley_out *out);
 
+/* ---- tandem line, single-server nodes, finite buffers, blocking after service:
+ * TandemBlockingSim.run (sim/networks/tandem_blocking.py:50-142) ---- */
+typedef struct {
+    double throughput, loss_prob, v0; /* tandem_blocking.py:131-137 */
+    double mean_jobs[MQO_NET_MAX_NODES];
+    double area[MQO_NET_MAX_NODES];
+    double t_end, t0, elapsed;
+    int64_t served, arrived, lost, departures;
+} mqo_tandem_out;
+
+/* capacity[i] < 0 means unlimited (None).  services[i]: node i's draws in start_service order. */
+int mqo_tandem_run(int m, const int64_t *capacity, mqo_src *arrivals, mqo_src *services,
+                   int64_t total_served, double warmup_fraction, mqo_tandem_out *out);
+
 const char *mqo_version(void);
 
 #ifdef __cplusplus

@@ -82,6 +82,13 @@ class MqoLindleyOut(C.Structure):
                 ("b", C.c_double)]
 
 
+class MqoTandemOut(C.Structure):
+    _fields_ = [("throughput", C.c_double), ("loss_prob", C.c_double), ("v0", C.c_double),
+                ("mean_jobs", C.c_double * 16), ("area", C.c_double * 16), ("t_end", C.c_double),
+                ("t0", C.c_double), ("elapsed", C.c_double), ("served", C.c_int64), ("arrived", C.c_int64),
+                ("lost", C.c_int64), ("departures", C.c_int64)]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
@@ -130,6 +137,9 @@ def lib():
         L.mqo_lindley_seq.argtypes = [dp, dp, C.c_int64, C.c_double, dp, C.POINTER(MqoLindleyOut)]
         L.mqo_lindley_tree.restype = C.c_int
         L.mqo_lindley_tree.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_int, dp, C.POINTER(MqoLindleyOut)]
+        L.mqo_tandem_run.restype = C.c_int
+        L.mqo_tandem_run.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(MqoSrc), C.POINTER(MqoSrc),
+                                     C.c_int64, C.c_double, C.POINTER(MqoTandemOut)]
         L.mqo_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -417,3 +427,31 @@ def lindley(A, S, N=None, w_in=0.0, tree=True, L=16):
     if rc != 0:
         raise RuntimeError(f"oracle lindley failed rc={rc}")
     return W, out
+
+
+# --------------------------------------------------------------------------- tandem with blocking
+def _tandem_run(capacity, arrivals, services, total_served, warmup_fraction):
+    m = len(capacity)
+    cap = (C.c_int64 * m)(*[-1 if (k is None or k == float("inf")) else int(k) for k in capacity])
+    S = (MqoSrc * m)(*services)
+    out = MqoTandemOut()
+    rc = lib().mqo_tandem_run(m, cap, C.byref(arrivals), S, int(total_served), float(warmup_fraction), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle tandem run failed rc={rc}")
+    out.a_used = arrivals.pos
+    out.s_used = [S[i].pos for i in range(m)]
+    out.m = m
+    return out
+
+
+def tandem_replay(capacity, A, S, total_served, warmup_fraction=0.05):
+    """TandemBlockingSim.run() on pre-generated external gaps A and per-node service draws S[i]."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    S = [np.ascontiguousarray(x, dtype=np.float64) for x in S]
+    return _tandem_run(capacity, _replay_src(A), [_replay_src(x) for x in S], total_served, warmup_fraction)
+
+
+def tandem_generate(capacity, source, servers, total_served, seed, rep, warmup_fraction=0.05):
+    m = len(capacity)
+    return _tandem_run(capacity, _gen_src(source, seed, m, rep, 0),
+                       [_gen_src(servers[i], seed, i, rep, 1) for i in range(m)], total_served, warmup_fraction)

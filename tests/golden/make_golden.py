@@ -293,6 +293,44 @@ def make_net():
              [rng.exponential(1.0, 3 * n)], n)
 
 
+# --------------------------------------------------------------------------- tandem with blocking
+def tandem_case(name, capacity, A, S, total_served, warmup_fraction=0.05):
+    from most_queue.sim.networks.tandem_blocking import TandemBlockingSim
+
+    m = len(capacity)
+    sim = TandemBlockingSim(seed=1)
+    sim.set_sources(1.0)
+    sim.set_nodes([{"type": "M", "params": 1.0} for _ in range(m)], capacity)
+    ia = [0]
+    isv = [[0] for _ in range(m)]
+    sim.source = ReplayDist(A, ia)
+    sim.servers = [ReplayDist(S[i], isv[i]) for i in range(m)]
+    res = sim.run(total_served, warmup_fraction=warmup_fraction)
+    out = dict(capacity=np.array([-1 if k is None else k for k in capacity]), total_served=total_served,
+               warmup_fraction=warmup_fraction, A=np.asarray(A), throughput=float(sim.throughput),
+               loss_prob=float(sim.loss_prob), mean_jobs=np.array(res.mean_jobs, dtype=np.float64),
+               v0=float(res.v[0]), served=int(res.served), a_used=ia[0], s_used=np.array([x[0] for x in isv]))
+    for i in range(m):
+        out[f"S{i}"] = np.asarray(S[i])
+    np.savez_compressed(os.path.join(OUT, f"tandem_{name}.npz"), **out)
+    print(f"tandem_{name}: thr={sim.throughput:.5f} loss={sim.loss_prob:.5f} L={[round(x, 4) for x in res.mean_jobs]}")
+
+
+def make_tandem():
+    rng = np.random.default_rng(20260404)
+    n = 3000
+    # tests/test_tandem_blocking.py:79-96: three nodes, tight middle buffer
+    mu = [1.0, 0.9, 1.1]
+    tandem_case("k523", [5, 2, 3], rng.exponential(1 / 0.7, 3 * n), [rng.exponential(1 / x, 3 * n) for x in mu], n)
+    # unlimited buffers (test_infinite_buffers_reduce_to_jackson), non-exponential service
+    tandem_case("inf2", [None, None], rng.exponential(1.0, 2 * n), [rng.gamma(2.0, 0.3, 2 * n), rng.gamma(0.7, 1.0, 2 * n)], n)
+    # heavy blocking: capacity 1 everywhere, overloaded first node, lattice times (exact ties)
+    tandem_case("k111_lattice", [1, 1, 1], rng.integers(1, 3, 6 * n) * 0.5,
+                [rng.integers(1, 4, 6 * n) * 0.5 for _ in range(3)], n, warmup_fraction=0.0)
+    tandem_case("k3_single", [3], rng.exponential(0.8, 4 * n), [rng.exponential(1.0, 4 * n)], n, warmup_fraction=0.2)
+    tandem_case("k2241_five", [2, 2, 4, 1, None], rng.exponential(1.1, 4 * n), [rng.exponential(0.9, 4 * n) for _ in range(5)], n)
+
+
 # --------------------------------------------------------------------------- theory
 def make_theory():
     """Analytical values used by the generator-mode (statistical) tests."""
@@ -352,12 +390,14 @@ def make_theory():
 
 if __name__ == "__main__":
     import_reference()
-    which = sys.argv[1:] or ["fifo", "prio", "net", "theory"]
+    which = sys.argv[1:] or ["fifo", "prio", "net", "tandem", "theory"]
     if "fifo" in which:
         make_fifo()
     if "prio" in which:
         make_prio()
     if "net" in which and "make_net" in globals():
         make_net()
+    if "tandem" in which:
+        make_tandem()
     if "theory" in which:
         make_theory()
