@@ -95,12 +95,17 @@ int mqo_tandem_run(int m, const int64_t *capacity, mqo_src *arrivals, mqo_src *s
     out->departures = departures;
     out->throughput = (double)departures / elapsed;
     out->loss_prob = arrived ? (double)lost / (double)arrived : 0.0;
-    double sum = 0.0;
+    /* v = sum(mean_jobs) / throughput (:136): CPython >= 3.12 sums floats with Neumaier compensation
+     * (Python/bltinmodule.c), which is what the reference ran with when the fixtures were generated */
+    double sum = 0.0, comp = 0.0;
     for (int i = 0; i < m; ++i) {
         out->area[i] = area[i];
         out->mean_jobs[i] = area[i] / elapsed;
-        sum += out->mean_jobs[i];
+        const double x = out->mean_jobs[i], tt = sum + x;
+        if (fabs(sum) >= fabs(x)) comp += (sum - tt) + x; else comp += (x - tt) + sum;
+        sum = tt;
     }
+    if (comp != 0.0 && isfinite(comp)) sum += comp;
     out->v0 = out->throughput > 0 ? sum / out->throughput : 0.0;
     return 0;
 }
