@@ -279,18 +279,25 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
                 const bool is_arr = q0 || tA <= d0;
                 const float te = is_arr ? tA : d0;
                 // _update_state_probs (base.py:327-340)
-                if (q0) {
-                    // between t and te the c servers finish in key order: state (c - j) lasts until key j
-                    float prev = t;
+                const float dt = te - t;
+                {
+                    // nobody waits: between t and te the c servers finish in key order, state (c - j) lasts
+                    // until key j.  With r_j = saturate((key_j - t) / dt) the time in state (c - j) is
+                    // (r_j - r_{j-1}) dt: one FFMA.SAT per key on the FMA pipe instead of two FMNMX clamps.
+                    // Lanes with waiting jobs run the same code with a zero weight (no divergent arm).
+                    const float inv = (q0 && dt > 0.0f) ? fast_rcp(dt) : 0.0f;
+                    const float wgt = q0 ? dt : 0.0f;
+                    const float nt = -t * inv;
+                    float prev = 0.0f;
 #pragma unroll
                     for (int j = 0; j < CT; ++j) {
-                        const float e = fminf(fmaxf(L[j], t), te);
-                        hs[CT - j] += e - prev;
-                        prev = e;
+                        const float r = __saturatef(fmaf(L[j], inv, nt));
+                        hs[CT - j] = fmaf(r - prev, wgt, hs[CT - j]);
+                        prev = r;
                     }
-                    hs[0] += te - prev;
-                } else {
-                    add_q_state(q, te - t);
+                    hs[0] = fmaf(1.0f - prev, wgt, hs[0]);
+                    // somebody waits: all servers are busy, the state is c + q (q = 0 adds 0 to the first bin)
+                    add_q_state(q0 ? 1u : q, q0 ? 0.0f : dt);
                 }
                 t = te;
 

@@ -54,6 +54,13 @@ __device__ __forceinline__ float fast_ex2(float x)
     return y;
 }
 
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // (w + 0.5) * 2^-32, in (0, 1]
 __device__ __forceinline__ float u01(uint32_t w)
 {
