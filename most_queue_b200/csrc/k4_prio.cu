@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(K4_BLOCK) k4_prio(const K4Params P)
             }
             if (midx >= 0 && mt < et) ev = K;
 
+            // The service draw of the job that starts in this event is made at ONE site after the event logic
+            // (draw_cls / draw_srv), so lanes in different branches share the sampler code.  Streams are per
+            // class, so the order of draws within a class is what the reference's is.
+            int draw_cls = -1, draw_srv = 0;
             if (ev < K) {
                 const int k = ev;
                 ttek = arrival_time[k];
@@ -197,53 +201,49 @@ __global__ void __launch_bounds__(K4_BLOCK) k4_prio(const K4Params P)
                 if (free_channels != 0) {
                     const int j = __ffs(~busy) - 1;  // lowest free index
                     taked[k]++;
-                    total_time[j] = next_service(k);
-                    if (status) break;
-                    end[j] = __dadd_rn(ttek, total_time[j]);
+                    draw_cls = k;
+                    draw_srv = j;
                     on[j] = nj;
                     busy |= 1u << j;
                     free_channels--;
-                    continue;
-                }
-                if (P.prty == 0) {  // NP: priority.py:331-332
+                } else if (P.prty == 0) {  // NP: priority.py:331-332
                     nj.start_wait = ttek;
                     push(nj);
-                    continue;
-                }
-                // arrive_with_absolute_prty priority.py:390-455
-                bool found = false;
-                for (int j = 0; j < c; ++j) {
-                    if (on[j].k > k) {
-                        const double time_to_end = end[j];
-                        const double tot = total_time[j];
-                        K4Job victim = on[j];
-                        taked[k]++;
-                        victim.start_wait = ttek;
-                        victim.is_pr = 1;
-                        if (P.prty == 1)
-                            victim.tte = __dsub_rn(time_to_end, ttek);
-                        else if (P.prty == 2)
-                            victim.tte = next_service(k);  // priority.py:425
-                        else
-                            victim.tte = tot;
-                        push(victim);
-                        total_time[j] = next_service(k);
-                        end[j] = __dadd_rn(ttek, total_time[j]);
-                        on[j] = nj;
-                        found = true;
-                        break;
+                } else {
+                    // arrive_with_absolute_prty priority.py:390-455
+                    bool found = false;
+                    for (int j = 0; j < c; ++j) {
+                        if (on[j].k > k) {
+                            const double time_to_end = end[j];
+                            const double tot = total_time[j];
+                            K4Job victim = on[j];
+                            taked[k]++;
+                            victim.start_wait = ttek;
+                            victim.is_pr = 1;
+                            if (P.prty == 1)
+                                victim.tte = __dsub_rn(time_to_end, ttek);
+                            else if (P.prty == 2)
+                                victim.tte = next_service(k);  // priority.py:425, drawn before the new job's
+                            else
+                                victim.tte = tot;
+                            push(victim);
+                            draw_cls = k;
+                            draw_srv = j;
+                            on[j] = nj;
+                            found = true;
+                            break;
+                        }
                     }
-                }
-                if (status) break;
-                if (!found) {
-                    long long qtot = 0;
-                    for (int kk = 0; kk < K; ++kk) qtot += qsize[kk];
-                    if (P.buffer <= 0 || qtot < P.buffer) {
-                        nj.start_wait = ttek;
-                        push(nj);
-                    } else {
-                        dropped[k]++;
-                        in_sys[k]--;
+                    if (!found) {
+                        long long qtot = 0;
+                        for (int kk = 0; kk < K; ++kk) qtot += qsize[kk];
+                        if (P.buffer <= 0 || qtot < P.buffer) {
+                            nj.start_wait = ttek;
+                            push(nj);
+                        } else {
+                            dropped[k]++;
+                            in_sys[k]--;
+                        }
                     }
                 }
             } else {
@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(K4_BLOCK) k4_prio(const K4Params P)
                         if (qj.is_pr) {
                             end[j] = __dadd_rn(ttek, qj.tte);  // servers.py:237-239
                         } else {
-                            total_time[j] = next_service(kk);
-                            end[j] = __dadd_rn(ttek, total_time[j]);
+                            draw_cls = kk;
+                            draw_srv = j;
                         }
                         on[j] = qj;
                         busy |= 1u << j;
@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(K4_BLOCK) k4_prio(const K4Params P)
                         break;
                     }
                 }
+            }
+            if (draw_cls >= 0) {  // ServerPriority.start_service, servers.py:241-243
+                total_time[draw_srv] = next_service(draw_cls);
+                end[draw_srv] = __dadd_rn(ttek, total_time[draw_srv]);
             }
         }
 
