@@ -99,7 +99,10 @@ typedef struct {
     int64_t rep0;         /* global id of the first one: Philox counter word            */
     uint64_t seed;        /* QsSim(seed=...) -> Philox key                 base_core.py:23 */
     int32_t flags;        /* reserved, 0                                                */
-    int32_t reserved;
+    int32_t warmup;       /* additive (0 = the reference's behaviour): statistics restart at the     */
+                          /* instant of the warmup-th start of service; w / v then cover the jobs     */
+                          /* started after it (rows TAKED / SERVED hold those sample counts) and      */
+                          /* p / TTEK the time after it.  Removes QsSim's O(1/N) start-up bias.       */
 } mq_fifo_cfg;
 
 #define MQ_MAX_PBINS 1024

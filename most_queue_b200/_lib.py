@@ -50,7 +50,7 @@ class MqFifoCfg(C.Structure):
         ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64),
         ("src", MqDist), ("srv", MqDist),
         ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64),
-        ("seed", C.c_uint64), ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("seed", C.c_uint64), ("flags", C.c_int32), ("warmup", C.c_int32),
     ]
 
 
@@ -299,13 +299,14 @@ class Context:
 
     # ---- K2 ----
     def sim_fifo(self, c, buffer, src: MqDist, srv: MqDist, total_served, replications, rep0, seed,
-                 p_bins=128, per_replication=False):
+                 p_bins=128, per_replication=False, warmup=0):
         cfg = MqFifoCfg()
         cfg.c, cfg.p_bins = int(c), int(p_bins)
         cfg.buffer = -1 if buffer is None else int(buffer)
         cfg.src, cfg.srv = src, srv
         cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.warmup = int(warmup)
         agg = np.zeros(agg_len(p_bins))
         rec = np.empty((rec_rows(p_bins), int(replications))) if per_replication else None
         check(self._L.mq_sim_fifo(

@@ -53,6 +53,7 @@ struct K2Params {
     long long reps;
     uint32_t rep0;
     uint32_t key0;
+    uint32_t warm;     // statistics restart at the warm-th start of service (0: never)
     DistF src, srv;
     double *rec;      // [MQ_REC_ROWS(p_bins)][reps], zeroed by the caller
     float2 *ring;     // finite buffer: [buffer][total lanes]
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
         uint32_t head = 0;             // finite buffer: ring bookkeeping
         float a_anchor = 0.0f, a_lastq = 0.0f;
         uint32_t flags = 0;
+        double t_warm = 0.0;
 
         // first arrival: the draw set_sources makes (base.py:112)
         float tA, S_pend;
@@ -338,6 +340,24 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
                 acc4(sw, start ? w : 0.0f);
                 acc4(sv, start ? vv : 0.0f);
                 taked += start ? 1u : 0u;
+                if (start && taked == P.warm) {
+                    // end of the warm-up: forget every statistic gathered so far (the job that just started
+                    // included); jobs still in service are marked so that the final correction skips them
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        sw[k] = 0.0f;
+                        sv[k] = 0.0f;
+                        rec[(long long)(MQ_F_W + k) * R] = 0.0;
+                        rec[(long long)(MQ_F_V + k) * R] = 0.0;
+                    }
+#pragma unroll
+                    for (int m = 0; m <= CT; ++m) hs[m] = 0.0f;
+                    for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
+                    for (int k = 0; k < P.p_bins; ++k) rec[(long long)(MQ_F_P + k) * R] = 0.0;
+                    rec[(long long)MQ_F_POVER * R] = 0.0;
+                    for (int j = 0; j < CT; ++j) vslot[j * MQ_BLOCK] = -1.0f;
+                    t_warm = tbase + (double)t;
+                }
 
                 // ---- queue ----
                 const bool accept = start || !FINITE || q < cap;  // base.py:204-212
@@ -481,10 +501,13 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
 
         // ---- jobs still in service at the stop were counted at start: take them out ----
         double vfix[4] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t in_service = 0;
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
-            if (fabsf(L[j]) < MQ_KEY_LIM) {
-                const double x = (double)vslot[(__float_as_uint(L[j]) & Tag<CT>::MASK) * MQ_BLOCK];
+            const float xs = fabsf(L[j]) < MQ_KEY_LIM ? vslot[(__float_as_uint(L[j]) & Tag<CT>::MASK) * MQ_BLOCK] : -1.0f;
+            if (xs >= 0.0f) {  // in service and started after the warm-up
+                in_service++;
+                const double x = (double)xs;
                 const double x2 = x * x;
                 vfix[0] += x;
                 vfix[1] += x2;
@@ -495,10 +518,11 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
 #pragma unroll
         for (int k = 0; k < 4; ++k) rec[(long long)(MQ_F_V + k) * R] -= vfix[k];
         rec[(long long)MQ_F_ARRIVED * R] = (double)nxt;
-        rec[(long long)MQ_F_TAKED * R] = (double)taked;
-        rec[(long long)MQ_F_SERVED * R] = (double)N;
+        // sample counts: w over the jobs started (after the warm-up), v over those of them that left
+        rec[(long long)MQ_F_TAKED * R] = (double)(taked - P.warm);
+        rec[(long long)MQ_F_SERVED * R] = P.warm ? (double)(taked - P.warm - in_service) : (double)N;
         rec[(long long)MQ_F_DROPPED * R] = (double)dropped;
-        rec[(long long)MQ_F_TTEK * R] = tbase;
+        rec[(long long)MQ_F_TTEK * R] = tbase - t_warm;
         rec[(long long)MQ_F_FLAGS * R] = (double)flags;
     }
 }

@@ -271,6 +271,8 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
         return fail(MQ_E_INVALID, "mq_sim_fifo: total_served must be in 0..2^31-1");
     if (cfg->replications < 1 || cfg->rep0 < 0 || cfg->rep0 + cfg->replications > (1ll << 32))
         return fail(MQ_E_INVALID, "mq_sim_fifo: replication ids must fit 32 bits");
+    if (cfg->warmup < 0 || (cfg->warmup > 0 && cfg->warmup >= cfg->total_served))
+        return fail(MQ_E_INVALID, "mq_sim_fifo: warmup must be in 0..total_served-1");
     if (int rc = check_dist(cfg->src, "set_sources")) return rc;
     if (int rc = check_dist(cfg->srv, "set_servers")) return rc;
     CU(cudaSetDevice(ctx->device));
@@ -289,6 +291,7 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     P.reps = R;
     P.rep0 = (uint32_t)cfg->rep0;
     P.key0 = seed_to_key(cfg->seed);
+    P.warm = (uint32_t)cfg->warmup;
     P.src = make_distf(cfg->src);
     P.srv = make_distf(cfg->srv);
     P.rec = (double *)ctx->rec.p;

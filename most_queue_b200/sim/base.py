@@ -30,7 +30,7 @@ class QsSim:
     """Queueing system GI/G/n/r and GI/G/n (FIFO), batched over replications on one B200."""
 
     def __init__(self, num_of_channels, buffer=None, verbose=True, buffer_type="list", seed=None,
-                 replications=1, p_bins=128, device=None):
+                 replications=1, p_bins=128, device=None, warmup=0):
         if buffer_type not in ("list", "deque"):
             raise ValueError("Unknown queue type")  # base.py:73
         self.n = int(num_of_channels)
@@ -40,6 +40,9 @@ class QsSim:
         self.replications = int(replications)
         self.p_bins = int(p_bins)
         self.device = device
+        # additive: discard the statistics of the first `warmup` jobs that start service (the reference
+        # starts empty and keeps everything, base.py:488-528, which biases every replication by O(1/N))
+        self.warmup = int(warmup)
 
         self.num_of_states = DEFAULT_NUM_STATES
         self.w = [0, 0, 0, 0]
@@ -88,7 +91,7 @@ class QsSim:
         ctx = _lib.default_context(self.device)
         if count > 0:
             agg, rec = ctx.sim_fifo(self.n, self.buffer, self._src, self._srv, total_served, count, rep0, seed,
-                                    p_bins=self.p_bins, per_replication=keep_replications)
+                                    p_bins=self.p_bins, per_replication=keep_replications, warmup=self.warmup)
             self.timing = ctx.last_timing()
         else:
             agg, rec = np.zeros(_lib.agg_len(self.p_bins)), None

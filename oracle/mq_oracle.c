@@ -253,6 +253,7 @@ typedef struct {
     const mqo_dist *src, *srv;
     uint32_t seed, rep;
     int generate;
+    int64_t warm; /* additive: statistics restart at the warm-th start of service (0 = reference) */
 } fifo_input;
 
 #define MAX_C 64
@@ -263,8 +264,20 @@ static int fifo_loop(int c, int64_t buffer, const fifo_input *in, int64_t total_
 {
     if (c < 1 || c > MAX_C) return -2;
     double end[MAX_C], arr[MAX_C];
-    int busy[MAX_C];
-    for (int j = 0; j < c; ++j) { end[j] = MQO_FREE_SENTINEL; arr[j] = 0.0; busy[j] = 0; }
+    int busy[MAX_C], post[MAX_C];
+    const int64_t warm = in->warm;
+    double t_warm = 0.0;
+    int64_t v_n = 0;
+    for (int j = 0; j < c; ++j) { end[j] = MQO_FREE_SENTINEL; arr[j] = 0.0; busy[j] = 0; post[j] = 0; }
+#define WARM_RESET()                                                                  \
+    do {                                                                              \
+        if (warm > 0 && o->taked == warm) {                                           \
+            for (int k_ = 0; k_ < 4; ++k_) o->w_sum[k_] = o->v_sum[k_] = o->w_run[k_] = o->v_run[k_] = 0.0; \
+            for (int64_t k_ = 0; k_ < p_bins; ++k_) p[k_] = 0.0;                      \
+            o->p_over = 0.0;                                                          \
+            t_warm = ttek;                                                            \
+        }                                                                             \
+    } while (0)
     memset(o, 0, sizeof(*o));
     for (int64_t k = 0; k < p_bins; ++k) p[k] = 0.0;
     fifo_q q = {0, 0, 0, 0};
@@ -335,9 +348,10 @@ static int fifo_loop(int c, int64_t buffer, const fifo_input *in, int64_t total_
                 int j = 0;
                 while (busy[j]) ++j;
                 o->taked++;
-                refresh_moments(o->w_run, 4, 0.0, o->taked);
+                if (o->taked > warm) refresh_moments(o->w_run, 4, 0.0, o->taked - warm);
                 add_powers(o->w_sum, 0.0);
                 if (w_samples && o->taked <= w_cap) w_samples[o->taked - 1] = 0.0;
+                post[j] = o->taked > warm;
                 double sv;
                 if (in->generate) {
                     word_src s = {in->seed, 0u, in->rep, this_idx, 1, this_w1};
@@ -353,6 +367,7 @@ static int fifo_loop(int c, int64_t buffer, const fifo_input *in, int64_t total_
                 busy[j] = 1;
                 free_channels--;
                 if (free_channels == 0 && o->in_sys == c) start_busy = ttek;
+                WARM_RESET();
             }
         } else {
             /* serving(c) base.py:249-286 */
@@ -365,8 +380,11 @@ static int fifo_loop(int c, int64_t buffer, const fifo_input *in, int64_t total_
             o->served++;
             free_channels++;
             double v = ttek - arr[midx];
-            refresh_moments(o->v_run, 4, v, o->served);
-            add_powers(o->v_sum, v);
+            if (warm == 0 || post[midx]) {
+                v_n++;
+                refresh_moments(o->v_run, 4, v, v_n);
+                add_powers(o->v_sum, v);
+            }
             if (v_samples && o->served <= v_cap) v_samples[o->served - 1] = v;
             o->in_sys--;
             if (q.size == 0 && free_channels == 1 && o->in_sys == c - 1) {
@@ -379,9 +397,10 @@ static int fifo_loop(int c, int64_t buffer, const fifo_input *in, int64_t total_
                 if (free_channels == 1) start_busy = ttek;
                 o->taked++;
                 double w = 0.0 + (ttek - h.arr);
-                refresh_moments(o->w_run, 4, w, o->taked);
+                if (o->taked > warm) refresh_moments(o->w_run, 4, w, o->taked - warm);
                 add_powers(o->w_sum, w);
                 if (w_samples && o->taked <= w_cap) w_samples[o->taked - 1] = w;
+                post[midx] = o->taked > warm;
                 double sv;
                 if (in->generate) {
                     word_src s = {in->seed, 0u, in->rep, h.idx, 1, h.w1};
@@ -396,10 +415,14 @@ static int fifo_loop(int c, int64_t buffer, const fifo_input *in, int64_t total_
                 arr[midx] = h.arr;
                 busy[midx] = 1;
                 free_channels--;
+                WARM_RESET();
             }
         }
     }
     o->ttek = ttek;
+    o->v_count = warm ? v_n : o->served;
+    o->w_count = o->taked - warm;
+    o->t_obs = ttek - t_warm;
     o->queued = q.size;
     o->a_used = ia;
     o->s_used = is;
@@ -423,6 +446,7 @@ int mqo_fifo_replay(int c, int64_t buffer, const double *A, int64_t nA, int64_t 
 
 typedef struct {
     int c;
+    int64_t warm;
     int64_t buffer, total_served, rep0, reps, p_bins;
     const mqo_dist *src, *srv;
     uint32_t seed;
@@ -441,6 +465,7 @@ static void *gen_worker(void *arg)
         fifo_input in;
         memset(&in, 0, sizeof(in));
         in.generate = 1;
+        in.warm = g->warm;
         in.src = g->src; in.srv = g->srv; in.seed = g->seed;
         in.rep = (uint32_t)(g->rep0 + r);
         int rc = fifo_loop(g->c, g->buffer, &in, g->total_served, g->p + r * g->p_bins,
@@ -454,7 +479,14 @@ int mqo_fifo_generate(int c, int64_t buffer, const mqo_dist *src, const mqo_dist
                       int64_t total_served, uint32_t seed, int64_t rep0, int64_t reps,
                       double *p, int64_t p_bins, mqo_fifo_out *out, int threads)
 {
-    gen_job g = {c, buffer, total_served, rep0, reps, p_bins, src, srv, seed, p, out, 0, 0};
+    return mqo_fifo_generate_warm(c, buffer, src, srv, total_served, 0, seed, rep0, reps, p, p_bins, out, threads);
+}
+
+int mqo_fifo_generate_warm(int c, int64_t buffer, const mqo_dist *src, const mqo_dist *srv,
+                           int64_t total_served, int64_t warm, uint32_t seed, int64_t rep0, int64_t reps,
+                           double *p, int64_t p_bins, mqo_fifo_out *out, int threads)
+{
+    gen_job g = {c, warm, buffer, total_served, rep0, reps, p_bins, src, srv, seed, p, out, 0, 0};
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;
     if (threads > reps) threads = (int)(reps > 0 ? reps : 1);

@@ -55,6 +55,8 @@ typedef struct {
     double ttek;       /* clock at stop                                                   */
     double p_over;     /* time spent in states >= p_bins                                  */
     int64_t a_used, s_used; /* how many interarrival / service variates were consumed     */
+    int64_t w_count, v_count; /* sample counts behind w_* and v_* (differ from taked / served */
+    double t_obs;             /* and ttek only when a warm-up is requested)                   */
 } mqo_fifo_out;
 
 /* QsSim.run() with pre-generated variates (sim/base.py:488-528).
@@ -76,6 +78,12 @@ int mqo_fifo_replay(int c, int64_t buffer, const double *A, int64_t nA, int64_t 
 int mqo_fifo_generate(int c, int64_t buffer, const mqo_dist *src, const mqo_dist *srv,
                       int64_t total_served, uint32_t seed, int64_t rep0, int64_t reps,
                       double *p, int64_t p_bins, mqo_fifo_out *out, int threads);
+
+/* additive warm-up (not in the reference): statistics restart at the instant of the warm-th start of
+ * service; w / v then cover the jobs started after it, p and t_obs the time after it */
+int mqo_fifo_generate_warm(int c, int64_t buffer, const mqo_dist *src, const mqo_dist *srv,
+                           int64_t total_served, int64_t warm, uint32_t seed, int64_t rep0, int64_t reps,
+                           double *p, int64_t p_bins, mqo_fifo_out *out, int threads);
 
 /* generator building blocks, exported so that tests can pin them */
 void mqo_philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[2]);

@@ -42,6 +42,9 @@ class MqoFifoOut(C.Structure):
         ("p_over", C.c_double),
         ("a_used", C.c_int64),
         ("s_used", C.c_int64),
+        ("w_count", C.c_int64),
+        ("v_count", C.c_int64),
+        ("t_obs", C.c_double),
     ]
 
 
@@ -116,6 +119,11 @@ def lib():
         L.mqo_fifo_generate.restype = C.c_int
         L.mqo_fifo_generate.argtypes = [
             C.c_int, C.c_int64, C.POINTER(MqoDist), C.POINTER(MqoDist), C.c_int64, C.c_uint32,
+            C.c_int64, C.c_int64, dp, C.c_int64, C.POINTER(MqoFifoOut), C.c_int,
+        ]
+        L.mqo_fifo_generate_warm.restype = C.c_int
+        L.mqo_fifo_generate_warm.argtypes = [
+            C.c_int, C.c_int64, C.POINTER(MqoDist), C.POINTER(MqoDist), C.c_int64, C.c_int64, C.c_uint32,
             C.c_int64, C.c_int64, dp, C.c_int64, C.POINTER(MqoFifoOut), C.c_int,
         ]
         L.mqo_philox2x32_10.restype = None
@@ -198,6 +206,9 @@ class FifoResult:
     p_over: float
     a_used: int
     s_used: int
+    w_count: int = 0
+    v_count: int = 0
+    t_obs: float = 0.0
     w_samples: np.ndarray | None = None
     v_samples: np.ndarray | None = None
 
@@ -212,7 +223,8 @@ def _unpack(o: MqoFifoOut, p: np.ndarray, ws=None, vs=None) -> FifoResult:
         w=np.array(o.w_run[:]), v=np.array(o.v_run[:]), busy=np.array(o.busy_run[:]),
         busy_n=o.busy_n, arrived=o.arrived, taked=o.taked, served=o.served, dropped=o.dropped,
         in_sys=o.in_sys, queued=o.queued, ttek=o.ttek, p_time=p, p_over=o.p_over,
-        a_used=o.a_used, s_used=o.s_used, w_samples=ws, v_samples=vs,
+        a_used=o.a_used, s_used=o.s_used, w_count=o.w_count, v_count=o.v_count, t_obs=o.t_obs,
+        w_samples=ws, v_samples=vs,
     )
 
 
@@ -240,13 +252,13 @@ def fifo_replay(c: int, buffer, A: np.ndarray, S: np.ndarray, total_served: int,
 
 
 def fifo_generate(c: int, buffer, src, srv, total_served: int, seed: int, rep0: int, reps: int,
-                  p_bins: int = 64, threads: int = 1) -> list[FifoResult]:
+                  p_bins: int = 64, threads: int = 1, warmup: int = 0) -> list[FifoResult]:
     """Generator-mode oracle: src/srv are (kendall code, params) tuples."""
     ds, dv = make_dist(*src), make_dist(*srv)
     p = np.zeros((reps, p_bins))
     outs = (MqoFifoOut * reps)()
-    rc = lib().mqo_fifo_generate(
-        c, -1 if buffer is None else int(buffer), C.byref(ds), C.byref(dv), int(total_served),
+    rc = lib().mqo_fifo_generate_warm(
+        c, -1 if buffer is None else int(buffer), C.byref(ds), C.byref(dv), int(total_served), int(warmup),
         C.c_uint32(seed & 0xFFFFFFFF), int(rep0), int(reps), _dp(p), p_bins, outs, int(threads),
     )
     if rc != 0:

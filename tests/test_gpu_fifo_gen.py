@@ -185,3 +185,49 @@ def test_mh2_8_against_takahashi_takami():
     qs.set_servers(H2Params(**th["h2"]), "H")
     res = qs.run(20000)
     _check_vs_theory(res, th, bias_rel=4e-3, bias_p=10.0 / 20000)
+
+
+def test_warmup_matches_oracle_per_replication(ctx):
+    """Additive warm-up: statistics restart at the warmup-th start of service; same sample sets as the oracle."""
+    from most_queue_b200 import _lib
+    from oracle import oracle
+
+    src, srv = ("M", 1.0), ("H", P(p1=0.447586, mu1=0.0950716, mu2=0.619214))
+    seed, R, n, W, nb = 5, 64, 3000, 700, 48
+    agg, rec = ctx.sim_fifo(8, None, _lib.make_dist(*src), _lib.make_dist(*srv), n, R, 0, seed, p_bins=nb,
+                            per_replication=True, warmup=W)
+    ref = oracle.fifo_generate(8, None, src, srv, n, _lib.seed_to_key(seed), 0, R, p_bins=nb, threads=8, warmup=W)
+    L = _lib
+    same = 0
+    for r, o in enumerate(ref):
+        if int(rec[L.F_TAKED, r]) != o.w_count or int(rec[L.F_SERVED, r]) != o.v_count:
+            continue
+        same += 1
+        np.testing.assert_allclose(rec[L.F_TTEK, r], o.t_obs, rtol=2e-5)
+        np.testing.assert_allclose(rec[L.F_V:L.F_V + 4, r], o.v_sum, rtol=3e-4)
+        np.testing.assert_allclose(rec[L.F_W:L.F_W + 4, r], o.w_sum, rtol=3e-3, atol=1e-3 * n)
+        np.testing.assert_allclose(rec[L.F_P:L.F_P + nb, r], o.p_time, rtol=3e-3, atol=3e-3 * o.t_obs / 50)
+    assert same >= 0.9 * R
+    with pytest.raises(ValueError):
+        ctx.sim_fifo(8, None, _lib.make_dist(*src), _lib.make_dist(*srv), 100, 4, 0, 1, warmup=100)
+
+
+def test_warmup_removes_the_startup_bias():
+    """With the initial transient discarded the mean wait agrees with Takahashi-Takami within the plain 99 %
+    CI at a replication count where the reference's estimator (no warm-up) is biased beyond it."""
+    from most_queue_b200.random.utils.params import H2Params
+    from most_queue_b200.sim.base import QsSim
+
+    th = _theory()["mh2_8"]
+    out = {}
+    for W in (0, 2000):
+        qs = QsSim(8, seed=11, replications=400_000, warmup=W)
+        qs.set_sources(1.0, "M")
+        qs.set_servers(H2Params(**th["h2"]), "H")
+        out[W] = qs.run(20_000)
+    bias = out[0].w[0] - th["w"][0]
+    assert bias < -3 * out[0].ci["w"][0]                      # the reference's estimator: ~ -41/N
+    assert abs(out[2000].w[0] - th["w"][0]) < 1.5 * out[2000].ci["w"][0]
+    assert abs(out[2000].v[0] - th["v"][0]) < 1.5 * out[2000].ci["v"][0]
+    for j in range(8):
+        assert abs(out[2000].p[j] - th["p"][j]) < 1.5 * out[2000].ci["p"][j] + 2e-5
