@@ -253,6 +253,22 @@ def run_ours(args):
     except Exception:
         pass
 
+    # the same workload with the additive warm-up (first 5 % of the jobs discarded, v not censored at the
+    # stop): the estimator is then unbiased and must sit inside the plain 99 % CI of the theory
+    if moment_err is not None and world == 1:
+        try:
+            aggw, _ = ctx.sim_fifo(C_SERVERS, None, src, srv, jobs, reps, 0, 424242, p_bins=p_bins,
+                                   warmup=max(1, jobs // 20), v_at_start=True)
+            Rw = aggw[_lib.A_REPS]
+            w1, v1 = aggw[_lib.A_W] / Rw, aggw[_lib.A_V] / Rw
+            ciw = 2.5758 * np.sqrt(max(aggw[_lib.A_W2] / Rw - w1 * w1, 0.0) / Rw)
+            civ = 2.5758 * np.sqrt(max(aggw[_lib.A_V2] / Rw - v1 * v1, 0.0) / Rw)
+            moment_err["with_warmup"] = {"warmup_jobs": max(1, jobs // 20), "w1": w1, "w1_ci99": ciw,
+                                         "w1_minus_theory": w1 - moment_err["w1_theory"], "v1": v1, "v1_ci99": civ,
+                                         "v1_minus_theory": v1 - moment_err["v1_theory"]}
+        except Exception as e:
+            moment_err["with_warmup"] = {"error": repr(e)}
+
     if rank == 0:
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count

@@ -98,12 +98,17 @@ typedef struct {
     int64_t replications; /* replications simulated by THIS call (this rank's shard)    */
     int64_t rep0;         /* global id of the first one: Philox counter word            */
     uint64_t seed;        /* QsSim(seed=...) -> Philox key                 base_core.py:23 */
-    int32_t flags;        /* reserved, 0                                                */
+    int32_t flags;        /* MQ_FIFO_V_AT_START or 0                                    */
     int32_t warmup;       /* additive (0 = the reference's behaviour): statistics restart at the     */
                           /* instant of the warmup-th start of service; w / v then cover the jobs     */
                           /* started after it (rows TAKED / SERVED hold those sample counts) and      */
                           /* p / TTEK the time after it.  Removes QsSim's O(1/N) start-up bias.       */
 } mq_fifo_cfg;
+
+/* additive: sample v for every job that STARTED service before the stop (its completion time is known
+ * then) instead of only the jobs that left, which removes the right-censoring bias of the reference's
+ * stop rule (the <= c jobs in service at the stop are long ones); SERVED then equals TAKED */
+#define MQ_FIFO_V_AT_START 1
 
 #define MQ_MAX_PBINS 1024
 #define MQ_MAX_CHANNELS 32

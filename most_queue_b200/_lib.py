@@ -299,7 +299,7 @@ class Context:
 
     # ---- K2 ----
     def sim_fifo(self, c, buffer, src: MqDist, srv: MqDist, total_served, replications, rep0, seed,
-                 p_bins=128, per_replication=False, warmup=0):
+                 p_bins=128, per_replication=False, warmup=0, v_at_start=False):
         cfg = MqFifoCfg()
         cfg.c, cfg.p_bins = int(c), int(p_bins)
         cfg.buffer = -1 if buffer is None else int(buffer)
@@ -307,6 +307,7 @@ class Context:
         cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.warmup = int(warmup)
+        cfg.flags = 1 if v_at_start else 0  # MQ_FIFO_V_AT_START
         agg = np.zeros(agg_len(p_bins))
         rec = np.empty((rec_rows(p_bins), int(replications))) if per_replication else None
         check(self._L.mq_sim_fifo(

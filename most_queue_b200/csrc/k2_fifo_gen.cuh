@@ -54,6 +54,7 @@ struct K2Params {
     uint32_t rep0;
     uint32_t key0;
     uint32_t warm;     // statistics restart at the warm-th start of service (0: never)
+    int v_at_start;    // MQ_FIFO_V_AT_START: keep the v of the jobs still in service at the stop
     DistF src, srv;
     double *rec;      // [MQ_REC_ROWS(p_bins)][reps], zeroed by the caller
     float2 *ring;     // finite buffer: [buffer][total lanes]
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
             const float xs = fabsf(L[j]) < MQ_KEY_LIM ? vslot[(__float_as_uint(L[j]) & Tag<CT>::MASK) * MQ_BLOCK] : -1.0f;
-            if (xs >= 0.0f) {  // in service and started after the warm-up
+            if (xs >= 0.0f && !P.v_at_start) {  // in service and started after the warm-up
                 in_service++;
                 const double x = (double)xs;
                 const double x2 = x * x;
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
         rec[(long long)MQ_F_ARRIVED * R] = (double)nxt;
         // sample counts: w over the jobs started (after the warm-up), v over those of them that left
         rec[(long long)MQ_F_TAKED * R] = (double)(taked - P.warm);
-        rec[(long long)MQ_F_SERVED * R] = P.warm ? (double)(taked - P.warm - in_service) : (double)N;
+        rec[(long long)MQ_F_SERVED * R] = (P.warm || P.v_at_start) ? (double)(taked - P.warm - in_service) : (double)N;
         rec[(long long)MQ_F_DROPPED * R] = (double)dropped;
         rec[(long long)MQ_F_TTEK * R] = tbase - t_warm;
         rec[(long long)MQ_F_FLAGS * R] = (double)flags;

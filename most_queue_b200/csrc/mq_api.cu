@@ -292,6 +292,7 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     P.rep0 = (uint32_t)cfg->rep0;
     P.key0 = seed_to_key(cfg->seed);
     P.warm = (uint32_t)cfg->warmup;
+    P.v_at_start = (cfg->flags & MQ_FIFO_V_AT_START) ? 1 : 0;
     P.src = make_distf(cfg->src);
     P.srv = make_distf(cfg->srv);
     P.rec = (double *)ctx->rec.p;

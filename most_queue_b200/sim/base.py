@@ -30,7 +30,7 @@ class QsSim:
     """Queueing system GI/G/n/r and GI/G/n (FIFO), batched over replications on one B200."""
 
     def __init__(self, num_of_channels, buffer=None, verbose=True, buffer_type="list", seed=None,
-                 replications=1, p_bins=128, device=None, warmup=0):
+                 replications=1, p_bins=128, device=None, warmup=0, v_at_start=False):
         if buffer_type not in ("list", "deque"):
             raise ValueError("Unknown queue type")  # base.py:73
         self.n = int(num_of_channels)
@@ -43,6 +43,8 @@ class QsSim:
         # additive: discard the statistics of the first `warmup` jobs that start service (the reference
         # starts empty and keeps everything, base.py:488-528, which biases every replication by O(1/N))
         self.warmup = int(warmup)
+        # additive: sample v for every job that started service before the stop (no right-censoring)
+        self.v_at_start = bool(v_at_start)
 
         self.num_of_states = DEFAULT_NUM_STATES
         self.w = [0, 0, 0, 0]
@@ -91,7 +93,8 @@ class QsSim:
         ctx = _lib.default_context(self.device)
         if count > 0:
             agg, rec = ctx.sim_fifo(self.n, self.buffer, self._src, self._srv, total_served, count, rep0, seed,
-                                    p_bins=self.p_bins, per_replication=keep_replications, warmup=self.warmup)
+                                    p_bins=self.p_bins, per_replication=keep_replications, warmup=self.warmup,
+                                    v_at_start=self.v_at_start)
             self.timing = ctx.last_timing()
         else:
             agg, rec = np.zeros(_lib.agg_len(self.p_bins)), None

@@ -213,7 +213,7 @@ def test_warmup_matches_oracle_per_replication(ctx):
 
 
 def test_warmup_removes_the_startup_bias():
-    """With the initial transient discarded the mean wait agrees with Takahashi-Takami within the plain 99 %
+    """With the initial transient discarded (and v not censored at the stop) the mean wait and sojourn agree with Takahashi-Takami within the plain 99 %
     CI at a replication count where the reference's estimator (no warm-up) is biased beyond it."""
     from most_queue_b200.random.utils.params import H2Params
     from most_queue_b200.sim.base import QsSim
@@ -221,7 +221,8 @@ def test_warmup_removes_the_startup_bias():
     th = _theory()["mh2_8"]
     out = {}
     for W in (0, 2000):
-        qs = QsSim(8, seed=11, replications=400_000, warmup=W)
+        # v_at_start: v for every job that started (the stop rule drops the <= c long jobs still in service)
+        qs = QsSim(8, seed=11, replications=400_000, warmup=W, v_at_start=W > 0)
         qs.set_sources(1.0, "M")
         qs.set_servers(H2Params(**th["h2"]), "H")
         out[W] = qs.run(20_000)
