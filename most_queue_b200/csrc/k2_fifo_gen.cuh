@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
         float a_anchor = 0.0f, a_lastq = 0.0f;
         uint32_t flags = 0;
         double t_warm = 0.0;
+        bool warm_done = false;
+        uint32_t next_stop = (P.warm != 0u && P.warm < N) ? P.warm : N;
 
         // first arrival: the draw set_sources makes (base.py:112)
         float tA, S_pend;
@@ -341,25 +343,6 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
                 acc4(sw, start ? w : 0.0f);
                 acc4(sv, start ? vv : 0.0f);
                 taked += start ? 1u : 0u;
-                if (start && taked == P.warm) {
-                    // end of the warm-up: forget every statistic gathered so far (the job that just started
-                    // included); jobs still in service are marked so that the final correction skips them
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        sw[k] = 0.0f;
-                        sv[k] = 0.0f;
-                        rec[(long long)(MQ_F_W + k) * R] = 0.0;
-                        rec[(long long)(MQ_F_V + k) * R] = 0.0;
-                    }
-#pragma unroll
-                    for (int m = 0; m <= CT; ++m) hs[m] = 0.0f;
-                    for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
-                    for (int k = 0; k < P.p_bins; ++k) rec[(long long)(MQ_F_P + k) * R] = 0.0;
-                    rec[(long long)MQ_F_POVER * R] = 0.0;
-                    for (int j = 0; j < CT; ++j) vslot[j * MQ_BLOCK] = -1.0f;
-                    t_warm = tbase + (double)t;
-                }
-
                 // ---- queue ----
                 const bool accept = start || !FINITE || q < cap;  // base.py:204-212
                 const bool enq = is_arr && !start && accept;
@@ -382,9 +365,30 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const
                 nxt += is_arr ? 1u : 0u;
                 dropped += (is_arr && !accept) ? 1u : 0u;
                 q += (enq ? 1u : 0u) - (is_arr ? 0u : 1u);
-                if (taked >= N) break;
+                if (taked >= next_stop) break;  // the N-th start, or the end of the warm-up (handled between chunks)
             }
             rebase();
+            if (!warm_done && P.warm != 0u && taked == P.warm) {
+                // end of the warm-up (the clock was just re-based to this very instant): forget every statistic
+                // gathered so far, the job that just started included; jobs still in service are marked so that
+                // the final correction skips them
+                warm_done = true;
+                next_stop = N;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    sw[k] = 0.0f;
+                    sv[k] = 0.0f;
+                    rec[(long long)(MQ_F_W + k) * R] = 0.0;
+                    rec[(long long)(MQ_F_V + k) * R] = 0.0;
+                }
+#pragma unroll
+                for (int m = 0; m <= CT; ++m) hs[m] = 0.0f;
+                for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
+                for (int k = 0; k < P.p_bins; ++k) rec[(long long)(MQ_F_P + k) * R] = 0.0;
+                rec[(long long)MQ_F_POVER * R] = 0.0;
+                for (int j = 0; j < CT; ++j) vslot[j * MQ_BLOCK] = -1.0f;
+                t_warm = tbase;
+            }
             if ((++epoch % MQ_FLUSH) == 0) flush();
         }
 
