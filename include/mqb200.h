@@ -279,8 +279,16 @@ typedef struct {
     uint32_t chain;       /* chain id (generator stream)                                     */
     int32_t device_ptrs;  /* replay form: A, S (and W) are device pointers                   */
     int32_t last_range;   /* 1: this range ends the chain (apply the stop rule, base.py:505) */
-    int32_t flags;
+    int32_t flags;        /* MQ_SCAN_WANT_P or 0                                             */
+    int64_t jobs_ahead;   /* jobs of the chain after this range (0 for the last range); in   */
+                          /* the replay form A must then hold jobs + 1 + jobs_ahead gaps     */
 } mq_scan_cfg;
+
+/* also produce the time-in-state levels (base.py:327-340 for one channel): stats[MQ_S_LEVELS + m - 1] =
+ * time with N(t) >= m for m = 1..32 and stats[MQ_S_LEVELS + 32] = sum over m > 32 of that time;
+ * p[0] = 1 - T[>=1]/ttek, p[m] = (T[>=m] - T[>=m+1]) / ttek.  Only jobs 0..N-1 are counted (the
+ * reference also counts the few arrivals between the last arrival and the stop). */
+#define MQ_SCAN_WANT_P 1
 
 #define MQ_S_W 0       /* 4: sum of W^k over the jobs of the range (+ job N when last_range and it  */
                        /*    was already waiting at the N-th departure, base.py:300-305)            */
@@ -295,7 +303,8 @@ typedef struct {
 #define MQ_S_WOUT 15   /* carry into the next range                                                  */
 #define MQ_S_TAILRAW 16 /* W[n-1] + x[n-1] before clamping                                           */
 #define MQ_S_TAILV 17  /* W[n-1] + S[n-1]: clock at the last departure minus the last arrival time   */
-#define MQ_SCAN_LEN 20
+#define MQ_S_LEVELS 20 /* 33 entries, see MQ_SCAN_WANT_P                                             */
+#define MQ_SCAN_LEN 56
 
 /* A, S == NULL: generator form.  Replay form: A has jobs + 1 entries (x[n] uses A[n+1]), S has jobs.
  * summary: ab[2] = (a, b) of the range.  apply: walks the range from carry w_in; stats has

@@ -121,13 +121,15 @@ class MqNetCfg(C.Structure):
 
 
 S_W, S_V, S_SUMA, S_SUMS, S_TAKED, S_SERVED, S_A, S_B, S_WIN, S_WOUT, S_TAILRAW, S_TAILV, SCAN_LEN = (
-    0, 4, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20)
+    0, 4, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 56)
+S_LEVELS, SCAN_NLEVEL = 20, 33
 
 
 class MqScanCfg(C.Structure):
     _fields_ = [
         ("src", MqDist), ("srv", MqDist), ("jobs", C.c_int64), ("job0", C.c_int64), ("seed", C.c_uint64),
         ("chain", C.c_uint32), ("device_ptrs", C.c_int32), ("last_range", C.c_int32), ("flags", C.c_int32),
+        ("jobs_ahead", C.c_int64),
     ]
 
 
@@ -439,8 +441,10 @@ class Context:
         return agg, rec
 
     # ---- K3 ----
-    def _scan_cfg(self, src, srv, jobs, job0, seed, chain, device_ptrs, last_range):
+    def _scan_cfg(self, src, srv, jobs, job0, seed, chain, device_ptrs, last_range, want_p=False, jobs_ahead=0):
         cfg = MqScanCfg()
+        cfg.flags = 1 if want_p else 0  # MQ_SCAN_WANT_P
+        cfg.jobs_ahead = int(jobs_ahead)
         if src is not None:
             cfg.src, cfg.srv = src, srv
         cfg.jobs, cfg.job0 = int(jobs), int(job0)
@@ -457,9 +461,9 @@ class Context:
         return float(ab[0]), float(ab[1])
 
     def scan_apply(self, jobs, w_in, job0=0, src=None, srv=None, seed=0, chain=0, A=None, S=None,
-                   device_ptrs=False, last_range=True, want_w=False):
-        cfg = self._scan_cfg(src, srv, jobs, job0, seed, chain, device_ptrs, last_range)
-        pa, ps, _keep = _scan_ptrs(A, S, jobs, device_ptrs)
+                   device_ptrs=False, last_range=True, want_w=False, want_p=False, jobs_ahead=0):
+        cfg = self._scan_cfg(src, srv, jobs, job0, seed, chain, device_ptrs, last_range, want_p, jobs_ahead)
+        pa, ps, _keep = _scan_ptrs(A, S, jobs + (jobs_ahead if want_p else 0), device_ptrs)
         stats = np.zeros(SCAN_LEN)
         W = np.empty(int(jobs)) if want_w else None
         check(self._L.mq_scan_gg1_apply(self._h, C.byref(cfg), pa, ps, float(w_in),

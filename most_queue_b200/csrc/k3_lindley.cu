@@ -70,8 +70,12 @@ __device__ __forceinline__ MP cta_scan(MP mine, MP *smem, MP *total)
 // 16-job segment.  One pad word per 16 entries (index e + e/16) makes the strided per-thread reads
 // conflict free (two wavefronts per 64-bit warp access, the minimum).
 constexpr int K3_TILE = K3_THREADS * K3_L;
+constexpr int K3_HALO = 256;  // gaps staged beyond the tile for the level walk (WANT_P)
 constexpr int K3_PADDED = K3_TILE + K3_TILE / 16 + 2;
-constexpr size_t K3_STAGE_BYTES = sizeof(double) * 2 * K3_PADDED;
+constexpr int K3_PADDED_A = (K3_TILE + K3_HALO) + (K3_TILE + K3_HALO) / 16 + 2;
+constexpr int K3_PBL = 32;    // levels N >= 1..32 accumulated per lane in shared memory
+constexpr size_t K3_STAGE_BYTES = sizeof(double) * (K3_PADDED + K3_PADDED_A);
+constexpr size_t K3_LEVEL_BYTES = sizeof(float) * K3_PBL * K3_THREADS + sizeof(double) * (K3_THREADS / 32) * (K3_PBL + 1);
 
 __device__ __forceinline__ int k3_pad(int e) { return e + (e >> 4); }
 
@@ -82,20 +86,32 @@ __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_bas
         const int e = k * K3_THREADS + threadIdx.x;
         const long long n = tile_base + e;
         smS[k3_pad(e)] = n < P.n ? __ldcs(P.S + n) : 0.0;
-        smA[k3_pad(e)] = n <= P.n ? __ldcs(P.A + n) : 0.0;
+        smA[k3_pad(e)] = n <= P.n + P.n_ahead ? __ldcs(P.A + n) : 0.0;
     }
-    if (threadIdx.x == 0) {
-        const long long n = tile_base + K3_TILE;
-        smA[k3_pad(K3_TILE)] = n <= P.n ? __ldcs(P.A + n) : 0.0;
+    {   // one more gap for x of the last job, and the halo used by the level walk
+        const int e = K3_TILE + threadIdx.x;
+        const long long n = tile_base + e;
+        smA[k3_pad(e)] = n <= P.n + P.n_ahead ? __ldcs(P.A + n) : 0.0;
+        if (threadIdx.x == 0) {
+            const long long n2 = tile_base + K3_TILE + K3_HALO;
+            smA[k3_pad(K3_TILE + K3_HALO)] = n2 <= P.n + P.n_ahead ? __ldcs(P.A + n2) : 0.0;
+        }
     }
     __syncthreads();
 }
 
 // x[j] = S[n] - A[n+1] and S[j] for the K3_L jobs of this thread's segment; returns the sum of the
 // segment's gaps A[n]
-template <bool REPLAY>
+__device__ __forceinline__ double gen_gap(const K3Params &P, long long n)
+{
+    const unsigned long long g = (unsigned long long)(P.job0 + n);
+    uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+    return (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+}
+
+template <bool REPLAY, bool STORE_GAPS = false>
 __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, double (&x)[K3_L], double (&s)[K3_L],
-                                               const double *smS, const double *smA)
+                                               const double *smS, double *smA)
 {
     double sum_a = 0.0;
     if (REPLAY) {
@@ -125,8 +141,10 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
             s[j] = ok ? sv : 0.0;
             sum_a += ok ? gap : 0.0;
             x[j] = ok ? __dsub_rn(sv, gnext) : 0.0;
+            if (STORE_GAPS) smA[k3_pad(threadIdx.x * K3_L + j)] = gap;
             gap = gnext;
         }
+        if (STORE_GAPS) smA[k3_pad(threadIdx.x * K3_L + K3_L)] = gap;
     }
     return sum_a;
 }
@@ -173,7 +191,38 @@ __global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
     if (threadIdx.x == 0) *P.total = total;
 }
 
+// Time-in-state on the scan path.  With one server and FIFO, N(t) >= m while t lies in the (m-1)-th
+// interarrival interval after job k's arrival iff job k is still in the system, so
+//   T[N >= m] = sum over jobs k of | [t_k, t_k + v_k) intersected with [t_{k+m-1}, t_{k+m}) |.
+// Each job walks forward over the gaps that follow it until its sojourn is used up (1 + arrivals during the
+// sojourn steps); per-lane fp32 columns in shared memory, flushed to fp64 per warp.
 template <bool REPLAY>
+__device__ __noinline__ void level_walk(const K3Params &P, double v, int e, long long n, const double *smA,
+                                        float *lev, double &over)
+{
+    const long long n_all = P.n + P.n_ahead;  // jobs of the whole chain from this range's origin
+    double cum = 0.0;
+    for (int m = 1;; ++m) {
+        const long long nn = n + m;
+        double g;
+        if (nn >= n_all)
+            g = __longlong_as_double(0x7ff0000000000000ll);  // no counted arrival after the last job
+        else if (e + m <= K3_TILE + K3_HALO)
+            g = smA[k3_pad(e + m)];
+        else
+            g = REPLAY ? __ldg(P.A + nn) : gen_gap(P, nn);
+        const double hi = cum + g;
+        const double ov = fmin(v, hi) - cum;
+        if (m <= K3_PBL)
+            lev[(m - 1) * K3_THREADS] += (float)ov;
+        else
+            over += ov;
+        if (!(v > hi)) break;
+        cum = hi;
+    }
+}
+
+template <bool REPLAY, bool WANT_P>
 __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
@@ -184,11 +233,41 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
 
     extern __shared__ double stage[];
     double *smS = stage, *smA = stage + K3_PADDED;
+    float *lev = reinterpret_cast<float *>(stage + K3_PADDED + K3_PADDED_A) + threadIdx.x;  // [K3_PBL][lane]
+    double *lev_w = reinterpret_cast<double *>(reinterpret_cast<float *>(stage + K3_PADDED + K3_PADDED_A) +
+                                               K3_PBL * K3_THREADS);                       // [warp][K3_PBL + 1]
+    double over = 0.0;
+    int since_flush = 0;
+    if (WANT_P) {
+        for (int m = 0; m < K3_PBL; ++m) lev[m * K3_THREADS] = 0.0f;
+        if (threadIdx.x < (K3_THREADS / 32) * (K3_PBL + 1)) lev_w[threadIdx.x] = 0.0;
+        for (int i = threadIdx.x + K3_THREADS; i < (K3_THREADS / 32) * (K3_PBL + 1); i += K3_THREADS) lev_w[i] = 0.0;
+    }
+    auto flush_levels = [&]() {
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+        for (int m = 0; m < K3_PBL; ++m) {
+            double v = (double)lev[m * K3_THREADS];
+            lev[m * K3_THREADS] = 0.0f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+            if (lane_ == 0) lev_w[warp_ * (K3_PBL + 1) + m] += v;
+        }
+        double v = over;
+        over = 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane_ == 0) lev_w[warp_ * (K3_PBL + 1) + K3_PBL] += v;
+    };
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
         if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
-        acc[8] += load_segment<REPLAY>(P, n0, x, s, smS, smA);
+        acc[8] += load_segment<REPLAY, WANT_P && !REPLAY>(P, n0, x, s, smS, smA);
+        if (WANT_P && !REPLAY) {
+            // halo of generated gaps beyond the tile
+            const int e = K3_TILE + 1 + threadIdx.x;
+            if (e <= K3_TILE + K3_HALO) smA[k3_pad(e)] = gen_gap(P, t * K3_TILE + e);
+        }
         MP total;
         const MP ex = cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);
         const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
@@ -209,6 +288,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
                 acc[6] += v2 * v;
                 acc[7] += v2 * v2;
                 acc[9] += s[j];
+                if (WANT_P) level_walk<REPLAY>(P, v, threadIdx.x * K3_L + j, n, smA, lev, over);
                 const double raw = __dadd_rn(w, x[j]);
                 if (n == P.n - 1) {
                     P.tail[0] = raw;
@@ -216,6 +296,22 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
                 }
                 w = fmax(0.0, raw);
             }
+        }
+        if (WANT_P) {
+            if (++since_flush == 16) {
+                since_flush = 0;
+                flush_levels();
+            }
+            __syncthreads();  // every level walk has read the staged gaps before the next tile overwrites them
+        }
+    }
+    if (WANT_P) {
+        flush_levels();
+        __syncthreads();
+        if (threadIdx.x <= K3_PBL) {
+            double v = 0.0;
+            for (int wv = 0; wv < K3_THREADS / 32; ++wv) v += lev_w[wv * (K3_PBL + 1) + threadIdx.x];
+            P.level_partial[(long long)blockIdx.x * (K3_PBL + 1) + threadIdx.x] = v;
         }
     }
     // fixed-order CTA reduction of the partial sums
@@ -235,13 +331,20 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
     }
 }
 
-__global__ void k3_final(const double *partial, int grid, double *stats)
+__global__ void k3_final(const double *partial, const double *level_partial, int grid, double *stats)
 {
     const int i = threadIdx.x;
-    if (i >= K3_NSTAT) return;
-    double v = 0.0;
-    for (int b = 0; b < grid; ++b) v += partial[(long long)b * K3_NSTAT + i];
-    stats[i] = v;
+    if (i < K3_NSTAT) {
+        double v = 0.0;
+        for (int b = 0; b < grid; ++b) v += partial[(long long)b * K3_NSTAT + i];
+        stats[i] = v;
+    } else if (i < K3_NSTAT + K3_PBL + 1) {
+        const int m = i - K3_NSTAT;
+        double v = 0.0;
+        if (level_partial)
+            for (int b = 0; b < grid; ++b) v += level_partial[(long long)b * (K3_PBL + 1) + m];
+        stats[i] = v;
+    }
 }
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
@@ -265,38 +368,73 @@ cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st)
 
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st)
 {
+    const bool want_p = P.level_partial != nullptr;
+    const size_t smem = k3_walk_smem(P.replay != 0, want_p);
+    cudaError_t e = cudaSuccess;
     if (P.replay) {
-        cudaError_t e = cudaFuncSetAttribute(k3_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)K3_STAGE_BYTES);
-        if (e != cudaSuccess) return e;
-        k3_walk<true><<<grid, K3_THREADS, K3_STAGE_BYTES, st>>>(P);
+        if (want_p) {
+            e = cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k3_walk<true, true><<<grid, K3_THREADS, smem, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(k3_walk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k3_walk<true, false><<<grid, K3_THREADS, smem, st>>>(P);
+        }
     } else {
-        k3_walk<false><<<grid, K3_THREADS, 0, st>>>(P);
+        if (want_p) {
+            e = cudaFuncSetAttribute(k3_walk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k3_walk<false, true><<<grid, K3_THREADS, smem, st>>>(P);
+        } else {
+            k3_walk<false, false><<<grid, K3_THREADS, 0, st>>>(P);
+        }
     }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
-cudaError_t k3_launch_final(const double *partial, int grid, double *stats, cudaStream_t st)
+size_t k3_walk_smem(bool replay, bool want_p)
 {
-    k3_final<<<1, 32, 0, st>>>(partial, grid, stats);
+    if (!replay && !want_p) return 0;
+    return K3_STAGE_BYTES + (want_p ? K3_LEVEL_BYTES : 0);
+}
+
+cudaError_t k3_launch_final(const double *partial, const double *level_partial, int grid, double *stats,
+                            cudaStream_t st)
+{
+    k3_final<<<1, 64, 0, st>>>(partial, level_partial, grid, stats);
     return cudaGetLastError();
 }
 
-cudaError_t k3_occupancy(bool replay, int *summary_blocks, int *walk_blocks)
+cudaError_t k3_occupancy(bool replay, bool want_p, int *summary_blocks, int *walk_blocks)
 {
     int a = 0, b = 0;
     cudaError_t e;
+    const size_t wsm = k3_walk_smem(replay, want_p);
     if (replay) {
         e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k3_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
-        if (e == cudaSuccess)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
-        if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<true>, K3_THREADS, K3_STAGE_BYTES);
+        if (e == cudaSuccess) {
+            if (want_p) {
+                e = cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+                if (e == cudaSuccess)
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<true, true>, K3_THREADS, wsm);
+            } else {
+                e = cudaFuncSetAttribute(k3_walk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+                if (e == cudaSuccess)
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<true, false>, K3_THREADS, wsm);
+            }
+        }
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false>, K3_THREADS, 0);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<false>, K3_THREADS, 0);
+        if (e == cudaSuccess) {
+            if (want_p) {
+                e = cudaFuncSetAttribute(k3_walk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+                if (e == cudaSuccess)
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<false, true>, K3_THREADS, wsm);
+            } else {
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<false, false>, K3_THREADS, 0);
+            }
+        }
     }
     *summary_blocks = a;
     *walk_blocks = b;

@@ -9,6 +9,7 @@ constexpr int K3_THREADS = 256;   // segments per tile
 constexpr int K3_L = 16;          // jobs per segment (one 128-byte line of fp64 per array per thread)
 constexpr int K3_TOP = 1024;      // threads of the tile-level scan
 constexpr int K3_NSTAT = 16;      // per-block partial sums
+constexpr int K3_NLEVEL = 33;     // T[N >= 1..32] and the time-weighted excess above 32
 
 struct MP {
     double a, b;  // the map w -> max(a, w + b)
@@ -30,12 +31,16 @@ struct K3Params {
     double *tail;       // [2]: W[n-1] + x[n-1] (before clamping), W[n-1] + S[n-1]
     double *W;          // optional per-job waits
     long long ntiles;
+    long long n_ahead;       // jobs of the chain after this range (their gaps follow A[n])
+    double *level_partial;   // optional [grid][K3_NLEVEL]: time-in-state on the scan path
 };
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);
-cudaError_t k3_launch_final(const double *partial, int grid, double *stats, cudaStream_t st);
-cudaError_t k3_occupancy(bool replay, int *summary_blocks, int *walk_blocks);
+cudaError_t k3_launch_final(const double *partial, const double *level_partial, int grid, double *stats,
+                            cudaStream_t st);
+cudaError_t k3_occupancy(bool replay, bool want_p, int *summary_blocks, int *walk_blocks);
+size_t k3_walk_smem(bool replay, bool want_p);
 
 }  // namespace mq

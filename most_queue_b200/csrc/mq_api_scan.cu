@@ -33,13 +33,15 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     P.ntiles = (P.n + tile - 1) / tile;
 
     int occ_s = 0, occ_w = 0;
-    CU(k3_occupancy(replay, &occ_s, &occ_w));
+    const bool want_p = (cfg->flags & MQ_SCAN_WANT_P) != 0;
+    CU(k3_occupancy(replay, want_p, &occ_s, &occ_w));
     if (occ_s < 1 || occ_w < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     run.grid_sum = (int)std::min<long long>(P.ntiles, (long long)occ_s * ctx->sms);
     run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
 
     // scratch: tile_sum, tile_ex, total, tail, partial, stats
-    const size_t bytes = sizeof(MP) * (2 * (size_t)P.ntiles + 1) + sizeof(double) * (2 + (size_t)run.grid_walk * K3_NSTAT + K3_NSTAT);
+    const size_t bytes = sizeof(MP) * (2 * (size_t)P.ntiles + 1) +
+                         sizeof(double) * (2 + (size_t)run.grid_walk * (K3_NSTAT + K3_NLEVEL) + K3_NSTAT + K3_NLEVEL);
     if (int rc = ensure(ctx->rec, bytes)) return rc;
     char *base = (char *)ctx->rec.p;
     P.tile_sum = (MP *)base;
@@ -47,6 +49,8 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     P.total = P.tile_ex + P.ntiles;
     P.tail = (double *)(P.total + 1);
     P.partial = P.tail + 2;
+    P.level_partial = want_p ? P.partial + (size_t)run.grid_walk * K3_NSTAT + K3_NSTAT + K3_NLEVEL : nullptr;
+    P.n_ahead = cfg->jobs_ahead > 0 ? cfg->jobs_ahead : 0;
     if (int rc = ensure_host_agg(ctx, sizeof(double) * 64)) return rc;
 
     if (replay) {
@@ -92,14 +96,14 @@ int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, d
     P.W = dW;
     double *d_stats = P.partial + (size_t)run.grid_walk * K3_NSTAT;
     CU(k3_launch_walk(P, run.grid_walk, ctx->stream));
-    CU(k3_launch_final(P.partial, run.grid_walk, d_stats, ctx->stream));
+    CU(k3_launch_final(P.partial, P.level_partial, run.grid_walk, d_stats, ctx->stream));
     ctx->launches += 2;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     double *h = ctx->h_agg;
-    CU(cudaMemcpyAsync(h, d_stats, sizeof(double) * K3_NSTAT, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(h + 32, P.total, sizeof(MP), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(h + 34, P.tail, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h, d_stats, sizeof(double) * (K3_NSTAT + K3_NLEVEL), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h + 52, P.total, sizeof(MP), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h + 54, P.tail, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     if (W && !cfg->device_ptrs)
         CU(cudaMemcpyAsync(W, dW, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -114,18 +118,19 @@ int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, d
     stats[MQ_S_SUMS] = h[9];
     stats[MQ_S_TAKED] = (double)P.n;
     stats[MQ_S_SERVED] = (double)P.n;
-    stats[MQ_S_A] = h[32];
-    stats[MQ_S_B] = h[33];
+    stats[MQ_S_A] = h[52];
+    stats[MQ_S_B] = h[53];
     stats[MQ_S_WIN] = w_in;
-    stats[MQ_S_WOUT] = std::fmax(h[32], w_in + h[33]);
-    stats[MQ_S_TAILRAW] = h[34];
-    stats[MQ_S_TAILV] = h[35];
-    if (cfg->last_range && h[34] >= 0.0) {
+    stats[MQ_S_WOUT] = std::fmax(h[52], w_in + h[53]);
+    stats[MQ_S_TAILRAW] = h[54];
+    stats[MQ_S_TAILV] = h[55];
+    for (int m = 0; m < K3_NLEVEL; ++m) stats[MQ_S_LEVELS + m] = P.level_partial ? h[K3_NSTAT + m] : 0.0;
+    if (cfg->last_range && h[54] >= 0.0) {
         // job N arrived by the N-th departure: popped there and sampled (base.py:300-305)
-        double pw = h[34];
+        double pw = h[54];
         for (int k = 0; k < 4; ++k) {
             stats[MQ_S_W + k] += pw;
-            pw *= h[34];
+            pw *= h[54];
         }
         stats[MQ_S_TAKED] += 1.0;
     }

@@ -47,8 +47,20 @@ def fold_carries(pairs, w0=0.0):
     return carries, w
 
 
-def run_chain(source, server, total_served: int, seed=None, chain: int = 0, device=None) -> QueueResults:
-    """source / server: (kendall_notation, params) as for QsSim.set_sources / set_servers."""
+def levels_to_p(levels, ttek, p_bins=None):
+    """Time-in-state levels T[N >= m], m = 1..32 (+ the lumped excess) -> p[0..31] and the tail P(N >= 32)."""
+    L = _lib
+    tge = np.asarray(levels[:L.SCAN_NLEVEL - 1], dtype=np.float64)
+    p = np.empty(L.SCAN_NLEVEL - 1)
+    p[0] = 1.0 - tge[0] / ttek
+    p[1:] = (tge[:-1] - tge[1:]) / ttek
+    return [float(x) for x in p], float(tge[-1] / ttek)
+
+
+def run_chain(source, server, total_served: int, seed=None, chain: int = 0, device=None,
+              want_p: bool = True) -> QueueResults:
+    """source / server: (kendall_notation, params) as for QsSim.set_sources / set_servers.
+    want_p: also settle the time-in-state levels (p[0..31]); costs roughly one more pass of arithmetic."""
     start = time.process_time()
     L = _lib
     src, srv = L.make_dist(source[0], source[1]), L.make_dist(server[0], server[1])
@@ -61,14 +73,18 @@ def run_chain(source, server, total_served: int, seed=None, chain: int = 0, devi
     carries, _ = fold_carries(_gather_pairs(ab))
     if count > 0:
         stats, _ = ctx.scan_apply(count, carries[rank], job0=job0, src=src, srv=srv, seed=seed, chain=chain,
-                                  last_range=(rank == world - 1))
+                                  last_range=(rank == world - 1), want_p=want_p,
+                                  jobs_ahead=int(total_served) - (job0 + count))
         timing = ctx.last_timing()
     else:
         stats, timing = np.zeros(L.SCAN_LEN), None
     # everything that sums; the tail belongs to the last range only
     tail = np.array([stats[L.S_TAILV]]) if rank == world - 1 else np.zeros(1)
-    summed = dist.allreduce_sum(np.concatenate([stats[:L.S_A], tail]))
+    levels = stats[L.S_LEVELS:L.S_LEVELS + L.SCAN_NLEVEL]
+    summed = dist.allreduce_sum(np.concatenate([stats[:L.S_A], levels, tail]))
     res = _publish(summed[:L.S_A], float(summed[-1]), source, server)
+    if want_p:
+        res.p, res.p_tail = levels_to_p(summed[L.S_A:L.S_A + L.SCAN_NLEVEL], res.ttek)
     res.duration = time.process_time() - start
     res.timing = timing
     return res
@@ -88,7 +104,8 @@ def _publish(s, tail_v, source, server) -> QueueResults:
     return res
 
 
-def replay_chain(A, S, total_served: int | None = None, ranges: int = 1, want_w: bool = True, device=None):
+def replay_chain(A, S, total_served: int | None = None, ranges: int = 1, want_w: bool = True, device=None,
+                 want_p: bool = False):
     """Replay tier: A[n] = gap before job n (N + 1 entries), S[n] = service of job n.  `ranges` > 1
     evaluates the chain as that many contiguous ranges with summary / carry / apply, exactly what a
     multi-GPU run does, on one GPU.  Returns (stats dict, W array)."""
@@ -102,11 +119,14 @@ def replay_chain(A, S, total_served: int | None = None, ranges: int = 1, want_w:
              for g in range(ranges)]
     carries, w_out = fold_carries(pairs)
     tot = np.zeros(L.S_A)
+    levels = np.zeros(L.SCAN_NLEVEL)
     Ws, tail_v, tail_raw, sim_ms = [], 0.0, 0.0, 0.0
     for g in range(ranges):
         n = bounds[g + 1] - bounds[g]
         stats, W = ctx.scan_apply(n, carries[g], job0=bounds[g], A=A[bounds[g]:], S=S[bounds[g]:],
-                                  last_range=(g == ranges - 1), want_w=want_w)
+                                  last_range=(g == ranges - 1), want_w=want_w, want_p=want_p,
+                                  jobs_ahead=N - bounds[g + 1])
+        levels += stats[L.S_LEVELS:L.S_LEVELS + L.SCAN_NLEVEL]
         sim_ms += ctx.last_timing()["sim_ms"]
         tot += stats[:L.S_A]
         if want_w:
@@ -115,5 +135,7 @@ def replay_chain(A, S, total_served: int | None = None, ranges: int = 1, want_w:
     out = {"w_sum": tot[L.S_W:L.S_W + 4], "v_sum": tot[L.S_V:L.S_V + 4], "taked": int(tot[L.S_TAKED]),
            "served": int(tot[L.S_SERVED]), "sum_a": tot[L.S_SUMA], "sum_s": tot[L.S_SUMS], "pairs": pairs,
            "carries": carries, "w_out": w_out, "tail_raw": tail_raw, "ttek": tot[L.S_SUMA] + tail_v,
-           "sim_ms": sim_ms}
+           "sim_ms": sim_ms, "levels": levels}
+    if want_p:
+        out["p"], out["p_tail"] = levels_to_p(levels, out["ttek"])
     return out, (np.concatenate(Ws) if want_w else None)

@@ -39,7 +39,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.MqDist) == 40
     assert ctypes.sizeof(_lib.MqFifoCfg) == 8 + 8 + 80 + 8 * 4 + 8
     assert ctypes.sizeof(_lib.MqPrioCfg) == 16 + 8 * 5 + 8 + 40 * 16
-    assert ctypes.sizeof(_lib.MqScanCfg) == 80 + 24 + 16
+    assert ctypes.sizeof(_lib.MqScanCfg) == 80 + 24 + 16 + 8
 
 
 def test_no_cpu_fallback_without_device():

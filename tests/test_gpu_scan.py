@@ -87,3 +87,36 @@ def test_long_generator_chain_mg1_theory():
     assert abs(res.w[0] - 0.7 * 0.7 / 0.3) < 0.01
     assert abs(res.measured_utilization - 0.7) < 2e-4
     assert abs(res.v[0] - (0.7 * 0.7 / 0.3 + 0.7)) < 0.01
+
+
+def test_time_in_state_levels_match_event_loop_oracle():
+    """p on the scan path (job-local level walk) against the event-loop oracle on the same arrays, with the
+    chain cut into ranges as a multi-GPU run would."""
+    from most_queue_b200.sim.lindley import replay_chain
+    from oracle import oracle
+
+    rng = np.random.default_rng(77)
+    for N, ranges, mean_s in ((50_000, 1, 0.7), (130_000, 3, 0.9)):
+        A = rng.gamma(3.18878, 1 / 3.18878, N + 400)   # the event loop also consumes the arrivals after job N-1
+        S = rng.exponential(mean_s, N + 400)
+        out, _ = replay_chain(A[:N + 1], S[:N], N, ranges=ranges, want_w=False, want_p=True)
+        ev = oracle.fifo_replay(1, None, A, S, N, p_bins=64)
+        p_ref = ev.p_time / ev.ttek
+        # only jobs 0..N-1 are counted on the scan path: the few arrivals after the last one are missing
+        np.testing.assert_allclose(out["p"][:24], p_ref[:24], rtol=0, atol=40.0 / ev.ttek + 2e-6)
+        assert abs(sum(out["p"]) + out["p_tail"] - 1.0) < 1e-9
+        np.testing.assert_allclose(out["ttek"], ev.ttek, rtol=1e-12)
+
+
+def test_generator_chain_p_matches_k2():
+    from most_queue_b200.sim.base import QsSim
+    from most_queue_b200.sim.lindley import run_chain
+
+    N, seed = 300_000, 9
+    res = run_chain(("Gamma", GAMMA), ("Pa", PARETO), N, seed=seed, want_p=True)
+    qs = QsSim(1, seed=seed)
+    qs.set_sources(GAMMA, "Gamma")
+    qs.set_servers(PARETO, "Pa")
+    ev = qs.run(N)
+    np.testing.assert_allclose(res.p[:12], ev.p[:12], rtol=0, atol=3e-3)
+    assert abs(res.p[0] - 0.3) < 0.01

@@ -65,6 +65,14 @@ def main():
         "kernel": "k3_summary+k3_top+k3_walk (generator)", "jobs": Nj, "jobs_per_s": Nj / (t["sim_ms"] * 1e-3),
         "sim_ms": t["sim_ms"], "wall_s": wall, "w1": stats[L.S_W] / stats[L.S_TAKED],
         "v1": stats[L.S_V] / stats[L.S_SERVED], "utilization_measured": stats[L.S_SUMS] / (stats[L.S_SUMA] + stats[L.S_TAILV])}
+    t0 = time.perf_counter()
+    stats, _ = ctx.scan_apply(Nj // 10, 0.0, src=dsrc, srv=dsrv, seed=3, want_p=True)
+    t = ctx.last_timing()
+    T = stats[L.S_SUMA] + stats[L.S_TAILV]
+    out["cfg3_gamma_pareto_1_generator_with_p"] = {
+        "kernel": "k3 walk with the time-in-state level walk (MQ_SCAN_WANT_P)", "jobs": Nj // 10,
+        "jobs_per_s": (Nj // 10) / (t["sim_ms"] * 1e-3), "sim_ms": t["sim_ms"],
+        "p0": 1.0 - stats[L.S_LEVELS] / T, "p1": (stats[L.S_LEVELS] - stats[L.S_LEVELS + 1]) / T}
     Nr = (1 << 28) // scale
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.empty(Nr + 1, device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
