@@ -359,6 +359,65 @@ int mq_sim_tandem(mq_ctx *ctx, const mq_tandem_cfg *cfg, double *agg, double *re
 int mq_replay_tandem(mq_ctx *ctx, const mq_tandem_cfg *cfg, const double *A, int64_t n_a, const double *const *S,
                      const int64_t *n_s, double *agg, double *rep_out);
 
+/* ---- open network of priority nodes with per-class routing.  Replaces PriorityNetwork(k_num)
+ * .set_sources(L, R) / set_nodes(serv_params, n, prty, nodes_prty) / run(job_served)
+ * (sim/networks/priority_network.py:28,60,87,241) */
+#define MQ_PN_MAX_NODES 8
+#define MQ_PN_MAX_CLASSES 4
+#define MQ_PN_MAX_SERVERS 32 /* sum of channels over all nodes */
+
+typedef struct {
+    int32_t m;                                   /* nodes                                              */
+    int32_t K;                                   /* classes (k_num)                      :28           */
+    int32_t channels[MQ_PN_MAX_NODES];           /* n[i]                                 :87           */
+    int32_t prty[MQ_PN_MAX_NODES];               /* MQ_PRTY_* of node i                  :104-110      */
+    int32_t nodes_prty[MQ_PN_MAX_NODES * MQ_PN_MAX_CLASSES]; /* [i*K + k]: node class of real class k  */
+    double R[MQ_PN_MAX_CLASSES * (MQ_PN_MAX_NODES + 1) * (MQ_PN_MAX_NODES + 1)]; /* K matrices (m+1)x(m+1),  */
+                                                 /* packed with stride m+1, class-major  :60-76        */
+    mq_dist src[MQ_PN_MAX_CLASSES];              /* external flow of class k ("M", L[k]) :82           */
+    mq_dist srv[MQ_PN_MAX_NODES * MQ_PN_MAX_CLASSES]; /* [i*K + j]: service of NODE class j at node i, */
+                                                 /* i.e. serv_params[i][nodes_prty[i][j]] (:129-131)   */
+    int64_t job_served;                          /* run(job_served): departures of all classes :257    */
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+    int32_t queue_cap;                           /* per (node, class) waiting-line capacity (0: 128)   */
+    int32_t flags;
+} mq_prionet_cfg;
+
+/* per-replication record: 2 global rows (ttek, flags), then per class 16 rows, then per (node, node class) 20 */
+#define MQ_PNC_VSUM 0   /* 3: sum of (network sojourn)^k                                   :232      */
+#define MQ_PNC_WSUM 3   /* 3 */
+#define MQ_PNC_VRUN 6   /* 3: v_network[k] running moments                                 :152-161  */
+#define MQ_PNC_WRUN 9   /* 3 */
+#define MQ_PNC_SERVED 12
+#define MQ_PNC_ARRIVED 13
+#define MQ_PNC_AUSED 14
+#define MQ_PNC_ROWS 16
+#define MQ_PNN_VSUM 0   /* 4: node-level sojourn power sums of node class j (qs[i].v[j])              */
+#define MQ_PNN_WSUM 4
+#define MQ_PNN_VRUN 8
+#define MQ_PNN_WRUN 12
+#define MQ_PNN_SERVED 16
+#define MQ_PNN_TAKED 17
+#define MQ_PNN_SUSED 18
+#define MQ_PNN_ROWS 20
+#define MQ_PN_G_TTEK 0
+#define MQ_PN_G_FLAGS 1
+#define MQ_PN_G_UUSED 2
+#define MQ_PN_G_ROWS 4
+#define MQ_PN_REC_ROWS(m, K) (MQ_PN_G_ROWS + (K) * MQ_PNC_ROWS + (m) * (K) * MQ_PNN_ROWS)
+
+/* aggregate: [0] replications, [1] sum ttek, [2] flagged, [3] reserved, then per class 16 entries:
+ * v[3] (sum over reps of v_sum/served), v2[3] (squares), w[3], w2[3], served, arrived, 2 reserved */
+#define MQ_PN_AGG_LEN(K) (4 + 16 * (K))
+
+int mq_sim_prionet(mq_ctx *ctx, const mq_prionet_cfg *cfg, double *agg, double *rep_out);
+/* replay form: A[k] external gaps of class k, U routing uniforms, S[i*K + j] draws of node i, node class j */
+int mq_replay_prionet(mq_ctx *ctx, const mq_prionet_cfg *cfg, const double *const *A, const int64_t *n_a,
+                      const double *U, int64_t n_u, const double *const *S, const int64_t *n_s, double *agg,
+                      double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

@@ -64,6 +64,12 @@ class MqReplayCfg(C.Structure):
 
 MAX_CLASSES = 8
 PRTY = {"NP": 0, "PR": 1, "RS": 2, "RW": 3}
+
+
+def _prty_code(name):
+    if name not in PRTY:
+        raise ValueError(f"prty must be one of {sorted(PRTY)}, got {name!r}")
+    return PRTY[name]
 PG_TTEK, PG_FLAGS, PG_ROWS = 0, 1, 2
 PF_WSUM, PF_VSUM, PF_WRUN, PF_VRUN = 0, 4, 8, 12
 PF_ARRIVED, PF_TAKED, PF_SERVED, PF_DROPPED, PF_INSYS, PF_QUEUED, PF_TOLD, PF_POVER, PF_AUSED, PF_SUSED, PF_P = (
@@ -155,6 +161,34 @@ class MqTandemCfg(C.Structure):
     ]
 
 
+PN_MAX_NODES, PN_MAX_CLASSES, PN_MAX_SERVERS = 8, 4, 32
+
+
+class MqPrionetCfg(C.Structure):
+    _fields_ = [
+        ("m", C.c_int32), ("K", C.c_int32), ("channels", C.c_int32 * PN_MAX_NODES),
+        ("prty", C.c_int32 * PN_MAX_NODES), ("nodes_prty", C.c_int32 * (PN_MAX_NODES * PN_MAX_CLASSES)),
+        ("R", C.c_double * (PN_MAX_CLASSES * (PN_MAX_NODES + 1) * (PN_MAX_NODES + 1))),
+        ("src", MqDist * PN_MAX_CLASSES), ("srv", MqDist * (PN_MAX_NODES * PN_MAX_CLASSES)),
+        ("job_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
+        ("queue_cap", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+# record / aggregate rows of the priority network (include/mqb200.h MQ_PN*)
+PNC_VSUM, PNC_WSUM, PNC_VRUN, PNC_WRUN, PNC_SERVED, PNC_ARRIVED, PNC_AUSED, PNC_ROWS = 0, 3, 6, 9, 12, 13, 14, 16
+PNN_VSUM, PNN_WSUM, PNN_VRUN, PNN_WRUN, PNN_SERVED, PNN_TAKED, PNN_SUSED, PNN_ROWS = 0, 4, 8, 12, 16, 17, 18, 20
+PN_G_TTEK, PN_G_FLAGS, PN_G_UUSED, PN_G_ROWS = 0, 1, 2, 4
+
+
+def prionet_rec_rows(m, K):
+    return PN_G_ROWS + K * PNC_ROWS + m * K * PNN_ROWS
+
+
+def prionet_agg_len(K):
+    return 4 + 16 * K
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -211,6 +245,11 @@ def load():
         L.mq_replay_tandem.restype = C.c_int
         L.mq_replay_tandem.argtypes = [vp, C.POINTER(MqTandemCfg), vp, C.c_int64, C.POINTER(vp),
                                        C.POINTER(C.c_int64), dp, dp]
+        L.mq_sim_prionet.restype = C.c_int
+        L.mq_sim_prionet.argtypes = [vp, C.POINTER(MqPrionetCfg), dp, dp]
+        L.mq_replay_prionet.restype = C.c_int
+        L.mq_replay_prionet.argtypes = [vp, C.POINTER(MqPrionetCfg), C.POINTER(vp), C.POINTER(C.c_int64), vp,
+                                        C.c_int64, C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -510,6 +549,66 @@ class Context:
         check(self._L.mq_replay_tandem(self._h, C.byref(cfg), A.ctypes.data, A.shape[0], ps, ns,
                                        agg.ctypes.data_as(C.POINTER(C.c_double)),
                                        rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
+
+    # ---- K7 ----
+    def _prionet_cfg(self, R, channels, prty, nodes_prty, job_served, replications, rep0, seed, queue_cap):
+        m = len(channels)
+        Rm = np.asarray(R, dtype=np.float64)
+        if Rm.ndim != 3 or Rm.shape[1:] != (m + 1, m + 1):
+            raise ValueError(f"routing matrices must be K x {m + 1} x {m + 1} for {m} nodes")
+        K = Rm.shape[0]
+        if m > PN_MAX_NODES or K > PN_MAX_CLASSES:
+            raise MqError(MQ_E_UNSUPPORTED, f"at most {PN_MAX_NODES} nodes and {PN_MAX_CLASSES} classes")
+        cfg = MqPrionetCfg()
+        cfg.m, cfg.K = m, K
+        for i in range(m):
+            cfg.channels[i] = int(channels[i])
+            cfg.prty[i] = _prty_code(prty[i])
+            for k in range(K):
+                cfg.nodes_prty[i * K + k] = int(nodes_prty[i][k])
+        flat = Rm.reshape(-1)
+        for i in range(flat.size):
+            cfg.R[i] = float(flat[i])
+        cfg.job_served, cfg.replications, cfg.rep0 = int(job_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.queue_cap = int(queue_cap)
+        return cfg
+
+    def sim_prionet(self, R, channels, prty, nodes_prty, src, srv, job_served, replications, rep0, seed,
+                    queue_cap=0, per_replication=False):
+        """src[k]: MqDist of class k's external flow; srv[i][j]: MqDist of NODE class j at node i."""
+        cfg = self._prionet_cfg(R, channels, prty, nodes_prty, job_served, replications, rep0, seed, queue_cap)
+        m, K = cfg.m, cfg.K
+        for k in range(K):
+            cfg.src[k] = src[k]
+        for i in range(m):
+            for j in range(K):
+                cfg.srv[i * K + j] = srv[i][j]
+        agg = np.zeros(prionet_agg_len(K))
+        rec = np.empty((prionet_rec_rows(m, K), int(replications))) if per_replication else None
+        check(self._L.mq_sim_prionet(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                     rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_prionet(self, R, channels, prty, nodes_prty, A, U, S, job_served, queue_cap=0):
+        """A[k]: [n, reps] gaps of class k, U: [n_u, reps] routing uniforms, S[i][j]: [n, reps] draws of node i /
+        node class j (may be empty)."""
+        A = [np.ascontiguousarray(a, dtype=np.float64) for a in A]
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        reps = U.shape[1]
+        S = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1, reps) for row in S for x in row]
+        cfg = self._prionet_cfg(R, channels, prty, nodes_prty, job_served, reps, 0, 0, queue_cap)
+        m, K = cfg.m, cfg.K
+        pa = (C.c_void_p * K)(*[a.ctypes.data for a in A])
+        na = (C.c_int64 * K)(*[a.shape[0] for a in A])
+        ps = (C.c_void_p * (m * K))(*[x.ctypes.data if x.shape[0] else None for x in S])
+        ns = (C.c_int64 * (m * K))(*[x.shape[0] for x in S])
+        agg = np.zeros(prionet_agg_len(K))
+        rec = np.empty((prionet_rec_rows(m, K), reps))
+        check(self._L.mq_replay_prionet(self._h, C.byref(cfg), pa, na, U.ctypes.data, U.shape[0], ps, ns,
+                                        agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                        rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec
 
     def last_timing(self):

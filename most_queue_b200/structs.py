@@ -54,6 +54,21 @@ class NetworkResults:
 
 
 @dataclass
+class NetworkResultsPriority:
+    """Per-class network results (structs.py:132-145 of the reference); w, replications, ci are additive."""
+
+    v: list | None = None
+    intensities: list | None = None
+    loads: list | None = None
+    duration: float = 0.0
+    arrived: list | int = 0
+    served: list | int = 0
+    w: list | None = None
+    replications: int = 1
+    ci: dict | None = field(default=None)
+
+
+@dataclass
 class NetworkMeansResults(NetworkResults):
     """Mean-value results for open networks (structs.py:102-113 of the reference)."""
 

@@ -192,6 +192,29 @@ typedef struct {
 int mqo_tandem_run(int m, const int64_t *capacity, mqo_src *arrivals, mqo_src *services,
                    int64_t total_served, double warmup_fraction, mqo_tandem_out *out);
 
+/* ---- open network of PRIORITY nodes with per-class routing: PriorityNetwork.run
+ * (sim/networks/priority_network.py:241-276) ---- */
+#define MQO_PN_MAX_CLASSES 8
+typedef struct {
+    double v_run[3], w_run[3]; /* v_network[k], w_network[k] (math.pow moments, :152-173) */
+    double v_sum[3], w_sum[3];
+    int64_t served, arrived, in_sys;
+} mqo_pn_class_out;
+
+typedef struct {
+    double v_run[4], w_run[4]; /* qs[node].v[j] / .w[j] for node class j */
+    double v_sum[4], w_sum[4];
+    int64_t arrived, taked, served, in_sys, queued;
+} mqo_pn_node_class_out;
+
+/* m nodes, K classes.  R: K matrices (m+1)x(m+1) row-major, class-major.  prty[i]: MQO_NP / PR / RS / RW of
+ * node i.  nodes_prty[i*K + k]: node class of real class k at node i (:126-133).  arrivals[k]: external gaps of
+ * class k; routing: uniforms in consumption order; services[i*K + j]: draws of node i, NODE class j, in draw
+ * order.  out_cls[K]; out_node[m*K].  Free server = lowest index; victim = first weaker server. */
+int mqo_prionet_run(int m, int K, const int *channels, const int *prty, const int *nodes_prty, const double *R,
+                    mqo_src *arrivals, mqo_src *routing, mqo_src *services, int64_t job_served,
+                    mqo_pn_class_out *out_cls, mqo_pn_node_class_out *out_node, double *ttek_out);
+
 const char *mqo_version(void);
 
 #ifdef __cplusplus

@@ -92,6 +92,17 @@ class MqoTandemOut(C.Structure):
                 ("lost", C.c_int64), ("departures", C.c_int64)]
 
 
+class MqoPnClassOut(C.Structure):
+    _fields_ = [("v_run", C.c_double * 3), ("w_run", C.c_double * 3), ("v_sum", C.c_double * 3),
+                ("w_sum", C.c_double * 3), ("served", C.c_int64), ("arrived", C.c_int64), ("in_sys", C.c_int64)]
+
+
+class MqoPnNodeClassOut(C.Structure):
+    _fields_ = [("v_run", C.c_double * 4), ("w_run", C.c_double * 4), ("v_sum", C.c_double * 4),
+                ("w_sum", C.c_double * 4), ("arrived", C.c_int64), ("taked", C.c_int64), ("served", C.c_int64),
+                ("in_sys", C.c_int64), ("queued", C.c_int64)]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
@@ -148,6 +159,10 @@ def lib():
         L.mqo_tandem_run.restype = C.c_int
         L.mqo_tandem_run.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(MqoSrc), C.POINTER(MqoSrc),
                                      C.c_int64, C.c_double, C.POINTER(MqoTandemOut)]
+        L.mqo_prionet_run.restype = C.c_int
+        L.mqo_prionet_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), dp,
+                                      C.POINTER(MqoSrc), C.POINTER(MqoSrc), C.POINTER(MqoSrc), C.c_int64,
+                                      C.POINTER(MqoPnClassOut), C.POINTER(MqoPnNodeClassOut), dp]
         L.mqo_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -467,3 +482,72 @@ def tandem_generate(capacity, source, servers, total_served, seed, rep, warmup_f
     m = len(capacity)
     return _tandem_run(capacity, _gen_src(source, seed, m, rep, 0),
                        [_gen_src(servers[i], seed, i, rep, 1) for i in range(m)], total_served, warmup_fraction)
+
+
+# --------------------------------------------------------------------------- priority network
+@dataclass
+class PrioNetResult:
+    v: np.ndarray        # [K][3] v_network running moments
+    w: np.ndarray
+    v_sum: np.ndarray
+    w_sum: np.ndarray
+    served: np.ndarray
+    arrived: np.ndarray
+    ttek: float
+    node_v: np.ndarray   # [m][K][4]
+    node_w: np.ndarray
+    node_served: np.ndarray
+    node_taked: np.ndarray
+    a_used: np.ndarray
+    u_used: int
+    s_used: np.ndarray   # [m][K]
+
+
+def _prionet_run(R, channels, prty, nodes_prty, arrivals, routing, services, job_served) -> PrioNetResult:
+    m, K = len(channels), len(arrivals)
+    Rm = np.ascontiguousarray(np.asarray(R, dtype=np.float64))
+    assert Rm.shape == (K, m + 1, m + 1)
+    ch = (C.c_int * m)(*[int(x) for x in channels])
+    pt = (C.c_int * m)(*[PRTY[x] for x in prty])
+    npr = (C.c_int * (m * K))(*[int(nodes_prty[i][k]) for i in range(m) for k in range(K)])
+    A = (MqoSrc * K)(*arrivals)
+    S = (MqoSrc * (m * K))(*[services[i][j] for i in range(m) for j in range(K)])
+    oc = (MqoPnClassOut * K)()
+    on = (MqoPnNodeClassOut * (m * K))()
+    ttek = C.c_double()
+    rc = lib().mqo_prionet_run(m, K, ch, pt, npr, _dp(Rm), A, C.byref(routing), S, int(job_served), oc, on,
+                               C.byref(ttek))
+    if rc != 0:
+        raise RuntimeError(f"oracle prionet run failed rc={rc}")
+    gc = lambda n: np.array([list(getattr(oc[k], n)) for k in range(K)])
+    gn = lambda n: np.array([[list(getattr(on[i * K + k], n)) for k in range(K)] for i in range(m)])
+    fn = lambda n: np.array([[getattr(on[i * K + k], n) for k in range(K)] for i in range(m)])
+    return PrioNetResult(v=gc("v_run"), w=gc("w_run"), v_sum=gc("v_sum"), w_sum=gc("w_sum"),
+                         served=np.array([oc[k].served for k in range(K)]),
+                         arrived=np.array([oc[k].arrived for k in range(K)]), ttek=ttek.value,
+                         node_v=gn("v_run"), node_w=gn("w_run"), node_served=fn("served"), node_taked=fn("taked"),
+                         a_used=np.array([A[k].pos for k in range(K)]), u_used=routing.pos,
+                         s_used=np.array([[S[i * K + k].pos for k in range(K)] for i in range(m)]))
+
+
+def prionet_replay(R, channels, prty, nodes_prty, A, U, S, job_served) -> PrioNetResult:
+    """PriorityNetwork.run(): A[k] external gaps of class k, U routing uniforms, S[node][node_class] draws."""
+    A = [np.ascontiguousarray(a, dtype=np.float64) for a in A]
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    S = [[np.ascontiguousarray(x, dtype=np.float64) for x in row] for row in S]
+    return _prionet_run(R, channels, prty, nodes_prty, [_replay_src(a) for a in A], _replay_src(U),
+                        [[_replay_src(x) for x in row] for row in S], job_served)
+
+
+def prionet_generate(R, channels, prty, nodes_prty, sources, servers, job_served, seed, rep) -> PrioNetResult:
+    """Generator mode: stream sid = i*K + j serves node i / node class j (word 1), sid = m*K + k gives class k's
+    external gaps (word 0), sid = m*K + K the routing uniforms (word 1).  servers[i][j] is the law of NODE class j."""
+    m, K = len(channels), len(sources)
+
+    class U01:
+        mean, half_interval = 0.5, 0.5
+
+    return _prionet_run(R, channels, prty, nodes_prty, [_gen_src(sources[k], seed, m * K + k, rep, 0) for k in range(K)],
+                        _gen_src(("Uniform", U01), seed, m * K + K, rep, 1),
+                        [[_gen_src(servers[i][j], seed, i * K + j, rep, 1) for j in range(K)] for i in range(m)],
+                        job_served)

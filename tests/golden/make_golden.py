@@ -293,6 +293,72 @@ def make_net():
              [rng.exponential(1.0, 3 * n)], n)
 
 
+# --------------------------------------------------------------------------- priority network
+def prionet_case(name, R, channels, prty, nodes_prty, A, U, S, job_served):
+    import numpy
+
+    from most_queue.sim.networks.priority_network import PriorityNetwork
+
+    m, K = len(channels), len(A)
+    qn = PriorityNetwork(K)
+    qn.set_sources([1.0] * K, [np.matrix(R[k]) for k in range(K)])
+    qn.set_nodes([[{"type": "M", "params": 1.0} for _ in range(K)] for _ in range(m)], channels, prty, nodes_prty)
+    ia = [[0] for _ in range(K)]
+    iu = [0]
+    isv = [[[0] for _ in range(K)] for _ in range(m)]
+    for k in range(K):
+        qn.sources[k] = ReplayDist(A[k], ia[k])
+        qn.arrival_time[k] = qn.sources[k].generate()  # the draw set_sources makes (:83)
+    for i in range(m):
+        for srv in qn.qs[i].servers:
+            srv.dist = [ReplayDist(S[i][j], isv[i][j]) for j in range(K)]  # indexed by NODE class
+        qn.qs[i]._free_servers = LowestFirstSet(range(channels[i]))
+    ureplay = ReplayDist(U, iu)
+    orig = numpy.random.rand
+    numpy.random.rand = ureplay.generate  # choose_next_node (:145)
+    try:
+        with quiet():
+            while sum(qn.served) < job_served:  # run() minus tqdm (:257-258)
+                qn.run_one_step()
+    finally:
+        numpy.random.rand = orig
+    out = dict(R=np.array(R, dtype=np.float64), channels=np.array(channels), prty=np.array(prty),
+               nodes_prty=np.array(nodes_prty), job_served=job_served, U=np.asarray(U), ttek=float(qn.ttek),
+               served=np.array(qn.served), arrived=np.array(qn.arrived),
+               v=np.array(qn.v_network, dtype=np.float64), w=np.array(qn.w_network, dtype=np.float64),
+               a_used=np.array([x[0] for x in ia]), u_used=iu[0],
+               s_used=np.array([[isv[i][j][0] for j in range(K)] for i in range(m)]),
+               node_v=np.array([q.v for q in qn.qs], dtype=np.float64),
+               node_w=np.array([q.w for q in qn.qs], dtype=np.float64),
+               node_served=np.array([q.served for q in qn.qs]), node_taked=np.array([q.taked for q in qn.qs]))
+    for k in range(K):
+        out[f"A{k}"] = np.asarray(A[k])
+    for i in range(m):
+        for j in range(K):
+            out[f"S{i}_{j}"] = np.asarray(S[i][j])
+    np.savez_compressed(os.path.join(OUT, f"prionet_{name}.npz"), **out)
+    print(f"prionet_{name}: served={qn.served} v1={[round(float(x[0]), 4) for x in qn.v_network]} u_used={iu[0]}")
+
+
+def make_prionet():
+    rng = np.random.default_rng(20260505)
+    n = 2000
+    # 3 nodes, 2 classes, class-dependent routing, identity class maps
+    R0 = [[1, 0, 0, 0], [0, 0, 0.7, 0.3], [0, 0, 0, 1], [0, 0, 0, 1]]
+    R1 = [[0.5, 0.5, 0, 0], [0, 0, 0, 1], [0.2, 0, 0.3, 0.5], [0, 0, 0, 1]]
+    ch = [2, 1, 2]
+    for prty in ("NP", "PR", "RS", "RW"):
+        A = [rng.exponential(2.0, 2 * n), rng.exponential(1.6, 2 * n)]
+        S = [[rng.gamma(1.5, 0.5 / 1.5 * (1 + i + j), 6 * n) for j in range(2)] for i in range(3)]
+        prionet_case(f"m3k2_{prty}", [R0, R1], ch, [prty] * 3, [[0, 1], [0, 1], [0, 1]], A, rng.random(12 * n), S, n)
+    # mixed disciplines and a node that inverts the priorities (tests/test_network_im_prty.py style)
+    A = [rng.exponential(2.5, 2 * n), rng.exponential(2.0, 2 * n), rng.exponential(3.0, 2 * n)]
+    Rk = [[[1, 0, 0], [0, 0, 1], [0, 0, 1]] if k != 1 else [[0.6, 0.4, 0], [0, 0.5, 0.5], [0.1, 0, 0.9]]
+          for k in range(3)]
+    S = [[rng.exponential(0.5 + 0.2 * j, 8 * n) for j in range(3)] for i in range(2)]
+    prionet_case("m2k3_mixed", Rk, [2, 3], ["PR", "NP"], [[0, 1, 2], [2, 1, 0]], A, rng.random(12 * n), S, n)
+
+
 # --------------------------------------------------------------------------- tandem with blocking
 def tandem_case(name, capacity, A, S, total_served, warmup_fraction=0.05):
     from most_queue.sim.networks.tandem_blocking import TandemBlockingSim
@@ -390,13 +456,15 @@ def make_theory():
 
 if __name__ == "__main__":
     import_reference()
-    which = sys.argv[1:] or ["fifo", "prio", "net", "tandem", "theory"]
+    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "theory"]
     if "fifo" in which:
         make_fifo()
     if "prio" in which:
         make_prio()
     if "net" in which and "make_net" in globals():
         make_net()
+    if "prionet" in which:
+        make_prionet()
     if "tandem" in which:
         make_tandem()
     if "theory" in which:

@@ -19,7 +19,8 @@ def _declared():
 def test_header_declares_the_hot_path_entry_points():
     names = _declared()
     for must in ("mq_create", "mq_destroy", "mq_sim_fifo", "mq_replay_fifo", "mq_sim_prio", "mq_replay_prio",
-                 "mq_sim_net", "mq_replay_net", "mq_scan_gg1", "mq_scan_gg1_summary", "mq_scan_gg1_apply",
+                 "mq_sim_net", "mq_replay_net", "mq_sim_tandem", "mq_replay_tandem", "mq_sim_prionet",
+                 "mq_replay_prionet", "mq_scan_gg1", "mq_scan_gg1_summary", "mq_scan_gg1_apply",
                  "mq_last_error", "mq_version", "mq_device_count"):
         assert must in names
 
@@ -40,6 +41,10 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.MqFifoCfg) == 8 + 8 + 80 + 8 * 4 + 8
     assert ctypes.sizeof(_lib.MqPrioCfg) == 16 + 8 * 5 + 8 + 40 * 16
     assert ctypes.sizeof(_lib.MqScanCfg) == 80 + 24 + 16 + 8
+    # sizeof() printed by gcc for include/mqb200.h
+    assert ctypes.sizeof(_lib.MqNetCfg) == 3104
+    assert ctypes.sizeof(_lib.MqTandemCfg) == 856
+    assert ctypes.sizeof(_lib.MqPrionetCfg) == 4272
 
 
 def test_no_cpu_fallback_without_device():
