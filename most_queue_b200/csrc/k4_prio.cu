@@ -131,8 +131,10 @@ __global__ void __launch_bounds__(K4_BLOCK) k4_prio(const K4Params P)
             const double t = *qslot(k, slot, 3);
             jb.is_pr = t >= 0.0;
             jb.tte = t;
-            qhead[k] = slot + 1 >= P.qcap ? 0 : slot + 1;
             qsize[k]--;
+            // an emptied line restarts at slot 0: the ring only ever touches as many slots as the line was long,
+            // so its footprint stays cache-resident instead of walking all of qcap
+            qhead[k] = (qsize[k] == 0 || slot + 1 >= P.qcap) ? 0 : slot + 1;
             return jb;
         };
         auto p_add = [&](int k, double dt) {

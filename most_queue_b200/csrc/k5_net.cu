@@ -228,8 +228,9 @@ __global__ void __launch_bounds__(K5_BLOCK) k5_net(const K5Params P)
                     qj.arr_network = *qslot(node, slot, 0);
                     qj.wait_network = *qslot(node, slot, 1);
                     qj.arr_time = *qslot(node, slot, 2);
-                    qhead[node] = slot + 1 >= P.qcap ? 0 : slot + 1;
                     qsize[node]--;
+                    // an emptied line restarts at slot 0 (keeps the ring's footprint cache-resident)
+                    qhead[node] = (qsize[node] == 0 || slot + 1 >= P.qcap) ? 0 : slot + 1;
                     n_taked[node]++;
                     const double d = __dsub_rn(ttek, qj.arr_time);
                     const double wt = __dadd_rn(0.0, d);

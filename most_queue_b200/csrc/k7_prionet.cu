@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(K7_BLOCK) k7_prionet(const K7Params P)
             jb.k = pk & 255;
             jb.node_class = (pk >> 8) & 255;
             jb.is_pr = pk >> 16;
-            qhead[nk] = slot + 1 >= P.qcap ? 0 : slot + 1;
             qsize[nk]--;
+            // an emptied line restarts at slot 0 (keeps the ring's footprint cache-resident)
+            qhead[nk] = (qsize[nk] == 0 || slot + 1 >= P.qcap) ? 0 : slot + 1;
             return jb;
         };
         auto choose_next = [&](int real, int cur) -> int {

@@ -28,8 +28,7 @@ __global__ void __launch_bounds__(256) bench(uint32_t *out, uint32_t seed)
                 uint32_t lo, hi;
                 asm volatile("{ .reg .u64 t; mul.wide.u32 t, %2, 0xD256D193; mov.b64 {%0, %1}, t; }"
                              : "=r"(lo), "=r"(hi) : "r"(a[i]));
-                a[i] = lo;
-                b[i] = hi;
+                a[i] = lo + hi;  // one IADD keeps both halves live (IADD issues at full rate)
             } else if (OP == 1) {  // LOP3 (3-input xor)
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
             } else if (OP == 2) {  // FFMA
@@ -44,8 +43,14 @@ __global__ void __launch_bounds__(256) bench(uint32_t *out, uint32_t seed)
             } else if (OP == 6) {  // IMAD (32-bit low product + add)
                 asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
             } else if (OP == 7) {  // FSEL / SEL through setp + selp
-                asm volatile("{ .reg .pred p; setp.lt.f32 p, %0, %1; selp.f32 %0, %1, %0, p; }"
-                             : "+f"(f[i]) : "f"(g[i]));
+                asm volatile("{ .reg .pred p; setp.lt.f32 p, %0, %1; selp.f32 %0, %2, %0, p; }"
+                             : "+f"(f[i]) : "f"(g[i]), "f"(g[(i + 3) % CHAINS]));
+            } else if (OP == 9) {  // one Philox2x32 round: IMAD.WIDE.U32 + 3-input LOP3
+                uint32_t lo, hi;
+                asm volatile("{ .reg .u64 t; mul.wide.u32 t, %2, 0xD256D193; mov.b64 {%0, %1}, t; }"
+                             : "=r"(lo), "=r"(hi) : "r"(a[i]));
+                asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a[i]) : "r"(hi), "r"(b[i]), "r"(seed + it));
+                b[i] = lo;
             } else if (OP == 8) {  // DFMA
                 double d;
                 asm volatile("{ .reg .f64 x, y; cvt.f64.f32 x, %1; cvt.f64.f32 y, %2; fma.rn.f64 %0, x, y, x; }"
@@ -94,7 +99,7 @@ int main()
     cudaMalloc(&out, 4);
     const int sms = p.multiProcessorCount;
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d, \"unit\": \"lane-ops per clock per SM at clock_khz\"", p.name, sms, khz);
-    printf(", \"imad_wide_u32\": %.1f", run<0>(sms, 1, out, khz));
+    printf(", \"imad_wide_u32_plus_iadd\": %.1f", run<0>(sms, 1, out, khz));
     printf(", \"lop3\": %.1f", run<1>(sms, 1, out, khz));
     printf(", \"ffma\": %.1f", run<2>(sms, 1, out, khz));
     printf(", \"fmnmx\": %.1f", run<3>(sms, 2, out, khz));
@@ -103,6 +108,7 @@ int main()
     printf(", \"imad_lo\": %.1f", run<6>(sms, 1, out, khz));
     printf(", \"setp_selp\": %.1f", run<7>(sms, 1, out, khz));
     printf(", \"cvt_dfma_cvt\": %.1f", run<8>(sms, 1, out, khz));
+    printf(", \"philox_round_imadwide_plus_lop3\": %.1f", run<9>(sms, 1, out, khz));
     printf("}\n");
     return 0;
 }
