@@ -277,12 +277,14 @@ def _get(params, name):
     return getattr(params, name)
 
 
-def make_dist(kendall_notation: str, params) -> MqDist:
+def make_dist(kendall_notation: str, params, weibull_ok: bool = False) -> MqDist:
     """(Kendall code, reference-style params) -> mq_dist.
 
     Unknown codes raise ValueError exactly like create_distribution (random/utils/create.py:76).
     """
-    if kendall_notation not in KINDS or kendall_notation == "Weibull":
+    # create_distribution knows no Kendall code for Weibull (create.py:48-77); only the Weibull class itself
+    # (random/distributions.py) reaches the sampler
+    if kendall_notation not in KINDS or (kendall_notation == "Weibull" and not weibull_ok):
         raise ValueError(
             "Incorrect distribution type specified. Supported: M, H, E, Gamma, C, Pa, Uniform, Norm, D"
         )
@@ -306,6 +308,8 @@ def make_dist(kendall_notation: str, params) -> MqDist:
         vals = [float(_get(params, "mean")), float(_get(params, "half_interval"))]
     elif k == "Norm":
         vals = [float(_get(params, "mean")), float(_get(params, "std_dev"))]
+    elif k == "Weibull":
+        vals = [float(_get(params, "k")), float(_get(params, "W"))]
     else:  # pragma: no cover
         raise ValueError(k)
     for i, v in enumerate(vals):

@@ -449,6 +449,29 @@ def make_theory():
         pa = ParetoDistribution.get_params_by_mean_and_cv(mean, cv)
         fits[f"pareto_{mean}_{cv}"] = [float(pa.alpha), float(pa.K)]
     out["fits"] = fits
+    # moments of the remaining samplers' laws (most_queue/random/distributions.py calc_theory_moments)
+    from most_queue.random.distributions import (CoxDistribution, DeterministicDistribution, ErlangDistribution,
+                                                 ExpDistribution, NormalDistribution, UniformDistribution)
+    from most_queue.random.utils.params import Cox2Params, GaussianParams, UniformParams
+
+    u = UniformDistribution.get_params_by_mean_and_cv(2.0, 0.4)
+    n = NormalDistribution.get_params_by_mean_and_cv(5.0, 0.2)
+    e = ErlangDistribution.get_params_by_mean_and_cv(2.0, 0.5)
+    out["laws"] = {
+        "uniform": {"params": [float(u.mean), float(u.half_interval)],
+                    "moments": list(map(float, UniformDistribution.calc_theory_moments(u, 3))),
+                    "refit": [float(x) for x in (lambda q: (q.mean, q.half_interval))(
+                        UniformDistribution.get_params(UniformDistribution.calc_theory_moments(u, 3)))]},
+        "normal": {"params": [float(n.mean), float(n.std_dev)],
+                   "moments": list(map(float, NormalDistribution.calc_theory_moments(n, 2)))[:2]},
+        "cox": {"params": [0.7, 2.0, 0.5],
+                "moments": list(map(float, np.real(CoxDistribution.calc_theory_moments(
+                    Cox2Params(p1=0.7, mu1=2.0, mu2=0.5), 3))))},
+        "det": {"params": 1.7, "moments": list(map(float, DeterministicDistribution.calc_theory_moments(1.7, 3)))},
+        "erlang": {"params": [int(e.r), float(e.mu)],
+                   "moments": list(map(float, ErlangDistribution.calc_theory_moments(e, 3)))},
+        "exp": {"params": 0.8, "moments": list(map(float, ExpDistribution.calc_theory_moments(0.8, 3)))},
+    }
     with open(os.path.join(OUT, "theory.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("theory.json written")
