@@ -47,8 +47,6 @@ struct K1Params {
     const double *S;  // [n_s][reps]
     double *rec;      // [MQ_REPLAY_ROWS(p_bins)][reps], zeroed by the caller
     double *ring;     // finite buffer: [buffer][reps]
-    const double2 *inv;  // inv[k] = {1/k, 1 - 1/k} (round-to-nearest), k = 0..n_inv-1; shared by all lanes
-    long long n_inv;
 };
 
 constexpr size_t k1_smem_bytes(int ct) { return sizeof(double) * MQ_K1_BLOCK * (size_t)(MQ_K1_BF + MQ_K1_MOM + ct); }
@@ -89,7 +87,7 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
     long long ia = 1, is = 0;
     // infinite: lag cursor (index and arrival time of the queue head); finite: ring head
     long long h = 0;
-    double a_h = 0.0;
+    double a_h = 0.0, a_lag = 0.0;  // a_lag = A[h + 1], loaded one trip before the cursor moves
     long long head = 0;
     double p_over = 0.0;
     int status = 0;
@@ -100,7 +98,7 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
     if (P.n_a < 1) status = MQ_E_INPUT_SHORT;
     // the next draw of each stream is loaded one trip ahead of its use (hides the HBM latency)
     double a_next = P.n_a > 1 ? A[R] : 0.0;  // default caching: the lag cursor re-reads these rows from L2
-    double s_next = P.n_s > 0 ? __ldcs(S) : 0.0;
+    double s_next = P.n_s > 0 ? S[0] : 0.0;
 
     while (status == 0 && (pend != 0 || served < N)) {
         // _get_min_server_time base.py:312-325: strict '<', lowest index wins ties (pairwise tree, left operand
@@ -135,8 +133,9 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
                 double *hp = hist + (int)in_sys * MQ_K1_BLOCK;
                 *hp = __dadd_rn(*hp, dt);
             } else if (in_sys < P.p_bins) {
-                double *gp = &rec[(MQ_F_P + in_sys) * R];
-                *gp = __dadd_rn(*gp, dt);
+                // far states accumulate in the (zeroed) record with a fire-and-forget fp64 reduction: same
+                // round-to-nearest add, same order (one lane, one address), and no load to wait for
+                atomicAdd(&rec[(MQ_F_P + in_sys) * R], dt);
             } else {
                 p_over = __dadd_rn(p_over, dt);
             }
@@ -175,7 +174,8 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
             a_head = a_h;
             const bool more = is_pstart && q > 1;
             h += more;
-            if (more) a_h = __dadd_rn(a_h, A[h * R]);
+            a_h = more ? __dadd_rn(a_h, a_lag) : a_h;
+            if (first || more) a_lag = A[(h + 1) * R];  // h + 1 <= ia - 1 < n_a while somebody waits
             q += (long long)arr_q - (long long)is_pstart;
         } else {
             const bool accept = arr_q && q < cap;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
         const double e_new = __dadd_rn(ttek, s_next);  // servers.py:88
         is += start;
         if (start) {
-            s_next = is < P.n_s ? __ldcs(S + is * R) : 0.0;
+            s_next = is < P.n_s ? S[is * R] : 0.0;
             vv[slot * MQ_K1_BLOCK] = __dsub_rn(e_new, a_job);  // what serving() will compute as ttek - arrival
         }
         busy = start ? (busy | (1u << slot)) : busy;
@@ -224,15 +224,8 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
         if (which >= 0) {
             // refresh_moments_stat, stats_update.py:6-22, op for op (the busy period keeps 3 moments in the
             // reference; the 4th computed here is never read), plus the power sums the aggregate uses
-            double inv_count, one_minus;
-            if (count < P.n_inv) {  // 1/count and 1 - 1/count from the shared table (same roundings)
-                const double2 t = __ldg(P.inv + count);
-                inv_count = t.x;
-                one_minus = t.y;
-            } else {
-                inv_count = __ddiv_rn(1.0, (double)count);
-                one_minus = __dsub_rn(1.0, inv_count);
-            }
+            const double inv_count = __drcp_rn((double)count);  // == 1.0 / count, correctly rounded
+            const double one_minus = __dsub_rn(1.0, inv_count);
             double *mp = mom + which * (8 * MQ_K1_BLOCK);
             const bool sums = which < 2;
             double power = x;

@@ -172,15 +172,6 @@ static cudaError_t k1_dispatch(int ct, const K1Params &P, bool fin, cudaStream_t
     }
 }
 
-// the two constants of refresh_moments_stat (stats_update.py:16-17) for every count a run can reach
-__global__ void k1_fill_inv(double2 *inv, long long n)
-{
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double ic = k > 0 ? __ddiv_rn(1.0, (double)k) : 0.0;
-    inv[k] = make_double2(ic, __dsub_rn(1.0, ic));
-}
-
 __global__ void debug_philox_kernel(uint32_t c0, uint32_t c1, uint32_t key, uint32_t *out)
 {
     uint2 w = philox2x32_10(c0, c1, key);
@@ -388,16 +379,6 @@ int mq_replay_fifo(mq_ctx *ctx, const mq_replay_cfg *cfg, const double *A, const
     if (finite && cfg->buffer > 0) {
         if (int rc = ensure(ctx->ring, sizeof(double) * (size_t)cfg->buffer * (size_t)R)) return rc;
         P.ring = (double *)ctx->ring.p;
-    }
-    // table of 1/k, 1 - 1/k for every sample count the run can reach
-    {
-        const long long n_inv = std::min<long long>(cfg->n_s + 2, 1ll << 26);
-        if (int rc = ensure(ctx->desc, sizeof(double2) * (size_t)n_inv)) return rc;
-        k1_fill_inv<<<(unsigned)((n_inv + 255) / 256), 256, 0, ctx->stream>>>((double2 *)ctx->desc.p, n_inv);
-        CU(cudaGetLastError());
-        ctx->launches++;
-        P.inv = (const double2 *)ctx->desc.p;
-        P.n_inv = n_inv;
     }
     CU(cudaMemsetAsync(ctx->rec.p, 0, rec_bytes, ctx->stream));
     // the timed "sim" span starts after the input copies

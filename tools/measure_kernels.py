@@ -38,8 +38,22 @@ def main():
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     ctx = _lib.default_context(0)
     L = _lib
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle
+
+    ncpu = os.cpu_count() or 1
+
+    def cpu_rate(fn, jobs_per_call, calls):
+        """jobs/s of the CPU oracle port (oracle/, fp64, the same event loop) on all host threads: `calls`
+        independent replications through ctypes (the GIL is released inside the C call)."""
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(ncpu) as ex:
+            list(ex.map(fn, range(calls)))
+        return jobs_per_call * calls / (time.perf_counter() - t0)
     out = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": hbm}
     scale = 10 if args.quick else 1
+    args_quick = args.quick
 
     # ---- cfg1: M/M/3/100 (README quick start), 1e4 replications x 1e5 jobs, K2 finite buffer ----
     R, N = 10000, 100000 // scale
@@ -109,6 +123,11 @@ def main():
                                     "v1_class0": agg[b0 + 8] / R, "v1_class1": agg[b1 + 8] / R,
                                     "w1_class0": agg[b0] / R, "w1_class1": agg[b1] / R}
 
+    gsrv = [("Gamma", g0), ("Gamma", g1)]
+    out["cfg4_prio_PR"]["cpu_oracle_jobs_per_s"] = cpu_rate(
+        lambda r: oracle.prio_generate(4, 2, "PR", [("M", 0.3), ("M", 0.5)], gsrv, 20000, 7, r), 20000, 4 * ncpu)
+    out["cfg4_prio_PR"]["cpu_threads"] = ncpu
+
     # ---- cfg5: 5-node open network of H2 nodes (K5) ----
     R, N = 100000 // scale, 10000
     nsrv = [L.make_dist("H", H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2)) for c in NET_CH]
@@ -120,6 +139,66 @@ def main():
                            "network_jobs_per_s": agg[3] / (t["sim_ms"] * 1e-3),
                            "node_services_per_s": agg[3] * visits / (t["sim_ms"] * 1e-3), "visits_per_job": visits,
                            "sim_ms": t["sim_ms"], "v1": agg[5] / R}
+    h2n = [("H", H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2)) for c in NET_CH]
+    out["cfg5_network"]["cpu_oracle_network_jobs_per_s"] = cpu_rate(
+        lambda r: oracle.net_generate(NET_R, NET_CH, ("M", 1.0), h2n, 5000, 9, r), 5000, 4 * ncpu)
+    out["cfg5_network"]["cpu_threads"] = ncpu
+
+    # ---- tandem line with blocking (K6) and network of priority nodes (K7) ----
+    caps = [5, 3, 3, 2]
+    tsrv = [("M", 1.2), ("M", 1.0), ("M", 1.1), ("M", 1.3)]
+    R, N = 200000 // scale, 10000
+    ctx.sim_tandem(caps, L.make_dist("M", 0.9), [L.make_dist(*x) for x in tsrv], 500, 0.05, 4096, 0, 5)
+    agg, _ = ctx.sim_tandem(caps, L.make_dist("M", 0.9), [L.make_dist(*x) for x in tsrv], N, 0.05, R, 0, 5)
+    t = ctx.last_timing()
+    out["tandem_blocking_4_nodes"] = {
+        "kernel": "k6_tandem", "replications": R, "jobs": N, "jobs_per_s": R * N / (t["sim_ms"] * 1e-3),
+        "sim_ms": t["sim_ms"], "cpu_threads": ncpu,
+        "cpu_oracle_jobs_per_s": cpu_rate(lambda r: oracle.tandem_generate(caps, ("M", 0.9), tsrv, 20000, 5, r),
+                                          20000, 4 * ncpu)}
+    R0 = [[1, 0, 0, 0], [0, 0, 0.7, 0.3], [0, 0, 0, 1], [0, 0, 0, 1]]
+    R1 = [[0.5, 0.5, 0, 0], [0, 0, 0, 1], [0.2, 0, 0.3, 0.5], [0, 0, 0, 1]]
+    pn = dict(ch=[2, 1, 2], prty=["PR", "NP", "RS"], npr=[[0, 1], [1, 0], [0, 1]])
+    psv = [[("H", H2Distribution.get_params_by_mean_and_cv(0.5 + 0.2 * j + 0.1 * i, 1.3)) for j in range(2)]
+           for i in range(3)]
+    R, N = 100000 // scale, 5000
+    args = ([R0, R1], pn["ch"], pn["prty"], pn["npr"], [L.make_dist("M", 0.6), L.make_dist("M", 0.7)],
+            [[L.make_dist(*x) for x in row] for row in psv])
+    ctx.sim_prionet(*args, 500, 4096, 0, 11)
+    agg, _ = ctx.sim_prionet(*args, N, R, 0, 11)
+    t = ctx.last_timing()
+    out["priority_network_3_nodes_2_classes"] = {
+        "kernel": "k7_prionet", "replications": R, "network_jobs": N,
+        "network_jobs_per_s": R * N / (t["sim_ms"] * 1e-3), "sim_ms": t["sim_ms"], "cpu_threads": ncpu,
+        "cpu_oracle_network_jobs_per_s": cpu_rate(
+            lambda r: oracle.prionet_generate([R0, R1], pn["ch"], pn["prty"], pn["npr"], [("M", 0.6), ("M", 0.7)],
+                                              psv, 5000, 11, r), 5000, 4 * ncpu)}
+
+    # ---- cfg2r: replay tier (K1), 65 536 replications x 2 048 jobs of M/H2/8, inputs resident in HBM ----
+    R, N = 65536, 2048 // (2 if args_quick else 1)
+    h2 = H2Distribution.get_params_by_mean_and_cv(5.6, 1.5)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.empty((N + 256, R), device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
+    u = torch.rand((N + 256, R), device="cuda", dtype=torch.float64, generator=g)
+    S = torch.empty((N + 256, R), device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
+    S = torch.where(u < h2.p1, S / h2.mu1, S / h2.mu2).contiguous()
+    del u
+    rec = torch.empty((L.replay_rows(64), R), device="cuda", dtype=torch.float64)
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(4):
+        ctx.replay_fifo_device(8, None, A.data_ptr(), S.data_ptr(), N + 256, N + 256, R, N, rec.data_ptr(), p_bins=64)
+        if i:
+            ms.append(ctx.last_timing()["sim_ms"])
+    tm = float(np.mean(ms)) * 1e-3
+    a1, s1 = A[:, 0].cpu().numpy().copy(), S[:, 0].cpu().numpy().copy()
+    out["cfg2r_replay"] = {
+        "kernel": "k1_fifo_replay<8,infinite>", "replications": R, "jobs": N, "jobs_per_s": R * N / tm,
+        "sim_ms": tm * 1e3, "cpu_threads": ncpu,
+        "cpu_oracle_jobs_per_s": cpu_rate(lambda r: oracle.fifo_replay(8, None, a1, s1, N), N, 64 * ncpu),
+        "roofline": {"bound": "hbm", "achieved": 16.0 * R * N / tm / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": 16.0 * R * N / tm / 1e9 / hbm,
+                     "note": "algorithmic bytes 16 B/job; the kernel is latency / issue bound (fp64, bit-exact)"}}
     print(json.dumps(out, indent=1, default=float))
 
 
