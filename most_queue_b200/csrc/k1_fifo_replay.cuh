@@ -63,8 +63,11 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
     const long long R = P.reps;
     if (rep >= R) return;
     const int c = P.c;
-    const long long N = P.jobs;
-    const long long cap = FINITE ? P.buffer : 0;
+    // counters and cursors are 32 bit (the C ABI rejects jobs, n_a, n_s or buffer >= 2^31 for this kernel)
+    const uint32_t N = (uint32_t)P.jobs;
+    const uint32_t cap = FINITE ? (uint32_t)P.buffer : 0u;
+    const uint32_t n_a = (uint32_t)P.n_a, n_s = (uint32_t)P.n_s;
+    const uint32_t p_bins = (uint32_t)P.p_bins;
     const double *A = P.A + rep;
     const double *S = P.S + rep;
     double *rec = P.rec + rep;
@@ -81,24 +84,24 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
     const uint32_t cmask = (c >= 32) ? 0xffffffffu : ((1u << c) - 1u);
 
     double ttek = 0.0, start_busy = 0.0;
-    long long arrived = 0, taked = 0, served = 0, dropped = 0, busy_n = 0;
-    long long in_sys = 0, q = 0;
+    uint32_t arrived = 0, taked = 0, served = 0, dropped = 0, busy_n = 0;
+    uint32_t in_sys = 0, q = 0;
     int free_channels = c;
-    long long ia = 1, is = 0;
+    uint32_t ia = 1, is = 0;
     // infinite: lag cursor (index and arrival time of the queue head); finite: ring head
-    long long h = 0;
+    uint32_t h = 0;
     double a_h = 0.0, a_lag = 0.0;  // a_lag = A[h + 1], loaded one trip before the cursor moves
-    long long head = 0;
+    uint32_t head = 0;
     double p_over = 0.0;
     int status = 0;
     int pend = 0;   // second half of a departure: 2 = start the head of the queue, 3 = a busy period ended
     int pslot = 0;  // the slot the pending start goes to
 
-    double arrival_time = P.n_a > 0 ? A[0] : 0.0;  // base.py:112
-    if (P.n_a < 1) status = MQ_E_INPUT_SHORT;
+    double arrival_time = n_a > 0 ? A[0] : 0.0;  // base.py:112
+    if (n_a < 1) status = MQ_E_INPUT_SHORT;
     // the next draw of each stream is loaded one trip ahead of its use (hides the HBM latency)
-    double a_next = P.n_a > 1 ? A[R] : 0.0;  // default caching: the lag cursor re-reads these rows from L2
-    double s_next = P.n_s > 0 ? S[0] : 0.0;
+    double a_next = n_a > 1 ? A[R] : 0.0;  // default caching: the lag cursor re-reads these rows from L2
+    double s_next = n_s > 0 ? S[0] : 0.0;
 
     while (status == 0 && (pend != 0 || served < N)) {
         // _get_min_server_time base.py:312-325: strict '<', lowest index wins ties (pairwise tree, left operand
@@ -129,13 +132,13 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
         {
             // _update_state_probs base.py:327-340 (a pending trip adds +0.0: no change)
             const double dt = __dsub_rn(te, ttek);
-            if (in_sys < MQ_K1_BF) {
-                double *hp = hist + (int)in_sys * MQ_K1_BLOCK;
+            if (in_sys < (uint32_t)MQ_K1_BF) {
+                double *hp = hist + in_sys * MQ_K1_BLOCK;
                 *hp = __dadd_rn(*hp, dt);
-            } else if (in_sys < P.p_bins) {
+            } else if (in_sys < p_bins) {
                 // far states accumulate in the (zeroed) record with a fire-and-forget fp64 reduction: same
                 // round-to-nearest add, same order (one lane, one address), and no load to wait for
-                atomicAdd(&rec[(MQ_F_P + in_sys) * R], dt);
+                atomicAdd(&rec[(long long)(MQ_F_P + in_sys) * R], dt);
             } else {
                 p_over = __dadd_rn(p_over, dt);
             }
@@ -147,10 +150,10 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
         const bool is_pbusy = pend == 3;   // a busy period is over, base.py:276-281
         // arrival() base.py:214-247
         arrived += is_arr;
-        const bool short_a = is_arr && ia >= P.n_a;
+        const bool short_a = is_arr && ia >= n_a;
         arrival_time = is_arr ? __dadd_rn(ttek, a_next) : arrival_time;
         ia += is_arr;
-        if (is_arr) a_next = ia < P.n_a ? A[ia * R] : 0.0;
+        if (is_arr) a_next = ia < n_a ? A[(long long)ia * R] : 0.0;
         in_sys += is_arr;
         const bool full = free_channels == 0;
         const bool arr_start = is_arr && !full;  // send_task_to_channel base.py:155-184
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
         in_sys -= is_dep;
         const bool dep_q = is_dep && q != 0;
         const bool dep_nq = is_dep && q == 0;
-        const bool busy_over = dep_nq && free_channels == 1 && in_sys == c - 1;
+        const bool busy_over = dep_nq && free_channels == 1 && in_sys == (uint32_t)(c - 1);
         pslot = dep_q ? midx : pslot;
         // queue
         double a_head;
@@ -175,19 +178,19 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
             const bool more = is_pstart && q > 1;
             h += more;
             a_h = more ? __dadd_rn(a_h, a_lag) : a_h;
-            if (first || more) a_lag = A[(h + 1) * R];  // h + 1 <= ia - 1 < n_a while somebody waits
-            q += (long long)arr_q - (long long)is_pstart;
+            if (first || more) a_lag = A[(long long)(h + 1u) * R];  // h + 1 <= ia - 1 < n_a while somebody waits
+            q += (uint32_t)arr_q - (uint32_t)is_pstart;
         } else {
             const bool accept = arr_q && q < cap;
             const bool drop = arr_q && !accept;
-            long long sl = head + q;
+            uint32_t sl = head + q;
             sl = sl >= cap ? sl - cap : sl;
-            if (accept) ring[sl * R] = ttek;
+            if (accept) ring[(long long)sl * R] = ttek;
             a_head = 0.0;
-            if (is_pstart) a_head = ring[head * R];
+            if (is_pstart) a_head = ring[(long long)head * R];
             head += is_pstart;
-            head = head >= cap ? 0 : head;
-            q += (long long)accept - (long long)is_pstart;
+            head = head >= cap ? 0u : head;
+            q += (uint32_t)accept - (uint32_t)is_pstart;
             dropped += drop;
             in_sys -= drop;
         }
@@ -198,23 +201,23 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
         const int slot = is_arr ? __ffs(~busy & cmask) - 1 : pslot;
         const double a_job = is_arr ? ttek : a_head;
         taked += start;
-        const bool short_s = start && is >= P.n_s;
+        const bool short_s = start && is >= n_s;
         const double e_new = __dadd_rn(ttek, s_next);  // servers.py:88
         is += start;
         if (start) {
-            s_next = is < P.n_s ? S[is * R] : 0.0;
+            s_next = is < n_s ? S[(long long)is * R] : 0.0;
             vv[slot * MQ_K1_BLOCK] = __dsub_rn(e_new, a_job);  // what serving() will compute as ttek - arrival
         }
         busy = start ? (busy | (1u << slot)) : busy;
         free_channels -= start;
-        start_busy = (arr_start && free_channels == 0 && in_sys == c) ? ttek : start_busy;
+        start_busy = (arr_start && free_channels == 0 && in_sys == (uint32_t)c) ? ttek : start_busy;
         // the one server slot rewritten in this trip, the one running-moment sample of this trip
         const int wslot = start ? slot : (dep_nq ? midx : -1);
         const double wval = start ? e_new : 1e10;
         const int which = start ? 0 : (is_dep ? 1 : (is_pbusy ? 2 : -1));  // 0 = w, 1 = v, 2 = busy period
         const double x = start ? (is_arr ? 0.0 : __dadd_rn(0.0, __dsub_rn(ttek, a_job)))
                                : (is_dep ? v_dep : __dsub_rn(ttek, start_busy));
-        const long long count = start ? taked : (is_dep ? served : busy_n);
+        const uint32_t count = start ? taked : (is_dep ? served : busy_n);
         pend = dep_q ? 2 : (busy_over ? 3 : 0);
         if (short_a || short_s) status = MQ_E_INPUT_SHORT;
 #pragma unroll

@@ -341,6 +341,9 @@ int mq_replay_fifo(mq_ctx *ctx, const mq_replay_cfg *cfg, const double *A, const
     if (cfg->buffer < -1) return fail(MQ_E_INVALID, "mq_replay_fifo: buffer must be >= 0 or -1 (infinite)");
     if (cfg->total_served < 0 || cfg->replications < 1 || cfg->n_a < 1 || cfg->n_s < 0)
         return fail(MQ_E_INVALID, "mq_replay_fifo: bad sizes");
+    if (cfg->total_served >= (1ll << 31) || cfg->n_a >= (1ll << 31) || cfg->n_s >= (1ll << 31) ||
+        cfg->buffer >= (1ll << 31))
+        return fail(MQ_E_UNSUPPORTED, "mq_replay_fifo: total_served, n_a, n_s and buffer must be < 2^31");
     CU(cudaSetDevice(ctx->device));
 
     const long long R = cfg->replications;
