@@ -192,6 +192,32 @@ typedef struct {
 int mqo_tandem_run(int m, const int64_t *capacity, mqo_src *arrivals, mqo_src *services,
                    int64_t total_served, double warmup_fraction, mqo_tandem_out *out);
 
+/* ---- queue with warm-up, cold (vacation) and cold-delay periods: VacationQueueingSystemSimulator.run and
+ * NPolicyQueueSim.run (sim/vacations.py:12-364) ---- */
+typedef struct {
+    int c;
+    int64_t buffer;           /* < 0: infinite */
+    int warm_set, cold_set, delay_set;
+    int service_on_warm_up;   /* vacations.py:23 */
+    int multiple_vacations;   /* vacations.py:24 */
+    int64_t big_n;            /* > 0: N-policy (vacations.py:320-364) */
+} mqo_vac_cfg;
+
+typedef struct {
+    double w_sum[4], v_sum[4], w_run[4], v_run[4], busy_run[3];
+    int64_t busy_n, arrived, taked, served, dropped, in_sys, queued;
+    double ttek, p_over;
+    double warm_prob, cold_prob, delay_prob; /* QsPhase.prob: time in COMPLETED phases (phase.py:53) */
+    int64_t warm_starts, cold_starts, delay_starts, warm_after_cold;
+} mqo_vac_out;
+
+/* services: the servers' dist draws in start_service order (servers.py:88); warm_services: the draws of
+ * Server.warm_phase.dist (servers.py:90, is_service_on_warm_up); warm_src / cold_src / delay_src: durations of
+ * the three QsPhase periods in start() order (phase.py:47).  Unused sources may be NULL. */
+int mqo_vac_run(const mqo_vac_cfg *cfg, mqo_src *arrivals, mqo_src *services, mqo_src *warm_services,
+                mqo_src *warm_src, mqo_src *cold_src, mqo_src *delay_src, int64_t total_served, double *p,
+                int64_t p_bins, mqo_vac_out *out);
+
 /* ---- open network of PRIORITY nodes with per-class routing: PriorityNetwork.run
  * (sim/networks/priority_network.py:241-276) ---- */
 #define MQO_PN_MAX_CLASSES 8

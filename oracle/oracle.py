@@ -92,6 +92,22 @@ class MqoTandemOut(C.Structure):
                 ("lost", C.c_int64), ("departures", C.c_int64)]
 
 
+class MqoVacCfg(C.Structure):
+    _fields_ = [("c", C.c_int), ("buffer", C.c_int64), ("warm_set", C.c_int), ("cold_set", C.c_int),
+                ("delay_set", C.c_int), ("service_on_warm_up", C.c_int), ("multiple_vacations", C.c_int),
+                ("big_n", C.c_int64)]
+
+
+class MqoVacOut(C.Structure):
+    _fields_ = [("w_sum", C.c_double * 4), ("v_sum", C.c_double * 4), ("w_run", C.c_double * 4),
+                ("v_run", C.c_double * 4), ("busy_run", C.c_double * 3), ("busy_n", C.c_int64),
+                ("arrived", C.c_int64), ("taked", C.c_int64), ("served", C.c_int64), ("dropped", C.c_int64),
+                ("in_sys", C.c_int64), ("queued", C.c_int64), ("ttek", C.c_double), ("p_over", C.c_double),
+                ("warm_prob", C.c_double), ("cold_prob", C.c_double), ("delay_prob", C.c_double),
+                ("warm_starts", C.c_int64), ("cold_starts", C.c_int64), ("delay_starts", C.c_int64),
+                ("warm_after_cold", C.c_int64)]
+
+
 class MqoPnClassOut(C.Structure):
     _fields_ = [("v_run", C.c_double * 3), ("w_run", C.c_double * 3), ("v_sum", C.c_double * 3),
                 ("w_sum", C.c_double * 3), ("served", C.c_int64), ("arrived", C.c_int64), ("in_sys", C.c_int64)]
@@ -551,3 +567,75 @@ def prionet_generate(R, channels, prty, nodes_prty, sources, servers, job_served
                         _gen_src(("Uniform", U01), seed, m * K + K, rep, 1),
                         [[_gen_src(servers[i][j], seed, i * K + j, rep, 1) for j in range(K)] for i in range(m)],
                         job_served)
+
+
+# --------------------------------------------------------------------------- vacations / N-policy
+@dataclass
+class VacResult:
+    w: np.ndarray
+    v: np.ndarray
+    w_sum: np.ndarray
+    v_sum: np.ndarray
+    busy: np.ndarray
+    p_time: np.ndarray
+    ttek: float
+    arrived: int
+    taked: int
+    served: int
+    dropped: int
+    in_sys: int
+    queued: int
+    busy_n: int
+    warm_prob: float   # time in completed warm-up periods (QsPhase.prob, not yet divided by ttek)
+    cold_prob: float
+    delay_prob: float
+    starts: tuple      # (warm, cold, delay) starts_times
+    warm_after_cold: int
+    used: dict         # draws consumed per stream
+
+
+def _vac_run(c, buffer, srcs, total_served, service_on_warm_up, multiple_vacations, big_n, p_bins):
+    """srcs: dict with MqoSrc (or None) under arrivals, services, warm_services, warm, cold, delay."""
+    cfg = MqoVacCfg(c=int(c), buffer=-1 if buffer is None else int(buffer),
+                    warm_set=int(srcs.get("warm") is not None or srcs.get("warm_services") is not None),
+                    cold_set=int(srcs.get("cold") is not None), delay_set=int(srcs.get("delay") is not None),
+                    service_on_warm_up=int(bool(service_on_warm_up)), multiple_vacations=int(bool(multiple_vacations)),
+                    big_n=int(big_n or 0))
+    ref = lambda k: C.byref(srcs[k]) if srcs.get(k) is not None else None
+    p = np.zeros(int(p_bins))
+    out = MqoVacOut()
+    L = lib()
+    L.mqo_vac_run.restype = C.c_int
+    rc = L.mqo_vac_run(C.byref(cfg), ref("arrivals"), ref("services"), ref("warm_services"), ref("warm"), ref("cold"),
+                       ref("delay"), C.c_int64(int(total_served)), _dp(p), C.c_int64(int(p_bins)), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle vacation run failed rc={rc}")
+    return VacResult(w=np.array(out.w_run), v=np.array(out.v_run), w_sum=np.array(out.w_sum), v_sum=np.array(out.v_sum),
+                     busy=np.array(out.busy_run), p_time=p, ttek=out.ttek, arrived=out.arrived, taked=out.taked,
+                     served=out.served, dropped=out.dropped, in_sys=out.in_sys, queued=out.queued, busy_n=out.busy_n,
+                     warm_prob=out.warm_prob, cold_prob=out.cold_prob, delay_prob=out.delay_prob,
+                     starts=(out.warm_starts, out.cold_starts, out.delay_starts), warm_after_cold=out.warm_after_cold,
+                     used={k: (v.pos if v is not None else 0) for k, v in srcs.items()})
+
+
+VAC_STREAMS = ("arrivals", "services", "warm_services", "warm", "cold", "delay")
+
+
+def vac_replay(c, buffer, arrays: dict, total_served, service_on_warm_up=False, multiple_vacations=False, big_n=0,
+               p_bins=128) -> VacResult:
+    """VacationQueueingSystemSimulator.run() / NPolicyQueueSim.run() on pre-generated draws.  arrays maps the stream
+    names of VAC_STREAMS to 1-D arrays (absent = that law is not set)."""
+    keep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in arrays.items() if v is not None}
+    srcs = {k: (_replay_src(keep[k]) if k in keep else None) for k in VAC_STREAMS}
+    return _vac_run(c, buffer, srcs, total_served, service_on_warm_up, multiple_vacations, big_n, p_bins)
+
+
+def vac_generate(c, buffer, dists: dict, total_served, seed, rep, service_on_warm_up=False, multiple_vacations=False,
+                 big_n=0, p_bins=128) -> VacResult:
+    """Generator mode.  Streams: arrivals = word 0 and services = word 1 of stream sid 0 (as the FIFO kernel),
+    warm_services = word 1 of sid 1, warm / cold / delay = word 0 of sid 2 / 3 / 4."""
+    where = {"arrivals": (0, 0), "services": (0, 1), "warm_services": (1, 1), "warm": (2, 0), "cold": (3, 0),
+             "delay": (4, 0)}
+    srcs = {k: (_gen_src(dists[k], seed, where[k][0], rep, where[k][1]) if dists.get(k) is not None else None)
+            for k in VAC_STREAMS}
+    return _vac_run(c, buffer, srcs, total_served, service_on_warm_up, multiple_vacations, big_n, p_bins)

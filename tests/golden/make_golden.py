@@ -359,6 +359,82 @@ def make_prionet():
     prionet_case("m2k3_mixed", Rk, [2, 3], ["PR", "NP"], [[0, 1, 2], [2, 1, 0]], A, rng.random(12 * n), S, n)
 
 
+# --------------------------------------------------------------------------- vacations / N-policy
+def vac_case(name, c, buffer, streams, total_served, service_on_warm_up=False, multiple_vacations=False, big_n=0,
+             nprobs=128):
+    """streams: dict of arrays under arrivals, services and (optional) warm_services, warm, cold, delay."""
+    from most_queue.sim.vacations import NPolicyQueueSim, VacationQueueingSystemSimulator
+
+    kw = dict(buffer=buffer, is_service_on_warm_up=service_on_warm_up, is_multiple_vacations=multiple_vacations)
+    qs = NPolicyQueueSim(c, big_n, **kw) if big_n else VacationQueueingSystemSimulator(c, **kw)
+    qs.set_sources(1.0, "M")
+    qs.set_servers(1.0, "M")
+    if "warm" in streams or "warm_services" in streams:
+        qs.set_warm(1.0, "M")
+    if "cold" in streams:
+        qs.set_cold(1.0, "M")
+    if "delay" in streams:
+        qs.set_cold_delay(1.0, "M")
+    used = {k: [0] for k in streams}
+    qs.source = ReplayDist(streams["arrivals"], used["arrivals"])
+    for srv in qs.servers:
+        srv.dist = ReplayDist(streams["services"], used["services"])
+        if "warm_services" in streams:
+            srv.warm_phase.dist = ReplayDist(streams["warm_services"], used["warm_services"])
+    if "warm" in streams:
+        qs.warm_phase.dist = ReplayDist(streams["warm"], used["warm"])
+    if "cold" in streams:
+        qs.cold_phase.dist = ReplayDist(streams["cold"], used["cold"])
+    if "delay" in streams:
+        qs.cold_delay_phase.dist = ReplayDist(streams["delay"], used["delay"])
+    qs._free_servers = LowestFirstSet(range(c))
+    qs.arrival_time = qs.source.generate()  # the draw set_sources makes (base.py:112)
+    with quiet():
+        while qs.served < total_served:  # run() minus tqdm and calc_load
+            qs.run_one_step()
+    out = dict(c=c, buffer=-1 if buffer is None else buffer, total_served=total_served,
+               service_on_warm_up=int(service_on_warm_up), multiple_vacations=int(multiple_vacations), big_n=big_n,
+               w=np.array(qs.w, dtype=np.float64), v=np.array(qs.v, dtype=np.float64),
+               busy=np.array(qs.busy, dtype=np.float64), busy_n=qs.busy_moments,
+               p_time=np.array(qs.p[:nprobs], dtype=np.float64), ttek=float(qs.ttek), arrived=qs.arrived,
+               taked=qs.taked, served=qs.served, dropped=qs.dropped, in_sys=qs.in_sys, queued=qs.queue.size(),
+               warm_prob=float(qs.warm_phase.prob), cold_prob=float(qs.cold_phase.prob),
+               delay_prob=float(qs.cold_delay_phase.prob),
+               starts=np.array([qs.warm_phase.starts_times, qs.cold_phase.starts_times,
+                                qs.cold_delay_phase.starts_times]),
+               warm_after_cold=qs.warm_after_cold_starts)
+    for k, a in streams.items():
+        out["s_" + k] = np.asarray(a, dtype=np.float64)
+        out["used_" + k] = used[k][0]
+    np.savez_compressed(os.path.join(OUT, f"vac_{name}.npz"), **out)
+    print(f"vac_{name}: served={qs.served} taked={qs.taked} dropped={qs.dropped} w1={qs.w[0]:.5g} "
+          f"starts={out['starts'].tolist()} used={ {k: v[0] for k, v in used.items()} }")
+
+
+def make_vac():
+    rng = np.random.default_rng(20260606)
+    n = 3000
+    ex = lambda mean, m=2 * n: rng.exponential(mean, m)
+    # M/G/1 with a warm-up period before service resumes (tests/test_mg1_warmup.py shape, jobs wait during it)
+    vac_case("c1_warm", 1, None, dict(arrivals=ex(1.0), services=rng.gamma(0.7, 1.0, 2 * n), warm=ex(1.05)), n)
+    # the first job of a busy period is served with the warm law (is_service_on_warm_up)
+    vac_case("c1_service_on_warm", 1, None,
+             dict(arrivals=ex(1.0), services=ex(0.7), warm_services=rng.gamma(2.0, 0.6, 2 * n)), n,
+             service_on_warm_up=True)
+    # vacations: a cold period starts whenever the system empties (tests/test_mg1_vacations.py shape)
+    vac_case("c1_cold", 1, None, dict(arrivals=ex(1.0), services=ex(0.6), cold=ex(1.5)), n)
+    vac_case("c1_cold_multiple", 1, None, dict(arrivals=ex(1.0), services=ex(0.5), cold=ex(0.8)), n,
+             multiple_vacations=True)
+    # warm-up + cold + cold delay (tests/test_mgn_with_h2_delay_cold_warm.py shape), 3 channels
+    vac_case("c3_warm_cold_delay", 3, None,
+             dict(arrivals=ex(0.5), services=ex(1.0), warm=ex(0.6), cold=ex(0.9), delay=ex(0.7)), n)
+    # finite buffer with vacations: drops while the server is away
+    vac_case("c2_cold_buffer4", 2, 4, dict(arrivals=ex(0.6), services=ex(0.9), cold=ex(2.5)), n)
+    # N-policy (vacations.py:320-364)
+    vac_case("c1_npolicy4", 1, None, dict(arrivals=ex(1.0), services=ex(0.6)), n, big_n=4)
+    vac_case("c2_npolicy3_warm", 2, None, dict(arrivals=ex(0.6), services=ex(0.8), warm=ex(0.5)), n, big_n=3)
+
+
 # --------------------------------------------------------------------------- tandem with blocking
 def tandem_case(name, capacity, A, S, total_served, warmup_fraction=0.05):
     from most_queue.sim.networks.tandem_blocking import TandemBlockingSim
@@ -479,7 +555,7 @@ def make_theory():
 
 if __name__ == "__main__":
     import_reference()
-    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "theory"]
+    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "vac", "theory"]
     if "fifo" in which:
         make_fifo()
     if "prio" in which:
@@ -490,5 +566,7 @@ if __name__ == "__main__":
         make_prionet()
     if "tandem" in which:
         make_tandem()
+    if "vac" in which:
+        make_vac()
     if "theory" in which:
         make_theory()
