@@ -418,6 +418,72 @@ int mq_replay_prionet(mq_ctx *ctx, const mq_prionet_cfg *cfg, const double *cons
                       const double *U, int64_t n_u, const double *const *S, const int64_t *n_s, double *agg,
                       double *rep_out);
 
+/* ---- queue with warm-up, cold (vacation) and cold-delay periods, and the N-policy queue.  Replaces
+ * VacationQueueingSystemSimulator(n, buffer, is_service_on_warm_up, is_multiple_vacations)
+ * .set_sources / set_servers / set_warm / set_cold / set_cold_delay / run(total_served) and
+ * NPolicyQueueSim(n, big_n) (sim/vacations.py:12,52,79,89,303,320) */
+#define MQ_VAC_STREAMS 6 /* arrivals, services, warm services, warm-up, cold, cold-delay periods */
+#define MQ_VS_ARRIVALS 0
+#define MQ_VS_SERVICES 1
+#define MQ_VS_WARM_SERVICES 2
+#define MQ_VS_WARM 3
+#define MQ_VS_COLD 4
+#define MQ_VS_DELAY 5
+
+typedef struct {
+    int32_t c;                        /* num_of_channels (1..32)                             :19 */
+    int32_t p_bins;
+    int64_t buffer;                   /* < 0: infinite                                       :20 */
+    mq_dist dist[MQ_VAC_STREAMS];     /* law of each stream (generator form); see set[]            */
+    int32_t set[MQ_VAC_STREAMS];      /* set[MQ_VS_WARM]: set_warm was called (:52); set[MQ_VS_WARM_SERVICES]: */
+                                      /* the servers got the warm law (:66-76); set[MQ_VS_COLD] :79; DELAY :89  */
+    int32_t service_on_warm_up;       /* :23 */
+    int32_t multiple_vacations;       /* :24 */
+    int64_t big_n;                    /* > 0: N-policy, the cold law is the constant 1e100  :345  */
+    int64_t total_served;
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+    int32_t queue_cap;                /* infinite buffer: waiting-line capacity of the engine (0: 1024) */
+    int32_t flags;
+} mq_vac_cfg;
+
+/* per-replication record rows */
+#define MQ_V_TTEK 0
+#define MQ_V_FLAGS 1
+#define MQ_V_ARRIVED 2
+#define MQ_V_TAKED 3
+#define MQ_V_SERVED 4
+#define MQ_V_DROPPED 5
+#define MQ_V_INSYS 6
+#define MQ_V_QUEUED 7
+#define MQ_V_BUSYN 8
+#define MQ_V_POVER 9
+#define MQ_V_WSUM 10    /* 4 */
+#define MQ_V_VSUM 14    /* 4 */
+#define MQ_V_WRUN 18    /* 4: the reference's running moments (stats_update.py:6-22) */
+#define MQ_V_VRUN 22    /* 4 */
+#define MQ_V_BUSYRUN 26 /* 3 */
+#define MQ_V_WARMPROB 29  /* QsPhase.prob of the three periods: time in COMPLETED periods (phase.py:53) */
+#define MQ_V_COLDPROB 30
+#define MQ_V_DELAYPROB 31
+#define MQ_V_STARTS 32  /* 3: starts_times of warm, cold, delay */
+#define MQ_V_WARM_AFTER_COLD 35
+#define MQ_V_USED 36    /* 6: draws consumed per stream */
+#define MQ_V_P 44       /* p_bins time-in-state sums */
+#define MQ_V_ROWS(pb) (44 + (pb))
+
+/* aggregate: [0] replications, [1] sum ttek, [2] flagged, [3] sum served, [4] sum arrived, [5] sum dropped,
+ * [6] sum taked, [7] reserved; [8..11] sum over replications of w_sum/taked, [12..15] squares; [16..19] v_sum/served,
+ * [20..23] squares; [24..26] warm/cold/delay time fractions (prob/ttek), [27..29] squares; [32..32+pb) p = time in
+ * state / ttek, then pb squares */
+#define MQ_V_AGG_LEN(pb) (32 + 2 * (pb))
+
+int mq_sim_vacation(mq_ctx *ctx, const mq_vac_cfg *cfg, double *agg, double *rep_out);
+/* replay form: X[s] = draws of stream s ([n[s]][replications], NULL / 0 when unused) */
+int mq_replay_vacation(mq_ctx *ctx, const mq_vac_cfg *cfg, const double *const *X, const int64_t *n, double *agg,
+                       double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

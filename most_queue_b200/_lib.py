@@ -189,6 +189,32 @@ def prionet_agg_len(K):
     return 4 + 16 * K
 
 
+VAC_STREAMS = ("arrivals", "services", "warm_services", "warm", "cold", "delay")
+
+
+class MqVacCfg(C.Structure):
+    _fields_ = [
+        ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("dist", MqDist * 6), ("set", C.c_int32 * 6),
+        ("service_on_warm_up", C.c_int32), ("multiple_vacations", C.c_int32), ("big_n", C.c_int64),
+        ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
+        ("queue_cap", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+# record rows of the vacation kernel (include/mqb200.h MQ_V_*)
+(V_TTEK, V_FLAGS, V_ARRIVED, V_TAKED, V_SERVED, V_DROPPED, V_INSYS, V_QUEUED, V_BUSYN, V_POVER, V_WSUM, V_VSUM,
+ V_WRUN, V_VRUN, V_BUSYRUN, V_WARMPROB, V_COLDPROB, V_DELAYPROB, V_STARTS, V_WARM_AFTER_COLD, V_USED, V_P) = (
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 14, 18, 22, 26, 29, 30, 31, 32, 35, 36, 44)
+
+
+def vac_rec_rows(p_bins):
+    return 44 + int(p_bins)
+
+
+def vac_agg_len(p_bins):
+    return 32 + 2 * int(p_bins)
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -250,6 +276,10 @@ def load():
         L.mq_replay_prionet.restype = C.c_int
         L.mq_replay_prionet.argtypes = [vp, C.POINTER(MqPrionetCfg), C.POINTER(vp), C.POINTER(C.c_int64), vp,
                                         C.c_int64, C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
+        L.mq_sim_vacation.restype = C.c_int
+        L.mq_sim_vacation.argtypes = [vp, C.POINTER(MqVacCfg), dp, dp]
+        L.mq_replay_vacation.restype = C.c_int
+        L.mq_replay_vacation.argtypes = [vp, C.POINTER(MqVacCfg), C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -613,6 +643,50 @@ class Context:
         check(self._L.mq_replay_prionet(self._h, C.byref(cfg), pa, na, U.ctypes.data, U.shape[0], ps, ns,
                                         agg.ctypes.data_as(C.POINTER(C.c_double)),
                                         rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
+
+    # ---- K8 ----
+    def _vac_cfg(self, c, buffer, is_set, service_on_warm_up, multiple_vacations, big_n, total_served, replications,
+                 rep0, seed, p_bins, queue_cap):
+        cfg = MqVacCfg()
+        cfg.c, cfg.p_bins = int(c), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        for i, k in enumerate(VAC_STREAMS):
+            cfg.set[i] = int(bool(is_set.get(k)))
+        cfg.service_on_warm_up, cfg.multiple_vacations = int(bool(service_on_warm_up)), int(bool(multiple_vacations))
+        cfg.big_n = int(big_n or 0)
+        cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.queue_cap = int(queue_cap)
+        return cfg
+
+    def sim_vacation(self, c, buffer, dists: dict, total_served, replications, rep0, seed, service_on_warm_up=False,
+                     multiple_vacations=False, big_n=0, p_bins=128, queue_cap=0, per_replication=False):
+        """dists: MqDist under the names of VAC_STREAMS (absent / None = that law is not set)."""
+        cfg = self._vac_cfg(c, buffer, {k: dists.get(k) is not None for k in VAC_STREAMS}, service_on_warm_up,
+                            multiple_vacations, big_n, total_served, replications, rep0, seed, p_bins, queue_cap)
+        for i, k in enumerate(VAC_STREAMS):
+            if dists.get(k) is not None:
+                cfg.dist[i] = dists[k]
+        agg = np.zeros(vac_agg_len(p_bins))
+        rec = np.empty((vac_rec_rows(p_bins), int(replications))) if per_replication else None
+        check(self._L.mq_sim_vacation(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                      rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_vacation(self, c, buffer, arrays: dict, total_served, service_on_warm_up=False,
+                        multiple_vacations=False, big_n=0, p_bins=128, queue_cap=0):
+        """arrays: [n, reps] draws under the names of VAC_STREAMS (absent = that law is not set)."""
+        X = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in arrays.items() if v is not None}
+        reps = X["arrivals"].shape[1]
+        cfg = self._vac_cfg(c, buffer, {k: k in X for k in VAC_STREAMS}, service_on_warm_up, multiple_vacations,
+                            big_n, total_served, reps, 0, 0, p_bins, queue_cap)
+        ptr = (C.c_void_p * 6)(*[X[k].ctypes.data if k in X else None for k in VAC_STREAMS])
+        n = (C.c_int64 * 6)(*[X[k].shape[0] if k in X else 0 for k in VAC_STREAMS])
+        agg = np.zeros(vac_agg_len(p_bins))
+        rec = np.empty((vac_rec_rows(p_bins), reps))
+        check(self._L.mq_replay_vacation(self._h, C.byref(cfg), ptr, n, agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                         rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec
 
     def last_timing(self):

@@ -23,6 +23,16 @@ class QueueResults:
 
 
 @dataclass
+class VacationResults(QueueResults):
+    """Result of a queue with vacations (structs.py:60-68 of the reference)."""
+
+    warmup_prob: float = 0
+    cold_prob: float = 0
+    cold_delay_prob: float = 0
+    servers_busy_probs: list | None = None
+
+
+@dataclass
 class MulticlassResults:
     v: list | None = None
     w: list | None = None
