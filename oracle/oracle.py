@@ -586,6 +586,7 @@ class VacResult:
     in_sys: int
     queued: int
     busy_n: int
+    p_over: float
     warm_prob: float   # time in completed warm-up periods (QsPhase.prob, not yet divided by ttek)
     cold_prob: float
     delay_prob: float
@@ -613,7 +614,7 @@ def _vac_run(c, buffer, srcs, total_served, service_on_warm_up, multiple_vacatio
     return VacResult(w=np.array(out.w_run), v=np.array(out.v_run), w_sum=np.array(out.w_sum), v_sum=np.array(out.v_sum),
                      busy=np.array(out.busy_run), p_time=p, ttek=out.ttek, arrived=out.arrived, taked=out.taked,
                      served=out.served, dropped=out.dropped, in_sys=out.in_sys, queued=out.queued, busy_n=out.busy_n,
-                     warm_prob=out.warm_prob, cold_prob=out.cold_prob, delay_prob=out.delay_prob,
+                     p_over=out.p_over, warm_prob=out.warm_prob, cold_prob=out.cold_prob, delay_prob=out.delay_prob,
                      starts=(out.warm_starts, out.cold_starts, out.delay_starts), warm_after_cold=out.warm_after_cold,
                      used={k: (v.pos if v is not None else 0) for k, v in srcs.items()})
 
