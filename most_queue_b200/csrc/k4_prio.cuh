@@ -48,4 +48,9 @@ struct K4Params {
 cudaError_t k4_launch(const K4Params &P, int grid, cudaStream_t st);
 cudaError_t k4_occupancy(int *blocks_per_sm);
 
+// k4v2_prio.cu: the register / shared-memory resident predicated form for c <= 8, K <= 4 (same block size)
+bool k4v2_supported(int c, int K);
+cudaError_t k4v2_launch(const K4Params &P, int grid, cudaStream_t st);
+cudaError_t k4v2_occupancy(int c, int K, bool replay, int *blocks_per_sm);
+
 }  // namespace mq

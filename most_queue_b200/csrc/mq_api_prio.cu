@@ -2,6 +2,7 @@
 #include "k4_prio.cuh"
 #include "mq_host.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace mq;
@@ -90,8 +91,15 @@ static int prio_common(mq_ctx *ctx, const mq_prio_cfg *cfg, bool replay, const d
         }
     }
 
+    // c <= 8 and K <= 4 run the predicated, on-chip-state form (k4v2_prio.cu); MQ_K4_V1=1 forces the general kernel
+    bool v2 = k4v2_supported(cfg->c, K) && !std::getenv("MQ_K4_V1") && cfg->total_served < (1ll << 30);
+    if (replay)  // its counters and cursors are 32 bit
+        for (int k = 0; k < K; ++k) v2 = v2 && n_a[k] < (1ll << 31) && n_s[k] < (1ll << 31);
     int occ = 0;
-    CU(k4_occupancy(&occ));
+    if (v2)
+        CU(k4v2_occupancy(cfg->c, K, replay, &occ));
+    else
+        CU(k4_occupancy(&occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     long long grid = (long long)occ * ctx->sms;
     const long long need = (R + K4_BLOCK - 1) / K4_BLOCK;
@@ -132,7 +140,10 @@ static int prio_common(mq_ctx *ctx, const mq_prio_cfg *cfg, bool replay, const d
 
     CU(cudaMemsetAsync(ctx->rec.p, 0, rec_bytes, ctx->stream));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(k4_launch(P, (int)grid, ctx->stream));
+    if (v2)
+        CU(k4v2_launch(P, (int)grid, ctx->stream));
+    else
+        CU(k4_launch(P, (int)grid, ctx->stream));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(launch_reduce_ratio((const double *)ctx->rec.p, R, (const RatioDesc *)ctx->desc.p, nq, (double *)ctx->agg.p,
