@@ -20,6 +20,7 @@ namespace mq {
 
 constexpr int K4V_BLOCK = 64;
 constexpr int K4V_BF = 4;  // time-in-state bins per class kept in shared memory
+constexpr int K4V_SB = 4;  // generator tier: service draws kept ahead per class and lane (power of two)
 
 template <int CT, int KT, bool REPLAY>
 struct K4VLayout {
@@ -31,9 +32,10 @@ struct K4VLayout {
     static constexpr int ND = CLS0 + KT * DSTR;
     // 32-bit words, [word][lane]
     static constexpr int ARRIVED = 0, TAKED = 1, SERVED = 2, DROPPED = 3, INSYS = 4, AIDX = 5, SIDX = 6, QHEAD = 7,
-                         QSIZE = 8, ISTR = 9;
+                         QSIZE = 8, SFILL = 9, ISTR = 10;
     static constexpr int NI = KT * ISTR;
-    static constexpr size_t BYTES = (size_t)K4V_BLOCK * (8 * ND + 4 * NI);
+    static constexpr int NF = REPLAY ? 0 : KT * K4V_SB;  // fp32 service draws kept ahead
+    static constexpr size_t BYTES = (size_t)K4V_BLOCK * (8 * ND + 4 * NI + 4 * NF);
 };
 
 template <int CT, int KT, bool REPLAY>
@@ -44,10 +46,19 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
     const int tid = threadIdx.x;
     double *smd = k4v_sm + tid;
     int *smi = reinterpret_cast<int *>(k4v_sm + LY::ND * K4V_BLOCK) + tid;
+    float *smf = reinterpret_cast<float *>(smi - tid + LY::NI * K4V_BLOCK) + tid;
 #define SD(w) smd[(w) * K4V_BLOCK]
 #define SI(w) smi[(w) * K4V_BLOCK]
 #define DC(k, f) SD(LY::CLS0 + (k) * LY::DSTR + (f))
 #define IC(k, f) SI((k) * LY::ISTR + (f))
+
+    // the laws of the classes, read with a per-lane class index: shared memory instead of a thread-private copy
+    __shared__ DistF sh_src[KT], sh_srv[KT];
+    if (!REPLAY && tid < KT) {
+        sh_src[tid] = P.src[tid];
+        sh_srv[tid] = P.srv[tid];
+    }
+    __syncthreads();
 
     const long long gtid = (long long)blockIdx.x * K4V_BLOCK + tid;
     const long long R = P.reps;
@@ -80,7 +91,30 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
             }
             const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)k);
             uint2 w = philox2x32_10((uint32_t)i, rep, key);
-            return (double)sample<-1>(P.src[k], w.x, (uint32_t)i, rep, key, 0);
+            const DistF d = sh_src[k];
+            return (double)sample<-1>(d, w.x, (uint32_t)i, rep, key, 0);
+        };
+        // Generator tier: service draws are produced up to K4V_SB ahead per class by all lanes of the warp together
+        // (at the top of a trip) and consumed from a per-lane ring.  Draw j of a stream is a pure function of j, so
+        // drawing ahead changes nothing; it keeps the rejection-loop samplers out of the predicated event body,
+        // where only the lanes that start a service in this trip would run them.
+        auto refill_services = [&]() {
+            for (int k = 0; k < K; ++k) {
+                if (!__any_sync(__activemask(), IC(k, LY::SFILL) < 2)) continue;  // RS draws twice in one trip
+                const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)k);
+                const DistF d = sh_srv[k];
+                for (;;) {
+                    const int fill = IC(k, LY::SFILL);
+                    const bool more = fill < K4V_SB;
+                    if (!__any_sync(__activemask(), more)) break;
+                    if (more) {
+                        const uint32_t j = (uint32_t)(IC(k, LY::SIDX) + fill);
+                        uint2 w = philox2x32_10(j, rep, key);
+                        smf[(k * K4V_SB + (int)(j & (K4V_SB - 1))) * K4V_BLOCK] = sample<-1>(d, w.y, j, rep, key, 1);
+                        IC(k, LY::SFILL) = fill + 1;
+                    }
+                }
+            }
         };
         auto next_service = [&](int k) -> double {
             const int j = IC(k, LY::SIDX);
@@ -92,9 +126,8 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                 }
                 return P.S[P.soff[k] + (long long)j * R + rl];
             }
-            const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)k);
-            uint2 w = philox2x32_10((uint32_t)j, rep, key);
-            return (double)sample<-1>(P.srv[k], w.y, (uint32_t)j, rep, key, 1);
+            IC(k, LY::SFILL) -= 1;
+            return (double)smf[(k * K4V_SB + (j & (K4V_SB - 1))) * K4V_BLOCK];
         };
         auto qslot = [&](int k, int slot, int f) -> double * {
             return Q + (((long long)k * P.qcap + slot) * 4 + f) * P.lanes;
@@ -114,6 +147,7 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
         long long served_total = 0;
 
         while (served_total < P.jobs && status == 0) {
+            if (!REPLAY) refill_services();
             // ---- next event: _get_min_server_time priority.py:549-562 (busy servers only, strict '<', lowest index
             // on ties) against the earliest class arrival (lowest class on ties); an arrival wins a tie
             double mv[CT];
