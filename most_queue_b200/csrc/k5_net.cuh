@@ -26,4 +26,9 @@ struct K5Params {
 cudaError_t k5_launch(const K5Params &P, int grid, cudaStream_t st);
 cudaError_t k5_occupancy(int *blocks_per_sm);
 
+// k5v2_net.cu: the register / shared-memory resident predicated form for <= 8 nodes and <= 16 servers
+bool k5v2_supported(int m, int nserv);
+cudaError_t k5v2_launch(const K5Params &P, int grid, cudaStream_t st);
+cudaError_t k5v2_occupancy(const K5Params &P, int *blocks_per_sm);
+
 }  // namespace mq

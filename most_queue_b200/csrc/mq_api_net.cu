@@ -2,6 +2,7 @@
 #include "k5_net.cuh"
 #include "mq_host.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace mq;
@@ -92,8 +93,18 @@ static int net_common(mq_ctx *ctx, const mq_net_cfg *cfg, bool replay, const dou
         for (int i = 0; i < m; ++i) P.srv[i] = make_distf(cfg->srv[i]);
     }
 
+    // small networks run the predicated, on-chip-state form (k5v2_net.cu); MQ_K5_V1=1 forces the general kernel.
+    // Its cursors are 32 bit.
+    bool v2 = k5v2_supported(m, P.nserv) && !std::getenv("MQ_K5_V1") && cfg->job_served < (1ll << 28);
+    if (replay) {
+        v2 = v2 && n_a < (1ll << 31) && n_u < (1ll << 31);
+        for (int i = 0; i < m; ++i) v2 = v2 && n_s[i] < (1ll << 31);
+    }
     int occ = 0;
-    CU(k5_occupancy(&occ));
+    if (v2)
+        CU(k5v2_occupancy(P, &occ));
+    else
+        CU(k5_occupancy(&occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     long long grid = (long long)occ * ctx->sms;
     const long long need = (R + K5_BLOCK - 1) / K5_BLOCK;
@@ -132,7 +143,10 @@ static int net_common(mq_ctx *ctx, const mq_net_cfg *cfg, bool replay, const dou
 
     CU(cudaMemsetAsync(ctx->rec.p, 0, rec_bytes, ctx->stream));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(k5_launch(P, (int)grid, ctx->stream));
+    if (v2)
+        CU(k5v2_launch(P, (int)grid, ctx->stream));
+    else
+        CU(k5_launch(P, (int)grid, ctx->stream));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(launch_reduce_ratio((const double *)ctx->rec.p, R, (const RatioDesc *)ctx->desc.p, nq, (double *)ctx->agg.p,
