@@ -218,6 +218,22 @@ int mqo_vac_run(const mqo_vac_cfg *cfg, mqo_src *arrivals, mqo_src *services, mq
                 mqo_src *warm_src, mqo_src *cold_src, mqo_src *delay_src, int64_t total_served, double *p,
                 int64_t p_bins, mqo_vac_out *out);
 
+/* ---- queue with negative arrivals: QsSimNegatives.run (sim/negative.py:57-575), DISASTER / CLEAR_SYSTEM and
+ * RCS / REMOVE ---- */
+enum { MQO_NEG_DISASTER = 1, MQO_NEG_RCS = 2 }; /* NegativeServiceType values, negative.py:21-24 */
+
+typedef struct {
+    double w_sum[4], v_sum[4], vs_sum[4], vb_sum[4]; /* waits; sojourns of all / served / broken jobs */
+    double w_run[4], v_run[4], vs_run[4], vb_run[4]; /* the reference's running moments                */
+    int64_t positive_arrived, negative_arrived, taked, served, broken, total, dropped, in_sys, queued;
+    double ttek, p_over;
+} mqo_neg_out;
+
+/* positives / negatives: gaps of the two sources; services: draws in start_service order; choices: uniforms that
+ * pick the floor(u * busy)-th busy server (RCS only, may be NULL otherwise). */
+int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *negatives, mqo_src *services,
+                mqo_src *choices, int64_t total_served, double *p, int64_t p_bins, mqo_neg_out *out);
+
 /* ---- open network of PRIORITY nodes with per-class routing: PriorityNetwork.run
  * (sim/networks/priority_network.py:241-276) ---- */
 #define MQO_PN_MAX_CLASSES 8

@@ -108,6 +108,12 @@ class MqoVacOut(C.Structure):
                 ("warm_after_cold", C.c_int64)]
 
 
+class MqoNegOut(C.Structure):
+    _fields_ = [(n, C.c_double * 4) for n in ("w_sum", "v_sum", "vs_sum", "vb_sum", "w_run", "v_run", "vs_run", "vb_run")] + [
+        (n, C.c_int64) for n in ("positive_arrived", "negative_arrived", "taked", "served", "broken", "total", "dropped",
+                                 "in_sys", "queued")] + [("ttek", C.c_double), ("p_over", C.c_double)]
+
+
 class MqoPnClassOut(C.Structure):
     _fields_ = [("v_run", C.c_double * 3), ("w_run", C.c_double * 3), ("v_sum", C.c_double * 3),
                 ("w_sum", C.c_double * 3), ("served", C.c_int64), ("arrived", C.c_int64), ("in_sys", C.c_int64)]
@@ -640,3 +646,63 @@ def vac_generate(c, buffer, dists: dict, total_served, seed, rep, service_on_war
     srcs = {k: (_gen_src(dists[k], seed, where[k][0], rep, where[k][1]) if dists.get(k) is not None else None)
             for k in VAC_STREAMS}
     return _vac_run(c, buffer, srcs, total_served, service_on_warm_up, multiple_vacations, big_n, p_bins)
+
+
+# --------------------------------------------------------------------------- negative arrivals
+NEG_TYPES = {"DISASTER": 1, "RCS": 2}
+
+
+@dataclass
+class NegResult:
+    w: np.ndarray
+    v: np.ndarray
+    v_served: np.ndarray
+    v_broken: np.ndarray
+    w_sum: np.ndarray
+    v_sum: np.ndarray
+    vs_sum: np.ndarray
+    vb_sum: np.ndarray
+    p_time: np.ndarray
+    p_over: float
+    ttek: float
+    counts: dict
+    used: dict
+
+
+def _neg_run(c, buffer, neg_type, srcs, total_served, p_bins):
+    p = np.zeros(int(p_bins))
+    out = MqoNegOut()
+    ref = lambda k: C.byref(srcs[k]) if srcs.get(k) is not None else None
+    rc = lib().mqo_neg_run(int(c), C.c_int64(-1 if buffer is None else int(buffer)), NEG_TYPES[neg_type],
+                           ref("positives"), ref("negatives"), ref("services"), ref("choices"),
+                           C.c_int64(int(total_served)), _dp(p), C.c_int64(int(p_bins)), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle negative-arrivals run failed rc={rc}")
+    names = ("positive_arrived", "negative_arrived", "taked", "served", "broken", "total", "dropped", "in_sys", "queued")
+    return NegResult(w=np.array(out.w_run), v=np.array(out.v_run), v_served=np.array(out.vs_run),
+                     v_broken=np.array(out.vb_run), w_sum=np.array(out.w_sum), v_sum=np.array(out.v_sum),
+                     vs_sum=np.array(out.vs_sum), vb_sum=np.array(out.vb_sum), p_time=p, p_over=out.p_over,
+                     ttek=out.ttek, counts={n: getattr(out, n) for n in names},
+                     used={k: (v.pos if v is not None else 0) for k, v in srcs.items()})
+
+
+NEG_STREAMS = ("positives", "negatives", "services", "choices")
+
+
+def neg_replay(c, buffer, neg_type, arrays: dict, total_served, p_bins=128) -> NegResult:
+    """QsSimNegatives.run() on pre-generated draws; arrays maps NEG_STREAMS names to 1-D arrays."""
+    keep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in arrays.items() if v is not None}
+    return _neg_run(c, buffer, neg_type, {k: (_replay_src(keep[k]) if k in keep else None) for k in NEG_STREAMS},
+                    total_served, p_bins)
+
+
+def neg_generate(c, buffer, neg_type, positive, negative, service, total_served, seed, rep, p_bins=128) -> NegResult:
+    """Generator mode: positive gaps = word 0 and services = word 1 of stream sid 0 (as the FIFO kernel), negative
+    gaps = word 0 and server choices = word 1 of stream sid 1."""
+
+    class U01:
+        mean, half_interval = 0.5, 0.5
+
+    srcs = {"positives": _gen_src(positive, seed, 0, rep, 0), "services": _gen_src(service, seed, 0, rep, 1),
+            "negatives": _gen_src(negative, seed, 1, rep, 0), "choices": _gen_src(("Uniform", U01), seed, 1, rep, 1)}
+    return _neg_run(c, buffer, neg_type, srcs, total_served, p_bins)

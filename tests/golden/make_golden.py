@@ -435,6 +435,79 @@ def make_vac():
     vac_case("c2_npolicy3_warm", 2, None, dict(arrivals=ex(0.6), services=ex(0.8), warm=ex(0.5)), n, big_n=3)
 
 
+# --------------------------------------------------------------------------- negative arrivals
+class ReplayChoice:
+    """Stands in for the `random` module inside most_queue.sim.negative: choice(seq) picks element
+    floor(u * len(seq)) with u from a replayed uniform stream (the reference calls random.choice, negative.py:345)."""
+
+    def __init__(self, arr, counter):
+        self.arr, self.counter = arr, counter
+
+    def choice(self, seq):
+        i = self.counter[0]
+        self.counter[0] = i + 1
+        return seq[min(int(self.arr[i] * len(seq)), len(seq) - 1)]
+
+
+def neg_case(name, c, buffer, neg_type, streams, total_served, nprobs=128):
+    import most_queue.sim.negative as negmod
+    from most_queue.sim.negative import NegativeServiceType, QsSimNegatives
+
+    qs = QsSimNegatives(c, getattr(NegativeServiceType, neg_type), buffer=buffer)
+    qs.set_positive_sources(1.0, "M")
+    qs.set_negative_sources(1.0, "M")
+    qs.set_servers(1.0, "M")
+    used = {k: [0] for k in streams}
+    qs.positive_source = ReplayDist(streams["positives"], used["positives"])
+    qs.negative_source = ReplayDist(streams["negatives"], used["negatives"])
+    for srv in qs.servers:
+        srv.dist = ReplayDist(streams["services"], used["services"])
+    qs._free_servers = LowestFirstSet(range(c))
+    qs.positive_arrival_time = qs.positive_source.generate()  # negative.py:135
+    qs.negative_arrival_time = qs.negative_source.generate()  # negative.py:153
+    saved = negmod.random
+    if "choices" in streams:
+        negmod.random = ReplayChoice(streams["choices"], used["choices"])
+    try:
+        with quiet():
+            while qs.served < total_served:
+                qs.run_one_step()
+                if not isinstance(qs._free_servers, LowestFirstSet):  # DISASTER rebuilds the set (negative.py:295)
+                    qs._free_servers = LowestFirstSet(qs._free_servers)
+    finally:
+        negmod.random = saved
+    out = dict(c=c, buffer=-1 if buffer is None else buffer, neg_type=neg_type, total_served=total_served,
+               w=np.array(qs.w, dtype=np.float64), v=np.array(qs.v, dtype=np.float64),
+               v_served=np.array(qs.v_served, dtype=np.float64), v_broken=np.array(qs.v_broken, dtype=np.float64),
+               p_time=np.array(qs.p[:nprobs], dtype=np.float64), ttek=float(qs.ttek),
+               positive_arrived=qs.positive_arrived, negative_arrived=qs.negative_arrived, taked=qs.taked,
+               served=qs.served, broken=qs.broken, total=qs.total, dropped=qs.dropped, in_sys=qs.in_sys,
+               queued=qs.queue.size())
+    for k, a in streams.items():
+        out["s_" + k] = np.asarray(a, dtype=np.float64)
+        out["used_" + k] = used[k][0]
+    np.savez_compressed(os.path.join(OUT, f"neg_{name}.npz"), **out)
+    print(f"neg_{name}: served={qs.served} broken={qs.broken} total={qs.total} dropped={qs.dropped} "
+          f"v1={qs.v[0]:.5g} used={ {k: v[0] for k, v in used.items()} }")
+
+
+def make_neg():
+    rng = np.random.default_rng(20260707)
+    n = 3000
+    ex = lambda mean, m=3 * n: rng.exponential(mean, m)
+    # M/G/1 and M/G/n with disasters (tests/test_mg1_disaster.py, test_mgn_disaster.py shapes)
+    neg_case("disaster_c1", 1, None, "DISASTER", dict(positives=ex(1.0), negatives=ex(4.0), services=rng.gamma(0.7, 1.0, 3 * n)), n)
+    neg_case("disaster_c3", 3, None, "DISASTER", dict(positives=ex(0.4), negatives=ex(3.0), services=ex(1.0)), n)
+    neg_case("disaster_c2_buffer3", 2, 3, "DISASTER", dict(positives=ex(0.4), negatives=ex(5.0), services=ex(0.9)), n)
+    # remove the customer in service (tests/test_mg1_rcs.py, test_mgn_rcs.py shapes)
+    neg_case("rcs_c1", 1, None, "RCS", dict(positives=ex(1.0), negatives=ex(2.5), services=rng.gamma(0.7, 1.0, 3 * n),
+                                            choices=rng.random(3 * n)), n)
+    neg_case("rcs_c3", 3, None, "RCS", dict(positives=ex(0.4), negatives=ex(1.5), services=ex(1.0),
+                                            choices=rng.random(3 * n)), n)
+    neg_case("rcs_c2_buffer2", 2, 2, "RCS", dict(positives=ex(0.4), negatives=ex(2.0), services=ex(0.9),
+                                                 choices=rng.random(3 * n)), n)
+
+
 # --------------------------------------------------------------------------- tandem with blocking
 def tandem_case(name, capacity, A, S, total_served, warmup_fraction=0.05):
     from most_queue.sim.networks.tandem_blocking import TandemBlockingSim
@@ -555,7 +628,7 @@ def make_theory():
 
 if __name__ == "__main__":
     import_reference()
-    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "vac", "theory"]
+    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "vac", "neg", "theory"]
     if "fifo" in which:
         make_fifo()
     if "prio" in which:
@@ -568,5 +641,7 @@ if __name__ == "__main__":
         make_tandem()
     if "vac" in which:
         make_vac()
+    if "neg" in which:
+        make_neg()
     if "theory" in which:
         make_theory()
