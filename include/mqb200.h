@@ -484,6 +484,67 @@ int mq_sim_vacation(mq_ctx *ctx, const mq_vac_cfg *cfg, double *agg, double *rep
 int mq_replay_vacation(mq_ctx *ctx, const mq_vac_cfg *cfg, const double *const *X, const int64_t *n, double *agg,
                        double *rep_out);
 
+/* ---- queue with negative arrivals.  Replaces QsSimNegatives(n, type_of_negatives, buffer).set_positive_sources /
+ * set_negative_sources / set_servers / run(total_served) (sim/negative.py:62,116,134,184) for the DISASTER type with
+ * the CLEAR_SYSTEM scenario and the RCS type with the REMOVE scenario (the defaults); other types and scenarios are
+ * rejected with MQ_E_UNSUPPORTED */
+#define MQ_NEG_DISASTER 1 /* NegativeServiceType.DISASTER, negative.py:21 */
+#define MQ_NEG_RCS 2      /* NegativeServiceType.RCS,      negative.py:22 */
+#define MQ_NEG_STREAMS 4
+#define MQ_NS_POSITIVES 0
+#define MQ_NS_NEGATIVES 1
+#define MQ_NS_SERVICES 2
+#define MQ_NS_CHOICES 3 /* uniforms: RCS removes the floor(u * busy)-th busy server in index order */
+
+typedef struct {
+    int32_t c;               /* num_of_channels (1..32) */
+    int32_t p_bins;
+    int64_t buffer;          /* < 0: infinite */
+    int32_t type;            /* MQ_NEG_DISASTER or MQ_NEG_RCS */
+    int32_t queue_cap;       /* infinite buffer: waiting-line capacity of the engine (0: 1024) */
+    mq_dist positive, negative, service;
+    int64_t total_served;
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+} mq_neg_cfg;
+
+/* per-replication record rows */
+#define MQ_N_TTEK 0
+#define MQ_N_FLAGS 1
+#define MQ_N_POS_ARRIVED 2
+#define MQ_N_NEG_ARRIVED 3
+#define MQ_N_TAKED 4
+#define MQ_N_SERVED 5
+#define MQ_N_BROKEN 6
+#define MQ_N_TOTAL 7
+#define MQ_N_DROPPED 8
+#define MQ_N_INSYS 9
+#define MQ_N_QUEUED 10
+#define MQ_N_POVER 11
+#define MQ_N_WSUM 12   /* 4: waits                                   */
+#define MQ_N_VSUM 16   /* 4: sojourn of all jobs (served and broken) */
+#define MQ_N_VSSUM 20  /* 4: served jobs only                        */
+#define MQ_N_VBSUM 24  /* 4: broken jobs only                        */
+#define MQ_N_WRUN 28   /* 4 x 4: the reference's running moments in the same order */
+#define MQ_N_VRUN 32
+#define MQ_N_VSRUN 36
+#define MQ_N_VBRUN 40
+#define MQ_N_USED 44   /* 4: draws consumed per stream */
+#define MQ_N_P 48
+#define MQ_N_ROWS(pb) (48 + (pb))
+
+/* aggregate: [0] replications, [1] sum ttek, [2] flagged, [3] sum served, [4] sum broken, [5] sum total, [6] sum
+ * positive arrivals, [7] sum dropped; [8..11] w (sum over replications of w_sum/taked), [12..15] squares; [16..19] v
+ * (/total), [20..23] squares; [24..27] v_served (/served), [28..31] squares; [32..35] v_broken (/broken), [36..39]
+ * squares; [40] q = served/total, [41] its square; [48..48+pb) p = time in state / ttek, then pb squares */
+#define MQ_N_AGG_LEN(pb) (48 + 2 * (pb))
+
+int mq_sim_negatives(mq_ctx *ctx, const mq_neg_cfg *cfg, double *agg, double *rep_out);
+/* replay form: X[s] = draws of stream s ([n[s]][replications]; choices may be NULL for DISASTER) */
+int mq_replay_negatives(mq_ctx *ctx, const mq_neg_cfg *cfg, const double *const *X, const int64_t *n, double *agg,
+                        double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

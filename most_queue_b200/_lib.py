@@ -215,6 +215,32 @@ def vac_agg_len(p_bins):
     return 32 + 2 * int(p_bins)
 
 
+NEG_STREAMS = ("positives", "negatives", "services", "choices")
+NEG_TYPES = {"DISASTER": 1, "RCS": 2}
+
+
+class MqNegCfg(C.Structure):
+    _fields_ = [
+        ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("type", C.c_int32), ("queue_cap", C.c_int32),
+        ("positive", MqDist), ("negative", MqDist), ("service", MqDist),
+        ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
+    ]
+
+
+# record rows of the negative-arrivals kernel (include/mqb200.h MQ_N_*)
+(N_TTEK, N_FLAGS, N_POS_ARRIVED, N_NEG_ARRIVED, N_TAKED, N_SERVED, N_BROKEN, N_TOTAL, N_DROPPED, N_INSYS, N_QUEUED,
+ N_POVER, N_WSUM, N_VSUM, N_VSSUM, N_VBSUM, N_WRUN, N_VRUN, N_VSRUN, N_VBRUN, N_USED, N_P) = (
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48)
+
+
+def neg_rec_rows(p_bins):
+    return 48 + int(p_bins)
+
+
+def neg_agg_len(p_bins):
+    return 48 + 2 * int(p_bins)
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -280,6 +306,10 @@ def load():
         L.mq_sim_vacation.argtypes = [vp, C.POINTER(MqVacCfg), dp, dp]
         L.mq_replay_vacation.restype = C.c_int
         L.mq_replay_vacation.argtypes = [vp, C.POINTER(MqVacCfg), C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
+        L.mq_sim_negatives.restype = C.c_int
+        L.mq_sim_negatives.argtypes = [vp, C.POINTER(MqNegCfg), dp, dp]
+        L.mq_replay_negatives.restype = C.c_int
+        L.mq_replay_negatives.argtypes = [vp, C.POINTER(MqNegCfg), C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -687,6 +717,40 @@ class Context:
         rec = np.empty((vac_rec_rows(p_bins), reps))
         check(self._L.mq_replay_vacation(self._h, C.byref(cfg), ptr, n, agg.ctypes.data_as(C.POINTER(C.c_double)),
                                          rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
+
+    # ---- K9 ----
+    def _neg_cfg(self, c, buffer, neg_type, total_served, replications, rep0, seed, p_bins, queue_cap):
+        cfg = MqNegCfg()
+        cfg.c, cfg.p_bins = int(c), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        cfg.type = int(neg_type)
+        cfg.queue_cap = int(queue_cap)
+        cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        return cfg
+
+    def sim_negatives(self, c, buffer, neg_type, positive, negative, service, total_served, replications, rep0, seed,
+                      p_bins=128, queue_cap=0, per_replication=False):
+        cfg = self._neg_cfg(c, buffer, neg_type, total_served, replications, rep0, seed, p_bins, queue_cap)
+        cfg.positive, cfg.negative, cfg.service = positive, negative, service
+        agg = np.zeros(neg_agg_len(p_bins))
+        rec = np.empty((neg_rec_rows(p_bins), int(replications))) if per_replication else None
+        check(self._L.mq_sim_negatives(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                       rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_negatives(self, c, buffer, neg_type, arrays: dict, total_served, p_bins=128, queue_cap=0):
+        """arrays: [n, reps] draws under the names of NEG_STREAMS (choices only for RCS)."""
+        X = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in arrays.items() if v is not None}
+        reps = X["positives"].shape[1]
+        cfg = self._neg_cfg(c, buffer, neg_type, total_served, reps, 0, 0, p_bins, queue_cap)
+        ptr = (C.c_void_p * 4)(*[X[k].ctypes.data if k in X else None for k in NEG_STREAMS])
+        n = (C.c_int64 * 4)(*[X[k].shape[0] if k in X else 0 for k in NEG_STREAMS])
+        agg = np.zeros(neg_agg_len(p_bins))
+        rec = np.empty((neg_rec_rows(p_bins), reps))
+        check(self._L.mq_replay_negatives(self._h, C.byref(cfg), ptr, n, agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                          rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec
 
     def last_timing(self):

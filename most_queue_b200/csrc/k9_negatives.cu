@@ -1,0 +1,262 @@
+// k9_negatives.cu -- K9: GI/G/c/r queue with negative arrivals, one lane per replication.
+//
+// Walks QsSimNegatives.run (most_queue/sim/negative.py) event for event:
+//   event selection   negative.py:385-408   candidates in the order positive_arrival, negative_arrival, serving;
+//                                           the first minimum wins
+//   positive_arrival  negative.py:225-241   base arrival logic (queue when no channel is free)
+//   negative_arrival  negative.py:243-383   no effect on an empty system;
+//       DISASTER / CLEAR_SYSTEM (:277-304)  every job in service (index order), then every waiting job (FIFO
+//                                           order) leaves as "broken"; waiting jobs also contribute their wait
+//       RCS / REMOVE (:338-383)             one busy server, chosen uniformly, loses its job ("broken"); the head
+//                                           of the waiting line takes the server
+//   serving           negative.py:425-450   v over ALL departures counts `total`, v_served counts `served`
+// The reference picks the RCS victim with Python's global random.choice; here it is the floor(u * busy)-th busy
+// server in index order, u from the `choices` stream (replay array, or word 1 of generator stream 1).  fp64 with
+// explicit round-to-nearest intrinsics in the reference's order: in replay mode every output is bit-identical.
+// Generator streams: positive gaps = word 0 and services = word 1 of stream 0 (as the FIFO kernel), negative gaps =
+// word 0 and choices = word 1 of stream 1.
+#include "k9_negatives.cuh"
+
+namespace mq {
+
+__device__ __forceinline__ void k9_sample(double *run, double *sum, double x, long long count)
+{
+    // refresh_moments_stat (stats_update.py:6-22) + plain power sums
+    const double inv_count = __drcp_rn((double)count);
+    const double one_minus = __dsub_rn(1.0, inv_count);
+    double power = x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        run[i] = __dadd_rn(__dmul_rn(run[i], one_minus), __dmul_rn(power, inv_count));
+        sum[i] = __dadd_rn(sum[i], power);
+        power = __dmul_rn(power, x);
+    }
+}
+
+__global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
+{
+    const long long gtid = (long long)blockIdx.x * K9_BLOCK + threadIdx.x;
+    const long long R = P.reps;
+    const int c = P.c;
+    const DistF law_pos = P.positive, law_neg = P.negative, law_srv = P.service;
+
+    for (long long rl = gtid; rl < R; rl += P.lanes) {
+        const uint32_t rep = P.rep0 + (uint32_t)rl;
+        double *rec = P.rec + rl;
+        double *Q = P.queue + gtid;
+        double end[K9_MAXC], arr[K9_MAXC];
+        uint32_t busy = 0;
+        for (int j = 0; j < c; ++j) {
+            end[j] = 1e10;
+            arr[j] = 0.0;
+        }
+        long long used[MQ_NEG_STREAMS] = {0, 0, 0, 0};
+        int status = 0;
+
+        auto draw = [&](int s) -> double {
+            const long long i = used[s]++;
+            if (P.replay) {
+                if (i >= P.n[s]) {
+                    status = MQ_E_INPUT_SHORT;
+                    return 0.0;
+                }
+                return P.X[P.off[s] + i * R + rl];
+            }
+            const uint32_t sid = (s == MQ_NS_NEGATIVES || s == MQ_NS_CHOICES) ? 1u : 0u;
+            const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * sid);
+            uint2 w = philox2x32_10((uint32_t)i, rep, key);
+            if (s == MQ_NS_POSITIVES) return (double)sample<-1>(law_pos, w.x, (uint32_t)i, rep, key, 0);
+            if (s == MQ_NS_NEGATIVES) return (double)sample<-1>(law_neg, w.x, (uint32_t)i, rep, key, 0);
+            if (s == MQ_NS_SERVICES) return (double)sample<-1>(law_srv, w.y, (uint32_t)i, rep, key, 1);
+            return ((double)w.y + 0.5) * 0x1p-32;
+        };
+
+        double ttek = 0.0, p_over = 0.0;
+        long long pos_arrived = 0, neg_arrived = 0, taked = 0, served = 0, broken = 0, total = 0, dropped = 0,
+                  in_sys = 0;
+        int free_channels = c, qhead = 0, qsize = 0;
+        double w_run[4] = {0, 0, 0, 0}, v_run[4] = {0, 0, 0, 0}, vs_run[4] = {0, 0, 0, 0}, vb_run[4] = {0, 0, 0, 0};
+        double w_sum[4] = {0, 0, 0, 0}, v_sum[4] = {0, 0, 0, 0}, vs_sum[4] = {0, 0, 0, 0}, vb_sum[4] = {0, 0, 0, 0};
+
+        auto p_add = [&](double t_new) {  // _update_state_probs base.py:327-340
+            const double dt = __dsub_rn(t_new, ttek);
+            if (in_sys < P.p_bins)
+                atomicAdd(&rec[(long long)(MQ_N_P + in_sys) * R], dt);  // fire-and-forget fp64 add, same rounding
+            else
+                p_over = __dadd_rn(p_over, dt);
+        };
+        auto broken_sample = [&](double a) {  // negative.py:283-288
+            broken++;
+            total++;
+            const double sj = __dsub_rn(ttek, a);
+            k9_sample(v_run, v_sum, sj, total);
+            k9_sample(vb_run, vb_sum, sj, broken);
+        };
+        auto q_pop = [&]() -> double {
+            const double a = Q[(long long)qhead * P.lanes];
+            qsize--;
+            qhead = (qsize == 0 || qhead + 1 >= P.qcap) ? 0 : qhead + 1;
+            return a;
+        };
+        auto head_to_channel = [&](int ch) {  // send_head_of_queue_to_channel base.py:288-310
+            const double a = q_pop();
+            taked++;
+            k9_sample(w_run, w_sum, __dadd_rn(0.0, __dsub_rn(ttek, a)), taked);
+            arr[ch] = a;
+            end[ch] = __dadd_rn(ttek, draw(MQ_NS_SERVICES));
+            busy |= 1u << ch;
+            free_channels--;
+        };
+
+        double pos_time = draw(MQ_NS_POSITIVES);  // negative.py:135
+        double neg_time = draw(MQ_NS_NEGATIVES);  // negative.py:153
+
+        while (served < P.jobs && status == 0) {
+            int midx = -1;
+            double mt = 1e16;
+            for (int j = 0; j < c; ++j) {
+                if (end[j] < mt) {
+                    mt = end[j];
+                    midx = j;
+                }
+            }
+            int ev = 0;  // 0 positive arrival, 1 negative arrival, 2 serving
+            double et = pos_time;
+            if (neg_time < et) {
+                ev = 1;
+                et = neg_time;
+            }
+            if (midx >= 0 && mt < et) ev = 2;
+
+            if (ev == 0) {
+                // positive_arrival negative.py:225-241
+                pos_arrived++;
+                p_add(pos_time);
+                in_sys++;
+                ttek = pos_time;
+                pos_time = __dadd_rn(ttek, draw(MQ_NS_POSITIVES));
+                if (free_channels == 0) {
+                    // send_task_to_queue base.py:186-212
+                    if (P.buffer < 0 || qsize < P.buffer) {
+                        if (qsize >= P.qcap) {
+                            status = MQ_E_OVERFLOW;
+                        } else {
+                            int slot = qhead + qsize;
+                            if (slot >= P.qcap) slot -= P.qcap;
+                            Q[(long long)slot * P.lanes] = ttek;
+                            qsize++;
+                        }
+                    } else {
+                        dropped++;
+                        in_sys--;
+                    }
+                } else {
+                    // send_task_to_channel base.py:155-184, lowest free channel
+                    const int j = __ffs(~busy) - 1;
+                    taked++;
+                    k9_sample(w_run, w_sum, 0.0, taked);
+                    arr[j] = ttek;
+                    end[j] = __dadd_rn(ttek, draw(MQ_NS_SERVICES));
+                    busy |= 1u << j;
+                    free_channels--;
+                }
+            } else if (ev == 1) {
+                // negative_arrival negative.py:243-383
+                neg_arrived++;
+                p_add(neg_time);
+                ttek = neg_time;
+                neg_time = __dadd_rn(ttek, draw(MQ_NS_NEGATIVES));
+                if (in_sys != 0) {
+                    if (P.type == MQ_NEG_DISASTER) {
+                        for (int j = 0; j < c; ++j) {
+                            if (!((busy >> j) & 1u)) continue;
+                            const double a = arr[j];
+                            end[j] = 1e10;
+                            broken_sample(a);
+                        }
+                        busy = 0;
+                        in_sys = 0;
+                        free_channels = c;
+                        while (qsize > 0) {
+                            const double a = q_pop();
+                            taked++;
+                            total++;
+                            broken++;
+                            k9_sample(w_run, w_sum, __dadd_rn(0.0, __dsub_rn(ttek, a)), taked);
+                            const double sj = __dsub_rn(ttek, a);
+                            k9_sample(v_run, v_sum, sj, total);
+                            k9_sample(vb_run, vb_sum, sj, broken);
+                        }
+                    } else if (busy != 0) {
+                        const int nb = __popc(busy);
+                        int pick = (int)(draw(MQ_NS_CHOICES) * (double)nb);
+                        if (pick >= nb) pick = nb - 1;
+                        uint32_t left = busy;
+                        for (int q = 0; q < pick; ++q) left &= left - 1u;  // drop the `pick` lowest busy servers
+                        const int j = __ffs(left) - 1;
+                        const double a = arr[j];
+                        end[j] = 1e10;
+                        busy &= ~(1u << j);
+                        free_channels++;
+                        broken_sample(a);
+                        in_sys--;
+                        if (qsize != 0) head_to_channel(j);
+                    }
+                }
+            } else {
+                // serving negative.py:425-450
+                const double time_to_end = end[midx];
+                const double a = arr[midx];
+                end[midx] = 1e10;
+                busy &= ~(1u << midx);
+                p_add(time_to_end);
+                ttek = time_to_end;
+                free_channels++;
+                served++;
+                total++;
+                const double sj = __dsub_rn(ttek, a);
+                k9_sample(v_run, v_sum, sj, total);
+                k9_sample(vs_run, vs_sum, sj, served);
+                in_sys--;
+                if (qsize != 0) head_to_channel(midx);
+            }
+        }
+
+        rec[(long long)MQ_N_TTEK * R] = ttek;
+        rec[(long long)MQ_N_FLAGS * R] = (double)(status ? -status : 0);
+        rec[(long long)MQ_N_POS_ARRIVED * R] = (double)pos_arrived;
+        rec[(long long)MQ_N_NEG_ARRIVED * R] = (double)neg_arrived;
+        rec[(long long)MQ_N_TAKED * R] = (double)taked;
+        rec[(long long)MQ_N_SERVED * R] = (double)served;
+        rec[(long long)MQ_N_BROKEN * R] = (double)broken;
+        rec[(long long)MQ_N_TOTAL * R] = (double)total;
+        rec[(long long)MQ_N_DROPPED * R] = (double)dropped;
+        rec[(long long)MQ_N_INSYS * R] = (double)in_sys;
+        rec[(long long)MQ_N_QUEUED * R] = (double)qsize;
+        rec[(long long)MQ_N_POVER * R] = p_over;
+        for (int i = 0; i < 4; ++i) {
+            rec[(long long)(MQ_N_WSUM + i) * R] = w_sum[i];
+            rec[(long long)(MQ_N_VSUM + i) * R] = v_sum[i];
+            rec[(long long)(MQ_N_VSSUM + i) * R] = vs_sum[i];
+            rec[(long long)(MQ_N_VBSUM + i) * R] = vb_sum[i];
+            rec[(long long)(MQ_N_WRUN + i) * R] = w_run[i];
+            rec[(long long)(MQ_N_VRUN + i) * R] = v_run[i];
+            rec[(long long)(MQ_N_VSRUN + i) * R] = vs_run[i];
+            rec[(long long)(MQ_N_VBRUN + i) * R] = vb_run[i];
+        }
+        for (int s = 0; s < MQ_NEG_STREAMS; ++s) rec[(long long)(MQ_N_USED + s) * R] = (double)used[s];
+    }
+}
+
+cudaError_t k9_launch(const K9Params &P, int grid, cudaStream_t st)
+{
+    k9_negatives<<<grid, K9_BLOCK, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t k9_occupancy(int *blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k9_negatives, K9_BLOCK, 0);
+}
+
+}  // namespace mq

@@ -33,6 +33,15 @@ class VacationResults(QueueResults):
 
 
 @dataclass
+class NegativeArrivalsResults(QueueResults):
+    """Results of a queue with negative arrivals (structs.py:147-158 of the reference)."""
+
+    v_served: list | None = None
+    v_broken: list | None = None
+    q: float | None = None
+
+
+@dataclass
 class MulticlassResults:
     v: list | None = None
     w: list | None = None
