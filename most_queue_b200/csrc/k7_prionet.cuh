@@ -28,4 +28,9 @@ struct K7Params {
 cudaError_t k7_launch(const K7Params &P, int grid, cudaStream_t st);
 cudaError_t k7_occupancy(int *blocks_per_sm);
 
+// k7v2_prionet.cu: the register / shared-memory resident predicated form for <= 16 servers in total
+bool k7v2_supported(int m, int K, int nserv);
+cudaError_t k7v2_launch(const K7Params &P, int grid, cudaStream_t st);
+cudaError_t k7v2_occupancy(const K7Params &P, int *blocks_per_sm);
+
 }  // namespace mq

@@ -2,6 +2,7 @@
 #include "k7_prionet.cuh"
 #include "mq_host.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace mq;
@@ -108,8 +109,19 @@ static int prionet_common(mq_ctx *ctx, const mq_prionet_cfg *cfg, bool replay, c
         for (int k = 0; k < K; ++k) P.src[k] = make_distf(cfg->src[k]);
         for (int i = 0; i < m * K; ++i) P.srv[i] = make_distf(cfg->srv[i]);
     }
+    // small networks run the predicated, on-chip-state form (k7v2_prionet.cu); MQ_K7_V1=1 forces the general kernel.
+    // Its cursors are 32 bit.
+    bool v2 = k7v2_supported(m, K, P.nserv) && !std::getenv("MQ_K7_V1") && cfg->job_served < (1ll << 28);
+    if (replay) {
+        v2 = v2 && n_u < (1ll << 31);
+        for (int k = 0; k < K; ++k) v2 = v2 && n_a[k] < (1ll << 31);
+        for (int i = 0; i < m * K; ++i) v2 = v2 && n_s[i] < (1ll << 31);
+    }
     int occ = 0;
-    CU(k7_occupancy(&occ));
+    if (v2)
+        CU(k7v2_occupancy(P, &occ));
+    else
+        CU(k7_occupancy(&occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     if (occ > 8) occ = 8;  // bounds the waiting-line scratch
     long long grid = (long long)occ * ctx->sms;
@@ -139,7 +151,10 @@ static int prionet_common(mq_ctx *ctx, const mq_prionet_cfg *cfg, bool replay, c
     CU(cudaMemcpyAsync(ctx->desc.p, desc.data(), sizeof(RatioDesc) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->rec.p, 0, rec_bytes, ctx->stream));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(k7_launch(P, (int)grid, ctx->stream));
+    if (v2)
+        CU(k7v2_launch(P, (int)grid, ctx->stream));
+    else
+        CU(k7_launch(P, (int)grid, ctx->stream));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(launch_reduce_ratio((const double *)ctx->rec.p, R, (const RatioDesc *)ctx->desc.p, nq, (double *)ctx->agg.p,

@@ -57,7 +57,7 @@ elif which == "k6":
         ctx.sim_tandem(caps, L.make_dist("M", 0.9), srv, N, 0.05, R, 0, 5)
     t = ctx.last_timing()
     print("k6", t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
-else:
+elif which == "k7":
     R0 = [[1, 0, 0, 0], [0, 0, 0.7, 0.3], [0, 0, 0, 1], [0, 0, 0, 1]]
     R1 = [[0.5, 0.5, 0, 0], [0, 0, 0, 1], [0.2, 0, 0.3, 0.5], [0, 0, 0, 1]]
     srv = [[L.make_dist("H", H2Distribution.get_params_by_mean_and_cv(0.5 + 0.2 * j + 0.1 * i, 1.3)) for j in range(2)]
@@ -68,3 +68,17 @@ else:
                         [L.make_dist("M", 0.6), L.make_dist("M", 0.7)], srv, N, R, 0, 11)
     t = ctx.last_timing()
     print("k7", t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
+if which in ("k8", "k9"):
+    import time as _t
+    R, N = 200000, 5000
+    if which == "k8":
+        d = {"arrivals": L.make_dist("M", 1.0), "services": L.make_dist("M", 1.6), "warm": L.make_dist("M", 2.0),
+             "cold": L.make_dist("M", 1.5)}
+        for _ in range(2):
+            ctx.sim_vacation(1, None, d, N, R, 0, 3, p_bins=32)
+    else:
+        for _ in range(2):
+            ctx.sim_negatives(2, None, L.NEG_TYPES["RCS"], L.make_dist("M", 1.0), L.make_dist("M", 0.3),
+                              L.make_dist("M", 0.8), N, R, 0, 3, p_bins=32)
+    t = ctx.last_timing()
+    print(which, t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
