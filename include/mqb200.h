@@ -485,11 +485,14 @@ int mq_replay_vacation(mq_ctx *ctx, const mq_vac_cfg *cfg, const double *const *
                        double *rep_out);
 
 /* ---- queue with negative arrivals.  Replaces QsSimNegatives(n, type_of_negatives, buffer).set_positive_sources /
- * set_negative_sources / set_servers / run(total_served) (sim/negative.py:62,116,134,184) for the DISASTER type with
- * the CLEAR_SYSTEM scenario and the RCS type with the REMOVE scenario (the defaults); other types and scenarios are
- * rejected with MQ_E_UNSUPPORTED */
+ * set_negative_sources / set_servers / run(total_served) (sim/negative.py:62,116,134,184) for the DISASTER and RCS
+ * types with all four scenarios each (negative.py:27-54); the RCH / RCE types are rejected with MQ_E_UNSUPPORTED */
 #define MQ_NEG_DISASTER 1 /* NegativeServiceType.DISASTER, negative.py:21 */
 #define MQ_NEG_RCS 2      /* NegativeServiceType.RCS,      negative.py:22 */
+#define MQ_NEG_REMOVE 1        /* DisasterScenario.CLEAR_SYSTEM / RcsScenario.REMOVE: the jobs leave as "broken"        */
+#define MQ_NEG_REQUEUE 2       /* REQUEUE_ALL / REQUEUE: the interrupted jobs restart with a new service draw         */
+#define MQ_NEG_RESUME 3        /* RESUME_ALL / RESUME: they continue with their remaining service time                */
+#define MQ_NEG_REQUEUE_FIXED 4 /* REQUEUE_ALL_NO_RESAMPLING / REQUEUE_NO_RESAMPLING: they restart with the same total */
 #define MQ_NEG_STREAMS 4
 #define MQ_NS_POSITIVES 0
 #define MQ_NS_NEGATIVES 1
@@ -502,6 +505,8 @@ typedef struct {
     int64_t buffer;          /* < 0: infinite */
     int32_t type;            /* MQ_NEG_DISASTER or MQ_NEG_RCS */
     int32_t queue_cap;       /* infinite buffer: waiting-line capacity of the engine (0: 1024) */
+    int32_t scenario;        /* MQ_NEG_REMOVE (0 means the same) .. MQ_NEG_REQUEUE_FIXED */
+    int32_t reserved;
     mq_dist positive, negative, service;
     int64_t total_served;
     int64_t replications;

@@ -217,12 +217,14 @@ def vac_agg_len(p_bins):
 
 NEG_STREAMS = ("positives", "negatives", "services", "choices")
 NEG_TYPES = {"DISASTER": 1, "RCS": 2}
+NEG_SCENARIOS = {"CLEAR_SYSTEM": 1, "REMOVE": 1, "REQUEUE_ALL": 2, "REQUEUE": 2, "RESUME_ALL": 3, "RESUME": 3,
+                 "REQUEUE_ALL_NO_RESAMPLING": 4, "REQUEUE_NO_RESAMPLING": 4}
 
 
 class MqNegCfg(C.Structure):
     _fields_ = [
         ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("type", C.c_int32), ("queue_cap", C.c_int32),
-        ("positive", MqDist), ("negative", MqDist), ("service", MqDist),
+        ("scenario", C.c_int32), ("reserved", C.c_int32), ("positive", MqDist), ("negative", MqDist), ("service", MqDist),
         ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
     ]
 
@@ -720,8 +722,9 @@ class Context:
         return agg, rec
 
     # ---- K9 ----
-    def _neg_cfg(self, c, buffer, neg_type, total_served, replications, rep0, seed, p_bins, queue_cap):
+    def _neg_cfg(self, c, buffer, neg_type, total_served, replications, rep0, seed, p_bins, queue_cap, scenario=1):
         cfg = MqNegCfg()
+        cfg.scenario = int(scenario)
         cfg.c, cfg.p_bins = int(c), int(p_bins)
         cfg.buffer = -1 if buffer is None else int(buffer)
         cfg.type = int(neg_type)
@@ -731,8 +734,8 @@ class Context:
         return cfg
 
     def sim_negatives(self, c, buffer, neg_type, positive, negative, service, total_served, replications, rep0, seed,
-                      p_bins=128, queue_cap=0, per_replication=False):
-        cfg = self._neg_cfg(c, buffer, neg_type, total_served, replications, rep0, seed, p_bins, queue_cap)
+                      p_bins=128, queue_cap=0, per_replication=False, scenario=1):
+        cfg = self._neg_cfg(c, buffer, neg_type, total_served, replications, rep0, seed, p_bins, queue_cap, scenario)
         cfg.positive, cfg.negative, cfg.service = positive, negative, service
         agg = np.zeros(neg_agg_len(p_bins))
         rec = np.empty((neg_rec_rows(p_bins), int(replications))) if per_replication else None
@@ -740,11 +743,11 @@ class Context:
                                        rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
         return agg, rec
 
-    def replay_negatives(self, c, buffer, neg_type, arrays: dict, total_served, p_bins=128, queue_cap=0):
+    def replay_negatives(self, c, buffer, neg_type, arrays: dict, total_served, p_bins=128, queue_cap=0, scenario=1):
         """arrays: [n, reps] draws under the names of NEG_STREAMS (choices only for RCS)."""
         X = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in arrays.items() if v is not None}
         reps = X["positives"].shape[1]
-        cfg = self._neg_cfg(c, buffer, neg_type, total_served, reps, 0, 0, p_bins, queue_cap)
+        cfg = self._neg_cfg(c, buffer, neg_type, total_served, reps, 0, 0, p_bins, queue_cap, scenario)
         ptr = (C.c_void_p * 4)(*[X[k].ctypes.data if k in X else None for k in NEG_STREAMS])
         n = (C.c_int64 * 4)(*[X[k].shape[0] if k in X else 0 for k in NEG_STREAMS])
         agg = np.zeros(neg_agg_len(p_bins))

@@ -9,6 +9,11 @@
 //                                           order) leaves as "broken"; waiting jobs also contribute their wait
 //       RCS / REMOVE (:338-383)             one busy server, chosen uniformly, loses its job ("broken"); the head
 //                                           of the waiting line takes the server
+//       REQUEUE / RESUME / ..NO_RESAMPLING  (:253-276, :347-372) the interrupted jobs go back to the head of the line
+//                                           and, servers being free, restart at once: one more `taked`, one more
+//                                           sample of their unchanged wait, and a completion time from a new draw /
+//                                           the remaining time / the original total; DISASTER hands the servers out
+//                                           again in order of arrival (stable sort, lowest server first)
 //   serving           negative.py:425-450   v over ALL departures counts `total`, v_served counts `served`
 // The reference picks the RCS victim with Python's global random.choice; here it is the floor(u * busy)-th busy
 // server in index order, u from the `choices` stream (replay array, or word 1 of generator stream 1).  fp64 with
@@ -44,11 +49,11 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
         const uint32_t rep = P.rep0 + (uint32_t)rl;
         double *rec = P.rec + rl;
         double *Q = P.queue + gtid;
-        double end[K9_MAXC], arr[K9_MAXC];
+        double end[K9_MAXC], arr[K9_MAXC], wait[K9_MAXC], tot[K9_MAXC];
         uint32_t busy = 0;
         for (int j = 0; j < c; ++j) {
             end[j] = 1e10;
-            arr[j] = 0.0;
+            arr[j] = wait[j] = tot[j] = 0.0;
         }
         long long used[MQ_NEG_STREAMS] = {0, 0, 0, 0};
         int status = 0;
@@ -101,9 +106,29 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
         auto head_to_channel = [&](int ch) {  // send_head_of_queue_to_channel base.py:288-310
             const double a = q_pop();
             taked++;
-            k9_sample(w_run, w_sum, __dadd_rn(0.0, __dsub_rn(ttek, a)), taked);
+            const double w = __dadd_rn(0.0, __dsub_rn(ttek, a));
+            k9_sample(w_run, w_sum, w, taked);
             arr[ch] = a;
-            end[ch] = __dadd_rn(ttek, draw(MQ_NS_SERVICES));
+            wait[ch] = w;
+            tot[ch] = draw(MQ_NS_SERVICES);
+            end[ch] = __dadd_rn(ttek, tot[ch]);
+            busy |= 1u << ch;
+            free_channels--;
+        };
+        // an interrupted job restarts on server ch (see the header): rem = its remaining time, t = its total
+        auto restart = [&](int ch, double a, double w, double rem, double t) {
+            taked++;
+            const double wt = __dadd_rn(w, __dsub_rn(ttek, ttek));
+            k9_sample(w_run, w_sum, wt, taked);
+            arr[ch] = a;
+            wait[ch] = wt;
+            if (P.scenario == MQ_NEG_REQUEUE) {
+                tot[ch] = draw(MQ_NS_SERVICES);
+                end[ch] = __dadd_rn(ttek, tot[ch]);
+            } else {
+                tot[ch] = t;
+                end[ch] = __dadd_rn(ttek, P.scenario == MQ_NEG_RESUME ? rem : t);
+            }
             busy |= 1u << ch;
             free_channels--;
         };
@@ -156,7 +181,9 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
                     taked++;
                     k9_sample(w_run, w_sum, 0.0, taked);
                     arr[j] = ttek;
-                    end[j] = __dadd_rn(ttek, draw(MQ_NS_SERVICES));
+                    wait[j] = 0.0;
+                    tot[j] = draw(MQ_NS_SERVICES);
+                    end[j] = __dadd_rn(ttek, tot[j]);
                     busy |= 1u << j;
                     free_channels--;
                 }
@@ -167,7 +194,34 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
                 ttek = neg_time;
                 neg_time = __dadd_rn(ttek, draw(MQ_NS_NEGATIVES));
                 if (in_sys != 0) {
-                    if (P.type == MQ_NEG_DISASTER) {
+                    if (P.type == MQ_NEG_DISASTER && P.scenario != MQ_NEG_REMOVE) {
+                        // the jobs in service, in order of arrival (stable), take servers 0, 1, ... again
+                        int nb = 0, idx[K9_MAXC];
+                        double ja[K9_MAXC], jw[K9_MAXC], jr[K9_MAXC], jt[K9_MAXC];
+                        for (int j = 0; j < c; ++j) {
+                            if (!((busy >> j) & 1u)) continue;
+                            const double rem = __dsub_rn(end[j], ttek);
+                            ja[nb] = arr[j];
+                            jw[nb] = wait[j];
+                            jr[nb] = rem > 0.0 ? rem : 0.0;
+                            jt[nb] = tot[j];
+                            idx[nb] = nb;
+                            nb++;
+                            end[j] = 1e10;
+                        }
+                        for (int a = 1; a < nb; ++a) {
+                            const int t = idx[a];
+                            int b = a - 1;
+                            while (b >= 0 && ja[idx[b]] > ja[t]) {
+                                idx[b + 1] = idx[b];
+                                --b;
+                            }
+                            idx[b + 1] = t;
+                        }
+                        busy = 0;
+                        free_channels = c;
+                        for (int q = 0; q < nb; ++q) restart(q, ja[idx[q]], jw[idx[q]], jr[idx[q]], jt[idx[q]]);
+                    } else if (P.type == MQ_NEG_DISASTER) {
                         for (int j = 0; j < c; ++j) {
                             if (!((busy >> j) & 1u)) continue;
                             const double a = arr[j];
@@ -195,12 +249,17 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
                         for (int q = 0; q < pick; ++q) left &= left - 1u;  // drop the `pick` lowest busy servers
                         const int j = __ffs(left) - 1;
                         const double a = arr[j];
+                        const double rem = __dsub_rn(end[j], ttek);
                         end[j] = 1e10;
                         busy &= ~(1u << j);
                         free_channels++;
-                        broken_sample(a);
-                        in_sys--;
-                        if (qsize != 0) head_to_channel(j);
+                        if (P.scenario != MQ_NEG_REMOVE) {
+                            restart(j, a, wait[j], rem > 0.0 ? rem : 0.0, tot[j]);
+                        } else {
+                            broken_sample(a);
+                            in_sys--;
+                            if (qsize != 0) head_to_channel(j);
+                        }
                     }
                 }
             } else {

@@ -9,7 +9,7 @@ constexpr int K9_BLOCK = 128;
 constexpr int K9_MAXC = 32;
 
 struct K9Params {
-    int c, p_bins, replay, qcap, type;
+    int c, p_bins, replay, qcap, type, scenario;
     long long buffer;
     long long jobs, reps;
     uint32_t rep0, key0;

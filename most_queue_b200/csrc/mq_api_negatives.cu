@@ -13,7 +13,8 @@ static int negatives_common(mq_ctx *ctx, const mq_neg_cfg *cfg, bool replay, con
     if (cfg->c < 1) return fail(MQ_E_INVALID, "%s: num_of_channels must be >= 1", who);
     if (cfg->c > K9_MAXC) return fail(MQ_E_UNSUPPORTED, "%s: num_of_channels %d > %d", who, cfg->c, K9_MAXC);
     if (cfg->type != MQ_NEG_DISASTER && cfg->type != MQ_NEG_RCS)
-        return fail(MQ_E_UNSUPPORTED, "%s: only DISASTER / CLEAR_SYSTEM and RCS / REMOVE negatives are implemented", who);
+        return fail(MQ_E_UNSUPPORTED, "%s: only the DISASTER and RCS types of negatives are implemented", who);
+    if (cfg->scenario < 0 || cfg->scenario > MQ_NEG_REQUEUE_FIXED) return fail(MQ_E_INVALID, "%s: unknown scenario", who);
     if (cfg->p_bins < 1 || cfg->p_bins > MQ_MAX_PBINS) return fail(MQ_E_INVALID, "%s: p_bins must be in 1..%d", who, MQ_MAX_PBINS);
     if (cfg->total_served < 0 || cfg->replications < 1 || cfg->rep0 < 0 || cfg->rep0 + cfg->replications > (1ll << 32))
         return fail(MQ_E_INVALID, "%s: bad sizes", who);
@@ -40,6 +41,7 @@ static int negatives_common(mq_ctx *ctx, const mq_neg_cfg *cfg, bool replay, con
     P.p_bins = pb;
     P.replay = replay ? 1 : 0;
     P.type = cfg->type;
+    P.scenario = cfg->scenario == 0 ? MQ_NEG_REMOVE : cfg->scenario;
     P.buffer = cfg->buffer < 0 ? -1 : cfg->buffer;
     P.jobs = cfg->total_served;
     P.reps = R;

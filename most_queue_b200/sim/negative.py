@@ -4,8 +4,9 @@ Mirrors most_queue/sim/negative.py: NegativeServiceType / DisasterScenario / Rcs
 QsSimNegatives(num_of_channels, type_of_negatives, buffer, verbose, buffer_type, disaster_scenario, rcs_scenario)
 (:62), set_positive_sources (:116), set_negative_sources (:134), set_servers, run(total_served) ->
 NegativeArrivalsResults(v, w, p, v_served, v_broken, utilization, q) (:184-203), get_v_served / get_v_broken.
-Implemented on the GPU (csrc/k9_negatives.cu): DISASTER with CLEAR_SYSTEM and RCS with REMOVE (the defaults); the
-RCH / RCE types and the requeue / resume scenarios raise NotImplementedError.  Additive: `seed=`, `replications=`.
+Implemented on the GPU (csrc/k9_negatives.cu): the DISASTER and RCS types with all four scenarios each; the RCH / RCE
+types raise NotImplementedError (their reference code reads the tail of the line without removing it in the default
+"list" buffer and fails on an empty line, negative.py:306-336).  Additive: `seed=`, `replications=`.
 """
 
 from __future__ import annotations
@@ -43,15 +44,14 @@ class RcsScenario(Enum):
     REQUEUE_NO_RESAMPLING = 4
 
 
-def _engine_type(type_of_negatives, disaster_scenario, rcs_scenario) -> int:
+def _engine_type(type_of_negatives, disaster_scenario, rcs_scenario):
+    """(type code, scenario code) of the C ABI."""
     name = getattr(type_of_negatives, "name", str(type_of_negatives))
-    if name == "DISASTER" and getattr(disaster_scenario, "name", "CLEAR_SYSTEM") == "CLEAR_SYSTEM":
-        return _lib.NEG_TYPES["DISASTER"]
-    if name == "RCS" and getattr(rcs_scenario, "name", "REMOVE") == "REMOVE":
-        return _lib.NEG_TYPES["RCS"]
-    raise NotImplementedError(
-        f"negatives of type {name} with this scenario are not implemented on the GPU engine "
-        "(available: DISASTER / CLEAR_SYSTEM, RCS / REMOVE)")
+    if name == "DISASTER":
+        return _lib.NEG_TYPES["DISASTER"], _lib.NEG_SCENARIOS[getattr(disaster_scenario, "name", str(disaster_scenario))]
+    if name == "RCS":
+        return _lib.NEG_TYPES["RCS"], _lib.NEG_SCENARIOS[getattr(rcs_scenario, "name", str(rcs_scenario))]
+    raise NotImplementedError(f"negatives of type {name} are not implemented on the GPU engine (available: DISASTER, RCS)")
 
 
 class QsSimNegatives(QsSim):
@@ -63,7 +63,7 @@ class QsSimNegatives(QsSim):
         self.type_of_negatives = type_of_negatives
         self.disaster_scenario = disaster_scenario
         self.rcs_scenario = rcs_scenario
-        self._type = _engine_type(type_of_negatives, disaster_scenario, rcs_scenario)
+        self._type, self._scenario = _engine_type(type_of_negatives, disaster_scenario, rcs_scenario)
         self.queue_cap = int(queue_cap)
         self.v_served = [0, 0, 0, 0]
         self.v_broken = [0, 0, 0, 0]
@@ -105,7 +105,7 @@ class QsSimNegatives(QsSim):
         if count > 0:
             agg, rec = ctx.sim_negatives(self.n, self.buffer, self._type, self._pos, self._neg, self._srv, total_served,
                                          count, rep0, seed, p_bins=self.p_bins, queue_cap=self.queue_cap,
-                                         per_replication=keep_replications)
+                                         per_replication=keep_replications, scenario=self._scenario)
             self.timing = ctx.last_timing()
         else:
             agg, rec = np.zeros(_lib.neg_agg_len(self.p_bins)), None
@@ -152,15 +152,16 @@ class QsSimNegatives(QsSim):
 
 
 def replay(num_of_channels, buffer, type_of_negatives, streams: dict, total_served, p_bins=128, queue_cap=0,
-           device=None):
+           device=None, scenario=None):
     """Replay tier: the event loop on pre-generated draws, fp64, bit-exact with the reference.  streams maps
     positives / negatives / services (and choices for RCS) to [n, replications] arrays."""
     L = _lib
     ctx = L.default_context(device)
-    t = _engine_type(type_of_negatives if not isinstance(type_of_negatives, str)
-                     else NegativeServiceType[type_of_negatives], DisasterScenario.CLEAR_SYSTEM, RcsScenario.REMOVE)
+    tt = type_of_negatives if not isinstance(type_of_negatives, str) else NegativeServiceType[type_of_negatives]
+    sc = scenario if scenario is not None else ("CLEAR_SYSTEM" if tt.name == "DISASTER" else "REMOVE")
+    t, s_code = _engine_type(tt, sc, sc)
     agg, rec = ctx.replay_negatives(num_of_channels, buffer, t, streams, total_served, p_bins=p_bins,
-                                    queue_cap=queue_cap)
+                                    queue_cap=queue_cap, scenario=s_code)
     flags = rec[L.N_FLAGS]
     if np.any(flags != 0):
         bad = int(np.flatnonzero(flags)[0])

@@ -231,7 +231,8 @@ typedef struct {
 
 /* positives / negatives: gaps of the two sources; services: draws in start_service order; choices: uniforms that
  * pick the floor(u * busy)-th busy server (RCS only, may be NULL otherwise). */
-int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *negatives, mqo_src *services,
+/* scenario: 1 = CLEAR_SYSTEM / REMOVE, 2 = REQUEUE(_ALL), 3 = RESUME(_ALL), 4 = REQUEUE(_ALL)_NO_RESAMPLING (negative.py:27-54) */
+int mqo_neg_run(int c, int64_t buffer, int type, int scenario, mqo_src *positives, mqo_src *negatives, mqo_src *services,
                 mqo_src *choices, int64_t total_served, double *p, int64_t p_bins, mqo_neg_out *out);
 
 /* ---- open network of PRIORITY nodes with per-class routing: PriorityNetwork.run

@@ -31,15 +31,15 @@ static inline void neg_add4(double *s, double x)
     for (int i = 0; i < 4; ++i) { s[i] += pw; pw *= x; }
 }
 
-int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *negatives, mqo_src *services,
+int mqo_neg_run(int c, int64_t buffer, int type, int scenario, mqo_src *positives, mqo_src *negatives, mqo_src *services,
                 mqo_src *choices, int64_t total_served, double *p, int64_t p_bins, mqo_neg_out *out)
 {
-    if (c < 1 || c > 64 || (type != MQO_NEG_DISASTER && type != MQO_NEG_RCS)) return -2;
+    if (c < 1 || c > 64 || (type != MQO_NEG_DISASTER && type != MQO_NEG_RCS) || scenario < 1 || scenario > 4) return -2;
     memset(out, 0, sizeof(*out));
     for (int64_t i = 0; i < p_bins; ++i) p[i] = 0.0;
-    double end[64], arr[64];
+    double end[64], arr[64], wait[64], tot[64];
     int is_free[64];
-    for (int j = 0; j < c; ++j) { end[j] = 1e10; arr[j] = 0.0; is_free[j] = 1; }
+    for (int j = 0; j < c; ++j) { end[j] = 1e10; arr[j] = 0.0; wait[j] = 0.0; tot[j] = 0.0; is_free[j] = 1; }
     int64_t qcap = 1024, qhead = 0, qsize = 0;
     double *queue = (double *)malloc(sizeof(double) * (size_t)qcap);
     int err = 0;
@@ -76,9 +76,28 @@ int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *ne
         neg_refresh(w_run, w_, taked);                                          \
         neg_add4(w_sum, w_);                                                    \
         arr[ch_] = a_;                                                          \
-        end[ch_] = ttek + mqo_src_next(services, &err);                         \
+        wait[ch_] = w_;                                                         \
+        tot[ch_] = mqo_src_next(services, &err);                                \
+        end[ch_] = ttek + tot[ch_];                                             \
         is_free[ch_] = 0;                                                       \
         free_channels--;                                                        \
+    } while (0)
+    /* a job interrupted by a negative arrival goes back to the head of the line and, a server being free, restarts at
+     * once (negative.py:262-275, 366-372 -> base.py:288-310 -> servers.py:57-88): one more `taked`, one more sample
+     * of its unchanged wait, and a completion time that depends on the scenario */
+#define RESTART(ch_, a_, w_, rem_, tot_)                                                \
+    do {                                                                                \
+        taked++;                                                                        \
+        const double wt_ = (w_) + (ttek - ttek);                                        \
+        neg_refresh(w_run, wt_, taked);                                                 \
+        neg_add4(w_sum, wt_);                                                           \
+        arr[ch_] = (a_);                                                                \
+        wait[ch_] = wt_;                                                                \
+        if (scenario == 2) { tot[ch_] = mqo_src_next(services, &err); end[ch_] = ttek + tot[ch_]; } \
+        else if (scenario == 3) { tot[ch_] = (tot_); end[ch_] = ttek + (rem_); }        \
+        else { tot[ch_] = (tot_); end[ch_] = ttek + (tot_); }                           \
+        is_free[ch_] = 0;                                                               \
+        free_channels--;                                                                \
     } while (0)
 
     while (served < total_served && !err) {
@@ -120,7 +139,9 @@ int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *ne
                 neg_refresh(w_run, 0.0, taked);
                 neg_add4(w_sum, 0.0);
                 arr[j] = ttek;
-                end[j] = ttek + mqo_src_next(services, &err);
+                wait[j] = 0.0;
+                tot[j] = mqo_src_next(services, &err);
+                end[j] = ttek + tot[j];
                 is_free[j] = 0;
                 free_channels--;
             }
@@ -131,7 +152,32 @@ int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *ne
             ttek = neg_time;
             neg_time = ttek + mqo_src_next(negatives, &err);
             if (in_sys == 0) continue;
-            if (type == MQO_NEG_DISASTER) {
+            if (type == MQO_NEG_DISASTER && scenario != 1) {
+                /* REQUEUE_ALL / RESUME_ALL / REQUEUE_ALL_NO_RESAMPLING negative.py:253-276 */
+                int nb = 0, idx[64];
+                double ja[64], jw[64], jrem[64], jtot[64];
+                for (int j = 0; j < c; ++j) {
+                    if (is_free[j]) continue;
+                    const double rem = end[j] - ttek;
+                    ja[nb] = arr[j]; jw[nb] = wait[j]; jrem[nb] = rem > 0.0 ? rem : 0.0; jtot[nb] = tot[j];
+                    idx[nb] = nb;
+                    nb++;
+                    end[j] = 1e10;
+                    is_free[j] = 1;
+                }
+                /* stable sort by arrival time (negative.py:269) */
+                for (int a = 1; a < nb; ++a) {
+                    const int t = idx[a];
+                    int b = a - 1;
+                    while (b >= 0 && ja[idx[b]] > ja[t]) { idx[b + 1] = idx[b]; --b; }
+                    idx[b + 1] = t;
+                }
+                free_channels = c;
+                for (int q = 0; q < nb; ++q) {
+                    const int t = idx[q];
+                    RESTART(q, ja[t], jw[t], jrem[t], jtot[t]);
+                }
+            } else if (type == MQO_NEG_DISASTER) {
                 for (int j = 0; j < c; ++j) {
                     if (is_free[j]) continue;
                     const double a = arr[j];
@@ -167,12 +213,18 @@ int mqo_neg_run(int c, int64_t buffer, int type, mqo_src *positives, mqo_src *ne
                 if (pick >= nb) pick = nb - 1;
                 const int j = busy_idx[pick];
                 const double a = arr[j];
+                const double rem0 = end[j] - ttek;
                 end[j] = 1e10;
                 is_free[j] = 1;
                 free_channels++;
-                BROKEN_SAMPLE(a);
-                in_sys--;
-                if (qsize != 0) HEAD_TO_CHANNEL(j);
+                if (scenario != 1) {
+                    /* REQUEUE / RESUME / REQUEUE_NO_RESAMPLING negative.py:347-372 */
+                    RESTART(j, a, wait[j], rem0 > 0.0 ? rem0 : 0.0, tot[j]);
+                } else {
+                    BROKEN_SAMPLE(a);
+                    in_sys--;
+                    if (qsize != 0) HEAD_TO_CHANNEL(j);
+                }
             }
         } else {
             /* serving negative.py:425-450 */

@@ -669,12 +669,17 @@ class NegResult:
     used: dict
 
 
-def _neg_run(c, buffer, neg_type, srcs, total_served, p_bins):
+NEG_SCENARIOS = {"CLEAR_SYSTEM": 1, "REMOVE": 1, "REQUEUE_ALL": 2, "REQUEUE": 2, "RESUME_ALL": 3, "RESUME": 3,
+                 "REQUEUE_ALL_NO_RESAMPLING": 4, "REQUEUE_NO_RESAMPLING": 4}
+
+
+def _neg_run(c, buffer, neg_type, srcs, total_served, p_bins, scenario=1):
     p = np.zeros(int(p_bins))
     out = MqoNegOut()
     ref = lambda k: C.byref(srcs[k]) if srcs.get(k) is not None else None
+    scenario = NEG_SCENARIOS.get(scenario, scenario)
     rc = lib().mqo_neg_run(int(c), C.c_int64(-1 if buffer is None else int(buffer)), NEG_TYPES[neg_type],
-                           ref("positives"), ref("negatives"), ref("services"), ref("choices"),
+                           int(scenario), ref("positives"), ref("negatives"), ref("services"), ref("choices"),
                            C.c_int64(int(total_served)), _dp(p), C.c_int64(int(p_bins)), C.byref(out))
     if rc != 0:
         raise RuntimeError(f"oracle negative-arrivals run failed rc={rc}")
@@ -689,14 +694,15 @@ def _neg_run(c, buffer, neg_type, srcs, total_served, p_bins):
 NEG_STREAMS = ("positives", "negatives", "services", "choices")
 
 
-def neg_replay(c, buffer, neg_type, arrays: dict, total_served, p_bins=128) -> NegResult:
+def neg_replay(c, buffer, neg_type, arrays: dict, total_served, p_bins=128, scenario=1) -> NegResult:
     """QsSimNegatives.run() on pre-generated draws; arrays maps NEG_STREAMS names to 1-D arrays."""
     keep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in arrays.items() if v is not None}
     return _neg_run(c, buffer, neg_type, {k: (_replay_src(keep[k]) if k in keep else None) for k in NEG_STREAMS},
-                    total_served, p_bins)
+                    total_served, p_bins, scenario)
 
 
-def neg_generate(c, buffer, neg_type, positive, negative, service, total_served, seed, rep, p_bins=128) -> NegResult:
+def neg_generate(c, buffer, neg_type, positive, negative, service, total_served, seed, rep, p_bins=128,
+                 scenario=1) -> NegResult:
     """Generator mode: positive gaps = word 0 and services = word 1 of stream sid 0 (as the FIFO kernel), negative
     gaps = word 0 and server choices = word 1 of stream sid 1."""
 
@@ -705,4 +711,4 @@ def neg_generate(c, buffer, neg_type, positive, negative, service, total_served,
 
     srcs = {"positives": _gen_src(positive, seed, 0, rep, 0), "services": _gen_src(service, seed, 0, rep, 1),
             "negatives": _gen_src(negative, seed, 1, rep, 0), "choices": _gen_src(("Uniform", U01), seed, 1, rep, 1)}
-    return _neg_run(c, buffer, neg_type, srcs, total_served, p_bins)
+    return _neg_run(c, buffer, neg_type, srcs, total_served, p_bins, scenario)

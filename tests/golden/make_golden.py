@@ -449,11 +449,17 @@ class ReplayChoice:
         return seq[min(int(self.arr[i] * len(seq)), len(seq) - 1)]
 
 
-def neg_case(name, c, buffer, neg_type, streams, total_served, nprobs=128):
+def neg_case(name, c, buffer, neg_type, streams, total_served, nprobs=128, scenario=None):
     import most_queue.sim.negative as negmod
-    from most_queue.sim.negative import NegativeServiceType, QsSimNegatives
+    from most_queue.sim.negative import DisasterScenario, NegativeServiceType, QsSimNegatives, RcsScenario
 
-    qs = QsSimNegatives(c, getattr(NegativeServiceType, neg_type), buffer=buffer)
+    kw = {}
+    if scenario is not None:
+        if neg_type == "DISASTER":
+            kw["disaster_scenario"] = getattr(DisasterScenario, scenario)
+        else:
+            kw["rcs_scenario"] = getattr(RcsScenario, scenario)
+    qs = QsSimNegatives(c, getattr(NegativeServiceType, neg_type), buffer=buffer, **kw)
     qs.set_positive_sources(1.0, "M")
     qs.set_negative_sources(1.0, "M")
     qs.set_servers(1.0, "M")
@@ -477,6 +483,7 @@ def neg_case(name, c, buffer, neg_type, streams, total_served, nprobs=128):
     finally:
         negmod.random = saved
     out = dict(c=c, buffer=-1 if buffer is None else buffer, neg_type=neg_type, total_served=total_served,
+               scenario=scenario or ("CLEAR_SYSTEM" if neg_type == "DISASTER" else "REMOVE"),
                w=np.array(qs.w, dtype=np.float64), v=np.array(qs.v, dtype=np.float64),
                v_served=np.array(qs.v_served, dtype=np.float64), v_broken=np.array(qs.v_broken, dtype=np.float64),
                p_time=np.array(qs.p[:nprobs], dtype=np.float64), ttek=float(qs.ttek),
@@ -506,6 +513,14 @@ def make_neg():
                                             choices=rng.random(3 * n)), n)
     neg_case("rcs_c2_buffer2", 2, 2, "RCS", dict(positives=ex(0.4), negatives=ex(2.0), services=ex(0.9),
                                                  choices=rng.random(3 * n)), n)
+    # interrupted jobs go back to the head of the line and restart (tests/test_mgn_disaster.py, test_mg1_repeat.py)
+    for sc in ("REQUEUE_ALL", "RESUME_ALL", "REQUEUE_ALL_NO_RESAMPLING"):
+        neg_case(f"disaster_c3_{sc.lower()}", 3, None, "DISASTER",
+                 dict(positives=ex(0.5), negatives=ex(4.0), services=rng.gamma(0.8, 1.1, 4 * n)), n, scenario=sc)
+    for sc in ("REQUEUE", "RESUME", "REQUEUE_NO_RESAMPLING"):
+        neg_case(f"rcs_c2_{sc.lower()}", 2, None, "RCS",
+                 dict(positives=ex(0.7), negatives=ex(3.0), services=rng.gamma(0.8, 0.9, 4 * n),
+                      choices=rng.random(3 * n)), n, scenario=sc)
 
 
 # --------------------------------------------------------------------------- tandem with blocking

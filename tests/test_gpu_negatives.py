@@ -27,7 +27,7 @@ def test_replay_matches_reference(path):
     buffer = None if int(g["buffer"]) < 0 else int(g["buffer"])
     rep = lambda a: np.repeat(np.asarray(a)[:, None], 3, axis=1)
     out = replay(int(g["c"]), buffer, str(g["neg_type"]), {k: rep(v) for k, v in _streams(g).items()},
-                 int(g["total_served"]), p_bins=len(g["p_time"]))
+                 int(g["total_served"]), p_bins=len(g["p_time"]), scenario=str(g["scenario"]))
     for r in range(3):
         assert out["ttek"][r] == float(g["ttek"])
         for k in COUNTS:
@@ -39,9 +39,12 @@ def test_replay_matches_reference(path):
             assert out["used"][k][r] == int(g["used_" + k]), k
 
 
-@pytest.mark.parametrize("neg_type,c,buffer", [("DISASTER", 1, None), ("DISASTER", 4, 5), ("RCS", 1, None),
-                                               ("RCS", 3, None), ("RCS", 2, 3)])
-def test_replay_matches_oracle_many_replications(neg_type, c, buffer):
+@pytest.mark.parametrize("neg_type,c,buffer,scenario", [
+    ("DISASTER", 1, None, "CLEAR_SYSTEM"), ("DISASTER", 4, 5, "CLEAR_SYSTEM"), ("RCS", 1, None, "REMOVE"),
+    ("RCS", 3, None, "REMOVE"), ("RCS", 2, 3, "REMOVE"), ("DISASTER", 3, None, "REQUEUE_ALL"),
+    ("DISASTER", 4, 6, "RESUME_ALL"), ("DISASTER", 2, None, "REQUEUE_ALL_NO_RESAMPLING"), ("RCS", 3, None, "REQUEUE"),
+    ("RCS", 2, 4, "RESUME"), ("RCS", 4, None, "REQUEUE_NO_RESAMPLING")])
+def test_replay_matches_oracle_many_replications(neg_type, c, buffer, scenario):
     from most_queue_b200.sim.negative import replay
     from oracle import oracle
 
@@ -49,9 +52,10 @@ def test_replay_matches_oracle_many_replications(neg_type, c, buffer):
     reps, n = 40, 400
     X = {"positives": rng.exponential(0.9 / c, (4 * n, reps)), "negatives": rng.exponential(3.0, (2 * n, reps)),
          "services": rng.gamma(0.8, 1.1, (4 * n, reps)), "choices": rng.random((2 * n, reps))}
-    out = replay(c, buffer, neg_type, X, n, p_bins=64)
+    out = replay(c, buffer, neg_type, X, n, p_bins=64, scenario=scenario)
     for r in range(reps):
-        o = oracle.neg_replay(c, buffer, neg_type, {k: v[:, r].copy() for k, v in X.items()}, n, p_bins=64)
+        o = oracle.neg_replay(c, buffer, neg_type, {k: v[:, r].copy() for k, v in X.items()}, n, p_bins=64,
+                              scenario=scenario)
         assert o.ttek == out["ttek"][r]
         for k in COUNTS:
             assert o.counts[k] == out[k][r], k
@@ -77,9 +81,9 @@ def test_errors_and_unsupported_scenarios():
     with pytest.raises(NotImplementedError):
         QsSimNegatives(1, NegativeServiceType.RCH)
     with pytest.raises(NotImplementedError):
-        QsSimNegatives(1, NegativeServiceType.DISASTER, disaster_scenario=DisasterScenario.REQUEUE_ALL)
-    with pytest.raises(NotImplementedError):
-        QsSimNegatives(2, NegativeServiceType.RCS, rcs_scenario=RcsScenario.RESUME)
+        QsSimNegatives(1, NegativeServiceType.RCE)
+    assert QsSimNegatives(1, NegativeServiceType.DISASTER, disaster_scenario=DisasterScenario.REQUEUE_ALL)._scenario == 2
+    assert QsSimNegatives(2, NegativeServiceType.RCS, rcs_scenario=RcsScenario.RESUME)._scenario == 3
     with pytest.raises(RuntimeError):
         QsSimNegatives(1).run(10)
 
@@ -127,3 +131,19 @@ def test_mm1_disaster_closed_form():
     assert abs(res.v[0] - v_theory) < res.ci["v"][0] + 5e-3 * v_theory, (res.v[0], v_theory)
     assert abs(res.p[0] - (1 - r)) < 5e-3
     assert 0.0 < res.q < 1.0 and res.v_broken[0] > 0 and res.v_served[0] > 0
+
+
+def test_mm1_resume_scenario_is_work_conserving():
+    """RCS / RESUME on one exponential server interrupts and resumes the job in service without losing work, so the
+    sojourn time is that of the plain M/M/1 queue: 1 / (mu - lam)."""
+    from most_queue_b200.sim.negative import NegativeServiceType, QsSimNegatives, RcsScenario
+
+    lam, mu = 0.7, 1.0
+    sim = QsSimNegatives(1, NegativeServiceType.RCS, rcs_scenario=RcsScenario.RESUME, seed=3, replications=512)
+    sim.set_positive_sources(lam, "M")
+    sim.set_negative_sources(0.5, "M")
+    sim.set_servers(mu, "M")
+    res = sim.run(20000)
+    v_theory = 1.0 / (mu - lam)
+    assert abs(res.v[0] - v_theory) < res.ci["v"][0] + 5e-3 * v_theory, (res.v[0], v_theory)
+    assert res.q == pytest.approx(1.0) and sim.broken == 0

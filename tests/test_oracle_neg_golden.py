@@ -19,7 +19,7 @@ def streams_of(g):
 
 
 def test_fixtures_present():
-    assert len(CASES) >= 6
+    assert len(CASES) >= 12
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
@@ -27,7 +27,7 @@ def test_oracle_matches_reference_bitwise(path):
     g = np.load(path)
     buffer = None if int(g["buffer"]) < 0 else int(g["buffer"])
     r = oracle.neg_replay(int(g["c"]), buffer, str(g["neg_type"]), streams_of(g), int(g["total_served"]),
-                          p_bins=len(g["p_time"]))
+                          p_bins=len(g["p_time"]), scenario=str(g["scenario"]))
     assert r.ttek == float(g["ttek"])
     for k in COUNTS:
         assert r.counts[k] == int(g[k]), k
