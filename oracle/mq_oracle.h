@@ -235,6 +235,20 @@ typedef struct {
 int mqo_neg_run(int c, int64_t buffer, int type, int scenario, mqo_src *positives, mqo_src *negatives, mqo_src *services,
                 mqo_src *choices, int64_t total_served, double *p, int64_t p_bins, mqo_neg_out *out);
 
+/* ---- size-based single-server disciplines: SizeBasedQsSim.run (sim/size_based.py:64-248) ---- */
+enum { MQO_SZ_FCFS = 0, MQO_SZ_SJF = 1, MQO_SZ_PSJF = 2, MQO_SZ_SRPT = 3 };
+
+typedef struct {
+    double w_sum[4], v_sum[4], w_run[4], v_run[4], busy_run[3];
+    double slowdown_sum[2]; /* sum and sum of squares of sojourn / size over completed jobs (non-FCFS) */
+    int64_t busy_n, arrived, taked, served, dropped, in_sys, queued, preemptions;
+    double ttek, p_over;
+} mqo_size_out;
+
+/* sizes: job sizes in arrival order (size_based.py:155-164); for FCFS the service draws in start order */
+int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *sizes, int64_t total_served, double *p,
+                 int64_t p_bins, mqo_size_out *out);
+
 /* ---- open network of PRIORITY nodes with per-class routing: PriorityNetwork.run
  * (sim/networks/priority_network.py:241-276) ---- */
 #define MQO_PN_MAX_CLASSES 8

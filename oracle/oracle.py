@@ -114,6 +114,13 @@ class MqoNegOut(C.Structure):
                                  "in_sys", "queued")] + [("ttek", C.c_double), ("p_over", C.c_double)]
 
 
+class MqoSizeOut(C.Structure):
+    _fields_ = [("w_sum", C.c_double * 4), ("v_sum", C.c_double * 4), ("w_run", C.c_double * 4),
+                ("v_run", C.c_double * 4), ("busy_run", C.c_double * 3), ("slowdown_sum", C.c_double * 2)] + [
+        (n, C.c_int64) for n in ("busy_n", "arrived", "taked", "served", "dropped", "in_sys", "queued", "preemptions")] + [
+        ("ttek", C.c_double), ("p_over", C.c_double)]
+
+
 class MqoPnClassOut(C.Structure):
     _fields_ = [("v_run", C.c_double * 3), ("w_run", C.c_double * 3), ("v_sum", C.c_double * 3),
                 ("w_sum", C.c_double * 3), ("served", C.c_int64), ("arrived", C.c_int64), ("in_sys", C.c_int64)]
@@ -712,3 +719,51 @@ def neg_generate(c, buffer, neg_type, positive, negative, service, total_served,
     srcs = {"positives": _gen_src(positive, seed, 0, rep, 0), "services": _gen_src(service, seed, 0, rep, 1),
             "negatives": _gen_src(negative, seed, 1, rep, 0), "choices": _gen_src(("Uniform", U01), seed, 1, rep, 1)}
     return _neg_run(c, buffer, neg_type, srcs, total_served, p_bins, scenario)
+
+
+# --------------------------------------------------------------------------- size-based disciplines
+SIZE_DISCIPLINES = {"FCFS": 0, "SJF": 1, "PSJF": 2, "SRPT": 3, "SPJF": 1, "PSPJF": 2, "SPRPT": 3}  # perfect predictor
+
+
+@dataclass
+class SizeResult:
+    w: np.ndarray
+    v: np.ndarray
+    w_sum: np.ndarray
+    v_sum: np.ndarray
+    busy: np.ndarray
+    slowdown_sum: np.ndarray
+    p_time: np.ndarray
+    p_over: float
+    ttek: float
+    counts: dict
+    a_used: int
+    s_used: int
+
+
+def _size_run(discipline, buffer, arrivals, sizes, total_served, p_bins):
+    p = np.zeros(int(p_bins))
+    out = MqoSizeOut()
+    rc = lib().mqo_size_run(SIZE_DISCIPLINES[discipline], C.c_int64(-1 if buffer is None else int(buffer)),
+                            C.byref(arrivals), C.byref(sizes), C.c_int64(int(total_served)), _dp(p),
+                            C.c_int64(int(p_bins)), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle size-based run failed rc={rc}")
+    names = ("busy_n", "arrived", "taked", "served", "dropped", "in_sys", "queued", "preemptions")
+    return SizeResult(w=np.array(out.w_run), v=np.array(out.v_run), w_sum=np.array(out.w_sum),
+                      v_sum=np.array(out.v_sum), busy=np.array(out.busy_run), slowdown_sum=np.array(out.slowdown_sum),
+                      p_time=p, p_over=out.p_over, ttek=out.ttek, counts={n: getattr(out, n) for n in names},
+                      a_used=arrivals.pos, s_used=sizes.pos)
+
+
+def size_replay(discipline, buffer, A, S, total_served, p_bins=128) -> SizeResult:
+    """SizeBasedQsSim.run() on pre-generated gaps A and sizes S (arrival order; FCFS: services in start order)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    return _size_run(discipline, buffer, _replay_src(A), _replay_src(S), total_served, p_bins)
+
+
+def size_generate(discipline, buffer, source, server, total_served, seed, rep, p_bins=128) -> SizeResult:
+    """Generator mode: gaps = word 0 and sizes = word 1 of stream 0 (as the FIFO kernel)."""
+    return _size_run(discipline, buffer, _gen_src(source, seed, 0, rep, 0), _gen_src(server, seed, 0, rep, 1),
+                     total_served, p_bins)

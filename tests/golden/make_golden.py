@@ -523,6 +523,43 @@ def make_neg():
                       choices=rng.random(3 * n)), n, scenario=sc)
 
 
+# --------------------------------------------------------------------------- size-based disciplines
+def size_case(name, discipline, buffer, A, S, total_served, nprobs=128):
+    from most_queue.sim.size_based import SizeBasedQsSim
+
+    qs = SizeBasedQsSim(1, discipline, buffer=buffer, track_slowdown=True)
+    qs.set_sources(1.0, "M")
+    qs.set_servers(1.0, "M")
+    ia, isv = [0], [0]
+    qs.source = ReplayDist(A, ia)
+    qs._size_dist = ReplayDist(S, isv)       # sizes at arrival (size_based.py:121-124)
+    for srv in qs.servers:
+        srv.dist = ReplayDist(S, isv)        # FCFS draws the service at start from the server's law
+    qs.arrival_time = qs.source.generate()
+    with quiet():
+        while qs.served < total_served:
+            qs.run_one_step()
+    sd = np.array(qs.get_slowdown(), dtype=np.float64)
+    np.savez_compressed(
+        os.path.join(OUT, f"size_{name}.npz"), discipline=discipline, buffer=-1 if buffer is None else buffer,
+        total_served=total_served, A=np.asarray(A), S=np.asarray(S), w=np.array(qs.w, dtype=np.float64),
+        v=np.array(qs.v, dtype=np.float64), busy=np.array(qs.busy, dtype=np.float64), busy_n=qs.busy_moments,
+        p_time=np.array(qs.p[:nprobs], dtype=np.float64), ttek=float(qs.ttek), arrived=qs.arrived, taked=qs.taked,
+        served=qs.served, dropped=qs.dropped, in_sys=qs.in_sys, queued=qs.queue.size(), a_used=ia[0], s_used=isv[0],
+        slowdown=sd)
+    print(f"size_{name}: served={qs.served} taked={qs.taked} dropped={qs.dropped} v1={qs.v[0]:.5g} "
+          f"slowdown={sd.mean() if len(sd) else 0:.4g} used={ia[0]},{isv[0]}")
+
+
+def make_size():
+    rng = np.random.default_rng(20260808)
+    n = 3000
+    for d in ("FCFS", "SJF", "PSJF", "SRPT", "SPJF", "SPRPT"):
+        size_case(d.lower(), d, None, rng.exponential(1.0, 2 * n), rng.gamma(0.5, 1.6, 2 * n), n)
+    size_case("srpt_buffer5", "SRPT", 5, rng.exponential(1.0, 3 * n), rng.gamma(0.5, 1.9, 3 * n), n)
+    size_case("sjf_heavy", "SJF", None, rng.exponential(1.0, 2 * n), 0.3 * (rng.pareto(2.2, 2 * n) + 1.0), n)
+
+
 # --------------------------------------------------------------------------- tandem with blocking
 def tandem_case(name, capacity, A, S, total_served, warmup_fraction=0.05):
     from most_queue.sim.networks.tandem_blocking import TandemBlockingSim
@@ -643,7 +680,7 @@ def make_theory():
 
 if __name__ == "__main__":
     import_reference()
-    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "vac", "neg", "theory"]
+    which = sys.argv[1:] or ["fifo", "prio", "net", "prionet", "tandem", "vac", "neg", "size", "theory"]
     if "fifo" in which:
         make_fifo()
     if "prio" in which:
@@ -658,5 +695,7 @@ if __name__ == "__main__":
         make_vac()
     if "neg" in which:
         make_neg()
+    if "size" in which:
+        make_size()
     if "theory" in which:
         make_theory()
