@@ -550,6 +550,60 @@ int mq_sim_negatives(mq_ctx *ctx, const mq_neg_cfg *cfg, double *agg, double *re
 int mq_replay_negatives(mq_ctx *ctx, const mq_neg_cfg *cfg, const double *const *X, const int64_t *n, double *agg,
                         double *rep_out);
 
+/* ---- size-based single-server disciplines.  Replaces SizeBasedQsSim(1, discipline, buffer, track_slowdown)
+ * .set_sources / set_servers / run(total_served) (sim/size_based.py:64,121,216) with the default perfect predictor,
+ * under which SPJF / PSPJF / SPRPT rank exactly like SJF / PSJF / SRPT (size_based.py:128-153) */
+#define MQ_SZ_FCFS 0
+#define MQ_SZ_SJF 1   /* also SPJF  */
+#define MQ_SZ_PSJF 2  /* also PSPJF */
+#define MQ_SZ_SRPT 3  /* also SPRPT */
+
+typedef struct {
+    int32_t discipline;
+    int32_t p_bins;
+    int64_t buffer;      /* < 0: infinite */
+    mq_dist src, srv;    /* interarrival law; job-size law (= service law, size_based.py:121-124) */
+    int64_t total_served;
+    int64_t replications;
+    int64_t rep0;
+    uint64_t seed;
+    int32_t queue_cap;   /* infinite buffer: waiting-line capacity of the engine (0: 256) */
+    int32_t flags;
+} mq_size_cfg;
+
+/* per-replication record rows */
+#define MQ_Z_TTEK 0
+#define MQ_Z_FLAGS 1
+#define MQ_Z_ARRIVED 2
+#define MQ_Z_TAKED 3
+#define MQ_Z_SERVED 4
+#define MQ_Z_DROPPED 5
+#define MQ_Z_INSYS 6
+#define MQ_Z_QUEUED 7
+#define MQ_Z_BUSYN 8
+#define MQ_Z_POVER 9
+#define MQ_Z_PREEMPTIONS 10
+#define MQ_Z_AUSED 11
+#define MQ_Z_SUSED 12
+#define MQ_Z_SLOWDOWN 14 /* 2: sum and sum of squares of sojourn / size (size_based.py:110-119) */
+#define MQ_Z_WSUM 16     /* 4 */
+#define MQ_Z_VSUM 20     /* 4 */
+#define MQ_Z_WRUN 24     /* 4 */
+#define MQ_Z_VRUN 28     /* 4 */
+#define MQ_Z_BUSYRUN 32  /* 3 */
+#define MQ_Z_P 36
+#define MQ_Z_ROWS(pb) (36 + (pb))
+
+/* aggregate: [0] replications, [1] sum ttek, [2] flagged, [3] sum served, [4] sum arrived, [5] sum dropped, [6] sum
+ * taked, [7] sum preemptions; [8..11] w (w_sum/taked), [12..15] squares; [16..19] v (v_sum/served), [20..23] squares;
+ * [24] mean slowdown (slowdown_sum/served), [25] its square; [32..32+pb) p, then pb squares */
+#define MQ_Z_AGG_LEN(pb) (32 + 2 * (pb))
+
+int mq_sim_size(mq_ctx *ctx, const mq_size_cfg *cfg, double *agg, double *rep_out);
+/* replay form: A = gaps [n_a][replications], S = job sizes in arrival order (FCFS: services in start order) */
+int mq_replay_size(mq_ctx *ctx, const mq_size_cfg *cfg, const double *A, int64_t n_a, const double *S, int64_t n_s,
+                   double *agg, double *rep_out);
+
 int mq_version(void);
 int mq_device_count(void);
 const char *mq_last_error(void);

@@ -243,6 +243,31 @@ def neg_agg_len(p_bins):
     return 48 + 2 * int(p_bins)
 
 
+SIZE_DISCIPLINES = {"FCFS": 0, "SJF": 1, "PSJF": 2, "SRPT": 3, "SPJF": 1, "PSPJF": 2, "SPRPT": 3}
+
+
+class MqSizeCfg(C.Structure):
+    _fields_ = [
+        ("discipline", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("src", MqDist), ("srv", MqDist),
+        ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
+        ("queue_cap", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+# record rows of the size-based kernel (include/mqb200.h MQ_Z_*)
+(Z_TTEK, Z_FLAGS, Z_ARRIVED, Z_TAKED, Z_SERVED, Z_DROPPED, Z_INSYS, Z_QUEUED, Z_BUSYN, Z_POVER, Z_PREEMPTIONS, Z_AUSED,
+ Z_SUSED, Z_SLOWDOWN, Z_WSUM, Z_VSUM, Z_WRUN, Z_VRUN, Z_BUSYRUN, Z_P) = (
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 20, 24, 28, 32, 36)
+
+
+def size_rec_rows(p_bins):
+    return 36 + int(p_bins)
+
+
+def size_agg_len(p_bins):
+    return 32 + 2 * int(p_bins)
+
+
 class MqError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmqb200 error {code}: {msg}")
@@ -312,6 +337,10 @@ def load():
         L.mq_sim_negatives.argtypes = [vp, C.POINTER(MqNegCfg), dp, dp]
         L.mq_replay_negatives.restype = C.c_int
         L.mq_replay_negatives.argtypes = [vp, C.POINTER(MqNegCfg), C.POINTER(vp), C.POINTER(C.c_int64), dp, dp]
+        L.mq_sim_size.restype = C.c_int
+        L.mq_sim_size.argtypes = [vp, C.POINTER(MqSizeCfg), dp, dp]
+        L.mq_replay_size.restype = C.c_int
+        L.mq_replay_size.argtypes = [vp, C.POINTER(MqSizeCfg), vp, C.c_int64, vp, C.c_int64, dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -754,6 +783,38 @@ class Context:
         rec = np.empty((neg_rec_rows(p_bins), reps))
         check(self._L.mq_replay_negatives(self._h, C.byref(cfg), ptr, n, agg.ctypes.data_as(C.POINTER(C.c_double)),
                                           rec.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, rec
+
+    # ---- K10 ----
+    def _size_cfg(self, discipline, buffer, total_served, replications, rep0, seed, p_bins, queue_cap):
+        cfg = MqSizeCfg()
+        cfg.discipline, cfg.p_bins = int(discipline), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.queue_cap = int(queue_cap)
+        return cfg
+
+    def sim_size(self, discipline, buffer, src, srv, total_served, replications, rep0, seed, p_bins=128, queue_cap=0,
+                 per_replication=False):
+        cfg = self._size_cfg(discipline, buffer, total_served, replications, rep0, seed, p_bins, queue_cap)
+        cfg.src, cfg.srv = src, srv
+        agg = np.zeros(size_agg_len(p_bins))
+        rec = np.empty((size_rec_rows(p_bins), int(replications))) if per_replication else None
+        check(self._L.mq_sim_size(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                  rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
+        return agg, rec
+
+    def replay_size(self, discipline, buffer, A, S, total_served, p_bins=128, queue_cap=0):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        reps = A.shape[1]
+        cfg = self._size_cfg(discipline, buffer, total_served, reps, 0, 0, p_bins, queue_cap)
+        agg = np.zeros(size_agg_len(p_bins))
+        rec = np.empty((size_rec_rows(p_bins), reps))
+        check(self._L.mq_replay_size(self._h, C.byref(cfg), A.ctypes.data, A.shape[0], S.ctypes.data, S.shape[0],
+                                     agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                     rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec
 
     def last_timing(self):

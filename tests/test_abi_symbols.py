@@ -20,7 +20,7 @@ def test_header_declares_the_hot_path_entry_points():
     names = _declared()
     for must in ("mq_create", "mq_destroy", "mq_sim_fifo", "mq_replay_fifo", "mq_sim_prio", "mq_replay_prio",
                  "mq_sim_net", "mq_replay_net", "mq_sim_tandem", "mq_replay_tandem", "mq_sim_prionet",
-                 "mq_replay_prionet", "mq_sim_vacation", "mq_replay_vacation", "mq_sim_negatives", "mq_replay_negatives", "mq_scan_gg1", "mq_scan_gg1_summary", "mq_scan_gg1_apply",
+                 "mq_replay_prionet", "mq_sim_vacation", "mq_replay_vacation", "mq_sim_negatives", "mq_replay_negatives", "mq_sim_size", "mq_replay_size", "mq_scan_gg1", "mq_scan_gg1_summary", "mq_scan_gg1_apply",
                  "mq_last_error", "mq_version", "mq_device_count"):
         assert must in names
 
@@ -47,6 +47,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.MqPrionetCfg) == 4272
     assert ctypes.sizeof(_lib.MqVacCfg) == 336
     assert ctypes.sizeof(_lib.MqNegCfg) == 184
+    assert ctypes.sizeof(_lib.MqSizeCfg) == 136
 
 
 def test_no_cpu_fallback_without_device():
