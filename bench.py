@@ -310,9 +310,62 @@ def run_ours(args):
                 line["replay"] = replay_leg(ctx, peaks, peak_src)
             except Exception as e:  # the headline must not be lost to the secondary measurement
                 line["replay"] = {"error": repr(e)}
+        if world == 1 and not args.no_others:
+            try:
+                line["other_configs"] = other_configs_leg()
+            except Exception as e:
+                line["other_configs"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
+
+
+def other_configs_leg():
+    """The other BASELINE.json configurations through the public API (parity-test cases, reported for reference:
+    device time of the simulation kernels from the library's CUDA events, one run each after a small warm-up)."""
+    from most_queue_b200.random.distributions import GammaDistribution, H2Distribution, ParetoDistribution
+    from most_queue_b200.sim.base import QsSim
+    from most_queue_b200.sim.lindley import run_chain
+    from most_queue_b200.sim.networks.network import NetworkSimulator
+    from most_queue_b200.sim.priority import PriorityQueueSimulator
+
+    out = {}
+    # cfg1: M/M/3/100 (README quick start), 1e4 replications x 1e5 jobs
+    qs = QsSim(3, buffer=100, seed=1, replications=10_000)
+    qs.set_sources(2.0, "M")
+    qs.set_servers(1.0, "M")
+    qs.run(1000)
+    r = qs.run(100_000)
+    out["cfg1_mm3_r100"] = {"jobs_per_s": 1e4 * 1e5 / (qs.timing["sim_ms"] * 1e-3), "w1": r.w[0], "w1_theory": 4.0 / 9.0}
+    # cfg3: Gamma/Pareto/1, one chain of 1e10 jobs (max-plus Lindley scan)
+    gam = GammaDistribution.get_params_by_mean_and_cv(1.0, 0.56)
+    par = ParetoDistribution.get_params_by_mean_and_cv(0.7, 1.2)
+    run_chain(("Gamma", gam), ("Pa", par), 1 << 24, seed=3, want_p=False)
+    c3 = run_chain(("Gamma", gam), ("Pa", par), 10_000_000_000, seed=3, want_p=False)
+    out["cfg3_gamma_pareto_1_chain"] = {"jobs_per_s": 1e10 / (c3.timing["sim_ms"] * 1e-3), "w1": c3.w[0],
+                                        "utilization": c3.utilization}
+    # cfg4: M/Gamma/4, two classes, NP and PR, 1e5 replications x 1e5 jobs
+    g0 = GammaDistribution.get_params_by_mean_and_cv(2.0, 1.2)
+    g1 = GammaDistribution.get_params_by_mean_and_cv(4.0, 1.2)
+    for prty in ("NP", "PR"):
+        ps = PriorityQueueSimulator(4, 2, prty, seed=7, replications=100_000, p_bins=32)
+        ps.set_sources([{"type": "M", "params": 0.3}, {"type": "M", "params": 0.5}])
+        ps.set_servers([{"type": "Gamma", "params": g0}, {"type": "Gamma", "params": g1}])
+        ps.run(1000, replications=4096)
+        r = ps.run(100_000)
+        out[f"cfg4_mg4_2class_{prty}"] = {"jobs_per_s": 1e5 * 1e5 / (ps.timing["sim_ms"] * 1e-3),
+                                         "v1": [r.v[0][0], r.v[1][0]]}
+    # cfg5: 5-node open network of H2 nodes, 1e5 replications x 1e4 network jobs
+    R = [[1, 0, 0, 0, 0, 0], [0, 0.4, 0.6, 0, 0, 0], [0, 0, 0.2, 0.4, 0.4, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 1, 0],
+         [0, 0, 0, 0, 0, 1]]
+    ch = [3, 2, 3, 4, 3]
+    net = NetworkSimulator(seed=9, replications=100_000)
+    net.set_sources(1.0, np.array(R, dtype=float))
+    net.set_nodes([{"type": "H", "params": H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2)} for c in ch], ch)
+    net.run(500, replications=4096)
+    r = net.run(10_000)
+    out["cfg5_network_5_nodes"] = {"network_jobs_per_s": 1e5 * 1e4 / (net.timing["sim_ms"] * 1e-3), "v1": r.v[0]}
+    return out
 
 
 def replay_leg(ctx, peaks, peak_src, reps=65536, rows=4096, steps=3):
@@ -358,6 +411,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-replay", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
