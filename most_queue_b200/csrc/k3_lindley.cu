@@ -79,8 +79,37 @@ constexpr size_t K3_LEVEL_BYTES = sizeof(float) * K3_PBL * K3_THREADS + sizeof(d
 
 __device__ __forceinline__ int k3_pad(int e) { return e + (e >> 4); }
 
+__device__ __forceinline__ double gen_gap(const K3Params &P, long long n);
+
+// the same staging from the fp32 stash written by the summary pass of the generator form (gaps beyond the range --
+// the halo of the level walk in the last tile -- are drawn)
+__device__ __forceinline__ void stage_tile_stash(const K3Params &P, long long tile_base, double *smS, double *smA)
+{
+    auto gap_at = [&](long long n) -> double {
+        if (n <= P.n) return (double)__ldcs(P.stG + n);
+        return n <= P.n + P.n_ahead ? gen_gap(P, n) : 0.0;
+    };
+#pragma unroll
+    for (int k = 0; k < K3_L; ++k) {
+        const int e = k * K3_THREADS + threadIdx.x;
+        const long long n = tile_base + e;
+        smS[k3_pad(e)] = n < P.n ? (double)__ldcs(P.stV + n) : 0.0;
+        smA[k3_pad(e)] = gap_at(n);
+    }
+    {
+        const int e = K3_TILE + threadIdx.x;
+        smA[k3_pad(e)] = gap_at(tile_base + e);
+        if (threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = gap_at(tile_base + K3_TILE + K3_HALO);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_base, double *smS, double *smA)
 {
+    if (P.stG) {
+        stage_tile_stash(P, tile_base, smS, smA);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < K3_L; ++k) {
         const int e = k * K3_THREADS + threadIdx.x;
@@ -109,9 +138,10 @@ __device__ __forceinline__ double gen_gap(const K3Params &P, long long n)
     return (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
 }
 
-template <bool REPLAY, bool STORE_GAPS = false>
+template <bool REPLAY, bool STORE_GAPS = false, bool STASH_W = false>
 __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, double (&x)[K3_L], double (&s)[K3_L],
-                                               const double *smS, double *smA)
+                                               const double *smS, double *smA, float *stg = nullptr,
+                                               float *stv = nullptr)
 {
     double sum_a = 0.0;
     if (REPLAY) {
@@ -142,6 +172,12 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
             sum_a += ok ? gap : 0.0;
             x[j] = ok ? __dsub_rn(sv, gnext) : 0.0;
             if (STORE_GAPS) smA[k3_pad(threadIdx.x * K3_L + j)] = gap;
+            if (STASH_W) {  // both values came from fp32 samplers: the casts are exact.  Staged in shared memory
+                // (padded: conflict free) and written out by the CTA with coalesced stores
+                stg[k3_pad(threadIdx.x * K3_L + j)] = (float)gap;
+                stv[k3_pad(threadIdx.x * K3_L + j)] = (float)sv;
+                if (n == P.n - 1) P.stG[P.n] = (float)gnext;
+            }
             gap = gnext;
         }
         if (STORE_GAPS) smA[k3_pad(threadIdx.x * K3_L + K3_L)] = gap;
@@ -158,19 +194,34 @@ __device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, cons
     return f;
 }
 
-template <bool REPLAY>
+template <bool REPLAY, bool STASH_W = false>
 __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
     extern __shared__ double stage[];
     double *smS = stage, *smA = stage + K3_PADDED;
+    __shared__ float stash_stage[STASH_W ? 2 * K3_PADDED : 2];
+    float *stg = stash_stage, *stv = stash_stage + (STASH_W ? K3_PADDED : 1);
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
         if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
-        load_segment<REPLAY>(P, n0, x, s, smS, smA);
+        load_segment<REPLAY, false, STASH_W>(P, n0, x, s, smS, smA, stg, stv);
         MP total;
         cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);  // its barriers also fence the stage reuse
+        if (STASH_W) {
+            // (the scan's barriers have made the staged draws visible) one 128-byte line per warp and instruction
+            const long long tb = t * K3_TILE;
+#pragma unroll
+            for (int k = 0; k < K3_L; ++k) {
+                const int e = k * K3_THREADS + threadIdx.x;
+                if (tb + e < P.n) {
+                    __stcs(P.stG + tb + e, stg[k3_pad(e)]);
+                    __stcs(P.stV + tb + e, stv[k3_pad(e)]);
+                }
+            }
+            __syncthreads();  // before the next tile overwrites the staging arrays
+        }
         if (threadIdx.x == 0) P.tile_sum[t] = total;
     }
 }
@@ -210,7 +261,7 @@ __device__ __noinline__ void level_walk(const K3Params &P, double v, int e, long
         else if (e + m <= K3_TILE + K3_HALO)
             g = smA[k3_pad(e + m)];
         else
-            g = REPLAY ? __ldg(P.A + nn) : gen_gap(P, nn);
+            g = (REPLAY && !P.stG) ? __ldg(P.A + nn) : ((REPLAY && nn <= P.n) ? (double)__ldg(P.stG + nn) : gen_gap(P, nn));
         const double hi = cum + g;
         const double ov = fmin(v, hi) - cum;
         if (m <= K3_PBL)
@@ -354,6 +405,8 @@ cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
                                              (int)K3_STAGE_BYTES);
         if (e != cudaSuccess) return e;
         k3_summary<true><<<grid, K3_THREADS, K3_STAGE_BYTES, st>>>(P);
+    } else if (P.stG) {
+        k3_summary<false, true><<<grid, K3_THREADS, 0, st>>>(P);
     } else {
         k3_summary<false><<<grid, K3_THREADS, 0, st>>>(P);
     }
@@ -369,9 +422,10 @@ cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st)
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st)
 {
     const bool want_p = P.level_partial != nullptr;
-    const size_t smem = k3_walk_smem(P.replay != 0, want_p);
+    const bool staged = P.replay != 0 || P.stG != nullptr;  // the stash is walked like replayed arrays
+    const size_t smem = k3_walk_smem(staged, want_p);
     cudaError_t e = cudaSuccess;
-    if (P.replay) {
+    if (staged) {
         if (want_p) {
             e = cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) k3_walk<true, true><<<grid, K3_THREADS, smem, st>>>(P);
@@ -404,15 +458,20 @@ cudaError_t k3_launch_final(const double *partial, const double *level_partial, 
     return cudaGetLastError();
 }
 
-cudaError_t k3_occupancy(bool replay, bool want_p, int *summary_blocks, int *walk_blocks)
+cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_blocks, int *walk_blocks)
 {
     int a = 0, b = 0;
     cudaError_t e;
-    const size_t wsm = k3_walk_smem(replay, want_p);
-    if (replay) {
-        e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
-        if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
+    const bool staged = replay || stash;
+    const size_t wsm = k3_walk_smem(staged, want_p);
+    if (staged) {
+        if (replay) {
+            e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
+            if (e == cudaSuccess)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
+        } else {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false, true>, K3_THREADS, 0);
+        }
         if (e == cudaSuccess) {
             if (want_p) {
                 e = cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);

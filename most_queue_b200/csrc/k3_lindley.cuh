@@ -33,6 +33,9 @@ struct K3Params {
     long long ntiles;
     long long n_ahead;       // jobs of the chain after this range (their gaps follow A[n])
     double *level_partial;   // optional [grid][K3_NLEVEL]: time-in-state on the scan path
+    // generator form, optional: the summary pass stashes its fp32 draws (gap of job i in stG[i], i = 0..n; service in
+    // stV[i]) and the walk pass reads them back instead of drawing everything a second time
+    float *stG, *stV;
 };
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
@@ -40,7 +43,7 @@ cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_final(const double *partial, const double *level_partial, int grid, double *stats,
                             cudaStream_t st);
-cudaError_t k3_occupancy(bool replay, bool want_p, int *summary_blocks, int *walk_blocks);
+cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_blocks, int *walk_blocks);
 size_t k3_walk_smem(bool replay, bool want_p);
 
 }  // namespace mq

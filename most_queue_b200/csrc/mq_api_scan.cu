@@ -2,6 +2,8 @@
 #include "k3_lindley.cuh"
 #include "mq_host.cuh"
 
+#include <cstdlib>
+
 using namespace mq;
 
 namespace {
@@ -12,7 +14,8 @@ struct ScanRun {
     bool staged_inputs = false;
 };
 
-int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, ScanRun &run, const char *who)
+int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, ScanRun &run, const char *who,
+                 bool will_walk = false)
 {
     if (!ctx || !cfg) return fail(MQ_E_INVALID, "%s: NULL argument", who);
     if (cfg->jobs < 1 || cfg->job0 < 0) return fail(MQ_E_INVALID, "%s: jobs must be >= 1 and job0 >= 0", who);
@@ -32,9 +35,30 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     const long long tile = (long long)K3_THREADS * K3_L;
     P.ntiles = (P.n + tile - 1) / tile;
 
+    // generator form followed by a walk: stash the fp32 draws of the summary pass (8 B per job) when they fit, so the
+    // walk does not draw everything a second time.  MQ_SCAN_NO_STASH=1 turns it off.
+    bool stash = false;
+    if (!replay && will_walk && !std::getenv("MQ_SCAN_NO_STASH")) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = sizeof(float) * (2 * (size_t)P.n + 64);
+        const size_t have = ctx->in_a.cap + ctx->in_s.cap;  // buffers that would be reused
+        stash = need <= have || need < (free_b + have) / 2;
+    }
+    if (stash) {
+        // an allocation failure only costs the optimisation
+        if (ensure(ctx->in_a, sizeof(float) * ((size_t)P.n + 32)) != MQ_OK ||
+            ensure(ctx->in_s, sizeof(float) * ((size_t)P.n + 32)) != MQ_OK) {
+            cudaGetLastError();
+            stash = false;
+        } else {
+            P.stG = (float *)ctx->in_a.p;
+            P.stV = (float *)ctx->in_s.p;
+        }
+    }
     int occ_s = 0, occ_w = 0;
     const bool want_p = (cfg->flags & MQ_SCAN_WANT_P) != 0;
-    CU(k3_occupancy(replay, want_p, &occ_s, &occ_w));
+    CU(k3_occupancy(replay, stash, want_p, &occ_s, &occ_w));
     if (occ_s < 1 || occ_w < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     run.grid_sum = (int)std::min<long long>(P.ntiles, (long long)occ_s * ctx->sms);
     run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
@@ -164,7 +188,7 @@ int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, cons
 {
     if (!stats) return fail(MQ_E_INVALID, "mq_scan_gg1_apply: NULL output");
     ScanRun run;
-    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_apply")) return rc;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_apply", true)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     // the tile prefixes are a function of the range only; recompute them (scratch is not kept between calls)
@@ -176,7 +200,7 @@ int mq_scan_gg1(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const doub
 {
     if (!stats) return fail(MQ_E_INVALID, "mq_scan_gg1: NULL output");
     ScanRun run;
-    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1")) return rc;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1", true)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (int rc = scan_summary(ctx, run)) return rc;
