@@ -168,7 +168,7 @@ __device__ __forceinline__ void restore_order(float (&L)[CT])
 }
 
 template <int CT, int SRCK, int SRVK, bool FINITE>
-__global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 7 : 2)) k2_fifo_gen(const K2Params P)
+__global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 8 : 2)) k2_fifo_gen(const K2Params P)
 {
     extern __shared__ float smem[];
     const int tid = threadIdx.x;
