@@ -1,0 +1,1 @@
+"""Open-network simulators computed on the GPU: NetworkSimulator, PriorityNetwork, TandemBlockingSim."""
