@@ -82,3 +82,11 @@ if which in ("k8", "k9"):
                               L.make_dist("M", 0.8), N, R, 0, 3, p_bins=32)
     t = ctx.last_timing()
     print(which, t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
+if which == "k10":
+    from most_queue_b200.random.distributions import H2Distribution as _H2
+    R, N = 200000, 5000
+    h2 = _H2.get_params_by_mean_and_cv(0.75, 1.6)
+    for _ in range(2):
+        ctx.sim_size(L.SIZE_DISCIPLINES["SRPT"], None, L.make_dist("M", 1.0), L.make_dist("H", h2), N, R, 0, 3, p_bins=32)
+    t = ctx.last_timing()
+    print(which, t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
