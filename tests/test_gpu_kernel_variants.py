@@ -1,0 +1,135 @@
+"""Every template instantiation and every general (fallback) kernel stays under the bit-exact oracle check: the small
+configurations run the register / shared-memory resident kernels (k4v2, k5v2, k7v2), larger ones the general kernels
+(k4_prio, k5_net, k7_prionet), and MQ_K*_V1=1 forces the general kernel on a small configuration."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_prio(c, K, prty, buffer, seed):
+    from most_queue_b200.sim.priority import replay
+    from oracle import oracle
+
+    rng = np.random.default_rng(seed)
+    R, n = 24, 250
+    A = [rng.exponential(K * 1.1 / c * (1 + 0.2 * k), (3 * n, R)) for k in range(K)]
+    S = [rng.gamma(0.7, 1.3 * (1 + 0.3 * k), (4 * n, R)) for k in range(K)]
+    out = replay(c, K, prty, A, S, n, buffer=buffer, p_bins=32)
+    for r in range(R):
+        o = oracle.prio_replay(c, K, prty, [a[:, r].copy() for a in A], [s[:, r].copy() for s in S], n, buffer=buffer,
+                               p_bins=32)
+        assert np.array_equal(out["v"][r], o.v) and np.array_equal(out["w"][r], o.w)
+        assert np.array_equal(out["p_time"][r], o.p_time) and out["ttek"][r] == o.ttek
+        assert np.array_equal(out["dropped"][r], o.dropped)
+
+
+@pytest.mark.parametrize("c,K,prty,buffer", [
+    (8, 2, "PR", None),   # k4v2<8,2>
+    (5, 1, "NP", None),   # k4v2<8,2>, one class
+    (7, 4, "RS", 4),      # k4v2<8,4>, finite buffer
+    (2, 4, "RW", 3),      # k4v2<4,4>, finite buffer
+    (10, 2, "PR", None),  # general kernel: c > 8
+    (3, 5, "NP", None),   # general kernel: K > 4
+    (12, 6, "RW", 5),     # general kernel
+])
+def test_priority_kernels_all_variants(c, K, prty, buffer):
+    _check_prio(c, K, prty, buffer, 1000 + 10 * c + K)
+
+
+def test_priority_general_kernel_on_a_small_configuration(monkeypatch):
+    monkeypatch.setenv("MQ_K4_V1", "1")
+    _check_prio(4, 2, "PR", None, 77)
+    _check_prio(3, 3, "RS", 4, 78)
+
+
+def _ring_network(m, ch, rng):
+    """Feed-forward ring with feedback: node i -> i+1 w.p. 0.6, back to 0 w.p. 0.1, out w.p. 0.3."""
+    Rm = np.zeros((m + 1, m + 1))
+    Rm[0, 0] = 1.0
+    for i in range(m):
+        nxt = (i + 1) % m
+        Rm[i + 1, nxt] += 0.6
+        Rm[i + 1, 0] += 0.1 if nxt != 0 else 0.0
+        Rm[i + 1, m] = 1.0 - Rm[i + 1, :m].sum()
+    return Rm
+
+
+def _check_net(m, ch, seed):
+    from most_queue_b200.sim.networks.network import replay
+    from oracle import oracle
+
+    rng = np.random.default_rng(seed)
+    Rm = _ring_network(m, ch, rng)
+    R, n = 16, 200
+    A = rng.exponential(1.0, (3 * n, R))
+    U = rng.random((16 * n, R))
+    S = [rng.gamma(0.8, 0.25 * c, (8 * n, R)) for c in ch]
+    out = replay(Rm, ch, A, U, S, n)
+    for r in range(R):
+        o = oracle.net_replay(Rm, ch, A[:, r].copy(), U[:, r].copy(), [s[:, r].copy() for s in S], n)
+        assert o.ttek == out["ttek"][r] and o.arrived == out["arrived"][r] and o.u_used == out["u_used"][r]
+        assert np.array_equal(o.v_sum, out["v_sum"][r]) and np.array_equal(o.w_sum, out["w_sum"][r])
+        assert np.array_equal(o.node_v, out["node_v"][r]) and np.array_equal(o.node_w, out["node_w"][r])
+        assert np.array_equal(o.s_used, out["s_used"][r]) and np.array_equal(o.node_taked, out["node_taked"][r])
+
+
+@pytest.mark.parametrize("m,ch", [
+    (2, [1, 2]),                    # k5v2<8>
+    (4, [2, 2, 2, 2]),              # k5v2<8>, exactly 8 servers
+    (6, [3, 2, 3, 2, 3, 3]),        # k5v2<16>, 16 servers
+    (3, [6, 6, 6]),                 # general kernel: 18 servers
+    (10, [1] * 10),                 # general kernel: 10 nodes
+])
+def test_network_kernels_all_variants(m, ch):
+    _check_net(m, ch, 2000 + m)
+
+
+def test_network_general_kernel_on_a_small_configuration(monkeypatch):
+    monkeypatch.setenv("MQ_K5_V1", "1")
+    _check_net(3, [2, 1, 2], 88)
+
+
+def _check_prionet(m, K, ch, prty, seed):
+    from most_queue_b200.sim.networks.priority_network import replay
+    from oracle import oracle
+
+    rng = np.random.default_rng(seed)
+    Rk = []
+    for k in range(K):
+        Rm = np.zeros((m + 1, m + 1))
+        Rm[0, k % m] = 1.0
+        for i in range(m):
+            Rm[i + 1, (i + 1 + k) % m] = 0.5
+            Rm[i + 1, m] = 0.5
+        Rk.append(Rm)
+    npr = [[(k + i) % K for k in range(K)] for i in range(m)]
+    R, n = 12, 200
+    A = [rng.exponential(1.2 * K, (3 * n, R)) for _ in range(K)]
+    U = rng.random((12 * n, R))
+    S = [[rng.gamma(0.8, 0.4 * ch[i], (8 * n, R)) for _ in range(K)] for i in range(m)]
+    out = replay(Rk, ch, prty, npr, A, U, S, n)
+    for r in range(R):
+        o = oracle.prionet_replay(Rk, ch, prty, npr, [a[:, r].copy() for a in A], U[:, r].copy(),
+                                  [[x[:, r].copy() for x in row] for row in S], n)
+        assert o.ttek == out["ttek"][r] and o.u_used == out["u_used"][r]
+        assert np.array_equal(o.served, out["served"][r]) and np.array_equal(o.arrived, out["arrived"][r])
+        assert np.array_equal(o.v_sum, out["v_sum"][r]) and np.array_equal(o.w_sum, out["w_sum"][r])
+        assert np.array_equal(o.node_v, out["node_v"][r]) and np.array_equal(o.node_w, out["node_w"][r])
+        assert np.array_equal(o.s_used, out["s_used"][r]) and np.array_equal(o.node_taked, out["node_taked"][r])
+
+
+@pytest.mark.parametrize("m,K,ch,prty", [
+    (2, 2, [2, 2], ["PR", "NP"]),                          # k7v2<8>
+    (4, 3, [3, 3, 3, 3], ["RS", "RW", "PR", "NP"]),        # k7v2<16>, 12 servers
+    (5, 4, [3, 3, 3, 3, 4], ["PR", "RS", "NP", "RW", "PR"]),  # k7v2<16>, 16 servers, 4 classes
+    (4, 2, [5, 5, 5, 5], ["PR", "NP", "RS", "RW"]),        # general kernel: 20 servers
+])
+def test_priority_network_kernels_all_variants(m, K, ch, prty):
+    _check_prionet(m, K, ch, prty, 3000 + m * 10 + K)
+
+
+def test_priority_network_general_kernel_on_a_small_configuration(monkeypatch):
+    monkeypatch.setenv("MQ_K7_V1", "1")
+    _check_prionet(3, 2, [2, 1, 2], ["PR", "RS", "NP"], 99)
