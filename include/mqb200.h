@@ -551,12 +551,19 @@ int mq_replay_negatives(mq_ctx *ctx, const mq_neg_cfg *cfg, const double *const 
                         double *rep_out);
 
 /* ---- size-based single-server disciplines.  Replaces SizeBasedQsSim(1, discipline, buffer, track_slowdown)
- * .set_sources / set_servers / run(total_served) (sim/size_based.py:64,121,216) with the default perfect predictor,
- * under which SPJF / PSPJF / SPRPT rank exactly like SJF / PSJF / SRPT (size_based.py:128-153) */
+ * .set_sources / set_servers / set_predictor / run(total_served) (sim/size_based.py:64,105,121,216).  The predictors
+ * of sim/utils/predictor.py are built in: perfect (the default), exponential noise, log-normal noise */
 #define MQ_SZ_FCFS 0
-#define MQ_SZ_SJF 1   /* also SPJF  */
-#define MQ_SZ_PSJF 2  /* also PSPJF */
-#define MQ_SZ_SRPT 3  /* also SPRPT */
+#define MQ_SZ_SJF 1
+#define MQ_SZ_PSJF 2
+#define MQ_SZ_SRPT 3
+#define MQ_SZ_SPJF 4   /* ranks by the predicted size                                  size_based.py:141 */
+#define MQ_SZ_PSPJF 5  /* the same, pre-emptive                                                          */
+#define MQ_SZ_SPRPT 6  /* ranks by the predicted remaining work max(0, Y - served)     size_based.py:143-151 */
+#define MQ_PRED_PERFECT 0    /* Y = X                                   size_based.py:33-38            */
+#define MQ_PRED_EXP 1        /* Y | X = x ~ Exp(mean x)                 sim/utils/predictor.py:14-24   */
+#define MQ_PRED_LOGNORMAL 2  /* Y | X = x ~ LogNormal(log x, sigma)     sim/utils/predictor.py:27-43   */
+#define MQ_PRED_GIVEN 3      /* replay form: Y supplied by the caller                                    */
 
 typedef struct {
     int32_t discipline;
@@ -568,7 +575,8 @@ typedef struct {
     int64_t rep0;
     uint64_t seed;
     int32_t queue_cap;   /* infinite buffer: waiting-line capacity of the engine (0: 256) */
-    int32_t flags;
+    int32_t pred_kind;   /* MQ_PRED_* (generator form; the replay form uses Y when it is given) */
+    double pred_sigma;   /* MQ_PRED_LOGNORMAL */
 } mq_size_cfg;
 
 /* per-replication record rows */
@@ -585,6 +593,7 @@ typedef struct {
 #define MQ_Z_PREEMPTIONS 10
 #define MQ_Z_AUSED 11
 #define MQ_Z_SUSED 12
+#define MQ_Z_YUSED 13
 #define MQ_Z_SLOWDOWN 14 /* 2: sum and sum of squares of sojourn / size (size_based.py:110-119) */
 #define MQ_Z_WSUM 16     /* 4 */
 #define MQ_Z_VSUM 20     /* 4 */
@@ -600,9 +609,10 @@ typedef struct {
 #define MQ_Z_AGG_LEN(pb) (32 + 2 * (pb))
 
 int mq_sim_size(mq_ctx *ctx, const mq_size_cfg *cfg, double *agg, double *rep_out);
-/* replay form: A = gaps [n_a][replications], S = job sizes in arrival order (FCFS: services in start order) */
+/* replay form: A = gaps [n_a][replications], S = job sizes in arrival order (FCFS: services in start order), Y =
+ * predicted sizes in arrival order (NULL: perfect predictor) */
 int mq_replay_size(mq_ctx *ctx, const mq_size_cfg *cfg, const double *A, int64_t n_a, const double *S, int64_t n_s,
-                   double *agg, double *rep_out);
+                   const double *Y, int64_t n_y, double *agg, double *rep_out);
 
 int mq_version(void);
 int mq_device_count(void);

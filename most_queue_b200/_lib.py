@@ -243,21 +243,22 @@ def neg_agg_len(p_bins):
     return 48 + 2 * int(p_bins)
 
 
-SIZE_DISCIPLINES = {"FCFS": 0, "SJF": 1, "PSJF": 2, "SRPT": 3, "SPJF": 1, "PSPJF": 2, "SPRPT": 3}
+SIZE_DISCIPLINES = {"FCFS": 0, "SJF": 1, "PSJF": 2, "SRPT": 3, "SPJF": 4, "PSPJF": 5, "SPRPT": 6}
+PRED_KINDS = {"perfect": 0, "exp": 1, "lognormal": 2}
 
 
 class MqSizeCfg(C.Structure):
     _fields_ = [
         ("discipline", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("src", MqDist), ("srv", MqDist),
         ("total_served", C.c_int64), ("replications", C.c_int64), ("rep0", C.c_int64), ("seed", C.c_uint64),
-        ("queue_cap", C.c_int32), ("flags", C.c_int32),
+        ("queue_cap", C.c_int32), ("pred_kind", C.c_int32), ("pred_sigma", C.c_double),
     ]
 
 
 # record rows of the size-based kernel (include/mqb200.h MQ_Z_*)
 (Z_TTEK, Z_FLAGS, Z_ARRIVED, Z_TAKED, Z_SERVED, Z_DROPPED, Z_INSYS, Z_QUEUED, Z_BUSYN, Z_POVER, Z_PREEMPTIONS, Z_AUSED,
- Z_SUSED, Z_SLOWDOWN, Z_WSUM, Z_VSUM, Z_WRUN, Z_VRUN, Z_BUSYRUN, Z_P) = (
-    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 20, 24, 28, 32, 36)
+ Z_SUSED, Z_YUSED, Z_SLOWDOWN, Z_WSUM, Z_VSUM, Z_WRUN, Z_VRUN, Z_BUSYRUN, Z_P) = (
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 20, 24, 28, 32, 36)
 
 
 def size_rec_rows(p_bins):
@@ -340,7 +341,7 @@ def load():
         L.mq_sim_size.restype = C.c_int
         L.mq_sim_size.argtypes = [vp, C.POINTER(MqSizeCfg), dp, dp]
         L.mq_replay_size.restype = C.c_int
-        L.mq_replay_size.argtypes = [vp, C.POINTER(MqSizeCfg), vp, C.c_int64, vp, C.c_int64, dp, dp]
+        L.mq_replay_size.argtypes = [vp, C.POINTER(MqSizeCfg), vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, dp, dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -796,23 +797,26 @@ class Context:
         return cfg
 
     def sim_size(self, discipline, buffer, src, srv, total_served, replications, rep0, seed, p_bins=128, queue_cap=0,
-                 per_replication=False):
+                 per_replication=False, predictor="perfect", sigma=0.5):
         cfg = self._size_cfg(discipline, buffer, total_served, replications, rep0, seed, p_bins, queue_cap)
         cfg.src, cfg.srv = src, srv
+        cfg.pred_kind, cfg.pred_sigma = PRED_KINDS[predictor], float(sigma)
         agg = np.zeros(size_agg_len(p_bins))
         rec = np.empty((size_rec_rows(p_bins), int(replications))) if per_replication else None
         check(self._L.mq_sim_size(self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
                                   rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
         return agg, rec
 
-    def replay_size(self, discipline, buffer, A, S, total_served, p_bins=128, queue_cap=0):
+    def replay_size(self, discipline, buffer, A, S, total_served, p_bins=128, queue_cap=0, Y=None):
         A = np.ascontiguousarray(A, dtype=np.float64)
         S = np.ascontiguousarray(S, dtype=np.float64)
+        Y = None if Y is None else np.ascontiguousarray(Y, dtype=np.float64)
         reps = A.shape[1]
         cfg = self._size_cfg(discipline, buffer, total_served, reps, 0, 0, p_bins, queue_cap)
         agg = np.zeros(size_agg_len(p_bins))
         rec = np.empty((size_rec_rows(p_bins), reps))
         check(self._L.mq_replay_size(self._h, C.byref(cfg), A.ctypes.data, A.shape[0], S.ctypes.data, S.shape[0],
+                                     Y.ctypes.data if Y is not None else None, Y.shape[0] if Y is not None else 0,
                                      agg.ctypes.data_as(C.POINTER(C.c_double)),
                                      rec.ctypes.data_as(C.POINTER(C.c_double))))
         return agg, rec

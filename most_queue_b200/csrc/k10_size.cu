@@ -23,6 +23,7 @@ namespace mq {
 struct K10Job {
     double rank, arr, start_wait, wait, remaining, size;
     long long id;
+    double pred;
 };
 
 __device__ __forceinline__ void k10_sample(double *run, double *sum, int n, double x, long long count)
@@ -48,15 +49,17 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
 {
     const long long gtid = (long long)blockIdx.x * K10_BLOCK + threadIdx.x;
     const long long R = P.reps;
-    const DistF law_src = P.src, law_srv = P.srv;
+    const DistF law_src = P.src, law_srv = P.srv, law_pred = P.pred_law;
     const int disc = P.discipline;
-    const bool fcfs = disc == MQ_SZ_FCFS, preemptive = disc == MQ_SZ_PSJF || disc == MQ_SZ_SRPT;
+    const bool fcfs = disc == MQ_SZ_FCFS;
+    const bool preemptive = disc == MQ_SZ_PSJF || disc == MQ_SZ_SRPT || disc == MQ_SZ_PSPJF || disc == MQ_SZ_SPRPT;
+    const bool tracks_remaining = disc == MQ_SZ_SRPT || disc == MQ_SZ_SPRPT;
 
     for (long long rl = gtid; rl < R; rl += P.lanes) {
         const uint32_t rep = P.rep0 + (uint32_t)rl;
         double *rec = P.rec + rl;
         double *Q = P.queue + gtid;
-        long long a_idx = 0, s_idx = 0;
+        long long a_idx = 0, s_idx = 0, y_idx = 0;
         int status = 0;
 
         auto next_gap = [&]() -> double {
@@ -83,9 +86,25 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
             uint2 w = philox2x32_10((uint32_t)i, rep, P.key0);
             return (double)sample<-1>(law_srv, w.y, (uint32_t)i, rep, P.key0, 1);
         };
+        // predictor (size_based.py:163, sim/utils/predictor.py): perfect, x * Exp(1), x * exp(sigma Z), or replayed
+        auto predict = [&](double x) -> double {
+            if (P.pred_kind == MQ_PRED_PERFECT) return x;
+            const long long i = y_idx++;
+            if (P.replay) {
+                if (i >= P.n_y) {
+                    status = MQ_E_INPUT_SHORT;
+                    return 0.0;
+                }
+                return P.Y[i * R + rl];
+            }
+            const uint32_t key = P.key0 + MQ_KEY_STRIDE * 64u;  // stream 1
+            uint2 w = philox2x32_10((uint32_t)i, rep, key);
+            const double z = (double)sample<-1>(law_pred, w.x, (uint32_t)i, rep, key, 0);
+            return P.pred_kind == MQ_PRED_EXP ? __dmul_rn(x, z) : __dmul_rn(x, exp(__dmul_rn(P.pred_sigma, z)));
+        };
         auto qf = [&](int slot, int f) -> double * { return Q + ((long long)slot * K10_JOBF + f) * P.lanes; };
 
-        K10Job cur = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0};
+        K10Job cur = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0, 0.0};
         bool busy = false;
         double end = 1e10, ttek = 0.0, start_busy = 0.0, p_over = 0.0;
         long long arrived = 0, taked = 0, served = 0, dropped = 0, in_sys = 0, busy_n = 0, next_id = 0, preempt = 0;
@@ -100,7 +119,14 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
             else
                 p_over = __dadd_rn(p_over, dt);
         };
-        auto rank_of = [&](const K10Job &j) -> double { return fcfs ? j.arr : (disc == MQ_SZ_SRPT ? j.remaining : j.size); };
+        auto rank_of = [&](const K10Job &j) -> double {  // _rank_value size_based.py:128-153
+            if (fcfs) return j.arr;
+            if (disc == MQ_SZ_SJF || disc == MQ_SZ_PSJF) return j.size;
+            if (disc == MQ_SZ_SRPT) return j.remaining;
+            if (disc == MQ_SZ_SPJF || disc == MQ_SZ_PSPJF) return j.pred;
+            const double pr = __dsub_rn(j.pred, __dsub_rn(j.size, j.remaining));  // SPRPT: predicted remaining work
+            return pr > 0.0 ? pr : 0.0;
+        };
         auto q_push = [&](const K10Job &j) {
             if (qsize >= P.qcap) {
                 status = MQ_E_OVERFLOW;
@@ -113,6 +139,7 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
             *qf(qsize, 4) = j.remaining;
             *qf(qsize, 5) = j.size;
             *qf(qsize, 6) = (double)j.id;
+            *qf(qsize, 7) = j.pred;
             qsize++;
         };
         auto start = [&](const K10Job &j) {  // Server.start_service servers.py:57-88
@@ -131,10 +158,11 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
                 ttek = arrival_time;
                 arrival_time = __dadd_rn(ttek, next_gap());
                 in_sys++;
-                K10Job nj = {0.0, ttek, 0.0, 0.0, 0.0, 0.0, next_id++};
+                K10Job nj = {0.0, ttek, 0.0, 0.0, 0.0, 0.0, next_id++, 0.0};
                 if (!fcfs) {
                     nj.size = next_size();
                     nj.remaining = nj.size;
+                    nj.pred = predict(nj.size);
                 }
                 if (busy) {
                     nj.start_wait = ttek;
@@ -142,7 +170,7 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
                     if (preemptive) {
                         const double rem0 = __dsub_rn(end, ttek);
                         const double rem = rem0 > 0.0 ? rem0 : 0.0;
-                        if (disc == MQ_SZ_SRPT) cur.remaining = rem;  // _update_in_service_rank_fields :166-180
+                        if (tracks_remaining) cur.remaining = rem;  // _update_in_service_rank_fields :166-180
                         if (k10_less(rank_of(nj), nj.arr, nj.id, rank_of(cur), cur.arr, cur.id)) {
                             K10Job old = cur;
                             old.remaining = rem;  // preempt_service(preserve_remaining=True) servers.py:90-106
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
                             bi = id;
                         }
                     }
-                    K10Job qj = {br, ba, *qf(best, 2), *qf(best, 3), *qf(best, 4), *qf(best, 5), bi};
+                    K10Job qj = {br, ba, *qf(best, 2), *qf(best, 3), *qf(best, 4), *qf(best, 5), bi, *qf(best, 7)};
                     qsize--;
                     if (best != qsize)
                         for (int f = 0; f < K10_JOBF; ++f) *qf(best, f) = *qf(qsize, f);
@@ -229,6 +257,7 @@ __global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
         rec[(long long)MQ_Z_PREEMPTIONS * R] = (double)preempt;
         rec[(long long)MQ_Z_AUSED * R] = (double)a_idx;
         rec[(long long)MQ_Z_SUSED * R] = (double)s_idx;
+        rec[(long long)MQ_Z_YUSED * R] = (double)y_idx;
         rec[(long long)MQ_Z_SLOWDOWN * R] = sd1;
         rec[(long long)(MQ_Z_SLOWDOWN + 1) * R] = sd2;
         for (int i = 0; i < 4; ++i) {

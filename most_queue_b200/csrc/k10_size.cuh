@@ -6,16 +6,17 @@
 namespace mq {
 
 constexpr int K10_BLOCK = 128;
-constexpr int K10_JOBF = 7;  // doubles per waiting job: rank, arrival, start of wait, wait, remaining, size, id
+constexpr int K10_JOBF = 8;  // doubles per waiting job: rank, arrival, start of wait, wait, remaining, size, id, prediction
 
 struct K10Params {
-    int discipline, p_bins, replay, qcap;
+    int discipline, p_bins, replay, qcap, pred_kind;
+    double pred_sigma;
     long long buffer;
     long long jobs, reps;
     uint32_t rep0, key0;
-    DistF src, srv;
-    const double *A, *S;  // replay: [n_a][reps], [n_s][reps]
-    long long n_a, n_s;
+    DistF src, srv, pred_law;  // pred_law: Exp(1) or N(0,1) noise of the predictor (generator form)
+    const double *A, *S, *Y;  // replay: [n_a][reps], [n_s][reps], [n_y][reps] (Y may be null: perfect predictor)
+    long long n_a, n_s, n_y;
     double *rec;    // [MQ_Z_ROWS(p_bins)][reps], zeroed by the caller
     double *queue;  // [qcap][K10_JOBF][lanes]
     long long lanes;

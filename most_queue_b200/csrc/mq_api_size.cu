@@ -7,10 +7,10 @@
 using namespace mq;
 
 static int size_common(mq_ctx *ctx, const mq_size_cfg *cfg, bool replay, const double *A, int64_t n_a, const double *S,
-                       int64_t n_s, double *agg, double *rep_out, const char *who)
+                       int64_t n_s, const double *Y, int64_t n_y, double *agg, double *rep_out, const char *who)
 {
     if (!ctx || !cfg || !agg) return fail(MQ_E_INVALID, "%s: NULL argument", who);
-    if (cfg->discipline < MQ_SZ_FCFS || cfg->discipline > MQ_SZ_SRPT)
+    if (cfg->discipline < MQ_SZ_FCFS || cfg->discipline > MQ_SZ_SPRPT)
         return fail(MQ_E_INVALID, "%s: unknown discipline %d", who, cfg->discipline);
     if (cfg->p_bins < 1 || cfg->p_bins > MQ_MAX_PBINS) return fail(MQ_E_INVALID, "%s: p_bins must be in 1..%d", who, MQ_MAX_PBINS);
     if (cfg->total_served < 0 || cfg->replications < 1 || cfg->rep0 < 0 || cfg->rep0 + cfg->replications > (1ll << 32))
@@ -19,6 +19,10 @@ static int size_common(mq_ctx *ctx, const mq_size_cfg *cfg, bool replay, const d
         if (cfg->total_served >= (1ll << 31)) return fail(MQ_E_INVALID, "%s: total_served must be < 2^31", who);
         if (int rc = check_dist(cfg->src, "set_sources")) return rc;
         if (int rc = check_dist(cfg->srv, "set_servers")) return rc;
+        if (cfg->pred_kind < MQ_PRED_PERFECT || cfg->pred_kind > MQ_PRED_LOGNORMAL)
+            return fail(MQ_E_INVALID, "%s: unknown predictor kind %d", who, cfg->pred_kind);
+        if (cfg->pred_kind == MQ_PRED_LOGNORMAL && !(cfg->pred_sigma > 0.0))
+            return fail(MQ_E_INVALID, "sigma must be positive");  // predictor.py:37
     } else if (!A || !S || n_a < 1 || n_s < 1) {
         return fail(MQ_E_INVALID, "%s: NULL or empty arrays", who);
     }
@@ -37,6 +41,8 @@ static int size_common(mq_ctx *ctx, const mq_size_cfg *cfg, bool replay, const d
     P.p_bins = pb;
     P.replay = replay ? 1 : 0;
     P.buffer = cfg->buffer < 0 ? -1 : cfg->buffer;
+    P.pred_kind = replay ? (Y ? MQ_PRED_GIVEN : MQ_PRED_PERFECT) : cfg->pred_kind;
+    P.pred_sigma = cfg->pred_sigma;
     P.jobs = cfg->total_served;
     P.reps = R;
     P.rep0 = (uint32_t)cfg->rep0;
@@ -53,9 +59,16 @@ static int size_common(mq_ctx *ctx, const mq_size_cfg *cfg, bool replay, const d
     if (replay) {
         const size_t na = (size_t)n_a * R, ns = (size_t)n_s * R;
         if (int rc = ensure(ctx->in_a, sizeof(double) * na)) return rc;
-        if (int rc = ensure(ctx->in_s, sizeof(double) * ns)) return rc;
+        const size_t ny = Y ? (size_t)n_y * R : 0;
+        if (Y && n_y < 1) return fail(MQ_E_INVALID, "%s: empty prediction array", who);
+        if (int rc = ensure(ctx->in_s, sizeof(double) * (ns + ny))) return rc;
         CU(cudaMemcpyAsync(ctx->in_a.p, A, sizeof(double) * na, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->in_s.p, S, sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
+        if (Y) {
+            CU(cudaMemcpyAsync((double *)ctx->in_s.p + ns, Y, sizeof(double) * ny, cudaMemcpyHostToDevice, ctx->stream));
+            P.Y = (const double *)ctx->in_s.p + ns;
+            P.n_y = n_y;
+        }
         P.A = (const double *)ctx->in_a.p;
         P.S = (const double *)ctx->in_s.p;
         P.n_a = n_a;
@@ -63,6 +76,18 @@ static int size_common(mq_ctx *ctx, const mq_size_cfg *cfg, bool replay, const d
     } else {
         P.src = make_distf(cfg->src);
         P.srv = make_distf(cfg->srv);
+        mq_dist noise;
+        std::memset(&noise, 0, sizeof(noise));
+        if (cfg->pred_kind == MQ_PRED_EXP) {
+            noise.kind = MQ_M;
+            noise.p[0] = 1.0;
+            P.pred_law = make_distf(noise);
+        } else if (cfg->pred_kind == MQ_PRED_LOGNORMAL) {
+            noise.kind = MQ_NORM;
+            noise.p[0] = 0.0;
+            noise.p[1] = 1.0;
+            P.pred_law = make_distf(noise);
+        }
     }
     int occ = 0;
     CU(k10_occupancy(&occ));
@@ -129,13 +154,13 @@ extern "C" {
 
 int mq_sim_size(mq_ctx *ctx, const mq_size_cfg *cfg, double *agg, double *rep_out)
 {
-    return size_common(ctx, cfg, false, nullptr, 0, nullptr, 0, agg, rep_out, "mq_sim_size");
+    return size_common(ctx, cfg, false, nullptr, 0, nullptr, 0, nullptr, 0, agg, rep_out, "mq_sim_size");
 }
 
 int mq_replay_size(mq_ctx *ctx, const mq_size_cfg *cfg, const double *A, int64_t n_a, const double *S, int64_t n_s,
-                   double *agg, double *rep_out)
+                   const double *Y, int64_t n_y, double *agg, double *rep_out)
 {
-    return size_common(ctx, cfg, true, A, n_a, S, n_s, agg, rep_out, "mq_replay_size");
+    return size_common(ctx, cfg, true, A, n_a, S, n_s, Y, n_y, agg, rep_out, "mq_replay_size");
 }
 
 }  // extern "C"

@@ -3,9 +3,9 @@
 Mirrors most_queue/sim/size_based.py: SizeBasedQsSim(num_of_channels=1, discipline, buffer, verbose, buffer_type,
 track_slowdown) (:72), set_sources / set_servers (:121), set_predictor (:105), run(total_served) -> QueueResults,
 get_slowdown (:108).  Job sizes are drawn at arrival; the waiting line is ordered by (rank, arrival time, creation
-order); PSJF and SRPT pre-empt the job in service when a strictly better job arrives.  With the default perfect
-predictor SPJF / PSPJF / SPRPT are SJF / PSJF / SRPT (size_based.py:128-153); a custom predictor is a Python callback
-and is not supported by the GPU engine.  The event loop runs in csrc/k10_size.cu.  Additive: `seed=`, `replications=`;
+order); PSJF, SRPT, PSPJF and SPRPT pre-empt the job in service when a strictly better job arrives.  SPJF / PSPJF /
+SPRPT rank by the PREDICTED size (size_based.py:128-153); the predictors of sim/utils/predictor.py are built into the
+engine (perfect, exponential noise, log-normal noise); any other predictor is a Python callback and is rejected.  The event loop runs in csrc/k10_size.cu.  Additive: `seed=`, `replications=`;
 `get_slowdown()` returns the mean of sojourn / size over completed jobs (the reference returns the list of samples).
 """
 
@@ -20,7 +20,7 @@ from .. import _lib, dist
 from ..structs import QueueResults
 from .base import Z99, QsSim
 
-__all__ = ["SizeBasedQsSim", "PerfectSimPredictor", "replay"]
+__all__ = ["SizeBasedQsSim", "PerfectSimPredictor", "ExpNoiseSimPredictor", "LognormalNoiseSimPredictor", "replay"]
 
 
 class PerfectSimPredictor:
@@ -28,6 +28,19 @@ class PerfectSimPredictor:
 
     def predict(self, size: float, _rng) -> float:
         return float(size)
+
+
+class ExpNoiseSimPredictor:
+    """Y | X = x ~ Exp(mean x) (sim/utils/predictor.py:14-24); drawn on the GPU."""
+
+
+class LognormalNoiseSimPredictor:
+    """Y | X = x ~ LogNormal(log x, sigma) (sim/utils/predictor.py:27-43); drawn on the GPU."""
+
+    def __init__(self, sigma: float = 0.5) -> None:
+        if sigma <= 0:
+            raise ValueError("sigma must be positive")
+        self.sigma = float(sigma)
 
 
 class SizeBasedQsSim(QsSim):
@@ -46,11 +59,20 @@ class SizeBasedQsSim(QsSim):
         self.queue_cap = int(queue_cap)
         self.slowdown = 0.0
         self.preemptions = 0
+        self._pred_kind, self._pred_sigma = "perfect", 0.5
 
     def set_predictor(self, predictor) -> None:
-        if predictor is not None and not isinstance(predictor, PerfectSimPredictor):
+        """Accepts the reference's predictor objects too (matched by class name)."""
+        name = "PerfectSimPredictor" if predictor is None else type(predictor).__name__
+        if name == "PerfectSimPredictor":
+            self._pred_kind = "perfect"
+        elif name == "ExpNoiseSimPredictor":
+            self._pred_kind = "exp"
+        elif name == "LognormalNoiseSimPredictor":
+            self._pred_kind, self._pred_sigma = "lognormal", float(predictor.sigma)
+        else:
             raise NotImplementedError("custom size predictors are Python callbacks; the GPU engine implements the "
-                                      "perfect predictor (the reference's default) only")
+                                      "perfect, exponential-noise and log-normal-noise predictors")
 
     def get_slowdown(self) -> float:
         """Mean of sojourn / size over completed jobs (0 for FCFS, which draws no sizes)."""
@@ -69,7 +91,8 @@ class SizeBasedQsSim(QsSim):
         if count > 0:
             agg, rec = ctx.sim_size(_lib.SIZE_DISCIPLINES[self._discipline], self.buffer, self._src, self._srv,
                                     total_served, count, rep0, seed, p_bins=self.p_bins, queue_cap=self.queue_cap,
-                                    per_replication=keep_replications)
+                                    per_replication=keep_replications, predictor=self._pred_kind,
+                                    sigma=self._pred_sigma)
             self.timing = ctx.last_timing()
         else:
             agg, rec = np.zeros(_lib.size_agg_len(self.p_bins)), None
@@ -106,13 +129,13 @@ class SizeBasedQsSim(QsSim):
         self.ttek = float(agg[1] / R)
 
 
-def replay(discipline, buffer, A, S, total_served, p_bins=128, queue_cap=0, device=None):
-    """Replay tier: gaps A[i, r] and job sizes S[j, r] in arrival order (FCFS: services in start order); fp64,
-    bit-exact with the reference (csrc/k10_size.cu)."""
+def replay(discipline, buffer, A, S, total_served, p_bins=128, queue_cap=0, device=None, Y=None):
+    """Replay tier: gaps A[i, r] and job sizes S[j, r] in arrival order (FCFS: services in start order), optional
+    predicted sizes Y[j, r]; fp64, bit-exact with the reference (csrc/k10_size.cu)."""
     L = _lib
     ctx = L.default_context(device)
     agg, rec = ctx.replay_size(L.SIZE_DISCIPLINES[discipline], buffer, A, S, total_served, p_bins=p_bins,
-                               queue_cap=queue_cap)
+                               queue_cap=queue_cap, Y=Y)
     flags = rec[L.Z_FLAGS]
     if np.any(flags != 0):
         bad = int(np.flatnonzero(flags)[0])
@@ -126,5 +149,5 @@ def replay(discipline, buffer, A, S, total_served, p_bins=128, queue_cap=0, devi
         "p_time": rec[L.Z_P:L.Z_P + p_bins].T.copy(), "p_over": rec[L.Z_POVER].copy(), "ttek": rec[L.Z_TTEK].copy(),
         "arrived": i64(L.Z_ARRIVED), "taked": i64(L.Z_TAKED), "served": i64(L.Z_SERVED), "dropped": i64(L.Z_DROPPED),
         "in_sys": i64(L.Z_INSYS), "queued": i64(L.Z_QUEUED), "preemptions": i64(L.Z_PREEMPTIONS),
-        "a_used": i64(L.Z_AUSED), "s_used": i64(L.Z_SUSED), "agg": agg, "timing": ctx.last_timing(),
+        "a_used": i64(L.Z_AUSED), "s_used": i64(L.Z_SUSED), "y_used": i64(L.Z_YUSED), "agg": agg, "timing": ctx.last_timing(),
     }

@@ -236,7 +236,7 @@ int mqo_neg_run(int c, int64_t buffer, int type, int scenario, mqo_src *positive
                 mqo_src *choices, int64_t total_served, double *p, int64_t p_bins, mqo_neg_out *out);
 
 /* ---- size-based single-server disciplines: SizeBasedQsSim.run (sim/size_based.py:64-248) ---- */
-enum { MQO_SZ_FCFS = 0, MQO_SZ_SJF = 1, MQO_SZ_PSJF = 2, MQO_SZ_SRPT = 3 };
+enum { MQO_SZ_FCFS = 0, MQO_SZ_SJF = 1, MQO_SZ_PSJF = 2, MQO_SZ_SRPT = 3, MQO_SZ_SPJF = 4, MQO_SZ_PSPJF = 5, MQO_SZ_SPRPT = 6 };
 
 typedef struct {
     double w_sum[4], v_sum[4], w_run[4], v_run[4], busy_run[3];
@@ -246,8 +246,10 @@ typedef struct {
 } mqo_size_out;
 
 /* sizes: job sizes in arrival order (size_based.py:155-164); for FCFS the service draws in start order */
-int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *sizes, int64_t total_served, double *p,
-                 int64_t p_bins, mqo_size_out *out);
+/* pred_kind: 0 perfect predictor (Y = X), 1 Y = X * e with e from preds (Exp(1)), 2 Y = X * exp(sigma * z) with z from
+ * preds (N(0,1)), 3 Y taken from preds as it is (replay) -- sim/utils/predictor.py */
+int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *sizes, int pred_kind, double pred_sigma,
+                 mqo_src *preds, int64_t total_served, double *p, int64_t p_bins, mqo_size_out *out);
 
 /* ---- open network of PRIORITY nodes with per-class routing: PriorityNetwork.run
  * (sim/networks/priority_network.py:241-276) ---- */

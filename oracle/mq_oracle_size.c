@@ -11,7 +11,7 @@
 #include <string.h>
 
 typedef struct {
-    double rank, arr, start_wait, wait, remaining, size;
+    double rank, arr, start_wait, wait, remaining, size, pred;
     int64_t id;
 } sjob;
 
@@ -39,13 +39,33 @@ static inline int key_less(const sjob *a, const sjob *b)
     return a->id < b->id;
 }
 
-int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *sizes, int64_t total_served, double *p,
-                 int64_t p_bins, mqo_size_out *out)
+static inline double sz_rank(int discipline, const sjob *j)
+{ /* _rank_value size_based.py:128-153 */
+    switch (discipline) {
+    case MQO_SZ_FCFS: return j->arr;
+    case MQO_SZ_SJF:
+    case MQO_SZ_PSJF: return j->size;
+    case MQO_SZ_SRPT: return j->remaining;
+    case MQO_SZ_SPJF:
+    case MQO_SZ_PSPJF: return j->pred;
+    default: { /* SPRPT: predicted remaining work */
+        const double served = j->size - j->remaining;
+        const double pr = j->pred - served;
+        return pr > 0.0 ? pr : 0.0;
+    }
+    }
+}
+
+int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *sizes, int pred_kind, double pred_sigma,
+                 mqo_src *preds, int64_t total_served, double *p, int64_t p_bins, mqo_size_out *out)
 {
-    if (discipline < MQO_SZ_FCFS || discipline > MQO_SZ_SRPT) return -2;
+    if (discipline < MQO_SZ_FCFS || discipline > MQO_SZ_SPRPT) return -2;
+    if (pred_kind < 0 || pred_kind > 3 || (pred_kind != 0 && !preds)) return -2;
     memset(out, 0, sizeof(*out));
     for (int64_t i = 0; i < p_bins; ++i) p[i] = 0.0;
-    const int preemptive = discipline == MQO_SZ_PSJF || discipline == MQO_SZ_SRPT;
+    const int preemptive = discipline == MQO_SZ_PSJF || discipline == MQO_SZ_SRPT || discipline == MQO_SZ_PSPJF ||
+                           discipline == MQO_SZ_SPRPT;
+    const int tracks_remaining = discipline == MQO_SZ_SRPT || discipline == MQO_SZ_SPRPT;
     const int fcfs = discipline == MQO_SZ_FCFS;
     int64_t qcap = 1024, qsize = 0;
     sjob *queue = (sjob *)malloc(sizeof(sjob) * (size_t)qcap);
@@ -62,7 +82,7 @@ int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *siz
         const double dt_ = (t_new) - ttek;                        \
         if (in_sys < p_bins) p[in_sys] += dt_; else p_over += dt_; \
     } while (0)
-#define RANK_OF(j_) (fcfs ? (j_).arr : (discipline == MQO_SZ_SRPT ? (j_).remaining : (j_).size))
+#define RANK_OF(j_) sz_rank(discipline, &(j_))
 #define Q_PUSH(j_)                                                                \
     do {                                                                          \
         if (qsize == qcap) { qcap *= 2; queue = (sjob *)realloc(queue, sizeof(sjob) * (size_t)qcap); } \
@@ -92,13 +112,20 @@ int mqo_size_run(int discipline, int64_t buffer, mqo_src *arrivals, mqo_src *siz
             if (!fcfs) { /* _sample_size :155-164 */
                 nj.size = mqo_src_next(sizes, &err);
                 nj.remaining = nj.size;
+                /* predictor (size_based.py:163, sim/utils/predictor.py): perfect, x * Exp(1), x * exp(sigma * Z), or a
+                 * replayed value */
+                if (pred_kind == 0) nj.pred = nj.size;
+                else {
+                    const double z = mqo_src_next(preds, &err);
+                    nj.pred = pred_kind == 1 ? nj.size * z : (pred_kind == 2 ? nj.size * exp(pred_sigma * z) : z);
+                }
             }
             if (busy) {
                 nj.start_wait = ttek;
                 int handled = 0;
                 if (preemptive) {
                     /* _try_preempt_on_arrival :182-214 */
-                    if (discipline == MQO_SZ_SRPT) {
+                    if (tracks_remaining) {
                         const double rem = end - ttek;
                         cur.remaining = rem > 0.0 ? rem : 0.0; /* _update_in_service_rank_fields :166-180 */
                     }

@@ -722,7 +722,8 @@ def neg_generate(c, buffer, neg_type, positive, negative, service, total_served,
 
 
 # --------------------------------------------------------------------------- size-based disciplines
-SIZE_DISCIPLINES = {"FCFS": 0, "SJF": 1, "PSJF": 2, "SRPT": 3, "SPJF": 1, "PSPJF": 2, "SPRPT": 3}  # perfect predictor
+SIZE_DISCIPLINES = {"FCFS": 0, "SJF": 1, "PSJF": 2, "SRPT": 3, "SPJF": 4, "PSPJF": 5, "SPRPT": 6}
+PRED_KINDS = {"perfect": 0, "exp": 1, "lognormal": 2, "given": 3}
 
 
 @dataclass
@@ -741,11 +742,13 @@ class SizeResult:
     s_used: int
 
 
-def _size_run(discipline, buffer, arrivals, sizes, total_served, p_bins):
+def _size_run(discipline, buffer, arrivals, sizes, total_served, p_bins, pred_kind="perfect", pred_sigma=0.0,
+              preds=None):
     p = np.zeros(int(p_bins))
     out = MqoSizeOut()
     rc = lib().mqo_size_run(SIZE_DISCIPLINES[discipline], C.c_int64(-1 if buffer is None else int(buffer)),
-                            C.byref(arrivals), C.byref(sizes), C.c_int64(int(total_served)), _dp(p),
+                            C.byref(arrivals), C.byref(sizes), PRED_KINDS[pred_kind], C.c_double(float(pred_sigma)),
+                            C.byref(preds) if preds is not None else None, C.c_int64(int(total_served)), _dp(p),
                             C.c_int64(int(p_bins)), C.byref(out))
     if rc != 0:
         raise RuntimeError(f"oracle size-based run failed rc={rc}")
@@ -756,14 +759,30 @@ def _size_run(discipline, buffer, arrivals, sizes, total_served, p_bins):
                       a_used=arrivals.pos, s_used=sizes.pos)
 
 
-def size_replay(discipline, buffer, A, S, total_served, p_bins=128) -> SizeResult:
-    """SizeBasedQsSim.run() on pre-generated gaps A and sizes S (arrival order; FCFS: services in start order)."""
+def size_replay(discipline, buffer, A, S, total_served, p_bins=128, Y=None) -> SizeResult:
+    """SizeBasedQsSim.run() on pre-generated gaps A and sizes S (arrival order; FCFS: services in start order);
+    Y: predicted sizes in arrival order (None = perfect predictor)."""
     A = np.ascontiguousarray(A, dtype=np.float64)
     S = np.ascontiguousarray(S, dtype=np.float64)
-    return _size_run(discipline, buffer, _replay_src(A), _replay_src(S), total_served, p_bins)
+    if Y is None:
+        return _size_run(discipline, buffer, _replay_src(A), _replay_src(S), total_served, p_bins)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    return _size_run(discipline, buffer, _replay_src(A), _replay_src(S), total_served, p_bins, "given", 0.0,
+                     _replay_src(Y))
 
 
-def size_generate(discipline, buffer, source, server, total_served, seed, rep, p_bins=128) -> SizeResult:
-    """Generator mode: gaps = word 0 and sizes = word 1 of stream 0 (as the FIFO kernel)."""
+def size_generate(discipline, buffer, source, server, total_served, seed, rep, p_bins=128, predictor="perfect",
+                  sigma=0.5) -> SizeResult:
+    """Generator mode: gaps = word 0 and sizes = word 1 of stream 0 (as the FIFO kernel); the predictor's noise =
+    word 0 of stream 1 (Exp(1) for "exp", N(0,1) for "lognormal")."""
+
+    class N01:
+        mean, std_dev = 0.0, 1.0
+
+    preds = None
+    if predictor == "exp":
+        preds = _gen_src(("M", 1.0), seed, 1, rep, 0)
+    elif predictor == "lognormal":
+        preds = _gen_src(("Norm", N01), seed, 1, rep, 0)
     return _size_run(discipline, buffer, _gen_src(source, seed, 0, rep, 0), _gen_src(server, seed, 0, rep, 1),
-                     total_served, p_bins)
+                     total_served, p_bins, predictor, sigma, preds)

@@ -524,10 +524,24 @@ def make_neg():
 
 
 # --------------------------------------------------------------------------- size-based disciplines
-def size_case(name, discipline, buffer, A, S, total_served, nprobs=128):
+class ReplayPredictor:
+    """Stands in for a SizePredictor (size_based.py:24-30): returns pre-generated predicted sizes in call order."""
+
+    def __init__(self, arr):
+        self.arr, self.i = arr, 0
+
+    def predict(self, size, rng):
+        y = float(self.arr[self.i])
+        self.i += 1
+        return y
+
+
+def size_case(name, discipline, buffer, A, S, total_served, nprobs=128, Y=None):
     from most_queue.sim.size_based import SizeBasedQsSim
 
     qs = SizeBasedQsSim(1, discipline, buffer=buffer, track_slowdown=True)
+    if Y is not None:
+        qs.set_predictor(ReplayPredictor(Y))
     qs.set_sources(1.0, "M")
     qs.set_servers(1.0, "M")
     ia, isv = [0], [0]
@@ -546,7 +560,7 @@ def size_case(name, discipline, buffer, A, S, total_served, nprobs=128):
         v=np.array(qs.v, dtype=np.float64), busy=np.array(qs.busy, dtype=np.float64), busy_n=qs.busy_moments,
         p_time=np.array(qs.p[:nprobs], dtype=np.float64), ttek=float(qs.ttek), arrived=qs.arrived, taked=qs.taked,
         served=qs.served, dropped=qs.dropped, in_sys=qs.in_sys, queued=qs.queue.size(), a_used=ia[0], s_used=isv[0],
-        slowdown=sd)
+        slowdown=sd, **({"Y": np.asarray(Y), "y_used": qs._predictor.i} if Y is not None else {}))
     print(f"size_{name}: served={qs.served} taked={qs.taked} dropped={qs.dropped} v1={qs.v[0]:.5g} "
           f"slowdown={sd.mean() if len(sd) else 0:.4g} used={ia[0]},{isv[0]}")
 
@@ -558,6 +572,13 @@ def make_size():
         size_case(d.lower(), d, None, rng.exponential(1.0, 2 * n), rng.gamma(0.5, 1.6, 2 * n), n)
     size_case("srpt_buffer5", "SRPT", 5, rng.exponential(1.0, 3 * n), rng.gamma(0.5, 1.9, 3 * n), n)
     size_case("sjf_heavy", "SJF", None, rng.exponential(1.0, 2 * n), 0.3 * (rng.pareto(2.2, 2 * n) + 1.0), n)
+    # noisy predictions (sim/utils/predictor.py): Y = X * exp(sigma Z) and Y = X * Exp(1), replayed
+    for d in ("SPJF", "PSPJF", "SPRPT"):
+        S = rng.gamma(0.5, 1.6, 2 * n)
+        size_case(f"{d.lower()}_lognormal", d, None, rng.exponential(1.0, 2 * n), S, n,
+                  Y=S * np.exp(0.7 * rng.standard_normal(2 * n)))
+    S = rng.gamma(0.5, 1.6, 3 * n)
+    size_case("sprpt_expnoise_buffer6", "SPRPT", 6, rng.exponential(1.0, 3 * n), S, n, Y=S * rng.exponential(1.0, 3 * n))
 
 
 # --------------------------------------------------------------------------- tandem with blocking

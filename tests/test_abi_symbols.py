@@ -47,7 +47,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.MqPrionetCfg) == 4272
     assert ctypes.sizeof(_lib.MqVacCfg) == 336
     assert ctypes.sizeof(_lib.MqNegCfg) == 184
-    assert ctypes.sizeof(_lib.MqSizeCfg) == 136
+    assert ctypes.sizeof(_lib.MqSizeCfg) == 144
 
 
 def test_no_cpu_fallback_without_device():

@@ -20,7 +20,9 @@ def test_replay_matches_reference(path):
     g = np.load(path)
     buffer = None if int(g["buffer"]) < 0 else int(g["buffer"])
     rep = lambda a: np.repeat(np.asarray(a)[:, None], 3, axis=1)
-    out = replay(str(g["discipline"]), buffer, rep(g["A"]), rep(g["S"]), int(g["total_served"]), p_bins=len(g["p_time"]))
+    Y = rep(g["Y"]) if "Y" in g.files else None
+    out = replay(str(g["discipline"]), buffer, rep(g["A"]), rep(g["S"]), int(g["total_served"]), p_bins=len(g["p_time"]),
+                 Y=Y)
     sd = g["slowdown"]
     s1 = s2 = 0.0
     for x in sd:
@@ -34,11 +36,14 @@ def test_replay_matches_reference(path):
         assert np.array_equal(out["w"][r], g["w"]) and np.array_equal(out["v"][r], g["v"])
         assert np.array_equal(out["busy"][r], g["busy"]) and np.array_equal(out["p_time"][r], g["p_time"])
         assert out["slowdown_sum"][r].tolist() == [s1, s2]
+        if Y is not None:
+            assert out["y_used"][r] == int(g["y_used"])
 
 
-@pytest.mark.parametrize("discipline,buffer", [("FCFS", None), ("SJF", None), ("PSJF", None), ("SRPT", None),
-                                               ("SRPT", 4), ("SJF", 3), ("PSPJF", None)])
-def test_replay_matches_oracle_many_replications(discipline, buffer):
+@pytest.mark.parametrize("discipline,buffer,noisy", [
+    ("FCFS", None, False), ("SJF", None, False), ("PSJF", None, False), ("SRPT", None, False), ("SRPT", 4, False),
+    ("SJF", 3, False), ("PSPJF", None, False), ("SPJF", None, True), ("PSPJF", 5, True), ("SPRPT", None, True)])
+def test_replay_matches_oracle_many_replications(discipline, buffer, noisy):
     from most_queue_b200.sim.size_based import replay
     from oracle import oracle
 
@@ -46,9 +51,11 @@ def test_replay_matches_oracle_many_replications(discipline, buffer):
     reps, n = 40, 500
     A = rng.exponential(1.0, (3 * n, reps))
     S = rng.gamma(0.6, 1.4, (3 * n, reps))
-    out = replay(discipline, buffer, A, S, n, p_bins=64)
+    Y = S * np.exp(0.8 * rng.standard_normal(S.shape)) if noisy else None
+    out = replay(discipline, buffer, A, S, n, p_bins=64, Y=Y)
     for r in range(reps):
-        o = oracle.size_replay(discipline, buffer, A[:, r].copy(), S[:, r].copy(), n, p_bins=64)
+        o = oracle.size_replay(discipline, buffer, A[:, r].copy(), S[:, r].copy(), n, p_bins=64,
+                               Y=None if Y is None else Y[:, r].copy())
         assert o.ttek == out["ttek"][r]
         for k in COUNTS + ("preemptions",):
             assert o.counts[k] == out[k][r], k
@@ -70,9 +77,16 @@ def test_errors_and_api_validation():
         SizeBasedQsSim(2, "SRPT")
     with pytest.raises(ValueError):
         SizeBasedQsSim(1, "LIFO")
+    from most_queue_b200.sim.size_based import ExpNoiseSimPredictor, LognormalNoiseSimPredictor
+
     q = SizeBasedQsSim(1, "SPJF")
     q.set_predictor(None)
     q.set_predictor(PerfectSimPredictor())
+    q.set_predictor(ExpNoiseSimPredictor())
+    q.set_predictor(LognormalNoiseSimPredictor(0.3))
+    assert (q._pred_kind, q._pred_sigma) == ("lognormal", 0.3)
+    with pytest.raises(ValueError):
+        LognormalNoiseSimPredictor(0.0)
     with pytest.raises(NotImplementedError):
         q.set_predictor(object())
 
@@ -86,12 +100,13 @@ def test_generator_matches_oracle():
     h2 = H2Distribution.get_params_by_mean_and_cv(0.75, 1.6)
     ctx = L.default_context()
     seed, reps, n = 41, 32, 1500
-    for name in ("SJF", "SRPT"):
+    for name, pred in (("SJF", "perfect"), ("SRPT", "perfect"), ("SPJF", "exp"), ("SPRPT", "lognormal")):
         agg, rec = ctx.sim_size(L.SIZE_DISCIPLINES[name], None, L.make_dist("M", 1.0), L.make_dist("H", h2), n, reps, 2,
-                                seed, p_bins=64, per_replication=True)
+                                seed, p_bins=64, per_replication=True, predictor=pred, sigma=0.6)
         same = 0
         for r in range(reps):
-            o = oracle.size_generate(name, None, ("M", 1.0), ("H", h2), n, L.seed_to_key(seed), 2 + r, p_bins=64)
+            o = oracle.size_generate(name, None, ("M", 1.0), ("H", h2), n, L.seed_to_key(seed), 2 + r, p_bins=64,
+                                     predictor=pred, sigma=0.6)
             assert int(rec[L.Z_SERVED, r]) == n
             if int(rec[L.Z_TAKED, r]) == o.counts["taked"] and int(rec[L.Z_ARRIVED, r]) == o.counts["arrived"]:
                 same += 1
@@ -125,3 +140,20 @@ def test_mm1_disciplines_closed_forms():
     assert res["SRPT"][0].v[0] < res["SJF"][0].v[0] < res["FCFS"][0].v[0]
     assert res["SRPT"][1].preemptions > 0 and res["SJF"][1].preemptions == 0
     assert res["SRPT"][1].get_slowdown() < res["SJF"][1].get_slowdown()
+
+
+def test_noisy_predictions_cost_performance_but_beat_fcfs():
+    """M/M/1, rho = 0.7: SPRPT with log-normal prediction noise sits between SRPT (perfect information) and FCFS."""
+    from most_queue_b200.sim.size_based import LognormalNoiseSimPredictor, SizeBasedQsSim
+
+    def run(d, pred=None):
+        sim = SizeBasedQsSim(1, d, seed=6, replications=256)
+        sim.set_sources(0.7, "M")
+        sim.set_servers(1.0, "M")
+        if pred is not None:
+            sim.set_predictor(pred)
+        return sim.run(20000).v[0]
+
+    v_srpt, v_noisy, v_fcfs = run("SRPT"), run("SPRPT", LognormalNoiseSimPredictor(1.0)), run("FCFS")
+    assert v_srpt < v_noisy < v_fcfs, (v_srpt, v_noisy, v_fcfs)
+    assert abs(run("SPRPT") - v_srpt) < 1e-9  # the perfect predictor makes SPRPT the same schedule as SRPT

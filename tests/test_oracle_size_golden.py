@@ -15,14 +15,16 @@ COUNTS = ("busy_n", "arrived", "taked", "served", "dropped", "in_sys", "queued")
 
 
 def test_fixtures_present():
-    assert len(CASES) >= 8
+    assert len(CASES) >= 12
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])
 def test_oracle_matches_reference_bitwise(path):
     g = np.load(path)
     buffer = None if int(g["buffer"]) < 0 else int(g["buffer"])
-    r = oracle.size_replay(str(g["discipline"]), buffer, g["A"], g["S"], int(g["total_served"]), p_bins=len(g["p_time"]))
+    Y = g["Y"] if "Y" in g.files else None
+    r = oracle.size_replay(str(g["discipline"]), buffer, g["A"], g["S"], int(g["total_served"]), p_bins=len(g["p_time"]),
+                           Y=Y)
     assert r.ttek == float(g["ttek"])
     for k in COUNTS:
         assert r.counts[k] == int(g[k]), k
