@@ -45,7 +45,7 @@ __device__ __forceinline__ bool k10_less(double ra, double aa, long long ia, dou
     return ia < ib;
 }
 
-__global__ void __launch_bounds__(K10_BLOCK) k10_size(const K10Params P)
+__global__ void __launch_bounds__(K10_BLOCK, 4) k10_size(const K10Params P)
 {
     const long long gtid = (long long)blockIdx.x * K10_BLOCK + threadIdx.x;
     const long long R = P.reps;

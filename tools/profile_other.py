@@ -90,3 +90,13 @@ if which == "k10":
         ctx.sim_size(L.SIZE_DISCIPLINES["SRPT"], None, L.make_dist("M", 1.0), L.make_dist("H", h2), N, R, 0, 3, p_bins=32)
     t = ctx.last_timing()
     print(which, t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
+if which == "k8g":
+    from most_queue_b200.random.distributions import GammaDistribution as _G
+    R, N = 200000, 5000
+    g = _G.get_params_by_mean_and_cv(0.625, 0.8)
+    d = {"arrivals": L.make_dist("M", 1.0), "services": L.make_dist("Gamma", g), "warm": L.make_dist("Gamma", g),
+         "cold": L.make_dist("M", 1.5)}
+    for _ in range(2):
+        ctx.sim_vacation(1, None, d, N, R, 0, 3, p_bins=32)
+    t = ctx.last_timing()
+    print(which, t, "jobs/s", R * N / (t["sim_ms"] * 1e-3))
