@@ -104,9 +104,10 @@ __device__ __forceinline__ void stage_tile_stash(const K3Params &P, long long ti
     __syncthreads();
 }
 
+template <bool STASH = false>
 __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_base, double *smS, double *smA)
 {
-    if (P.stG) {
+    if (STASH) {
         stage_tile_stash(P, tile_base, smS, smA);
         return;
     }
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
 //   T[N >= m] = sum over jobs k of | [t_k, t_k + v_k) intersected with [t_{k+m-1}, t_{k+m}) |.
 // Each job walks forward over the gaps that follow it until its sojourn is used up (1 + arrivals during the
 // sojourn steps); per-lane fp32 columns in shared memory, flushed to fp64 per warp.
-template <bool REPLAY>
+// MODE: 0 = generator (everything is drawn), 1 = replay (caller arrays), 2 = the generator form walking its stash
+template <int MODE>
 __device__ __noinline__ void level_walk(const K3Params &P, double v, int e, long long n, const double *smA,
                                         float *lev, double &over)
 {
@@ -261,7 +263,7 @@ __device__ __noinline__ void level_walk(const K3Params &P, double v, int e, long
         else if (e + m <= K3_TILE + K3_HALO)
             g = smA[k3_pad(e + m)];
         else
-            g = (REPLAY && !P.stG) ? __ldg(P.A + nn) : ((REPLAY && nn <= P.n) ? (double)__ldg(P.stG + nn) : gen_gap(P, nn));
+            g = MODE == 1 ? __ldg(P.A + nn) : ((MODE == 2 && nn <= P.n) ? (double)__ldg(P.stG + nn) : gen_gap(P, nn));
         const double hi = cum + g;
         const double ov = fmin(v, hi) - cum;
         if (m <= K3_PBL)
@@ -273,9 +275,10 @@ __device__ __noinline__ void level_walk(const K3Params &P, double v, int e, long
     }
 }
 
-template <bool REPLAY, bool WANT_P>
-__global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
+template <int MODE, bool WANT_P>
+__global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : 2)) k3_walk(const K3Params P)
 {
+    constexpr bool REPLAY = MODE != 0;  // staged inputs: caller arrays or the stash
     __shared__ MP smem[K3_THREADS / 32];
     __shared__ double red[K3_THREADS / 32][K3_NSTAT];
     double acc[K3_NSTAT];
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
-        if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
+        if (REPLAY) stage_tile<MODE == 2>(P, t * K3_TILE, smS, smA);
         acc[8] += load_segment<REPLAY, WANT_P && !REPLAY>(P, n0, x, s, smS, smA);
         if (WANT_P && !REPLAY) {
             // halo of generated gaps beyond the tile
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_walk(const K3Params P)
                 acc[6] += v2 * v;
                 acc[7] += v2 * v2;
                 acc[9] += s[j];
-                if (WANT_P) level_walk<REPLAY>(P, v, threadIdx.x * K3_L + j, n, smA, lev, over);
+                if (WANT_P) level_walk<MODE>(P, v, threadIdx.x * K3_L + j, n, smA, lev, over);
                 const double raw = __dadd_rn(w, x[j]);
                 if (n == P.n - 1) {
                     P.tail[0] = raw;
@@ -419,30 +422,25 @@ cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <int MODE, bool WANT_P>
+static cudaError_t launch_walk_one(const K3Params &P, int grid, size_t smem, cudaStream_t st)
+{
+    if (smem > 0) {
+        cudaError_t e = cudaFuncSetAttribute(k3_walk<MODE, WANT_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k3_walk<MODE, WANT_P><<<grid, K3_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st)
 {
     const bool want_p = P.level_partial != nullptr;
-    const bool staged = P.replay != 0 || P.stG != nullptr;  // the stash is walked like replayed arrays
-    const size_t smem = k3_walk_smem(staged, want_p);
-    cudaError_t e = cudaSuccess;
-    if (staged) {
-        if (want_p) {
-            e = cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k3_walk<true, true><<<grid, K3_THREADS, smem, st>>>(P);
-        } else {
-            e = cudaFuncSetAttribute(k3_walk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k3_walk<true, false><<<grid, K3_THREADS, smem, st>>>(P);
-        }
-    } else {
-        if (want_p) {
-            e = cudaFuncSetAttribute(k3_walk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k3_walk<false, true><<<grid, K3_THREADS, smem, st>>>(P);
-        } else {
-            k3_walk<false, false><<<grid, K3_THREADS, 0, st>>>(P);
-        }
-    }
-    if (e != cudaSuccess) return e;
-    return cudaGetLastError();
+    const int mode = P.replay ? 1 : (P.stG ? 2 : 0);
+    const size_t smem = k3_walk_smem(mode != 0, want_p);
+    if (mode == 1) return want_p ? launch_walk_one<1, true>(P, grid, smem, st) : launch_walk_one<1, false>(P, grid, smem, st);
+    if (mode == 2) return want_p ? launch_walk_one<2, true>(P, grid, smem, st) : launch_walk_one<2, false>(P, grid, smem, st);
+    return want_p ? launch_walk_one<0, true>(P, grid, smem, st) : launch_walk_one<0, false>(P, grid, smem, st);
 }
 
 size_t k3_walk_smem(bool replay, bool want_p)
@@ -458,42 +456,38 @@ cudaError_t k3_launch_final(const double *partial, const double *level_partial, 
     return cudaGetLastError();
 }
 
+template <int MODE, bool WANT_P>
+static cudaError_t occ_walk_one(size_t smem, int *b)
+{
+    if (smem > 0) {
+        cudaError_t e = cudaFuncSetAttribute(k3_walk<MODE, WANT_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, k3_walk<MODE, WANT_P>, K3_THREADS, smem);
+}
+
 cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_blocks, int *walk_blocks)
 {
     int a = 0, b = 0;
     cudaError_t e;
-    const bool staged = replay || stash;
-    const size_t wsm = k3_walk_smem(staged, want_p);
-    if (staged) {
-        if (replay) {
-            e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
-            if (e == cudaSuccess)
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
-        } else {
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false, true>, K3_THREADS, 0);
-        }
-        if (e == cudaSuccess) {
-            if (want_p) {
-                e = cudaFuncSetAttribute(k3_walk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
-                if (e == cudaSuccess)
-                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<true, true>, K3_THREADS, wsm);
-            } else {
-                e = cudaFuncSetAttribute(k3_walk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
-                if (e == cudaSuccess)
-                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<true, false>, K3_THREADS, wsm);
-            }
-        }
+    const int mode = replay ? 1 : (stash ? 2 : 0);
+    const size_t wsm = k3_walk_smem(mode != 0, want_p);
+    if (replay) {
+        e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
+    } else if (stash) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false, true>, K3_THREADS, 0);
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false>, K3_THREADS, 0);
-        if (e == cudaSuccess) {
-            if (want_p) {
-                e = cudaFuncSetAttribute(k3_walk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
-                if (e == cudaSuccess)
-                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<false, true>, K3_THREADS, wsm);
-            } else {
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k3_walk<false, false>, K3_THREADS, 0);
-            }
-        }
+    }
+    if (e == cudaSuccess) {
+        if (mode == 1)
+            e = want_p ? occ_walk_one<1, true>(wsm, &b) : occ_walk_one<1, false>(wsm, &b);
+        else if (mode == 2)
+            e = want_p ? occ_walk_one<2, true>(wsm, &b) : occ_walk_one<2, false>(wsm, &b);
+        else
+            e = want_p ? occ_walk_one<0, true>(wsm, &b) : occ_walk_one<0, false>(wsm, &b);
     }
     *summary_blocks = a;
     *walk_blocks = b;
