@@ -79,6 +79,14 @@ constexpr size_t K3_LEVEL_BYTES = sizeof(float) * K3_PBL * K3_THREADS + sizeof(d
 
 __device__ __forceinline__ int k3_pad(int e) { return e + (e >> 4); }
 
+// number of valid entries among [base, base + span) when the valid ones are [0, limit): a 32-bit count, so that the
+// per-job bounds checks are one compare against it instead of 64-bit index arithmetic
+__device__ __forceinline__ int k3_valid(long long limit, long long base, int span)
+{
+    const long long r = limit - base;
+    return r <= 0 ? 0 : (r >= span ? span : (int)r);
+}
+
 __device__ __forceinline__ double gen_gap(const K3Params &P, long long n);
 
 // the same staging from the fp32 stash written by the summary pass of the generator form (gaps beyond the range --
@@ -111,21 +119,19 @@ __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_bas
         stage_tile_stash(P, tile_base, smS, smA);
         return;
     }
+    const int vs = k3_valid(P.n, tile_base, K3_TILE);                                    // services in range
+    const int va = k3_valid(P.n + P.n_ahead + 1, tile_base, K3_TILE + K3_HALO + 1);      // gaps in range
+    const double *S = P.S + tile_base, *A = P.A + tile_base;
 #pragma unroll
     for (int k = 0; k < K3_L; ++k) {
         const int e = k * K3_THREADS + threadIdx.x;
-        const long long n = tile_base + e;
-        smS[k3_pad(e)] = n < P.n ? __ldcs(P.S + n) : 0.0;
-        smA[k3_pad(e)] = n <= P.n + P.n_ahead ? __ldcs(P.A + n) : 0.0;
+        smS[k3_pad(e)] = e < vs ? __ldcs(S + e) : 0.0;
+        smA[k3_pad(e)] = e < va ? __ldcs(A + e) : 0.0;
     }
     {   // one more gap for x of the last job, and the halo used by the level walk
         const int e = K3_TILE + threadIdx.x;
-        const long long n = tile_base + e;
-        smA[k3_pad(e)] = n <= P.n + P.n_ahead ? __ldcs(P.A + n) : 0.0;
-        if (threadIdx.x == 0) {
-            const long long n2 = tile_base + K3_TILE + K3_HALO;
-            smA[k3_pad(K3_TILE + K3_HALO)] = n2 <= P.n + P.n_ahead ? __ldcs(P.A + n2) : 0.0;
-        }
+        smA[k3_pad(e)] = e < va ? __ldcs(A + e) : 0.0;
+        if (threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = K3_TILE + K3_HALO < va ? __ldcs(A + K3_TILE + K3_HALO) : 0.0;
     }
     __syncthreads();
 }
@@ -139,7 +145,8 @@ __device__ __forceinline__ double gen_gap(const K3Params &P, long long n)
     return (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
 }
 
-template <bool REPLAY, bool STORE_GAPS = false, bool STASH_W = false>
+// FULL: every job of the tile is inside the range (all tiles but the last one): no per-job bounds logic
+template <bool REPLAY, bool STORE_GAPS = false, bool STASH_W = false, bool FULL = false>
 __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, double (&x)[K3_L], double (&s)[K3_L],
                                                const double *smS, double *smA, float *stg = nullptr,
                                                float *stv = nullptr)
@@ -148,9 +155,10 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
     if (REPLAY) {
         const int e0 = threadIdx.x * K3_L;
         double an = smA[k3_pad(e0)];
+        const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
 #pragma unroll
         for (int j = 0; j < K3_L; ++j) {
-            const bool ok = n0 + j < P.n;
+            const bool ok = FULL || j < valid;
             s[j] = smS[k3_pad(e0 + j)];
             sum_a += ok ? an : 0.0;
             an = smA[k3_pad(e0 + j + 1)];
@@ -161,10 +169,11 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
         unsigned long long g = (unsigned long long)(P.job0 + n0);
         uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
         double gap = (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+        const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
 #pragma unroll
         for (int j = 0; j < K3_L; ++j) {
             const long long n = n0 + j;
-            const bool ok = n < P.n;
+            const bool ok = FULL || j < valid;
             const double sv = (double)sample<-1>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
             ++g;
             w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
@@ -177,7 +186,7 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
                 // (padded: conflict free) and written out by the CTA with coalesced stores
                 stg[k3_pad(threadIdx.x * K3_L + j)] = (float)gap;
                 stv[k3_pad(threadIdx.x * K3_L + j)] = (float)sv;
-                if (n == P.n - 1) P.stG[P.n] = (float)gnext;
+                if (!FULL && n == P.n - 1) P.stG[P.n] = (float)gnext;
             }
             gap = gnext;
         }
@@ -186,12 +195,14 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
     return sum_a;
 }
 
+template <bool FULL = false>
 __device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, const double (&x)[K3_L])
 {
     MP f = mp_id();
+    const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
 #pragma unroll
     for (int j = 0; j < K3_L; ++j)
-        if (n0 + j < P.n) f = mp_step(f, x[j]);
+        if (FULL || j < valid) f = mp_step(f, x[j]);
     return f;
 }
 
@@ -207,9 +218,17 @@ __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
         if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
-        load_segment<REPLAY, false, STASH_W>(P, n0, x, s, smS, smA, stg, stv);
+        const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
+        MP mine;
+        if (full_tile) {
+            load_segment<REPLAY, false, STASH_W, true>(P, n0, x, s, smS, smA, stg, stv);
+            mine = fold_segment<true>(P, n0, x);
+        } else {
+            load_segment<REPLAY, false, STASH_W, false>(P, n0, x, s, smS, smA, stg, stv);
+            mine = fold_segment<false>(P, n0, x);
+        }
         MP total;
-        cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);  // its barriers also fence the stage reuse
+        cta_scan<K3_THREADS>(mine, smem, &total);  // its barriers also fence the stage reuse
         if (STASH_W) {
             // (the scan's barriers have made the staged draws visible) one 128-byte line per warp and instruction
             const long long tb = t * K3_TILE;
@@ -275,6 +294,13 @@ __device__ __noinline__ void level_walk(const K3Params &P, double v, int e, long
     }
 }
 
+struct K3True {
+    static constexpr bool value = true;
+};
+struct K3False {
+    static constexpr bool value = false;
+};
+
 template <int MODE, bool WANT_P>
 __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : 2)) k3_walk(const K3Params P)
 {
@@ -316,41 +342,52 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : 2)) k3_walk(const
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
         if (REPLAY) stage_tile<MODE == 2>(P, t * K3_TILE, smS, smA);
-        acc[8] += load_segment<REPLAY, WANT_P && !REPLAY>(P, n0, x, s, smS, smA);
-        if (WANT_P && !REPLAY) {
-            // halo of generated gaps beyond the tile
-            const int e = K3_TILE + 1 + threadIdx.x;
-            if (e <= K3_TILE + K3_HALO) smA[k3_pad(e)] = gen_gap(P, t * K3_TILE + e);
-        }
-        MP total;
-        const MP ex = cta_scan<K3_THREADS>(fold_segment(P, n0, x), smem, &total);
-        const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
-        double w = mp_apply(ex, w_tile);
-#pragma unroll
-        for (int j = 0; j < K3_L; ++j) {
-            const long long n = n0 + j;
-            if (n < P.n) {
-                if (P.W) P.W[n] = w;
-                const double v = __dadd_rn(w, s[j]);
-                const double w2 = w * w, v2 = v * v;
-                acc[0] += w;
-                acc[1] += w2;
-                acc[2] += w2 * w;
-                acc[3] += w2 * w2;
-                acc[4] += v;
-                acc[5] += v2;
-                acc[6] += v2 * v;
-                acc[7] += v2 * v2;
-                acc[9] += s[j];
-                if (WANT_P) level_walk<MODE>(P, v, threadIdx.x * K3_L + j, n, smA, lev, over);
-                const double raw = __dadd_rn(w, x[j]);
-                if (n == P.n - 1) {
-                    P.tail[0] = raw;
-                    P.tail[1] = v;
-                }
-                w = fmax(0.0, raw);
+        const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
+        auto tile_body = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            acc[8] += load_segment<REPLAY, WANT_P && !REPLAY, false, FULL>(P, n0, x, s, smS, smA);
+            if (WANT_P && !REPLAY) {
+                // halo of generated gaps beyond the tile
+                const int e = K3_TILE + 1 + threadIdx.x;
+                if (e <= K3_TILE + K3_HALO) smA[k3_pad(e)] = gen_gap(P, t * K3_TILE + e);
             }
-        }
+            MP total;
+            const MP ex = cta_scan<K3_THREADS>(fold_segment<FULL>(P, n0, x), smem, &total);
+            const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
+            double w = mp_apply(ex, w_tile);
+            const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
+            const int last_j = (!FULL && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
+            double *Wp = P.W ? P.W + n0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < K3_L; ++j) {
+                const long long n = n0 + j;
+                if (FULL || j < valid) {
+                    if (Wp) Wp[j] = w;
+                    const double v = __dadd_rn(w, s[j]);
+                    const double w2 = w * w, v2 = v * v;
+                    acc[0] += w;
+                    acc[1] += w2;
+                    acc[2] += w2 * w;
+                    acc[3] += w2 * w2;
+                    acc[4] += v;
+                    acc[5] += v2;
+                    acc[6] += v2 * v;
+                    acc[7] += v2 * v2;
+                    acc[9] += s[j];
+                    if (WANT_P) level_walk<MODE>(P, v, threadIdx.x * K3_L + j, n, smA, lev, over);
+                    const double raw = __dadd_rn(w, x[j]);
+                    if (!FULL && j == last_j) {
+                        P.tail[0] = raw;
+                        P.tail[1] = v;
+                    }
+                    w = fmax(0.0, raw);
+                }
+            }
+        };
+        if (full_tile)
+            tile_body(K3True{});
+        else
+            tile_body(K3False{});
         if (WANT_P) {
             if (++since_flush == 16) {
                 since_flush = 0;
