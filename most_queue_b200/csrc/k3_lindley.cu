@@ -251,13 +251,32 @@ __global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
     __shared__ MP smem[K3_TOP / 32];
     const long long chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
     const long long lo = (long long)threadIdx.x * chunk;
+    const long long hi = lo + chunk < P.ntiles ? lo + chunk : P.ntiles;
+    constexpr int U = 8;  // summaries loaded ahead of the (sequential, order-fixed) fold: the loop is load-latency bound
     MP f = mp_id();
-    for (long long t = lo; t < lo + chunk && t < P.ntiles; ++t) f = mp_then(f, P.tile_sum[t]);
+    for (long long t = lo; t < hi; t += U) {
+        MP v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (t + u < hi) v[u] = P.tile_sum[t + u];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (t + u < hi) f = mp_then(f, v[u]);
+    }
     MP total;
     MP ex = cta_scan<K3_TOP>(f, smem, &total);
-    for (long long t = lo; t < lo + chunk && t < P.ntiles; ++t) {
-        P.tile_ex[t] = ex;
-        ex = mp_then(ex, P.tile_sum[t]);
+    for (long long t = lo; t < hi; t += U) {
+        MP v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (t + u < hi) v[u] = P.tile_sum[t + u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t + u < hi) {
+                P.tile_ex[t + u] = ex;
+                ex = mp_then(ex, v[u]);
+            }
+        }
     }
     if (threadIdx.x == 0) *P.total = total;
 }
