@@ -321,7 +321,7 @@ struct K3False {
 };
 
 template <int MODE, bool WANT_P>
-__global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : 2)) k3_walk(const K3Params P)
+__global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : ((MODE == 2 && !WANT_P) ? 3 : 2))) k3_walk(const K3Params P)
 {
     constexpr bool REPLAY = MODE != 0;  // staged inputs: caller arrays or the stash
     __shared__ MP smem[K3_THREADS / 32];
@@ -362,6 +362,55 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : 2)) k3_walk(const
         double x[K3_L], s[K3_L];
         if (REPLAY) stage_tile<MODE == 2>(P, t * K3_TILE, smS, smA);
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
+        // staged forms (replay, stash): the tile sits in shared memory, so nothing is carried in registers across the
+        // CTA scan -- the fold and the walk both read their operands from there (halves the register count of v1)
+        auto tile_body_staged = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int e0 = threadIdx.x * K3_L;
+            const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
+            MP f = mp_id();
+#pragma unroll
+            for (int j = 0; j < K3_L; ++j) {
+                const double xj = __dsub_rn(smS[k3_pad(e0 + j)], smA[k3_pad(e0 + j + 1)]);
+                if (FULL || j < valid) f = mp_step(f, xj);
+            }
+            MP total;
+            const MP ex = cta_scan<K3_THREADS>(f, smem, &total);
+            const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
+            double w = mp_apply(ex, w_tile);
+            const int last_j = (!FULL && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
+            double *Wp = P.W ? P.W + n0 : nullptr;
+            double an = smA[k3_pad(e0)];
+#pragma unroll
+            for (int j = 0; j < K3_L; ++j) {
+                const long long n = n0 + j;
+                const double sj = smS[k3_pad(e0 + j)];
+                const double a0 = an;
+                an = smA[k3_pad(e0 + j + 1)];
+                if (FULL || j < valid) {
+                    if (Wp) Wp[j] = w;
+                    const double v = __dadd_rn(w, sj);
+                    const double w2 = w * w, v2 = v * v;
+                    acc[0] += w;
+                    acc[1] += w2;
+                    acc[2] += w2 * w;
+                    acc[3] += w2 * w2;
+                    acc[4] += v;
+                    acc[5] += v2;
+                    acc[6] += v2 * v;
+                    acc[7] += v2 * v2;
+                    acc[8] += a0;
+                    acc[9] += sj;
+                    if (WANT_P) level_walk<MODE>(P, v, e0 + j, n, smA, lev, over);
+                    const double raw = __dadd_rn(w, __dsub_rn(sj, an));
+                    if (!FULL && j == last_j) {
+                        P.tail[0] = raw;
+                        P.tail[1] = v;
+                    }
+                    w = fmax(0.0, raw);
+                }
+            }
+        };
         auto tile_body = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             acc[8] += load_segment<REPLAY, WANT_P && !REPLAY, false, FULL>(P, n0, x, s, smS, smA);
@@ -403,10 +452,17 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : 2)) k3_walk(const
                 }
             }
         };
-        if (full_tile)
-            tile_body(K3True{});
-        else
-            tile_body(K3False{});
+        if (MODE == 2) {  // measured: the stash walk gains 7 % (3 CTAs/SM), the replay walk loses 2 % with it
+            if (full_tile)
+                tile_body_staged(K3True{});
+            else
+                tile_body_staged(K3False{});
+        } else {
+            if (full_tile)
+                tile_body(K3True{});
+            else
+                tile_body(K3False{});
+        }
         if (WANT_P) {
             if (++since_flush == 16) {
                 since_flush = 0;
