@@ -125,14 +125,16 @@ static __device__ __noinline__ float sample_gamma(const DistF &d, uint32_t w0, u
     float x = dd;
     for (uint32_t t = 0; t < 15; ++t) {
         uint2 e0 = ext_words(idx, rep, key0, which, 2 * t + 1);
-        uint2 e1 = ext_words(idx, rep, key0, which, 2 * t + 2);
         float rad = sqrtf(-1.3862943611198906f * fast_lg2(u01(e0.x)));  // sqrt(-2 ln u)
         float z = rad * cospif(2.0f * u01(e0.y));
         float v = fmaf(cc, z, 1.0f);
         if (v <= 0.0f) continue;
         v = v * v * v;
         x = dd * v;
-        float lhs = 0.6931471805599453f * fast_lg2(u01(e1.x));
+        // the acceptance uniform of the first attempt is the primary word itself when it is not needed for the
+        // alpha < 1 boost: one extension call per draw in the common case instead of two
+        const uint32_t wa = (t == 0 && !d.r) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
+        float lhs = 0.6931471805599453f * fast_lg2(u01(wa));
         float rhs = 0.5f * z * z + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
         if (lhs < rhs) break;
     }

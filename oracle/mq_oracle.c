@@ -134,13 +134,16 @@ static double variate_from(const mqo_dist *d, const word_src *s)
         for (uint32_t t = 0; t < 15; ++t) {
             uint32_t e0[2], e1[2];
             ws_ext(s, 2 * t + 1, e0);
-            ws_ext(s, 2 * t + 2, e1);
             double z = sqrt(-2.0 * log(u01(e0[0]))) * cos(6.283185307179586 * u01(e0[1]));
             double v = 1.0 + cc * z;
             if (v <= 0.0) continue;
             v = v * v * v;
             x = dd * v;
-            if (log(u01(e1[0])) < 0.5 * z * z + dd - dd * v + dd * log(v)) break;
+            /* acceptance uniform: the primary word on the first attempt when alpha >= 1 (it is otherwise unused),
+             * else word 0 of extension call 2t + 2 */
+            uint32_t wa = s->w0;
+            if (!(t == 0 && alpha >= 1.0)) { ws_ext(s, 2 * t + 2, e1); wa = e1[0]; }
+            if (log(u01(wa)) < 0.5 * z * z + dd - dd * v + dd * log(v)) break;
         }
         if (alpha < 1.0) x *= exp(log(u01(s->w0)) / alpha);
         return x / mu;
