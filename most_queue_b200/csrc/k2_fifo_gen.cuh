@@ -53,6 +53,7 @@ struct K2Params {
     long long reps;
     uint32_t rep0;
     uint32_t key0;
+    uint32_t rk[10];   // key0 + r * MQ_PHILOX_W: the Philox round keys of the primary call
     uint32_t warm;     // statistics restart at the warm-th start of service (0: never)
     int v_at_start;    // MQ_FIFO_V_AT_START: keep the v of the jobs still in service at the stop
     DistF src, srv;
@@ -167,8 +168,19 @@ __device__ __forceinline__ void restore_order(float (&L)[CT])
     }
 }
 
+#ifndef MQ_K2_MINB
+#define MQ_K2_MINB (CT == 8 ? 7 : 8)  // measured: 72 registers x 7 CTAs beat 64 x 8 once the round keys sit in uniform registers
+#endif
+#ifndef MQ_K2_UNROLL
+#define MQ_K2_UNROLL 1
+#endif
+#ifndef MQ_K2_RK
+#define MQ_K2_RK 1
+#endif
+constexpr int K2_UNROLL = MQ_K2_UNROLL;
+
 template <int CT, int SRCK, int SRVK, bool FINITE>
-__global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 8 : 2)) k2_fifo_gen(const K2Params P)
+__global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_gen(const K2Params P)
 {
     extern __shared__ float smem[];
     const int tid = threadIdx.x;
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 8 : 2)) k2_fifo_gen(const
         // ================= main phase: until the N-th job has STARTED service =================
         int epoch = 0;
         while (taked < N) {
-#pragma unroll 1
+#pragma unroll K2_UNROLL
             for (int ev = 0; ev < MQ_EV; ++ev) {
                 const float d0 = L[0];
                 const bool q0 = q == 0u;
@@ -312,7 +324,11 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? 8 : 2)) k2_fifo_gen(const
                 float gx = 0.0f, sx = 0.0f;
                 if (is_arr || pop_more) {
                     const uint32_t ridx = (is_arr ? nxt : nxt - q) + 1u;
+#if MQ_K2_RK
+                    uint2 w = philox2x32_10_rk(ridx, rep, P.rk);
+#else
                     uint2 w = philox2x32_10(ridx, rep, key0);
+#endif
                     gx = sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
                     sx = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
                 }

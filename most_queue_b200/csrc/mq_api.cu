@@ -282,6 +282,7 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     P.reps = R;
     P.rep0 = (uint32_t)cfg->rep0;
     P.key0 = seed_to_key(cfg->seed);
+    for (int r = 0; r < 10; ++r) P.rk[r] = P.key0 + (uint32_t)r * MQ_PHILOX_W;
     P.warm = (uint32_t)cfg->warmup;
     P.v_at_start = (cfg->flags & MQ_FIFO_V_AT_START) ? 1 : 0;
     P.src = make_distf(cfg->src);

@@ -40,6 +40,20 @@ __device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint2(c0, c1);
 }
 
+// the same function with the ten round keys key + r * W precomputed by the host (rk lives in the kernel
+// parameter block, so each round key is a constant-bank operand of the xor instead of an add per round)
+__device__ __forceinline__ uint2 philox2x32_10_rk(uint32_t c0, uint32_t c1, const uint32_t (&rk)[10])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi = __umulhi(MQ_PHILOX_M, c0);
+        uint32_t lo = MQ_PHILOX_M * c0;
+        c0 = hi ^ rk[r] ^ c1;
+        c1 = lo;
+    }
+    return make_uint2(c0, c1);
+}
+
 __device__ __forceinline__ float fast_lg2(float x)
 {
     float y;
