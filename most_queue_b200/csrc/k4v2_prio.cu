@@ -26,8 +26,10 @@ template <int CT, int KT, bool REPLAY>
 struct K4VLayout {
     // doubles, [word][lane]
     static constexpr int ARR = 0, WAIT = CT, TOT = 2 * CT, CLS0 = 3 * CT;
+    // replay: power sums and the reference's running means (read-modify-write) live here; generator tier: the power
+    // sums go straight to the zeroed record (fire-and-forget RED.ADD.F64), which frees 128 bytes per lane
     static constexpr int T_OLD = 0, P_OVER = 1, VSUM = 2, WSUM = 6, VRUN = 10, WRUN = 14;
-    static constexpr int HIST = REPLAY ? 18 : 10;
+    static constexpr int HIST = REPLAY ? 18 : 2;
     static constexpr int DSTR = HIST + K4V_BF;
     static constexpr int ND = CLS0 + KT * DSTR;
     // 32-bit words, [word][lane]
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
 #pragma unroll
         for (int j = 0; j < CT; ++j) end[j] = j < c ? 1e10 : 1e300;
         uint32_t busy = 0, cls_pack = 0;
+        uint32_t need = 1u;  // generator tier: some ring of this lane is (nearly) empty
         int status = 0;
 
         auto next_gap = [&](int k) -> double {
@@ -99,8 +102,11 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
         // drawing ahead changes nothing; it keeps the rejection-loop samplers out of the predicated event body,
         // where only the lanes that start a service in this trip would run them.
         auto refill_services = [&]() {
+            // when any lane of the warp is short of draws for some class (RS draws twice in one trip), all lanes top
+            // up all their rings together
+            if (!__any_sync(__activemask(), need != 0u)) return;
+            need = 0u;
             for (int k = 0; k < K; ++k) {
-                if (!__any_sync(__activemask(), IC(k, LY::SFILL) < 2)) continue;  // RS draws twice in one trip
                 const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)k);
                 const DistF d = sh_srv[k];
                 for (;;) {
@@ -126,12 +132,13 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                 }
                 return P.S[P.soff[k] + (long long)j * R + rl];
             }
-            IC(k, LY::SFILL) -= 1;
+            const int fill = IC(k, LY::SFILL) - 1;
+            IC(k, LY::SFILL) = fill;
+            need |= fill < 2 ? 1u : 0u;
             return (double)smf[(k * K4V_SB + (j & (K4V_SB - 1))) * K4V_BLOCK];
         };
-        auto qslot = [&](int k, int slot, int f) -> double * {
-            return Q + (((long long)k * P.qcap + slot) * 4 + f) * P.lanes;
-        };
+        const long long QL = P.lanes;  // field stride of a waiting-line record
+        auto qrec = [&](int k, int slot) -> double * { return Q + (long long)((k * P.qcap + slot) * 4) * QL; };
 
 #pragma unroll
         for (int k = 0; k < KT; ++k) at[k] = 1e300;
@@ -227,7 +234,8 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                 bool accept = full && P.prty == 0;  // NP: priority.py:331-332
                 if (pre_nf) {
                     long long qtot = 0;
-                    for (int kk = 0; kk < K; ++kk) qtot += IC(kk, LY::QSIZE);
+#pragma unroll
+                    for (int kk = 0; kk < KT; ++kk) qtot += kk < K ? IC(kk, LY::QSIZE) : 0;
                     accept = P.buffer <= 0 || qtot < P.buffer;
                     if (!accept) {
                         IC(ev, LY::DROPPED) += 1;
@@ -286,6 +294,8 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                         inv_count = __drcp_rn((double)n_served);  // == 1.0 / n, correctly rounded
                         one_minus = __dsub_rn(1.0, inv_count);
                     }
+                    double *gv = rec + (long long)(K4_G_ROWS + k * rows + K4_VSUM) * R;
+                    double *gw = rec + (long long)(K4_G_ROWS + k * rows + K4_WSUM) * R;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (REPLAY) {  // refresh_moments_stat, stats_update.py:6-22
@@ -293,9 +303,14 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                                 __dadd_rn(__dmul_rn(DC(k, LY::VRUN + i), one_minus), __dmul_rn(pv, inv_count));
                             DC(k, LY::WRUN + i) =
                                 __dadd_rn(__dmul_rn(DC(k, LY::WRUN + i), one_minus), __dmul_rn(pw, inv_count));
+                            DC(k, LY::VSUM + i) = __dadd_rn(DC(k, LY::VSUM + i), pv);
+                            DC(k, LY::WSUM + i) = __dadd_rn(DC(k, LY::WSUM + i), pw);
+                        } else {
+                            atomicAdd(gv, pv);
+                            atomicAdd(gw, pw);
+                            gv += R;
+                            gw += R;
                         }
-                        DC(k, LY::VSUM + i) = __dadd_rn(DC(k, LY::VSUM + i), pv);
-                        DC(k, LY::WSUM + i) = __dadd_rn(DC(k, LY::WSUM + i), pw);
                         pv = __dmul_rn(pv, v);
                         pw = __dmul_rn(pw, wt);
                     }
@@ -303,17 +318,20 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                 IC(k, LY::INSYS) -= 1;
                 // next job: NP scans all class lines, the pre-emptive disciplines start at the finished class
                 int kk = -1;
-                for (int q = K - 1; q >= (P.prty == 0 ? 0 : k); --q) kk = IC(q, LY::QSIZE) != 0 ? q : kk;
+                const int q_lo = P.prty == 0 ? 0 : k;
+#pragma unroll
+                for (int q = KT - 1; q >= 0; --q) kk = (q < K && q >= q_lo && IC(q, LY::QSIZE) != 0) ? q : kk;
                 if (kk >= 0) {
                     const int slot = IC(kk, LY::QHEAD);
                     const int qs = IC(kk, LY::QSIZE) - 1;
                     IC(kk, LY::QSIZE) = qs;
                     IC(kk, LY::QHEAD) = (qs == 0 || slot + 1 >= P.qcap) ? 0 : slot + 1;
                     IC(kk, LY::TAKED) += 1;
-                    s_arr = *qslot(kk, slot, 0);
-                    const double sw = *qslot(kk, slot, 1);
-                    s_wait = __dadd_rn(*qslot(kk, slot, 2), __dsub_rn(ttek, sw));
-                    s_tte = *qslot(kk, slot, 3);
+                    const double *qr = qrec(kk, slot);
+                    s_arr = qr[0];
+                    const double sw = qr[QL];
+                    s_wait = __dadd_rn(qr[2 * QL], __dsub_rn(ttek, sw));
+                    s_tte = qr[3 * QL];
                     s_ispr = s_tte >= 0.0;
                     start = true;
                     s_new_busy = true;
@@ -355,10 +373,11 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
                 } else {
                     int slot = IC(p_cls, LY::QHEAD) + qs;
                     if (slot >= P.qcap) slot -= P.qcap;
-                    *qslot(p_cls, slot, 0) = p_arr;
-                    *qslot(p_cls, slot, 1) = p_sw;
-                    *qslot(p_cls, slot, 2) = p_wait;
-                    *qslot(p_cls, slot, 3) = p_tte;
+                    double *qr = qrec(p_cls, slot);
+                    qr[0] = p_arr;
+                    qr[QL] = p_sw;
+                    qr[2 * QL] = p_wait;
+                    qr[3 * QL] = p_tte;
                     IC(p_cls, LY::QSIZE) = qs + 1;
                 }
             }
@@ -370,9 +389,13 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
             double *rk = rec + (long long)(K4_G_ROWS + k * rows) * R;
             const double n_served = (double)IC(k, LY::SERVED);
             for (int i = 0; i < 4; ++i) {
-                const double ws = DC(k, LY::WSUM + i), vs = DC(k, LY::VSUM + i);
-                rk[(long long)(K4_WSUM + i) * R] = ws;
-                rk[(long long)(K4_VSUM + i) * R] = vs;
+                // generator tier: the sums were accumulated in the record itself (this lane's own atomics)
+                const double ws = REPLAY ? DC(k, LY::WSUM + i) : __ldcg(&rk[(long long)(K4_WSUM + i) * R]);
+                const double vs = REPLAY ? DC(k, LY::VSUM + i) : __ldcg(&rk[(long long)(K4_VSUM + i) * R]);
+                if (REPLAY) {
+                    rk[(long long)(K4_WSUM + i) * R] = ws;
+                    rk[(long long)(K4_VSUM + i) * R] = vs;
+                }
                 // generator tier: the running means are not tracked per sample; report the equivalent ratio
                 rk[(long long)(K4_WRUN + i) * R] = REPLAY ? DC(k, LY::VRUN + 4 + i) : (n_served > 0 ? ws / n_served : 0.0);
                 rk[(long long)(K4_VRUN + i) * R] = REPLAY ? DC(k, LY::VRUN + i) : (n_served > 0 ? vs / n_served : 0.0);

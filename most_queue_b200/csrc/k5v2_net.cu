@@ -52,10 +52,23 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
     extern __shared__ double k5v_sm[];
     __shared__ DistF sh_srv[K5V_MAXN];
     __shared__ double sh_R[(K5V_MAXN + 1) * (K5V_MAXN + 1)];
-    __shared__ int sh_base[K5V_MAXN + 1], sh_ch[K5V_MAXN];
+    __shared__ int sh_base[K5V_MAXN + 1], sh_ch[K5V_MAXN], sh_nodeof[16];
     const int tid = threadIdx.x;
     const int m = P.m, nserv = P.nserv;
-    for (int i = tid; i < (m + 1) * (m + 1); i += K5V_BLOCK) sh_R[i] = P.R[i];
+    // sh_R holds the RUNNING row sums of the routing matrix, added left to right exactly as choose_next_node does
+    // (network.py:102-114), so a trip only compares
+    if (tid <= m) {
+        double sum_p = 0.0;
+        for (int i = 0; i <= m; ++i) {
+            sum_p = __dadd_rn(sum_p, P.R[tid * (m + 1) + i]);
+            sh_R[tid * (m + 1) + i] = sum_p;
+        }
+    }
+    if (tid < 16) {
+        int node = 0;
+        for (int i = 1; i < m; ++i) node += tid >= P.base[i];
+        sh_nodeof[tid] = node;
+    }
     if (tid <= m) sh_base[tid] = P.base[tid];
     if (tid < m) {
         sh_ch[tid] = P.channels[tid];
@@ -90,6 +103,7 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
         for (int s = 0; s < ST; ++s) end[s] = s < nserv ? 1e10 : 1e300;
         uint32_t busy = 0;
         int status = 0, a_idx = 0, u_idx = 0;
+        uint32_t need = 1u;  // generator tier: some ring of this lane is (nearly) empty
         long long served = 0, arrived = 0;
         const uint32_t key_m = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)m);
 
@@ -117,10 +131,12 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
             uint2 w = philox2x32_10((uint32_t)i, rep, key_m);
             return ((double)w.y + 0.5) * 0x1p-32;
         };
-        // generator tier: every node's service draws are topped up to K5V_SB by all lanes of the warp together
+        // generator tier: when any lane of the warp is short of draws for some node (fewer than the two starts a
+        // trip can make), all lanes top up all their rings to K5V_SB together
         auto refill_services = [&]() {
+            if (!__any_sync(__activemask(), need != 0u)) return;
+            need = 0u;
             for (int node = 0; node < m; ++node) {
-                if (!__any_sync(__activemask(), IN(node, SFILL) < 2)) continue;  // up to two starts per trip
                 const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)node);
                 const DistF d = sh_srv[node];
                 for (;;) {
@@ -146,12 +162,13 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 }
                 return P.S[P.soff[node] + (long long)j * R + rl];
             }
-            IN(node, SFILL) -= 1;
+            const int fill = IN(node, SFILL) - 1;
+            IN(node, SFILL) = fill;
+            need |= fill < 2 ? 1u : 0u;
             return (double)smf[(node * K5V_SB + (j & (K5V_SB - 1))) * K5V_BLOCK];
         };
-        auto qslot = [&](int node, int slot, int f) -> double * {
-            return Q + (((long long)node * P.qcap + slot) * 3 + f) * P.lanes;
-        };
+        const long long QL = P.lanes;  // field stride of a waiting-line record
+        auto qrec = [&](int node, int slot) -> double * { return Q + (long long)((node * P.qcap + slot) * 3) * QL; };
         double *rnode0 = rec + (long long)MQ_NG_ROWS * R;
         // a sample of a node-level moment set: row0 = MQ_NN_VSUM or MQ_NN_WSUM
         auto node_sample = [&](int node, int row0, double x, int count) {
@@ -171,7 +188,8 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 double pw = x;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    atomicAdd(g + (long long)i * R, pw);
+                    atomicAdd(g, pw);
+                    g += R;
                     pw = __dmul_rn(pw, x);
                 }
             }
@@ -220,8 +238,7 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 arrival_time = __dadd_rn(ttek, next_gap());
             } else {
                 // on_serving network.py:174-194: node.serving() first (base.py:249-310)
-                int node = 0;
-                for (int i = 1; i < m; ++i) node += ev >= sh_base[i];
+                const int node = sh_nodeof[ev];
                 cur = node;
                 j_arrn = SD(D_ARRN + ev);
                 j_waitn = SD(D_WAITN + ev);
@@ -240,9 +257,10 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 if (qs != 0) {
                     // send_head_of_queue_to_channel base.py:288-310
                     const int slot = IN(node, QHEAD);
-                    const double q_arrn = *qslot(node, slot, 0);
-                    const double q_waitn = *qslot(node, slot, 1);
-                    const double q_arrt = *qslot(node, slot, 2);
+                    const double *qr = qrec(node, slot);
+                    const double q_arrn = qr[0];
+                    const double q_waitn = qr[QL];
+                    const double q_arrt = qr[2 * QL];
                     IN(node, QSIZE) = qs - 1;
                     IN(node, QHEAD) = (qs == 1 || slot + 1 >= P.qcap) ? 0 : slot + 1;
                     int n_taked = 0;
@@ -268,12 +286,8 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
             const double pu = next_uniform();
             int next = -1;
             {
-                double sum_p = 0.0;
                 const double *row = sh_R + (cur + 1) * (m + 1);
-                for (int i = 0; i <= m; ++i) {
-                    sum_p = __dadd_rn(sum_p, row[i]);
-                    next = (next < 0 && sum_p > pu) ? i : next;
-                }
+                for (int i = 0; i <= m; ++i) next = (next < 0 && row[i] > pu) ? i : next;
                 next = next < 0 ? 0 : next;
             }
             if (status) break;
@@ -325,9 +339,10 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                     } else {
                         int slot = IN(node, QHEAD) + qs;
                         if (slot >= P.qcap) slot -= P.qcap;
-                        *qslot(node, slot, 0) = j_arrn;
-                        *qslot(node, slot, 1) = j_waitn;
-                        *qslot(node, slot, 2) = ttek;  // == start_waiting_time (base.py:199-201)
+                        double *qr = qrec(node, slot);
+                        qr[0] = j_arrn;
+                        qr[QL] = j_waitn;
+                        qr[2 * QL] = ttek;  // == start_waiting_time (base.py:199-201)
                         IN(node, QSIZE) = qs + 1;
                     }
                 } else {
