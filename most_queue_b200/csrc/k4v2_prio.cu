@@ -10,7 +10,7 @@
 //     service-draw site and one moment-update site per trip.
 //   * completion times, the class of the job on each slot (4 bits per slot) and the next arrival time of every
 //     class are registers; the job data of each slot, the per-class moments, counters, cursors and the first
-//     K4V_BF time-in-state bins are shared memory laid out [word][lane] (the bank depends on the lane only, so
+//     few time-in-state bins are shared memory laid out [word][lane] (the bank depends on the lane only, so
 //     per-lane slot / class indices never conflict); further bins go to the zeroed record with fire-and-forget
 //     RED.ADD.F64 (same rounding, same order per address).
 // Waiting lines stay rings of 4-double job records in HBM scratch ([class][slot][field][lane]).
@@ -19,8 +19,14 @@
 namespace mq {
 
 constexpr int K4V_BLOCK = 64;
-constexpr int K4V_BF = 4;  // time-in-state bins per class kept in shared memory
-constexpr int K4V_SB = 4;  // generator tier: service draws kept ahead per class and lane (power of two)
+#ifndef K4V_BF_GEN
+#define K4V_BF_GEN 2
+#endif
+constexpr int K4V_BF_REPLAY = 4;  // time-in-state bins per class kept in shared memory (replay tier)
+#ifndef K4V_SB_N
+#define K4V_SB_N 8
+#endif
+constexpr int K4V_SB = K4V_SB_N;  // generator tier: service draws kept ahead per class and lane (power of two)
 
 template <int CT, int KT, bool REPLAY>
 struct K4VLayout {
@@ -30,7 +36,8 @@ struct K4VLayout {
     // sums go straight to the zeroed record (fire-and-forget RED.ADD.F64), which frees 128 bytes per lane
     static constexpr int T_OLD = 0, P_OVER = 1, VSUM = 2, WSUM = 6, VRUN = 10, WRUN = 14;
     static constexpr int HIST = REPLAY ? 18 : 2;
-    static constexpr int DSTR = HIST + K4V_BF;
+    static constexpr int BF = REPLAY ? K4V_BF_REPLAY : K4V_BF_GEN;  // time-in-state bins kept on chip
+    static constexpr int DSTR = HIST + BF;
     static constexpr int ND = CLS0 + KT * DSTR;
     // 32-bit words, [word][lane]
     static constexpr int ARRIVED = 0, TAKED = 1, SERVED = 2, DROPPED = 3, INSYS = 4, AIDX = 5, SIDX = 6, QHEAD = 7,
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
             {
                 const int ins = IC(kev, LY::INSYS);
                 const double dt = __dsub_rn(te, DC(kev, LY::T_OLD));
-                if (ins < K4V_BF) {
+                if (ins < LY::BF) {
                     DC(kev, LY::HIST + ins) = __dadd_rn(DC(kev, LY::HIST + ins), dt);
                 } else if (ins < P.p_bins) {
                     atomicAdd(&rec[(long long)(K4_G_ROWS + kev * rows + K4_P + ins) * R], dt);
@@ -409,9 +416,9 @@ __global__ void __launch_bounds__(K4V_BLOCK) k4v2_prio(const K4Params P)
             rk[(long long)K4_TOLD * R] = DC(k, LY::T_OLD);
             rk[(long long)K4_AUSED * R] = (double)IC(k, LY::AIDX);
             rk[(long long)K4_SUSED * R] = (double)IC(k, LY::SIDX);
-            // bins kept on chip; bins >= K4V_BF accumulated in the (zeroed) record directly
+            // bins kept on chip; bins >= LY::BF accumulated in the (zeroed) record directly
             double over = DC(k, LY::P_OVER);
-            for (int b = 0; b < K4V_BF; ++b) {
+            for (int b = 0; b < LY::BF; ++b) {
                 if (b < P.p_bins)
                     rk[(long long)(K4_P + b) * R] = DC(k, LY::HIST + b);
                 else
