@@ -52,11 +52,24 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
     extern __shared__ double k7v_sm[];
     __shared__ DistF sh_srv[K7_MAXN * K7_MAXK], sh_src[K7_MAXK];
     __shared__ double sh_R[K7_MAXK * (K7_MAXN + 1) * (K7_MAXN + 1)];
-    __shared__ int sh_base[K7_MAXN + 1], sh_ch[K7_MAXN], sh_prty[K7_MAXN], sh_map[K7_MAXN * K7_MAXK];
+    __shared__ int sh_base[K7_MAXN + 1], sh_ch[K7_MAXN], sh_prty[K7_MAXN], sh_map[K7_MAXN * K7_MAXK], sh_nodeof[32];
     const int tid = threadIdx.x;
     const int m = P.m, K = P.K, nserv = P.nserv;
     const int RS = (m + 1) * (m + 1);
-    for (int i = tid; i < K * RS; i += K7V_BLOCK) sh_R[i] = P.R[i];
+    // sh_R holds the RUNNING row sums of the routing matrices, added left to right exactly as choose_next_node does
+    // (priority_network.py:137-150), so a trip only compares
+    for (int r = tid; r < K * (m + 1); r += K7V_BLOCK) {
+        double sum_p = 0.0;
+        for (int i = 0; i <= m; ++i) {
+            sum_p = __dadd_rn(sum_p, P.R[r * (m + 1) + i]);
+            sh_R[r * (m + 1) + i] = sum_p;
+        }
+    }
+    if (tid < 32) {
+        int node = 0;
+        for (int i = 1; i < m; ++i) node += tid >= P.base[i];
+        sh_nodeof[tid] = node;
+    }
     for (int i = tid; i < m * K; i += K7V_BLOCK) {
         sh_map[i] = P.nodes_prty[i];
         if (!REPLAY) sh_srv[i] = P.srv[i];
@@ -98,6 +111,7 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
         for (int s = 0; s < ST; ++s) end[s] = s < nserv ? 1e10 : 1e300;
         uint32_t busy = 0, k_pack = 0, nc_pack = 0;  // 2 bits per server: real class, node class
         int status = 0, u_idx = 0;
+        uint32_t need = 1u;  // generator tier: some ring of this lane is (nearly) empty
         long long served_total = 0;
 
         auto next_gap = [&](int k) -> double {
@@ -129,8 +143,10 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
             return ((double)w.y + 0.5) * 0x1p-32;
         };
         auto refill_services = [&]() {
+            // when any lane of the warp is short of draws for some stream, all lanes top up all their rings together
+            if (!__any_sync(__activemask(), need != 0u)) return;
+            need = 0u;
             for (int nk = 0; nk < m * K; ++nk) {
-                if (!__any_sync(__activemask(), IQ(nk, SFILL) < K7V_NEED)) continue;
                 const uint32_t key = P.key0 + MQ_KEY_STRIDE * (64u * (uint32_t)nk);
                 const DistF d = sh_srv[nk];
                 for (;;) {
@@ -156,12 +172,13 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
                 }
                 return P.S[P.soff[nk] + (long long)j * R + rl];
             }
-            IQ(nk, SFILL) -= 1;
+            const int fill = IQ(nk, SFILL) - 1;
+            IQ(nk, SFILL) = fill;
+            need |= fill < K7V_NEED ? 1u : 0u;
             return (double)smf[(nk * K7V_SB + (j & (K7V_SB - 1))) * K7V_BLOCK];
         };
-        auto qslot = [&](int nk, int slot, int f) -> double * {
-            return Q + (((long long)nk * P.qcap + slot) * K7_JOBF + f) * P.lanes;
-        };
+        const long long QL = P.lanes;  // field stride of a waiting-line record
+        auto qrec = [&](int nk, int slot) -> double * { return Q + (long long)((nk * P.qcap + slot) * K7_JOBF) * QL; };
         double *rcls0 = rec + (long long)MQ_PN_G_ROWS * R;
         double *rnode0 = rec + (long long)(MQ_PN_G_ROWS + K * MQ_PNC_ROWS) * R;
         auto node_sample = [&](int nk, double v, double w, int count) {  // qs[i].v[j] / .w[j], sim/priority.py:676-690
@@ -251,8 +268,7 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
                     if (k == ev_k) at[k] = na;
             } else {
                 // on_serving :217-240 ; node.serving(c, True) sim/priority.py:457-539
-                int node = 0;
-                for (int i = 1; i < m; ++i) node += ev >= sh_base[i];
+                const int node = sh_nodeof[ev];
                 cur = node;
                 const int kc = (int)((nc_pack >> (2 * ev)) & 3u);
                 real = (int)((k_pack >> (2 * ev)) & 3u);
@@ -278,10 +294,11 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
                     IQ(nkk, QSIZE) = qs;
                     IQ(nkk, QHEAD) = (qs == 0 || slot + 1 >= P.qcap) ? 0 : slot + 1;
                     node_count(nkk, MQ_PNN_TAKED);
-                    const double q_arrn = *qslot(nkk, slot, 0), q_waitn = *qslot(nkk, slot, 1);
-                    const double q_arrt = *qslot(nkk, slot, 2), q_sw = *qslot(nkk, slot, 3);
-                    const double q_wt = *qslot(nkk, slot, 4), q_tte = *qslot(nkk, slot, 5);
-                    const int pk = (int)*qslot(nkk, slot, 6);
+                    const double *qr = qrec(nkk, slot);
+                    const double q_arrn = qr[0], q_waitn = qr[QL];
+                    const double q_arrt = qr[2 * QL], q_sw = qr[3 * QL];
+                    const double q_wt = qr[4 * QL], q_tte = qr[5 * QL];
+                    const int pk = (int)qr[6 * QL];
                     const double d = __dsub_rn(ttek, q_sw);
                     if (pk >> 16) {
                         wval = __dadd_rn(ttek, q_tte);  // servers.py:237-239: resume with the stored time
@@ -307,12 +324,8 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
             const double pu = next_uniform();
             int next = -1;
             {
-                double sum_p = 0.0;
                 const double *row = sh_R + real * RS + (cur + 1) * (m + 1);
-                for (int i = 0; i <= m; ++i) {
-                    sum_p = __dadd_rn(sum_p, row[i]);
-                    next = (next < 0 && sum_p > pu) ? i : next;
-                }
+                for (int i = 0; i <= m; ++i) next = (next < 0 && row[i] > pu) ? i : next;
                 next = next < 0 ? 0 : next;
             }
             if (status) break;
@@ -395,13 +408,14 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
                     } else {
                         int slot = IQ(p_nk, QHEAD) + qs;
                         if (slot >= P.qcap) slot -= P.qcap;
-                        *qslot(p_nk, slot, 0) = p_arrn;
-                        *qslot(p_nk, slot, 1) = p_waitn;
-                        *qslot(p_nk, slot, 2) = p_arrt;
-                        *qslot(p_nk, slot, 3) = ttek;  // start_waiting_time
-                        *qslot(p_nk, slot, 4) = p_wt;
-                        *qslot(p_nk, slot, 5) = p_tte;
-                        *qslot(p_nk, slot, 6) = (double)p_pack;
+                        double *qr = qrec(p_nk, slot);
+                        qr[0] = p_arrn;
+                        qr[QL] = p_waitn;
+                        qr[2 * QL] = p_arrt;
+                        qr[3 * QL] = ttek;  // start_waiting_time
+                        qr[4 * QL] = p_wt;
+                        qr[5 * QL] = p_tte;
+                        qr[6 * QL] = (double)p_pack;
                         IQ(p_nk, QSIZE) = qs + 1;
                     }
                 }
