@@ -117,25 +117,26 @@ __device__ __forceinline__ float sample_pa(const DistF &d, uint32_t w0)
     return d.b * fast_ex2(fast_lg2(u01(w0)) * d.a);
 }
 
-static __device__ __noinline__ float sample_erlang(const DistF &d, uint32_t w0, uint32_t idx, uint32_t rep,
-                                            uint32_t key0, int which)
+// The two loop samplers are real functions (one copy per kernel); they take the law's fields BY VALUE: a
+// `const DistF &` parameter would force every caller to keep its DistF in local memory.
+static __device__ __noinline__ float sample_erlang(float scale, int order, uint32_t w0, uint32_t idx, uint32_t rep,
+                                                   uint32_t key0, int which)
 {
-    // distributions.py:807-820: -log(prod U)/mu, as a sum of logs; d.a = -ln2/mu
+    // distributions.py:807-820: -log(prod U)/mu, as a sum of logs; scale = -ln2/mu
     float acc = fast_lg2(u01(w0));
     uint2 e = make_uint2(0u, 0u);
-    for (int k = 1; k < d.r; ++k) {
+    for (int k = 1; k < order; ++k) {
         if (k & 1) e = ext_words(idx, rep, key0, which, (uint32_t)(k + 1) >> 1);
         acc += fast_lg2(u01((k & 1) ? e.x : e.y));
     }
-    return acc * d.a;
+    return acc * scale;
 }
 
-static __device__ __noinline__ float sample_gamma(const DistF &d, uint32_t w0, uint32_t idx, uint32_t rep,
-                                           uint32_t key0, int which)
+static __device__ __noinline__ float sample_gamma(float dd, float cc, float inv_mu, float inv_alpha, int small_alpha,
+                                                  uint32_t w0, uint32_t idx, uint32_t rep, uint32_t key0, int which)
 {
     // distributions.py:996-1003 (Generator.gamma(alpha, 1/mu)) restated as Marsaglia-Tsang
-    // with Box-Muller normals.  d.a = dd, d.b = cc, d.c = 1/mu, d.d = 1/alpha, d.r = alpha<1
-    const float dd = d.a, cc = d.b;
+    // with Box-Muller normals.  dd = d.a, cc = d.b, inv_mu = d.c, inv_alpha = d.d, small_alpha = d.r (alpha < 1)
     float x = dd;
     for (uint32_t t = 0; t < 15; ++t) {
         uint2 e0 = ext_words(idx, rep, key0, which, 2 * t + 1);
@@ -147,13 +148,13 @@ static __device__ __noinline__ float sample_gamma(const DistF &d, uint32_t w0, u
         x = dd * v;
         // the acceptance uniform of the first attempt is the primary word itself when it is not needed for the
         // alpha < 1 boost: one extension call per draw in the common case instead of two
-        const uint32_t wa = (t == 0 && !d.r) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
+        const uint32_t wa = (t == 0 && !small_alpha) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
         float lhs = 0.6931471805599453f * fast_lg2(u01(wa));
         float rhs = 0.5f * z * z + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
         if (lhs < rhs) break;
     }
-    if (d.r) x *= fast_ex2(fast_lg2(u01(w0)) * d.d);
-    return x * d.c;
+    if (small_alpha) x *= fast_ex2(fast_lg2(u01(w0)) * inv_alpha);
+    return x * inv_mu;
 }
 
 template <int KIND>
@@ -167,9 +168,9 @@ __device__ __forceinline__ float sample(const DistF &d, uint32_t w0, uint32_t id
     case MQ_H2:
         return sample_h2(d, w0);
     case MQ_E:
-        return sample_erlang(d, w0, idx, rep, key0, which);
+        return sample_erlang(d.a, d.r, w0, idx, rep, key0, which);
     case MQ_GAMMA:
-        return sample_gamma(d, w0, idx, rep, key0, which);
+        return sample_gamma(d.a, d.b, d.c, d.d, d.r, w0, idx, rep, key0, which);
     case MQ_PA:
         return sample_pa(d, w0);
     case MQ_D:  // distributions.py:614-626
