@@ -93,6 +93,28 @@ __device__ __forceinline__ double gen_gap(const K3Params &P, long long n);
 // the halo of the level walk in the last tile -- are drawn)
 __device__ __forceinline__ void stage_tile_stash(const K3Params &P, long long tile_base, double *smS, double *smA)
 {
+    if (tile_base + K3_TILE + K3_HALO <= P.n) {
+        // interior tile (uniform in the CTA): every index is inside the stash, so all loads are issued back to back
+        // before the first conversion waits for one of them
+        const float *G = P.stG + tile_base, *V = P.stV + tile_base;
+        float vS[K3_L], vA[K3_L];
+#pragma unroll
+        for (int k = 0; k < K3_L; ++k) {
+            vS[k] = __ldcs(V + k * K3_THREADS + threadIdx.x);
+            vA[k] = __ldcs(G + k * K3_THREADS + threadIdx.x);
+        }
+        const float h = __ldcs(G + K3_TILE + threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < K3_L; ++k) {
+            const int e = k * K3_THREADS + threadIdx.x;
+            smS[k3_pad(e)] = (double)vS[k];
+            smA[k3_pad(e)] = (double)vA[k];
+        }
+        smA[k3_pad(K3_TILE + threadIdx.x)] = (double)h;
+        if (threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = (double)__ldcs(G + K3_TILE + K3_HALO);
+        __syncthreads();
+        return;
+    }
     auto gap_at = [&](long long n) -> double {
         if (n <= P.n) return (double)__ldcs(P.stG + n);
         return n <= P.n + P.n_ahead ? gen_gap(P, n) : 0.0;
@@ -206,6 +228,38 @@ __device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, cons
     return f;
 }
 
+// Generator form of the summary pass: draw, fold and (optionally) stash one job at a time in a ROLLED loop.  The
+// unrolled load_segment + fold_segment pair inlines the sampler switch 32 times (the kernel then stalls on
+// instruction fetch); the fold is sequential in j either way, so the association order is unchanged.
+#ifndef K3_GEN_UNROLL
+#define K3_GEN_UNROLL 1
+#endif
+constexpr int K3_GEN_UNROLL_N = K3_GEN_UNROLL;
+template <bool STASH_W, bool FULL>
+__device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, float *stg, float *stv)
+{
+    unsigned long long g = (unsigned long long)(P.job0 + n0);
+    uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+    float gap = sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+    const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
+    MP f = mp_id();
+#pragma unroll K3_GEN_UNROLL_N
+    for (int j = 0; j < K3_L; ++j) {
+        const float sv = sample<-1>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
+        ++g;
+        w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+        const float gnext = sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+        if (FULL || j < valid) f = mp_step(f, __dsub_rn((double)sv, (double)gnext));
+        if (STASH_W) {
+            stg[k3_pad(threadIdx.x * K3_L + j)] = gap;
+            stv[k3_pad(threadIdx.x * K3_L + j)] = sv;
+            if (!FULL && n0 + j == P.n - 1) P.stG[P.n] = gnext;
+        }
+        gap = gnext;
+    }
+    return f;
+}
+
 template <bool REPLAY, bool STASH_W = false>
 __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
 {
@@ -220,7 +274,10 @@ __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
         if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
         MP mine;
-        if (full_tile) {
+        if (!REPLAY) {
+            mine = full_tile ? gen_fold_segment<STASH_W, true>(P, n0, stg, stv)
+                             : gen_fold_segment<STASH_W, false>(P, n0, stg, stv);
+        } else if (full_tile) {
             load_segment<REPLAY, false, STASH_W, true>(P, n0, x, s, smS, smA, stg, stv);
             mine = fold_segment<true>(P, n0, x);
         } else {
