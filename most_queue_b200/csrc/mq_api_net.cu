@@ -106,6 +106,10 @@ static int net_common(mq_ctx *ctx, const mq_net_cfg *cfg, bool replay, const dou
     else
         CU(k5_occupancy(&occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
+    if (const char *cap = std::getenv("MQ_K5_MAX_CTAS")) {  // measurement knob: resident CTAs per SM
+        const int v = std::atoi(cap);
+        if (v >= 1 && v < occ) occ = v;
+    }
     long long grid = (long long)occ * ctx->sms;
     const long long need = (R + K5_BLOCK - 1) / K5_BLOCK;
     if (grid > need) grid = need;
