@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
 
         while (served < P.jobs && status == 0) {
             if (!REPLAY) refill_services();
+            // every trip consumes exactly one routing uniform and it depends on nothing else: start it first, so the
+            // Philox chain (or the load, in the replay tier) overlaps the event selection
+            const double pu = next_uniform();
             // ---- next event, base_network_sim.py:184-227: external arrival first, then the busy servers in
             // node-major, channel-minor order; the first minimum wins
             double mv[ST];
@@ -240,6 +243,17 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 // on_serving network.py:174-194: node.serving() first (base.py:249-310)
                 const int node = sh_nodeof[ev];
                 cur = node;
+                // the head of this node's waiting line is needed a dozen instructions further down: load it now, so
+                // the L2 round trip overlaps the node statistics
+                const int qs = IN(node, QSIZE);
+                const int slot = IN(node, QHEAD);
+                double q_arrn = 0.0, q_waitn = 0.0, q_arrt = 0.0;
+                if (qs != 0) {
+                    const double *qr = qrec(node, slot);
+                    q_arrn = qr[0];
+                    q_waitn = qr[QL];
+                    q_arrt = qr[2 * QL];
+                }
                 j_arrn = SD(D_ARRN + ev);
                 j_waitn = SD(D_WAITN + ev);
                 const double a_t = SD(D_ARRT + ev);
@@ -253,14 +267,8 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 node_count(node, MQ_NN_SERVED, 1.0);
                 node_sample(node, MQ_NN_VSUM, __dsub_rn(ttek, a_t), n_served);
                 node_count(node, MQ_NN_INSYS, -1.0);
-                const int qs = IN(node, QSIZE);
                 if (qs != 0) {
                     // send_head_of_queue_to_channel base.py:288-310
-                    const int slot = IN(node, QHEAD);
-                    const double *qr = qrec(node, slot);
-                    const double q_arrn = qr[0];
-                    const double q_waitn = qr[QL];
-                    const double q_arrt = qr[2 * QL];
                     IN(node, QSIZE) = qs - 1;
                     IN(node, QHEAD) = (qs == 1 || slot + 1 >= P.qcap) ? 0 : slot + 1;
                     int n_taked = 0;
@@ -283,7 +291,6 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 if (s == wslot) end[s] = wval;
 
             // choose_next_node network.py:102-114: first column whose running row sum exceeds the uniform
-            const double pu = next_uniform();
             int next = -1;
             {
                 const double *row = sh_R + (cur + 1) * (m + 1);
