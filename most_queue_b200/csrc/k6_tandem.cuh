@@ -23,4 +23,9 @@ struct K6Params {
 cudaError_t k6_launch(const K6Params &P, int grid, cudaStream_t st);
 cudaError_t k6_occupancy(int *blocks_per_sm);
 
+// k6v2_tandem.cu: the predicated, register / shared-memory resident form for lines of at most 16 nodes
+bool k6v2_supported(int m);
+cudaError_t k6v2_launch(const K6Params &P, int grid, cudaStream_t st);
+cudaError_t k6v2_occupancy(int m, bool replay, int *blocks_per_sm);
+
 }  // namespace mq

@@ -2,6 +2,7 @@
 #include "k6_tandem.cuh"
 #include "mq_host.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace mq;
@@ -69,8 +70,18 @@ static int tandem_common(mq_ctx *ctx, const mq_tandem_cfg *cfg, bool replay, con
         P.src = make_distf(cfg->src);
         for (int i = 0; i < m; ++i) P.srv[i] = make_distf(cfg->srv[i]);
     }
+    // lines of at most 16 nodes run the predicated, on-chip-state form (k6v2_tandem.cu); MQ_K6_V1=1 forces the general kernel
+    const bool v2 = k6v2_supported(m) && !std::getenv("MQ_K6_V1") && P.jobs + P.warm < (1ll << 30) &&
+                    (!replay || [&] {
+                        for (int i = 0; i < m; ++i)
+                            if (n_s[i] >= (1ll << 31)) return false;
+                        return true;
+                    }());
     int occ = 0;
-    CU(k6_occupancy(&occ));
+    if (v2)
+        CU(k6v2_occupancy(m, replay, &occ));
+    else
+        CU(k6_occupancy(&occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     long long grid = (long long)occ * ctx->sms;
     const long long need = (R + K6_BLOCK - 1) / K6_BLOCK;
@@ -93,7 +104,10 @@ static int tandem_common(mq_ctx *ctx, const mq_tandem_cfg *cfg, bool replay, con
     CU(cudaMemcpyAsync(ctx->desc.p, desc.data(), sizeof(RatioDesc) * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->rec.p, 0, rec_bytes, ctx->stream));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(k6_launch(P, (int)grid, ctx->stream));
+    if (v2)
+        CU(k6v2_launch(P, (int)grid, ctx->stream));
+    else
+        CU(k6_launch(P, (int)grid, ctx->stream));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(launch_reduce_ratio((const double *)ctx->rec.p, R, (const RatioDesc *)ctx->desc.p, nq, (double *)ctx->agg.p,

@@ -1,6 +1,6 @@
 """Every template instantiation and every general (fallback) kernel stays under the bit-exact oracle check: the small
-configurations run the register / shared-memory resident kernels (k4v2, k5v2, k7v2), larger ones the general kernels
-(k4_prio, k5_net, k7_prionet), and MQ_K*_V1=1 forces the general kernel on a small configuration."""
+configurations run the register / shared-memory resident kernels (k4v2, k5v2, k6v2, k7v2), larger ones the general
+kernels (k4_prio, k5_net, k6_tandem, k7_prionet), and MQ_K*_V1=1 forces the general kernel on a small configuration."""
 
 import numpy as np
 import pytest
@@ -133,3 +133,55 @@ def test_priority_network_kernels_all_variants(m, K, ch, prty):
 def test_priority_network_general_kernel_on_a_small_configuration(monkeypatch):
     monkeypatch.setenv("MQ_K7_V1", "1")
     _check_prionet(3, 2, [2, 1, 2], ["PR", "RS", "NP"], 99)
+
+
+def _check_tandem(cap, seed, reps=24, n=300):
+    """Replay tier of the tandem line, bit-exact against the oracle, on a line that blocks often."""
+    from most_queue_b200.sim.networks.tandem_blocking import replay
+    from oracle import oracle
+
+    rng = np.random.default_rng(seed)
+    m = len(cap)
+    A = rng.exponential(0.6, (6 * n, reps))
+    S = [rng.gamma(1.2, (0.5 + 0.1 * (i % 3)) / 1.2, (6 * n, reps)) for i in range(m)]
+    out = replay(cap, A, S, n, 0.1)
+    for r in range(reps):
+        o = oracle.tandem_replay(cap, A[:, r].copy(), [s[:, r].copy() for s in S], n, 0.1)
+        assert out["throughput"][r] == o.throughput and out["loss_prob"][r] == o.loss_prob
+        assert np.array_equal(out["mean_jobs"][r], np.array(o.mean_jobs[:m])) and out["v0"][r] == o.v0
+        assert out["a_used"][r] == o.a_used and list(out["s_used"][r]) == o.s_used
+
+
+@pytest.mark.parametrize("cap", [
+    [3, 1],                                                     # k6v2<4>
+    [2, 1, 1, 2, 1, 3],                                         # k6v2<8>: long unblocking cascades
+    [4, 1, 2, 1, 1, 3, None, 1, 2, 1, 1, 2],                    # k6v2<16>
+    [3, 1, 1, 2, 1, 1, 2, 1, 1, 2, 1, 1, 2, 1, 1, 2],           # k6v2<16>, 16 nodes
+], ids=["m2", "m6", "m12", "m16"])
+def test_tandem_kernels_all_variants(cap):
+    _check_tandem(cap, 700 + len(cap))
+
+
+def test_tandem_general_kernel_on_a_small_configuration(monkeypatch):
+    monkeypatch.setenv("MQ_K6_V1", "1")
+    _check_tandem([2, 1, 1, 2], 77)
+
+
+def test_tandem_generator_tiers_agree():
+    """Generator tier: the predicated kernel and the general kernel draw the same streams and walk the same events."""
+    import os
+
+    from most_queue_b200 import _lib
+
+    ctx = _lib.default_context()
+    cap, mu = [3, 1, 2, 1, 2], [1.0, 0.9, 1.1, 0.8, 1.2]
+    laws = [_lib.make_dist("Gamma", {"mu": 1.5 * x, "alpha": 1.5}) if i % 2 else _lib.make_dist("M", x)
+            for i, x in enumerate(mu)]
+    args = (cap, _lib.make_dist("M", 0.9), laws, 1500, 0.1, 96, 0, 5)
+    _, rec2 = ctx.sim_tandem(*args, per_replication=True)
+    os.environ["MQ_K6_V1"] = "1"
+    try:
+        _, rec1 = ctx.sim_tandem(*args, per_replication=True)
+    finally:
+        del os.environ["MQ_K6_V1"]
+    assert np.array_equal(rec1, rec2)
