@@ -48,6 +48,9 @@ struct K8Phase {
     long long starts;
 };
 
+// CT: server slots of the thread-private arrays (the smallest of 1 / 2 / 4 / 8 / 32 that holds c): a lane's stack is then
+// a few hundred bytes instead of 1-2 KB and stays in L1
+template <int CT>
 __global__ void __launch_bounds__(K8_BLOCK) k8_vacation(const K8Params P)
 {
     const long long gtid = (long long)blockIdx.x * K8_BLOCK + threadIdx.x;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(K8_BLOCK) k8_vacation(const K8Params P)
         const uint32_t rep = P.rep0 + (uint32_t)rl;
         double *rec = P.rec + rl;
         double *Q = P.queue + gtid;
-        double end[K8_MAXC], arr[K8_MAXC];
+        double end[CT], arr[CT];
         uint32_t busy = 0;
         for (int j = 0; j < c; ++j) {
             end[j] = 1e10;
@@ -312,13 +315,17 @@ __global__ void __launch_bounds__(K8_BLOCK) k8_vacation(const K8Params P)
 
 cudaError_t k8_launch(const K8Params &P, int grid, cudaStream_t st)
 {
-    k8_vacation<<<grid, K8_BLOCK, 0, st>>>(P);
+#define K8_GO(n) k8_vacation<n><<<grid, K8_BLOCK, 0, st>>>(P)
+    if (P.c <= 1) K8_GO(1); else if (P.c <= 2) K8_GO(2); else if (P.c <= 4) K8_GO(4); else if (P.c <= 8) K8_GO(8); else K8_GO(32);
+#undef K8_GO
     return cudaGetLastError();
 }
 
-cudaError_t k8_occupancy(int *blocks_per_sm)
+cudaError_t k8_occupancy(int c, int *blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k8_vacation, K8_BLOCK, 0);
+#define K8_OCC(n) cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k8_vacation<n>, K8_BLOCK, 0)
+    return c <= 1 ? K8_OCC(1) : c <= 2 ? K8_OCC(2) : c <= 4 ? K8_OCC(4) : c <= 8 ? K8_OCC(8) : K8_OCC(32);
+#undef K8_OCC
 }
 
 }  // namespace mq

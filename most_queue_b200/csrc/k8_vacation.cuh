@@ -24,6 +24,6 @@ struct K8Params {
 };
 
 cudaError_t k8_launch(const K8Params &P, int grid, cudaStream_t st);
-cudaError_t k8_occupancy(int *blocks_per_sm);
+cudaError_t k8_occupancy(int c, int *blocks_per_sm);
 
 }  // namespace mq

@@ -38,6 +38,9 @@ __device__ __forceinline__ void k9_sample(double *run, double *sum, double x, lo
     }
 }
 
+// CT: server slots of the thread-private arrays (the smallest of 1 / 2 / 4 / 8 / 32 that holds c): a lane's stack is then
+// a few hundred bytes instead of 1-2 KB and stays in L1
+template <int CT>
 __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
 {
     const long long gtid = (long long)blockIdx.x * K9_BLOCK + threadIdx.x;
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
         const uint32_t rep = P.rep0 + (uint32_t)rl;
         double *rec = P.rec + rl;
         double *Q = P.queue + gtid;
-        double end[K9_MAXC], arr[K9_MAXC], wait[K9_MAXC], tot[K9_MAXC];
+        double end[CT], arr[CT], wait[CT], tot[CT];
         uint32_t busy = 0;
         for (int j = 0; j < c; ++j) {
             end[j] = 1e10;
@@ -196,8 +199,8 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
                 if (in_sys != 0) {
                     if (P.type == MQ_NEG_DISASTER && P.scenario != MQ_NEG_REMOVE) {
                         // the jobs in service, in order of arrival (stable), take servers 0, 1, ... again
-                        int nb = 0, idx[K9_MAXC];
-                        double ja[K9_MAXC], jw[K9_MAXC], jr[K9_MAXC], jt[K9_MAXC];
+                        int nb = 0, idx[CT];
+                        double ja[CT], jw[CT], jr[CT], jt[CT];
                         for (int j = 0; j < c; ++j) {
                             if (!((busy >> j) & 1u)) continue;
                             const double rem = __dsub_rn(end[j], ttek);
@@ -309,13 +312,17 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
 
 cudaError_t k9_launch(const K9Params &P, int grid, cudaStream_t st)
 {
-    k9_negatives<<<grid, K9_BLOCK, 0, st>>>(P);
+#define K9_GO(n) k9_negatives<n><<<grid, K9_BLOCK, 0, st>>>(P)
+    if (P.c <= 1) K9_GO(1); else if (P.c <= 2) K9_GO(2); else if (P.c <= 4) K9_GO(4); else if (P.c <= 8) K9_GO(8); else K9_GO(32);
+#undef K9_GO
     return cudaGetLastError();
 }
 
-cudaError_t k9_occupancy(int *blocks_per_sm)
+cudaError_t k9_occupancy(int c, int *blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k9_negatives, K9_BLOCK, 0);
+#define K9_OCC(n) cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k9_negatives<n>, K9_BLOCK, 0)
+    return c <= 1 ? K9_OCC(1) : c <= 2 ? K9_OCC(2) : c <= 4 ? K9_OCC(4) : c <= 8 ? K9_OCC(8) : K9_OCC(32);
+#undef K9_OCC
 }
 
 }  // namespace mq

@@ -22,6 +22,6 @@ struct K9Params {
 };
 
 cudaError_t k9_launch(const K9Params &P, int grid, cudaStream_t st);
-cudaError_t k9_occupancy(int *blocks_per_sm);
+cudaError_t k9_occupancy(int c, int *blocks_per_sm);
 
 }  // namespace mq

@@ -77,7 +77,7 @@ static int negatives_common(mq_ctx *ctx, const mq_neg_cfg *cfg, bool replay, con
         P.service = make_distf(cfg->service);
     }
     int occ = 0;
-    CU(k9_occupancy(&occ));
+    CU(k9_occupancy(cfg->c, &occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     long long grid = (long long)occ * ctx->sms;
     const long long want = (R + K9_BLOCK - 1) / K9_BLOCK;

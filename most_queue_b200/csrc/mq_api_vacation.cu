@@ -91,7 +91,7 @@ static int vacation_common(mq_ctx *ctx, const mq_vac_cfg *cfg, bool replay, cons
             if (need[s]) P.dist[s] = make_distf(cfg->dist[s]);
     }
     int occ = 0;
-    CU(k8_occupancy(&occ));
+    CU(k8_occupancy(cfg->c, &occ));
     if (occ < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     long long grid = (long long)occ * ctx->sms;
     const long long want = (R + K8_BLOCK - 1) / K8_BLOCK;

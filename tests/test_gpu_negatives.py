@@ -43,7 +43,9 @@ def test_replay_matches_reference(path):
     ("DISASTER", 1, None, "CLEAR_SYSTEM"), ("DISASTER", 4, 5, "CLEAR_SYSTEM"), ("RCS", 1, None, "REMOVE"),
     ("RCS", 3, None, "REMOVE"), ("RCS", 2, 3, "REMOVE"), ("DISASTER", 3, None, "REQUEUE_ALL"),
     ("DISASTER", 4, 6, "RESUME_ALL"), ("DISASTER", 2, None, "REQUEUE_ALL_NO_RESAMPLING"), ("RCS", 3, None, "REQUEUE"),
-    ("RCS", 2, 4, "RESUME"), ("RCS", 4, None, "REQUEUE_NO_RESAMPLING")])
+    ("RCS", 2, 4, "RESUME"), ("RCS", 4, None, "REQUEUE_NO_RESAMPLING"),
+    ("DISASTER", 6, None, "REQUEUE_ALL"), ("RCS", 7, 9, "REMOVE"),          # 8 server slots
+    ("DISASTER", 12, None, "RESUME_ALL"), ("RCS", 11, None, "REQUEUE")])    # 32 server slots
 def test_replay_matches_oracle_many_replications(neg_type, c, buffer, scenario):
     from most_queue_b200.sim.negative import replay
     from oracle import oracle

@@ -48,7 +48,9 @@ def test_replay_matches_reference(path):
     dict(c=3, buffer=6, use=("warm", "cold", "delay")),
     dict(c=1, buffer=None, use=("cold",), multi=True),
     dict(c=2, buffer=None, use=("warm",), big_n=5),
-], ids=["warm", "service_on_warm+cold", "buffer6_all", "multiple", "npolicy5_warm"])
+    dict(c=6, buffer=None, use=("warm", "cold", "delay")),   # 8 server slots
+    dict(c=12, buffer=20, use=("warm", "cold")),             # 32 server slots
+], ids=["warm", "service_on_warm+cold", "buffer6_all", "multiple", "npolicy5_warm", "c6_all", "c12_buffer20"])
 def test_replay_matches_oracle_many_replications(cfg):
     from most_queue_b200.sim.vacations import replay
     from oracle import oracle
