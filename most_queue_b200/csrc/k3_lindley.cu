@@ -303,13 +303,22 @@ __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
     }
 }
 
-__global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
+// Tile-level scan, the specification's "1024 chunks folded sequentially, Kogge-Stone over 32, sequential over 32", in
+// three small launches so that the strided gathers of the chunk folds are spread over 32 SMs instead of queueing behind
+// one SM's memory pipe (one 1024-thread CTA took 220 us for 65 536 tiles; the operations and their order are unchanged):
+//   k3_top_fold  <<<32, 32>>>   thread c folds the summaries of chunk c sequentially          -> chunk_f[c]
+//   k3_top_scan  <<<1, 1024>>>  the CTA scan over the 1024 chunk folds                        -> chunk_ex[c], total
+//   k3_top_apply <<<32, 32>>>   thread c walks its chunk again and writes every tile's prefix -> tile_ex[t]
+constexpr int K3_TOP_CTA = 32;
+constexpr int K3_TOP_U = 16;  // summaries loaded ahead of the (sequential, order-fixed) fold: the loops are load-latency bound
+
+__global__ void __launch_bounds__(K3_TOP_CTA) k3_top_fold(const K3Params P)
 {
-    __shared__ MP smem[K3_TOP / 32];
+    const int c = blockIdx.x * K3_TOP_CTA + threadIdx.x;
     const long long chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
-    const long long lo = (long long)threadIdx.x * chunk;
+    const long long lo = (long long)c * chunk;
     const long long hi = lo + chunk < P.ntiles ? lo + chunk : P.ntiles;
-    constexpr int U = 8;  // summaries loaded ahead of the (sequential, order-fixed) fold: the loop is load-latency bound
+    constexpr int U = K3_TOP_U;
     MP f = mp_id();
     for (long long t = lo; t < hi; t += U) {
         MP v[U];
@@ -320,8 +329,26 @@ __global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
         for (int u = 0; u < U; ++u)
             if (t + u < hi) f = mp_then(f, v[u]);
     }
+    P.chunk_f[c] = f;
+}
+
+__global__ void __launch_bounds__(K3_TOP) k3_top_scan(const K3Params P)
+{
+    __shared__ MP smem[K3_TOP / 32];
     MP total;
-    MP ex = cta_scan<K3_TOP>(f, smem, &total);
+    const MP ex = cta_scan<K3_TOP>(P.chunk_f[threadIdx.x], smem, &total);
+    P.chunk_ex[threadIdx.x] = ex;
+    if (threadIdx.x == 0) *P.total = total;
+}
+
+__global__ void __launch_bounds__(K3_TOP_CTA) k3_top_apply(const K3Params P)
+{
+    const int c = blockIdx.x * K3_TOP_CTA + threadIdx.x;
+    const long long chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
+    const long long lo = (long long)c * chunk;
+    const long long hi = lo + chunk < P.ntiles ? lo + chunk : P.ntiles;
+    constexpr int U = K3_TOP_U;
+    MP ex = P.chunk_ex[c];
     for (long long t = lo; t < hi; t += U) {
         MP v[U];
 #pragma unroll
@@ -335,7 +362,6 @@ __global__ void __launch_bounds__(K3_TOP) k3_top(const K3Params P)
             }
         }
     }
-    if (threadIdx.x == 0) *P.total = total;
 }
 
 // Time-in-state on the scan path.  With one server and FIFO, N(t) >= m while t lies in the (m-1)-th
@@ -554,20 +580,26 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : ((MODE == 2 && !W
     }
 }
 
-__global__ void k3_final(const double *partial, const double *level_partial, int grid, double *stats)
+__global__ void __launch_bounds__(32) k3_final(const double *partial, const double *level_partial, int grid, double *stats)
 {
-    const int i = threadIdx.x;
+    // one warp per statistic, fixed association: lane l adds the partials of CTAs l, l + 32, ... in order, then the
+    // lanes are folded by the shuffle tree (all loads of a lane are independent: one memory round trip)
+    const int i = blockIdx.x, lane = threadIdx.x;
+    const double *src = nullptr;
+    int stride = 0;
     if (i < K3_NSTAT) {
-        double v = 0.0;
-        for (int b = 0; b < grid; ++b) v += partial[(long long)b * K3_NSTAT + i];
-        stats[i] = v;
-    } else if (i < K3_NSTAT + K3_PBL + 1) {
-        const int m = i - K3_NSTAT;
-        double v = 0.0;
-        if (level_partial)
-            for (int b = 0; b < grid; ++b) v += level_partial[(long long)b * (K3_PBL + 1) + m];
-        stats[i] = v;
+        src = partial + i;
+        stride = K3_NSTAT;
+    } else if (level_partial) {
+        src = level_partial + (i - K3_NSTAT);
+        stride = K3_PBL + 1;
     }
+    double v = 0.0;
+    if (src)
+        for (int b = lane; b < grid; b += 32) v += src[(long long)b * stride];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) stats[i] = v;
 }
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
@@ -587,7 +619,9 @@ cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
 
 cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st)
 {
-    k3_top<<<1, K3_TOP, 0, st>>>(P);
+    k3_top_fold<<<K3_TOP / K3_TOP_CTA, K3_TOP_CTA, 0, st>>>(P);
+    k3_top_scan<<<1, K3_TOP, 0, st>>>(P);
+    k3_top_apply<<<K3_TOP / K3_TOP_CTA, K3_TOP_CTA, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -621,7 +655,7 @@ size_t k3_walk_smem(bool replay, bool want_p)
 cudaError_t k3_launch_final(const double *partial, const double *level_partial, int grid, double *stats,
                             cudaStream_t st)
 {
-    k3_final<<<1, 64, 0, st>>>(partial, level_partial, grid, stats);
+    k3_final<<<K3_NSTAT + K3_PBL + 1, 32, 0, st>>>(partial, level_partial, grid, stats);
     return cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@ struct K3Params {
     MP *tile_sum;       // [ntiles]
     MP *tile_ex;        // [ntiles]
     MP *total;          // [1]
+    MP *chunk_f;        // [K3_TOP] folds of the 1024 chunks of tile summaries
+    MP *chunk_ex;       // [K3_TOP] their exclusive prefixes
     double w_in;
     double *partial;    // [grid][K3_NSTAT]
     double *tail;       // [2]: W[n-1] + x[n-1] (before clamping), W[n-1] + S[n-1]

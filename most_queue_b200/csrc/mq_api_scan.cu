@@ -64,14 +64,16 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
 
     // scratch: tile_sum, tile_ex, total, tail, partial, stats
-    const size_t bytes = sizeof(MP) * (2 * (size_t)P.ntiles + 1) +
+    const size_t bytes = sizeof(MP) * (2 * (size_t)P.ntiles + 1 + 2 * K3_TOP) +
                          sizeof(double) * (2 + (size_t)run.grid_walk * (K3_NSTAT + K3_NLEVEL) + K3_NSTAT + K3_NLEVEL);
     if (int rc = ensure(ctx->rec, bytes)) return rc;
     char *base = (char *)ctx->rec.p;
     P.tile_sum = (MP *)base;
     P.tile_ex = P.tile_sum + P.ntiles;
     P.total = P.tile_ex + P.ntiles;
-    P.tail = (double *)(P.total + 1);
+    P.chunk_f = P.total + 1;
+    P.chunk_ex = P.chunk_f + K3_TOP;
+    P.tail = (double *)(P.chunk_ex + K3_TOP);
     P.partial = P.tail + 2;
     P.level_partial = want_p ? P.partial + (size_t)run.grid_walk * K3_NSTAT + K3_NSTAT + K3_NLEVEL : nullptr;
     P.n_ahead = cfg->jobs_ahead > 0 ? cfg->jobs_ahead : 0;
@@ -100,7 +102,7 @@ int scan_summary(mq_ctx *ctx, ScanRun &run)
 {
     CU(k3_launch_summary(run.P, run.grid_sum, ctx->stream));
     CU(k3_launch_top(run.P, ctx->stream));
-    ctx->launches += 2;
+    ctx->launches += 4;
     return MQ_OK;
 }
 
