@@ -552,6 +552,10 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : ((MODE == 2 && !W
                 flush_levels();
             }
             __syncthreads();  // every level walk has read the staged gaps before the next tile overwrites them
+        } else if (MODE == 2) {
+            // the staged body reads its operands from shared memory DURING the walk (the register form has read
+            // them before the scan's barriers): every warp must be done before the next tile is staged
+            __syncthreads();
         }
     }
     if (WANT_P) {

@@ -120,3 +120,36 @@ def test_generator_chain_p_matches_k2():
     ev = qs.run(N)
     np.testing.assert_allclose(res.p[:12], ev.p[:12], rtol=0, atol=3e-3)
     assert abs(res.p[0] - 0.3) < 0.01
+
+
+def test_generator_chain_sums_equal_the_sums_of_the_variates():
+    """The chain's sums of gaps and services are the fp64 sums of the very fp32 variates the generator spec defines
+    (here drawn a second time through the debug entry point), with and without the draw stash, in one range or two:
+    catches a walk that reads a tile's operands while another warp already stages the next tile."""
+    import os
+
+    from most_queue_b200 import _lib as L
+
+    ctx = L.default_context()
+    src, srv = L.make_dist("Gamma", GAMMA), L.make_dist("Pa", PARETO)
+    N, seed = 30_000_000, 3
+    S = ctx.variates(srv, seed, 0, 1, N).astype(np.float64)
+    A = ctx.variates(src, seed, 0, 0, N).astype(np.float64)
+    one, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=seed, last_range=False)
+    os.environ["MQ_SCAN_NO_STASH"] = "1"
+    try:
+        two, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=seed, last_range=False)
+    finally:
+        del os.environ["MQ_SCAN_NO_STASH"]
+    h = N // 2 + 7
+    p1, _ = ctx.scan_apply(h, 0.0, src=src, srv=srv, seed=seed, last_range=False)
+    p2, _ = ctx.scan_apply(N - h, p1[L.S_WOUT], job0=h, src=src, srv=srv, seed=seed, last_range=False)
+    for st in (one, two):
+        np.testing.assert_allclose(st[L.S_SUMS], S.sum(), rtol=1e-12)
+        np.testing.assert_allclose(st[L.S_SUMA], A.sum(), rtol=1e-12)
+    np.testing.assert_allclose(p1[L.S_SUMS] + p2[L.S_SUMS], S.sum(), rtol=1e-12)
+    np.testing.assert_allclose(p1[L.S_SUMA], A[:h].sum(), rtol=1e-12)
+    # the waits are functions of the same draws: both forms and both cuts agree to rounding
+    for row in (L.S_W, L.S_W + 1, L.S_V, L.S_V + 1):
+        np.testing.assert_allclose(two[row], one[row], rtol=1e-11)
+        np.testing.assert_allclose(p1[row] + p2[row], one[row], rtol=1e-10)
