@@ -185,3 +185,87 @@ def test_tandem_generator_tiers_agree():
     finally:
         del os.environ["MQ_K6_V1"]
     assert np.array_equal(rec1, rec2)
+
+
+def _both_kernels(env, call):
+    """The same generator-tier run through the predicated kernel and (env=1) through the general kernel."""
+    import os
+
+    new = call()
+    os.environ[env] = "1"
+    try:
+        old = call()
+    finally:
+        del os.environ[env]
+    return new, old
+
+
+def test_priority_generator_tiers_agree():
+    """Draw-ahead rings, RED-accumulated sums and the trip body of k4v2 against k4_prio on the same Philox streams:
+    every per-replication row is bit-equal (4 disciplines, Gamma and H2 service, finite buffer)."""
+    from most_queue_b200 import _lib as L
+    from most_queue_b200.random.distributions import GammaDistribution, H2Distribution
+
+    ctx = L.default_context()
+    g = [GammaDistribution.get_params_by_mean_and_cv(1.0 + 0.5 * k, 1.2) for k in range(3)]
+    h = H2Distribution.get_params_by_mean_and_cv(1.4, 1.5)
+    for prty, buffer in (("NP", None), ("PR", None), ("RS", 12), ("RW", None)):
+        src = [L.make_dist("M", 0.35), L.make_dist("M", 0.3), L.make_dist("E", {"r": 2, "mu": 0.5})]
+        srv = [L.make_dist("Gamma", g[0]), L.make_dist("H", h), L.make_dist("Gamma", g[2])]
+        new, old = _both_kernels("MQ_K4_V1", lambda: ctx.sim_prio(3, 3, prty, buffer, src, srv, 4000, 2048, 5, 17,
+                                                                   p_bins=16, per_replication=True))
+        # k4v2's generator tier reports sums / count in the running-mean rows (DESIGN 4, K4): equal to rounding only
+        rows = L.prio_rows(16)
+        soft = {L.PG_ROWS + k * rows + r for k in range(3) for r in range(L.PF_WRUN, L.PF_VRUN + 4)}
+        bad = set(np.nonzero((new[1] != old[1]).any(axis=1))[0].tolist())
+        assert bad <= soft, (prty, sorted(bad - soft))
+        np.testing.assert_allclose(new[1], old[1], rtol=1e-11, atol=0)
+        np.testing.assert_allclose(new[0], old[0], rtol=1e-11, atol=0)
+
+
+def test_network_generator_tiers_agree():
+    from most_queue_b200 import _lib as L
+    from most_queue_b200.random.distributions import GammaDistribution, H2Distribution
+
+    ctx = L.default_context()
+    Rm = [[1, 0, 0, 0, 0, 0], [0, 0.4, 0.6, 0, 0, 0], [0, 0, 0.2, 0.4, 0.4, 0], [0, 0, 0, 0, 1, 0],
+          [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 0, 1]]
+    ch = [3, 2, 3, 4, 3]
+    srv = [L.make_dist("H", H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2)) if i % 2 == 0 else
+           L.make_dist("Gamma", GammaDistribution.get_params_by_mean_and_cv(0.7 * c, 0.8)) for i, c in enumerate(ch)]
+    new, old = _both_kernels("MQ_K5_V1", lambda: ctx.sim_net(Rm, ch, L.make_dist("M", 1.0), srv, 1500, 2048, 3, 23,
+                                                              per_replication=True))
+    # the predicated kernel does not track the reference's running means in the generator tier (the aggregate is formed
+    # from the power sums): every other per-replication row is bit-equal
+    soft = set(range(L.NG_VRUN, L.NG_VRUN + 3)) | set(range(L.NG_WRUN, L.NG_WRUN + 3))
+    for i in range(5):
+        b = L.NG_ROWS + i * L.NN_ROWS
+        soft |= set(range(b + L.NN_VRUN, b + L.NN_VRUN + 4)) | set(range(b + L.NN_WRUN, b + L.NN_WRUN + 4))
+    bad = set(np.nonzero((new[1] != old[1]).any(axis=1))[0].tolist())
+    assert bad <= soft, sorted(bad - soft)
+    np.testing.assert_allclose(new[0], old[0], rtol=1e-11, atol=0)
+
+
+def test_priority_network_generator_tiers_agree():
+    from most_queue_b200 import _lib as L
+    from most_queue_b200.random.distributions import H2Distribution
+
+    ctx = L.default_context()
+    R0 = [[1, 0, 0, 0], [0, 0, 0.7, 0.3], [0, 0, 0, 1], [0, 0, 0, 1]]
+    R1 = [[0.5, 0.5, 0, 0], [0, 0, 0, 1], [0.2, 0, 0.3, 0.5], [0, 0, 0, 1]]
+    srv = [[L.make_dist("H", H2Distribution.get_params_by_mean_and_cv(0.5 + 0.2 * j + 0.1 * i, 1.3)) for j in range(2)]
+           for i in range(3)]
+    new, old = _both_kernels("MQ_K7_V1", lambda: ctx.sim_prionet(
+        [R0, R1], [2, 1, 2], ["PR", "NP", "RS"], [[0, 1], [1, 0], [0, 1]],
+        [L.make_dist("M", 0.6), L.make_dist("M", 0.7)], srv, 1500, 2048, 2, 11, per_replication=True))
+    m, K = 3, 2
+    soft = set()
+    for k in range(K):
+        b = L.PN_G_ROWS + k * L.PNC_ROWS
+        soft |= set(range(b + L.PNC_VRUN, b + L.PNC_VRUN + 3)) | set(range(b + L.PNC_WRUN, b + L.PNC_WRUN + 3))
+    for nk in range(m * K):
+        b = L.PN_G_ROWS + K * L.PNC_ROWS + nk * L.PNN_ROWS
+        soft |= set(range(b + L.PNN_VRUN, b + L.PNN_VRUN + 4)) | set(range(b + L.PNN_WRUN, b + L.PNN_WRUN + 4))
+    bad = set(np.nonzero((new[1] != old[1]).any(axis=1))[0].tolist())
+    assert bad <= soft, sorted(bad - soft)
+    np.testing.assert_allclose(new[0], old[0], rtol=1e-11, atol=0)
