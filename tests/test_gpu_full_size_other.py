@@ -134,3 +134,49 @@ def test_cfg5_network_full_size(L):
         assert abs(rho - 0.7 * e[i]) < 5e-3
     v1 = (rec[L.NG_VSUM] / rec[L.NG_SERVED]).mean()
     assert 8.0 < v1 < 12.0
+
+
+def test_cfg2r_replay_full_size(L):
+    """65 536 replications x 4 096 draws per stream (2 x 2 GiB of fp64 resident in HBM); the moments,
+    counters and time-in-state sums of a 1 024-replication subset are compared with the oracle bit for bit, the rest
+    through conservation, the tiling of the clock and Little's law as a sample-path bound."""
+    import torch
+
+    from oracle import oracle
+
+    ctx = L.default_context()
+    reps, rows, PB, c = 65536, 4096, 64, 8
+    h2 = dict(p1=0.447586, mu1=0.0950716, mu2=0.619214)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = -torch.log(1.0 - torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64))
+    br = torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64) < h2["p1"]
+    S = -torch.log(1.0 - torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64))
+    S = S / torch.where(br, h2["mu1"], h2["mu2"])
+    del br
+    n = int(rows * 0.9)
+    rec = torch.empty((L.replay_rows(PB), reps), device="cuda", dtype=torch.float64)
+    torch.cuda.synchronize()
+    agg = ctx.replay_fifo_device(c, None, A.data_ptr(), S.data_ptr(), rows, rows, reps, n, rec.data_ptr(), p_bins=PB)
+    r = rec.cpu().numpy()
+    ex = L.rec_rows(PB)
+    assert agg[L.A_SERVED] == reps * n
+    assert np.all(r[L.F_FLAGS] == 0) and np.all(r[L.F_SERVED] == n) and np.all(r[L.F_DROPPED] == 0)
+    assert np.all(r[L.F_ARRIVED] == r[L.F_TAKED] + r[ex + L.RF_QUEUED])
+    assert np.all(r[L.F_TAKED] == r[L.F_SERVED] + r[ex + L.RF_INSYS] - r[ex + L.RF_QUEUED])
+    tot = r[L.F_P:L.F_P + PB].sum(axis=0) + r[L.F_POVER]
+    np.testing.assert_allclose(tot, r[L.F_TTEK], rtol=1e-9)
+    exact = r[L.F_POVER] == 0
+    assert exact.mean() > 0.99
+    area = (np.arange(PB)[:, None] * r[L.F_P:L.F_P + PB]).sum(axis=0)
+    assert np.all(area[exact] >= r[L.F_V][exact] * (1 - 1e-9))
+    # the bitwise subset: every 64th replication
+    sub = np.arange(0, reps, 64)
+    Ah, Sh = A[:, sub].cpu().numpy(), S[:, sub].cpu().numpy()
+    for k, rep in enumerate(sub):
+        o = oracle.fifo_replay(c, None, Ah[:, k].copy(), Sh[:, k].copy(), n, p_bins=PB)
+        assert (o.arrived, o.taked, o.served) == (int(r[L.F_ARRIVED, rep]), int(r[L.F_TAKED, rep]), int(r[L.F_SERVED, rep]))
+        assert o.ttek == r[L.F_TTEK, rep]
+        assert np.array_equal(o.w_sum, r[L.F_W:L.F_W + 4, rep]) and np.array_equal(o.v_sum, r[L.F_V:L.F_V + 4, rep])
+        assert np.array_equal(o.w, r[ex + L.RF_WRUN:ex + L.RF_WRUN + 4, rep])
+        assert np.array_equal(o.v, r[ex + L.RF_VRUN:ex + L.RF_VRUN + 4, rep])
+        assert np.array_equal(o.p_time, r[L.F_P:L.F_P + PB, rep]) and o.p_over == r[L.F_POVER, rep]
