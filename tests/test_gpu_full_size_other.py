@@ -180,3 +180,32 @@ def test_cfg2r_replay_full_size(L):
         assert np.array_equal(o.w, r[ex + L.RF_WRUN:ex + L.RF_WRUN + 4, rep])
         assert np.array_equal(o.v, r[ex + L.RF_VRUN:ex + L.RF_VRUN + 4, rep])
         assert np.array_equal(o.p_time, r[L.F_P:L.F_P + PB, rep]) and o.p_over == r[L.F_POVER, rep]
+
+
+def test_chain_levels_tile_the_sojourns_at_scale(L):
+    """Time-in-state on the scan path (MQ_SCAN_WANT_P) for 3e8 jobs, generator form with the draw stash: the levels
+    T[N >= m] summed over m are the area under N(t), i.e. the sum of the sojourns of the counted jobs; with and
+    without the stash the levels agree."""
+    import os
+
+    from most_queue_b200.random.distributions import GammaDistribution, ParetoDistribution
+
+    ctx = L.default_context()
+    gam = GammaDistribution.get_params_by_mean_and_cv(1.0, 0.56)
+    par = ParetoDistribution.get_params_by_mean_and_cv(0.7, 1.2)
+    src, srv = L.make_dist("Gamma", gam), L.make_dist("Pa", par)
+    N = 300_000_000
+    st, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=5, last_range=False, want_p=True)
+    lev = st[L.S_LEVELS:L.S_LEVELS + L.SCAN_NLEVEL]
+    assert np.all(lev[:-1] >= 0) and np.all(np.diff(lev[:32]) <= 1e-6 * lev[0])   # T[N >= m] decreases in m
+    np.testing.assert_allclose(lev.sum(), st[L.S_V], rtol=2e-6)
+    # P(N >= 1) = utilisation
+    ttek = st[L.S_SUMA] + st[L.S_TAILV]
+    assert abs(lev[0] / ttek - 0.7) < 5e-4
+    os.environ["MQ_SCAN_NO_STASH"] = "1"
+    try:
+        st2, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=5, last_range=False, want_p=True)
+    finally:
+        del os.environ["MQ_SCAN_NO_STASH"]
+    np.testing.assert_allclose(st2[L.S_LEVELS:L.S_LEVELS + L.SCAN_NLEVEL], lev, rtol=1e-6, atol=1e-6 * lev[0])
+    np.testing.assert_allclose(st2[L.S_V], st[L.S_V], rtol=1e-11)
