@@ -1,0 +1,166 @@
+"""Randomised soak of the GENERATOR tier: the predicated kernels (k4v2, k5v2, k6v2, k7v2: draw-ahead rings, RED sums,
+pending states) against the general kernels (MQ_K*_V1=1) on the same Philox streams, random configurations and random
+laws of every kind; every per-replication row both kernels track must be bit-equal.
+
+    python tools/soak_gen.py [seconds]
+
+Exits non-zero on the first mismatch and prints the failing configuration.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from most_queue_b200 import _lib as L  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(int(os.environ.get("SOAK_SEED", "777")))
+t_end = time.time() + budget
+ctx = L.default_context()
+counts = {}
+
+
+def law(mean):
+    """A random law of the given mean."""
+    k = int(rng.integers(0, 8))
+    if k == 0:
+        return L.make_dist("M", 1.0 / mean)
+    if k == 1:
+        p1 = rng.uniform(0.2, 0.8)
+        m1 = rng.uniform(0.3, 0.9) * mean
+        m2 = (mean - p1 * m1) / (1 - p1)
+        return L.make_dist("H", {"p1": p1, "mu1": 1 / m1, "mu2": 1 / m2})
+    if k == 2:
+        r = int(rng.integers(1, 7))
+        return L.make_dist("E", {"r": r, "mu": r / mean})
+    if k == 3:
+        alpha = rng.uniform(0.4, 4.0)
+        return L.make_dist("Gamma", {"mu": alpha / mean, "alpha": alpha})
+    if k == 4:
+        alpha = rng.uniform(2.2, 4.0)
+        return L.make_dist("Pa", {"alpha": alpha, "K": mean * (alpha - 1) / alpha})
+    if k == 5:
+        return L.make_dist("D", mean)
+    if k == 6:
+        return L.make_dist("Uniform", {"mean": mean, "half_interval": mean * rng.uniform(0.1, 0.9)})
+    p1 = rng.uniform(0.2, 0.8)
+    return L.make_dist("C", {"p1": p1, "mu1": 2.0 / mean, "mu2": 2.0 * p1 / mean})
+
+
+def both(env, call):
+    new = call()
+    os.environ[env] = "1"
+    try:
+        old = call()
+    finally:
+        del os.environ[env]
+    return new, old
+
+
+def check(kind, cfg, new, old, soft):
+    bad = set(np.nonzero((new[1] != old[1]).any(axis=1))[0].tolist())
+    if not bad <= soft:
+        print("MISMATCH", kind, cfg, "rows", sorted(bad - soft))
+        sys.exit(1)
+    if not np.allclose(new[0], old[0], rtol=1e-10, atol=0):
+        print("MISMATCH (aggregate)", kind, cfg)
+        sys.exit(1)
+
+
+def prio():
+    c, K = int(rng.integers(1, 9)), int(rng.integers(1, 5))
+    prty = ["NP", "PR", "RS", "RW"][int(rng.integers(0, 4))]
+    buffer = None if rng.random() < 0.6 else int(rng.integers(1, 8))
+    rho = rng.uniform(0.4, 1.05)
+    src = [law(K / (rho * c) * rng.uniform(0.7, 1.4)) for _ in range(K)]
+    srv = [law(rng.uniform(0.6, 1.4)) for _ in range(K)]
+    n, reps, pb = int(rng.integers(200, 1500)), int(rng.integers(33, 400)), 12
+    cfg = dict(c=c, K=K, prty=prty, buffer=buffer, n=n, reps=reps, src=[d.kind for d in src], srv=[d.kind for d in srv])
+    new, old = both("MQ_K4_V1", lambda: ctx.sim_prio(c, K, prty, buffer, src, srv, n, reps, 3, 99,
+                                                     p_bins=pb, queue_cap=4096, per_replication=True))
+    rows = L.prio_rows(pb)
+    soft = {L.PG_ROWS + k * rows + r for k in range(K) for r in range(L.PF_WRUN, L.PF_VRUN + 4)}
+    check("prio", cfg, new, old, soft)
+
+
+def net():
+    m = int(rng.integers(1, 8))
+    ch = [int(rng.integers(1, 4)) for _ in range(m)]
+    while sum(ch) > 16:
+        ch[int(rng.integers(0, m))] = 1
+    Rm = np.zeros((m + 1, m + 1))
+    Rm[0, :m] = rng.dirichlet(np.ones(m))
+    for i in range(m):
+        row = rng.dirichlet(np.ones(m + 1)) * np.r_[np.full(m, 0.5), 1.0]
+        row[m] += 1.0 - row.sum()
+        Rm[i + 1] = row
+    srv = [law(0.35 * c) for c in ch]
+    n, reps = int(rng.integers(100, 800)), int(rng.integers(33, 300))
+    cfg = dict(m=m, ch=ch, n=n, reps=reps, srv=[d.kind for d in srv])
+    src = law(1.0)
+    new, old = both("MQ_K5_V1", lambda: ctx.sim_net(Rm, ch, src, srv, n, reps, 1, 5, queue_cap=4096, per_replication=True))
+    soft = set(range(L.NG_VRUN, L.NG_VRUN + 3)) | set(range(L.NG_WRUN, L.NG_WRUN + 3))
+    for i in range(m):
+        b = L.NG_ROWS + i * L.NN_ROWS
+        soft |= set(range(b + L.NN_VRUN, b + L.NN_VRUN + 4)) | set(range(b + L.NN_WRUN, b + L.NN_WRUN + 4))
+    check("net", cfg, new, old, soft)
+
+
+def tandem():
+    m = int(rng.integers(1, 17))
+    cap = [None if rng.random() < 0.2 else int(rng.integers(1, 5)) for _ in range(m)]
+    srv = [law(rng.uniform(0.5, 1.1)) for _ in range(m)]
+    n, reps = int(rng.integers(200, 1500)), int(rng.integers(33, 300))
+    src = law(rng.uniform(0.7, 1.3))
+    cfg = dict(cap=cap, n=n, reps=reps, srv=[d.kind for d in srv], src=src.kind)
+    new, old = both("MQ_K6_V1", lambda: ctx.sim_tandem(cap, src, srv, n, 0.1, reps, 2, 8, per_replication=True))
+    check("tandem", cfg, new, old, set())
+
+
+def prionet():
+    m, K = int(rng.integers(1, 6)), int(rng.integers(1, 5))
+    ch = [int(rng.integers(1, 4)) for _ in range(m)]
+    while sum(ch) > 16:
+        ch[int(rng.integers(0, m))] = 1
+    prty = [["NP", "PR", "RS", "RW"][int(rng.integers(0, 4))] for _ in range(m)]
+    npr = [[int(x) for x in rng.permutation(K)] for _ in range(m)]
+    Rk = []
+    for k in range(K):
+        Rm = np.zeros((m + 1, m + 1))
+        Rm[0, :m] = rng.dirichlet(np.ones(m))
+        for i in range(m):
+            row = rng.dirichlet(np.ones(m + 1)) * np.r_[np.full(m, 0.5), 1.0]
+            row[m] += 1.0 - row.sum()
+            Rm[i + 1] = row
+        Rk.append(Rm)
+    src = [law(1.3 * K) for _ in range(K)]
+    srv = [[law(0.3 * ch[i]) for _ in range(K)] for i in range(m)]
+    n, reps = int(rng.integers(100, 600)), int(rng.integers(33, 200))
+    cfg = dict(m=m, K=K, ch=ch, prty=prty, npr=npr, n=n, reps=reps)
+    new, old = both("MQ_K7_V1", lambda: ctx.sim_prionet(Rk, ch, prty, npr, src, srv, n, reps, 0, 4, queue_cap=2048,
+                                                        per_replication=True))
+    soft = set()
+    for k in range(K):
+        b = L.PN_G_ROWS + k * L.PNC_ROWS
+        soft |= set(range(b + L.PNC_VRUN, b + L.PNC_VRUN + 3)) | set(range(b + L.PNC_WRUN, b + L.PNC_WRUN + 3))
+    for nk in range(m * K):
+        b = L.PN_G_ROWS + K * L.PNC_ROWS + nk * L.PNN_ROWS
+        soft |= set(range(b + L.PNN_VRUN, b + L.PNN_VRUN + 4)) | set(range(b + L.PNN_WRUN, b + L.PNN_WRUN + 4))
+    check("prionet", cfg, new, old, soft)
+
+
+KINDS = [prio, net, tandem, prionet]
+while time.time() < t_end:
+    for f in KINDS:
+        try:
+            f()
+        except L.MqError as e:
+            # an overflowing waiting line is flagged by both kernels alike; anything else is a failure
+            if e.code != L.MQ_E_OVERFLOW:
+                raise
+            counts["overflow"] = counts.get("overflow", 0) + 1
+            continue
+        counts[f.__name__] = counts.get(f.__name__, 0) + 1
+print("soak_gen ok:", counts)
