@@ -1,6 +1,6 @@
 """Throughput of every kernel of the hot path on the BASELINE.json configurations (one GPU).
 
-    python tools/measure_kernels.py [--quick] > gpurun_out/kernels.json
+    python tests/soak/measure_kernels.py [--quick] > gpurun_out/kernels.json
 
 Device time comes from the library's CUDA events (mq_last_timing).  Prints one JSON object.
 """

@@ -1,6 +1,6 @@
 """Randomised soak of the replay tier: random configurations of every simulator, GPU result vs the CPU oracle, bit for bit.
 
-    python tools/soak.py [seconds]
+    python tests/soak/soak.py [seconds]
 
 Test infrastructure (uses oracle/).  Exits non-zero on the first mismatch and prints the failing configuration.
 """
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0

@@ -2,7 +2,7 @@
 pending states) against the general kernels (MQ_K*_V1=1) on the same Philox streams, random configurations and random
 laws of every kind; every per-replication row both kernels track must be bit-equal.
 
-    python tools/soak_gen.py [seconds]
+    python tests/soak/soak_gen.py [seconds]
 
 Exits non-zero on the first mismatch and prints the failing configuration.
 """
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from most_queue_b200 import _lib as L  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
