@@ -24,16 +24,21 @@
 
 namespace mq {
 
-__device__ __forceinline__ void k9_sample(double *run, double *sum, double x, long long count)
+// The four moment sets (wait, sojourn of all / served / broken jobs: 4 running means + 4 power sums each) live in shared
+// memory [set][word][lane], so that one sample site can serve whichever set a lane's event needs.
+enum { K9_W = 0, K9_V = 1, K9_VS = 2, K9_VB = 3 };
+
+__device__ __forceinline__ void k9_sample(double *acc, int set, double x, long long count)
 {
     // refresh_moments_stat (stats_update.py:6-22) + plain power sums
+    double *run = acc + set * (8 * K9_BLOCK), *sum = run + 4 * K9_BLOCK;
     const double inv_count = __drcp_rn((double)count);
     const double one_minus = __dsub_rn(1.0, inv_count);
     double power = x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        run[i] = __dadd_rn(__dmul_rn(run[i], one_minus), __dmul_rn(power, inv_count));
-        sum[i] = __dadd_rn(sum[i], power);
+        run[i * K9_BLOCK] = __dadd_rn(__dmul_rn(run[i * K9_BLOCK], one_minus), __dmul_rn(power, inv_count));
+        sum[i * K9_BLOCK] = __dadd_rn(sum[i * K9_BLOCK], power);
         power = __dmul_rn(power, x);
     }
 }
@@ -47,6 +52,8 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
     const long long R = P.reps;
     const int c = P.c;
     const DistF law_pos = P.positive, law_neg = P.negative, law_srv = P.service;
+    __shared__ double k9_acc[4 * 8 * K9_BLOCK];
+    double *acc = k9_acc + threadIdx.x;
 
     for (long long rl = gtid; rl < R; rl += P.lanes) {
         const uint32_t rep = P.rep0 + (uint32_t)rl;
@@ -83,8 +90,7 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
         long long pos_arrived = 0, neg_arrived = 0, taked = 0, served = 0, broken = 0, total = 0, dropped = 0,
                   in_sys = 0;
         int free_channels = c, qhead = 0, qsize = 0;
-        double w_run[4] = {0, 0, 0, 0}, v_run[4] = {0, 0, 0, 0}, vs_run[4] = {0, 0, 0, 0}, vb_run[4] = {0, 0, 0, 0};
-        double w_sum[4] = {0, 0, 0, 0}, v_sum[4] = {0, 0, 0, 0}, vs_sum[4] = {0, 0, 0, 0}, vb_sum[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 32; ++i) acc[i * K9_BLOCK] = 0.0;
 
         auto p_add = [&](double t_new) {  // _update_state_probs base.py:327-340
             const double dt = __dsub_rn(t_new, ttek);
@@ -97,8 +103,8 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
             broken++;
             total++;
             const double sj = __dsub_rn(ttek, a);
-            k9_sample(v_run, v_sum, sj, total);
-            k9_sample(vb_run, vb_sum, sj, broken);
+            k9_sample(acc, K9_V, sj, total);
+            k9_sample(acc, K9_VB, sj, broken);
         };
         auto q_pop = [&]() -> double {
             const double a = Q[(long long)qhead * P.lanes];
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
             const double a = q_pop();
             taked++;
             const double w = __dadd_rn(0.0, __dsub_rn(ttek, a));
-            k9_sample(w_run, w_sum, w, taked);
+            k9_sample(acc, K9_W, w, taked);
             arr[ch] = a;
             wait[ch] = w;
             tot[ch] = draw(MQ_NS_SERVICES);
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
         auto restart = [&](int ch, double a, double w, double rem, double t) {
             taked++;
             const double wt = __dadd_rn(w, __dsub_rn(ttek, ttek));
-            k9_sample(w_run, w_sum, wt, taked);
+            k9_sample(acc, K9_W, wt, taked);
             arr[ch] = a;
             wait[ch] = wt;
             if (P.scenario == MQ_NEG_REQUEUE) {
@@ -156,41 +162,7 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
             }
             if (midx >= 0 && mt < et) ev = 2;
 
-            if (ev == 0) {
-                // positive_arrival negative.py:225-241
-                pos_arrived++;
-                p_add(pos_time);
-                in_sys++;
-                ttek = pos_time;
-                pos_time = __dadd_rn(ttek, draw(MQ_NS_POSITIVES));
-                if (free_channels == 0) {
-                    // send_task_to_queue base.py:186-212
-                    if (P.buffer < 0 || qsize < P.buffer) {
-                        if (qsize >= P.qcap) {
-                            status = MQ_E_OVERFLOW;
-                        } else {
-                            int slot = qhead + qsize;
-                            if (slot >= P.qcap) slot -= P.qcap;
-                            Q[(long long)slot * P.lanes] = ttek;
-                            qsize++;
-                        }
-                    } else {
-                        dropped++;
-                        in_sys--;
-                    }
-                } else {
-                    // send_task_to_channel base.py:155-184, lowest free channel
-                    const int j = __ffs(~busy) - 1;
-                    taked++;
-                    k9_sample(w_run, w_sum, 0.0, taked);
-                    arr[j] = ttek;
-                    wait[j] = 0.0;
-                    tot[j] = draw(MQ_NS_SERVICES);
-                    end[j] = __dadd_rn(ttek, tot[j]);
-                    busy |= 1u << j;
-                    free_channels--;
-                }
-            } else if (ev == 1) {
+            if (ev == 1) {
                 // negative_arrival negative.py:243-383
                 neg_arrived++;
                 p_add(neg_time);
@@ -239,10 +211,10 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
                             taked++;
                             total++;
                             broken++;
-                            k9_sample(w_run, w_sum, __dadd_rn(0.0, __dsub_rn(ttek, a)), taked);
+                            k9_sample(acc, K9_W, __dadd_rn(0.0, __dsub_rn(ttek, a)), taked);
                             const double sj = __dsub_rn(ttek, a);
-                            k9_sample(v_run, v_sum, sj, total);
-                            k9_sample(vb_run, vb_sum, sj, broken);
+                            k9_sample(acc, K9_V, sj, total);
+                            k9_sample(acc, K9_VB, sj, broken);
                         }
                     } else if (busy != 0) {
                         const int nb = __popc(busy);
@@ -266,21 +238,68 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
                     }
                 }
             } else {
-                // serving negative.py:425-450
-                const double time_to_end = end[midx];
-                const double a = arr[midx];
-                end[midx] = 1e10;
-                busy &= ~(1u << midx);
-                p_add(time_to_end);
-                ttek = time_to_end;
-                free_channels++;
-                served++;
-                total++;
-                const double sj = __dsub_rn(ttek, a);
-                k9_sample(v_run, v_sum, sj, total);
-                k9_sample(vs_run, vs_sum, sj, served);
-                in_sys--;
-                if (qsize != 0) head_to_channel(midx);
+                // positive_arrival (negative.py:225-241) and serving (negative.py:425-450) through ONE body: the clock and
+                // time-in-state update, at most one "a job starts on a server" site (the arriving job on the lowest free
+                // server, or the head of the line on the server that just finished) with its wait sample and its
+                // service draw, and the sojourn samples of a departure
+                const bool is_arr = ev == 0;
+                const int jd = is_arr ? 0 : midx;
+                const double te = is_arr ? pos_time : end[jd];
+                const double a_dep = arr[jd];
+                if (!is_arr) {
+                    end[jd] = 1e10;
+                    busy &= ~(1u << jd);
+                }
+                p_add(te);
+                ttek = te;
+                bool start;
+                int slot;
+                double a_job = ttek;
+                if (is_arr) {
+                    pos_arrived++;
+                    in_sys++;
+                    pos_time = __dadd_rn(ttek, draw(MQ_NS_POSITIVES));
+                    start = free_channels != 0;
+                    slot = __ffs(~busy) - 1;  // send_task_to_channel base.py:155-184, lowest free channel
+                    if (!start) {
+                        // send_task_to_queue base.py:186-212
+                        if (P.buffer < 0 || qsize < P.buffer) {
+                            if (qsize >= P.qcap) {
+                                status = MQ_E_OVERFLOW;
+                            } else {
+                                int qs = qhead + qsize;
+                                if (qs >= P.qcap) qs -= P.qcap;
+                                Q[(long long)qs * P.lanes] = ttek;
+                                qsize++;
+                            }
+                        } else {
+                            dropped++;
+                            in_sys--;
+                        }
+                    }
+                } else {
+                    free_channels++;
+                    served++;
+                    total++;
+                    in_sys--;
+                    start = qsize != 0;  // send_head_of_queue_to_channel base.py:288-310
+                    slot = jd;
+                    if (start) a_job = q_pop();
+                    const double sj = __dsub_rn(ttek, a_dep);
+                    k9_sample(acc, K9_V, sj, total);
+                    k9_sample(acc, K9_VS, sj, served);
+                }
+                if (start) {
+                    taked++;
+                    const double w = is_arr ? 0.0 : __dadd_rn(0.0, __dsub_rn(ttek, a_job));
+                    k9_sample(acc, K9_W, w, taked);
+                    arr[slot] = a_job;
+                    wait[slot] = w;
+                    tot[slot] = draw(MQ_NS_SERVICES);
+                    end[slot] = __dadd_rn(ttek, tot[slot]);
+                    busy |= 1u << slot;
+                    free_channels--;
+                }
             }
         }
 
@@ -297,14 +316,14 @@ __global__ void __launch_bounds__(K9_BLOCK) k9_negatives(const K9Params P)
         rec[(long long)MQ_N_QUEUED * R] = (double)qsize;
         rec[(long long)MQ_N_POVER * R] = p_over;
         for (int i = 0; i < 4; ++i) {
-            rec[(long long)(MQ_N_WSUM + i) * R] = w_sum[i];
-            rec[(long long)(MQ_N_VSUM + i) * R] = v_sum[i];
-            rec[(long long)(MQ_N_VSSUM + i) * R] = vs_sum[i];
-            rec[(long long)(MQ_N_VBSUM + i) * R] = vb_sum[i];
-            rec[(long long)(MQ_N_WRUN + i) * R] = w_run[i];
-            rec[(long long)(MQ_N_VRUN + i) * R] = v_run[i];
-            rec[(long long)(MQ_N_VSRUN + i) * R] = vs_run[i];
-            rec[(long long)(MQ_N_VBRUN + i) * R] = vb_run[i];
+            rec[(long long)(MQ_N_WSUM + i) * R] = acc[(K9_W * 8 + 4 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_VSUM + i) * R] = acc[(K9_V * 8 + 4 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_VSSUM + i) * R] = acc[(K9_VS * 8 + 4 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_VBSUM + i) * R] = acc[(K9_VB * 8 + 4 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_WRUN + i) * R] = acc[(K9_W * 8 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_VRUN + i) * R] = acc[(K9_V * 8 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_VSRUN + i) * R] = acc[(K9_VS * 8 + i) * K9_BLOCK];
+            rec[(long long)(MQ_N_VBRUN + i) * R] = acc[(K9_VB * 8 + i) * K9_BLOCK];
         }
         for (int s = 0; s < MQ_NEG_STREAMS; ++s) rec[(long long)(MQ_N_USED + s) * R] = (double)used[s];
     }
