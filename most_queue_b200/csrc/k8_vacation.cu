@@ -131,17 +131,6 @@ __global__ void __launch_bounds__(K8_BLOCK) k8_vacation(const K8Params P)
                 in_sys--;
             }
         };
-        auto to_channel = [&](bool is_warm) {  // send_task_to_channel base.py:155-184, lowest free channel
-            const int j = __ffs(~busy) - 1;
-            taked++;
-            k8_refresh(w_run, 4, 0.0, taked);
-            k8_add4(w_sum, 0.0);
-            arr[j] = ttek;
-            end[j] = __dadd_rn(ttek, draw(is_warm ? MQ_VS_WARM_SERVICES : MQ_VS_SERVICES));
-            busy |= 1u << j;
-            free_channels--;
-            if (free_channels == 0 && in_sys == c) start_busy = ttek;
-        };
         auto head_to_channel = [&](int ch) {  // send_head_of_queue_to_channel base.py:288-310
             const double a = Q[(long long)qhead * P.lanes];
             qsize--;
@@ -205,68 +194,98 @@ __global__ void __launch_bounds__(K8_BLOCK) k8_vacation(const K8Params P)
                 et = delay.end_time;
             }
 
-            if (ev == 0) {
-                // arrival() vacations.py:126-189
-                arrived++;
-                p_add(arrival_time);
-                in_sys++;
-                ttek = arrival_time;
-                arrival_time = __dadd_rn(ttek, draw(MQ_VS_ARRIVALS));
-                if (free_channels == 0) {
-                    to_queue();
-                } else if (cold_set && cold.is_start) {
-                    to_queue();
-                } else if (delay_set && delay.is_start) {
-                    delay.is_start = 0;
-                    delay.end_time = 1e16;
-                    delay.prob = __dadd_rn(delay.prob, __dsub_rn(ttek, delay.start_mom));
-                    to_channel(false);
-                } else if (warm_set) {
-                    if (warm.is_start) {
-                        to_queue();
-                    } else if (free_channels == c) {
-                        if (P.service_on_warm_up) {
-                            to_channel(true);
+            if (ev <= 1) {
+                // arrival() (vacations.py:126-189) and serving() (vacations.py:191-234) through ONE body: the clock and
+                // time-in-state update, then at most one "a job starts on a server" site -- the arriving job on the
+                // lowest free server (send_task_to_channel base.py:155-184) or the head of the line on the server that
+                // just finished (send_head_of_queue_to_channel base.py:288-310) -- with its wait sample and service draw
+                const bool is_arr = ev == 0;
+                const int jd = is_arr ? 0 : midx;
+                const double te = is_arr ? arrival_time : end[jd];
+                const double a_dep = arr[jd];
+                if (!is_arr) {
+                    end[jd] = 1e10;
+                    busy &= ~(1u << jd);
+                }
+                p_add(te);
+                ttek = te;
+                bool start = false, warm_srv = false;
+                int slot = jd;
+                double a_job = ttek;
+                if (is_arr) {
+                    arrived++;
+                    in_sys++;
+                    arrival_time = __dadd_rn(ttek, draw(MQ_VS_ARRIVALS));
+                    bool queue = false;
+                    if (free_channels == 0) {
+                        queue = true;
+                    } else if (cold_set && cold.is_start) {
+                        queue = true;
+                    } else if (delay_set && delay.is_start) {
+                        delay.is_start = 0;
+                        delay.end_time = 1e16;
+                        delay.prob = __dadd_rn(delay.prob, __dsub_rn(ttek, delay.start_mom));
+                        start = true;
+                    } else if (warm_set) {
+                        if (warm.is_start) {
+                            queue = true;
+                        } else if (free_channels == c) {
+                            if (P.service_on_warm_up) {
+                                start = true;
+                                warm_srv = true;
+                            } else {
+                                phase_start(warm, ttek, draw(MQ_VS_WARM));
+                                queue = true;
+                            }
                         } else {
-                            phase_start(warm, ttek, draw(MQ_VS_WARM));
-                            to_queue();
+                            start = true;
                         }
                     } else {
-                        to_channel(false);
+                        start = true;
                     }
+                    if (queue) to_queue();
+                    slot = __ffs(~busy) - 1;
                 } else {
-                    to_channel(false);
+                    served++;
+                    free_channels++;
+                    const double v = __dsub_rn(ttek, a_dep);
+                    k8_refresh(v_run, 4, v, served);
+                    k8_add4(v_sum, v);
+                    in_sys--;
+                    if (qsize == 0 && free_channels == 1 && in_sys == c - 1) {
+                        busy_n++;
+                        k8_refresh(busy_run, 3, __dsub_rn(ttek, start_busy), busy_n);
+                    }
+                    if (cold_set && qsize == 0 && free_channels == c) {
+                        if (delay_set)
+                            phase_start(delay, ttek, draw(MQ_VS_DELAY));
+                        else
+                            phase_start(cold, ttek, cold_duration());
+                    }
+                    start = qsize != 0;
+                    if (start) {
+                        a_job = Q[(long long)qhead * P.lanes];
+                        qsize--;
+                        qhead = (qsize == 0 || qhead + 1 >= P.qcap) ? 0 : qhead + 1;
+                        if (free_channels == 1) start_busy = ttek;
+                    }
+                }
+                if (start) {
+                    taked++;
+                    const double w = is_arr ? 0.0 : __dadd_rn(0.0, __dsub_rn(ttek, a_job));
+                    k8_refresh(w_run, 4, w, taked);
+                    k8_add4(w_sum, w);
+                    arr[slot] = a_job;
+                    end[slot] = __dadd_rn(ttek, draw(warm_srv ? MQ_VS_WARM_SERVICES : MQ_VS_SERVICES));
+                    busy |= 1u << slot;
+                    free_channels--;
+                    if (is_arr && free_channels == 0 && in_sys == c) start_busy = ttek;
                 }
                 // NPolicyQueueSim.arrival vacations.py:354-364
-                if (P.big_n > 0 && cold.is_start && in_sys >= P.big_n) {
+                if (is_arr && P.big_n > 0 && cold.is_start && in_sys >= P.big_n) {
                     cold.end_time = ttek;
                     on_end_cold();
                 }
-            } else if (ev == 1) {
-                // serving() vacations.py:191-234
-                const double time_to_end = end[midx];
-                const double a_dep = arr[midx];
-                end[midx] = 1e10;
-                busy &= ~(1u << midx);
-                p_add(time_to_end);
-                ttek = time_to_end;
-                served++;
-                free_channels++;
-                const double v = __dsub_rn(ttek, a_dep);
-                k8_refresh(v_run, 4, v, served);
-                k8_add4(v_sum, v);
-                in_sys--;
-                if (qsize == 0 && free_channels == 1 && in_sys == c - 1) {
-                    busy_n++;
-                    k8_refresh(busy_run, 3, __dsub_rn(ttek, start_busy), busy_n);
-                }
-                if (cold_set && qsize == 0 && free_channels == c) {
-                    if (delay_set)
-                        phase_start(delay, ttek, draw(MQ_VS_DELAY));
-                    else
-                        phase_start(cold, ttek, cold_duration());
-                }
-                if (qsize != 0) head_to_channel(midx);
             } else if (ev == 2) {
                 // on_end_warming vacations.py:236-250
                 p_add(warm.end_time);
