@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(K10_BLOCK, 4) k10_size(const K10Params P)
         double arrival_time = next_gap();
 
         while (served < P.jobs && status == 0) {
+            // at most one job starts service per event -- the arriving job (idle server, or pre-emption) or the best job
+            // of the line after a departure -- through ONE start site (wait sample, size draw for FCFS, completion time)
+            bool do_start = false;
+            K10Job sj = cur;
             if (arrival_time <= (busy ? end : 1e10)) {
                 // arrival() size_based.py:216-247
                 arrived++;
@@ -176,9 +180,8 @@ __global__ void __launch_bounds__(K10_BLOCK, 4) k10_size(const K10Params P)
                             old.remaining = rem;  // preempt_service(preserve_remaining=True) servers.py:90-106
                             old.start_wait = ttek;
                             q_push(old);
-                            taked++;
-                            k10_sample(w_run, w_sum, 4, nj.wait, taked);
-                            start(nj);
+                            do_start = true;
+                            sj = nj;
                             preempt++;
                             handled = true;
                         }
@@ -192,9 +195,8 @@ __global__ void __launch_bounds__(K10_BLOCK, 4) k10_size(const K10Params P)
                         }
                     }
                 } else {
-                    taked++;
-                    k10_sample(w_run, w_sum, 4, 0.0, taked);
-                    start(nj);
+                    do_start = true;
+                    sj = nj;  // nj.wait == 0.0
                     if (in_sys == 1) start_busy = ttek;
                 }
             } else {
@@ -236,11 +238,15 @@ __global__ void __launch_bounds__(K10_BLOCK, 4) k10_size(const K10Params P)
                     if (best != qsize)
                         for (int f = 0; f < K10_JOBF; ++f) *qf(best, f) = *qf(qsize, f);
                     start_busy = ttek;
-                    taked++;
                     qj.wait = __dadd_rn(qj.wait, __dsub_rn(ttek, qj.start_wait));
-                    k10_sample(w_run, w_sum, 4, qj.wait, taked);
-                    start(qj);
+                    do_start = true;
+                    sj = qj;
                 }
+            }
+            if (do_start) {
+                taked++;
+                k10_sample(w_run, w_sum, 4, sj.wait, taked);
+                start(sj);
             }
         }
 
