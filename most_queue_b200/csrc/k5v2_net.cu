@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 }
                 node_count(node, MQ_NN_SERVED, 1.0);
                 node_sample(node, MQ_NN_VSUM, __dsub_rn(ttek, a_t), n_served);
-                node_count(node, MQ_NN_INSYS, -1.0);
                 if (qs != 0) {
                     // send_head_of_queue_to_channel base.py:288-310
                     IN(node, QSIZE) = qs - 1;
@@ -336,7 +335,6 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 // the job arrives at node `next`: sim/base.py:214-247 with (moment, ts)
                 const int node = next;
                 node_count(node, MQ_NN_ARRIVED, 1.0);
-                node_count(node, MQ_NN_INSYS, 1.0);
                 const int b = sh_base[node], ch = sh_ch[node];
                 const uint32_t mask = (busy >> b) & ((1u << ch) - 1u);
                 if (mask == (1u << ch) - 1u) {
@@ -398,6 +396,8 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                     rn[(long long)(MQ_NN_WRUN + k) * R] = SD(D_NODE + 16 * i + 12 + k);
                 }
             }
+            // jobs inside the node = arrived - served (this lane's own atomics on those two rows; exact small integers)
+            rn[(long long)MQ_NN_INSYS * R] = __dsub_rn(__ldcg(&rn[(long long)MQ_NN_ARRIVED * R]), __ldcg(&rn[(long long)MQ_NN_SERVED * R]));
             rn[(long long)MQ_NN_SUSED * R] = (double)IN(i, SIDX);
             rn[(long long)MQ_NN_QUEUED * R] = (double)IN(i, QSIZE);
         }
