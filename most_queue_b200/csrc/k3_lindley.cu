@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
             mine = fold_segment<false>(P, n0, x);
         }
         MP total;
-        cta_scan<K3_THREADS>(mine, smem, &total);  // its barriers also fence the stage reuse
+        const MP ex_seg = cta_scan<K3_THREADS>(mine, smem, &total);  // its barriers also fence the stage reuse
+        if (P.thread_ex)
+            __stcs(reinterpret_cast<double2 *>(P.thread_ex) + t * K3_THREADS + threadIdx.x, make_double2(ex_seg.a, ex_seg.b));
         if (STASH_W) {
             // (the scan's barriers have made the staged draws visible) one 128-byte line per warp and instruction
             const long long tb = t * K3_TILE;
@@ -451,14 +453,20 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : ((MODE == 2 && !W
             constexpr bool FULL = decltype(full_tag)::value;
             const int e0 = threadIdx.x * K3_L;
             const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
-            MP f = mp_id();
+            MP ex;
+            if (P.thread_ex) {  // uniform: the summary pass kept every segment's prefix
+                const double2 v = __ldcs(reinterpret_cast<const double2 *>(P.thread_ex) + t * K3_THREADS + threadIdx.x);
+                ex = MP{v.x, v.y};
+            } else {
+                MP f = mp_id();
 #pragma unroll
-            for (int j = 0; j < K3_L; ++j) {
-                const double xj = __dsub_rn(smS[k3_pad(e0 + j)], smA[k3_pad(e0 + j + 1)]);
-                if (FULL || j < valid) f = mp_step(f, xj);
+                for (int j = 0; j < K3_L; ++j) {
+                    const double xj = __dsub_rn(smS[k3_pad(e0 + j)], smA[k3_pad(e0 + j + 1)]);
+                    if (FULL || j < valid) f = mp_step(f, xj);
+                }
+                MP total;
+                ex = cta_scan<K3_THREADS>(f, smem, &total);
             }
-            MP total;
-            const MP ex = cta_scan<K3_THREADS>(f, smem, &total);
             const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
             double w = mp_apply(ex, w_tile);
             const int last_j = (!FULL && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
@@ -502,8 +510,15 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : ((MODE == 2 && !W
                 const int e = K3_TILE + 1 + threadIdx.x;
                 if (e <= K3_TILE + K3_HALO) smA[k3_pad(e)] = gen_gap(P, t * K3_TILE + e);
             }
-            MP total;
-            const MP ex = cta_scan<K3_THREADS>(fold_segment<FULL>(P, n0, x), smem, &total);
+            MP ex;
+            if (P.thread_ex) {
+                const double2 v = __ldcs(reinterpret_cast<const double2 *>(P.thread_ex) + t * K3_THREADS + threadIdx.x);
+                ex = MP{v.x, v.y};
+                if (REPLAY || WANT_P) __syncthreads();  // (what the scan's barriers did) the staged tile has been read
+            } else {
+                MP total;
+                ex = cta_scan<K3_THREADS>(fold_segment<FULL>(P, n0, x), smem, &total);
+            }
             const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
             double w = mp_apply(ex, w_tile);
             const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);

@@ -28,6 +28,8 @@ struct K3Params {
     MP *total;          // [1]
     MP *chunk_f;        // [K3_TOP] folds of the 1024 chunks of tile summaries
     MP *chunk_ex;       // [K3_TOP] their exclusive prefixes
+    MP *thread_ex;      // optional [ntiles][K3_THREADS]: every segment's exclusive prefix inside its tile, kept by the
+                        // summary pass so that the walk neither folds nor scans again (4 KB per 64 KB tile)
     double w_in;
     double *partial;    // [grid][K3_NSTAT]
     double *tail;       // [2]: W[n-1] + x[n-1] (before clamping), W[n-1] + S[n-1]

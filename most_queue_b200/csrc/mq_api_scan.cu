@@ -56,6 +56,19 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
             P.stV = (float *)ctx->in_s.p;
         }
     }
+    // the summary pass can keep every segment's exclusive prefix (4 KB per tile) so that the walk skips its own fold and
+    // CTA scan; MQ_SCAN_NO_PREFIX=1 turns it off
+    if (will_walk && !std::getenv("MQ_SCAN_NO_PREFIX")) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = sizeof(MP) * (size_t)K3_THREADS * (size_t)P.ntiles;
+        if (need <= ctx->agg.cap || need < (free_b + ctx->agg.cap) / 4) {
+            if (ensure(ctx->agg, need) == MQ_OK)
+                P.thread_ex = (MP *)ctx->agg.p;
+            else
+                cudaGetLastError();
+        }
+    }
     int occ_s = 0, occ_w = 0;
     const bool want_p = (cfg->flags & MQ_SCAN_WANT_P) != 0;
     CU(k3_occupancy(replay, stash, want_p, &occ_s, &occ_w));

@@ -149,6 +149,14 @@ def test_generator_chain_sums_equal_the_sums_of_the_variates():
         np.testing.assert_allclose(st[L.S_SUMA], A.sum(), rtol=1e-12)
     np.testing.assert_allclose(p1[L.S_SUMS] + p2[L.S_SUMS], S.sum(), rtol=1e-12)
     np.testing.assert_allclose(p1[L.S_SUMA], A[:h].sum(), rtol=1e-12)
+    # the walk that reuses the summary pass's per-segment prefixes does the same arithmetic as the one that folds and
+    # scans again: identical statistics
+    os.environ["MQ_SCAN_NO_PREFIX"] = "1"
+    try:
+        three, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=seed, last_range=False)
+    finally:
+        del os.environ["MQ_SCAN_NO_PREFIX"]
+    assert np.array_equal(three, one)
     # the waits are functions of the same draws: both forms and both cuts agree to rounding
     for row in (L.S_W, L.S_W + 1, L.S_V, L.S_V + 1):
         np.testing.assert_allclose(two[row], one[row], rtol=1e-11)
