@@ -163,7 +163,7 @@ __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_bas
 __device__ __forceinline__ double gen_gap(const K3Params &P, long long n)
 {
     const unsigned long long g = (unsigned long long)(P.job0 + n);
-    uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+    uint2 w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
     return (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
 }
 
@@ -189,7 +189,7 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
     } else {
         // word 0 of call n = gap before job n, word 1 of call n = service of job n
         unsigned long long g = (unsigned long long)(P.job0 + n0);
-        uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+        uint2 w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
         double gap = (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
         const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
 #pragma unroll
@@ -198,7 +198,7 @@ __device__ __forceinline__ double load_segment(const K3Params &P, long long n0, 
             const bool ok = FULL || j < valid;
             const double sv = (double)sample<-1>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
             ++g;
-            w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+            w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
             const double gnext = (double)sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
             s[j] = ok ? sv : 0.0;
             sum_a += ok ? gap : 0.0;
@@ -239,7 +239,7 @@ template <bool STASH_W, bool FULL>
 __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, float *stg, float *stv)
 {
     unsigned long long g = (unsigned long long)(P.job0 + n0);
-    uint2 w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+    uint2 w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
     float gap = sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
     const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
     MP f = mp_id();
@@ -247,7 +247,7 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
     for (int j = 0; j < K3_L; ++j) {
         const float sv = sample<-1>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
         ++g;
-        w = philox2x32_10((uint32_t)g, (uint32_t)(g >> 32), P.key);
+        w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
         const float gnext = sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
         if (FULL || j < valid) f = mp_step(f, __dsub_rn((double)sv, (double)gnext));
         if (STASH_W) {

@@ -20,6 +20,7 @@ struct K3Params {
     long long job0;     // global index of the first one (Philox counter)
     int replay;
     uint32_t key;       // key0 + STRIDE * 64 * chain
+    uint32_t rk[10];    // key + r * MQ_PHILOX_W: the round keys of the primary Philox call
     DistF src, srv;
     const double *A;    // replay: A[0] = gap before job job0; n + 1 entries
     const double *S;    // replay: n entries

@@ -32,6 +32,7 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     P.job0 = cfg->job0;
     P.replay = replay ? 1 : 0;
     P.key = seed_to_key(cfg->seed) + MQ_KEY_STRIDE * (64u * cfg->chain);
+    for (int r = 0; r < 10; ++r) P.rk[r] = P.key + (uint32_t)r * MQ_PHILOX_W;
     const long long tile = (long long)K3_THREADS * K3_L;
     P.ntiles = (P.n + tile - 1) / tile;
 
