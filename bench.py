@@ -344,6 +344,34 @@ def other_configs_leg():
     c3 = run_chain(("Gamma", gam), ("Pa", par), 10_000_000_000, seed=3, want_p=False)
     out["cfg3_gamma_pareto_1_chain"] = {"jobs_per_s": 1e10 / (c3.timing["sim_ms"] * 1e-3), "w1": c3.w[0],
                                         "utilization": c3.utilization}
+    # cfg3, replay form (2^28 jobs = 4 GiB of fp64 A, S resident in HBM, 16 B/job): the HBM-bound kernel of the set
+    try:
+        import torch
+
+        from most_queue_b200 import _lib
+
+        ctx = _lib.default_context()
+        nr = 1 << 28
+        g = torch.Generator(device="cuda").manual_seed(1)
+        A = torch.empty(nr + 1, device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
+        S = torch.empty(nr, device="cuda", dtype=torch.float64).exponential_(1.0 / 0.7, generator=g)
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(4):
+            st, _ = ctx.scan_apply(nr, 0.0, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)
+            if i:
+                ms.append(ctx.last_timing()["sim_ms"])
+        del A, S
+        t = float(np.mean(ms)) * 1e-3
+        peaks, peak_src = _peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        out["cfg3_replay_2p28"] = {
+            "jobs_per_s": nr / t, "ms": t * 1e3, "w1": float(st[_lib.S_W] / st[_lib.S_TAKED]), "w1_theory_mm1": 0.7 * 0.7 / 0.3,
+            "roofline": {"bound": "hbm", "achieved": 16.0 * nr / t / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": None,
+                         "note": "algorithmic bytes 16 B/job (A and S read once); the two passes move 34 B/job; peak " + peak_src}}
+    except Exception as e:  # reported, never fatal for the headline line
+        out["cfg3_replay_2p28"] = {"error": repr(e)[:200]}
     # cfg4: M/Gamma/4, two classes, NP and PR, 1e5 replications x 1e5 jobs
     g0 = GammaDistribution.get_params_by_mean_and_cv(2.0, 1.2)
     g1 = GammaDistribution.get_params_by_mean_and_cv(4.0, 1.2)
