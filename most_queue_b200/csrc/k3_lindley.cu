@@ -91,6 +91,9 @@ __device__ __forceinline__ double gen_gap(const K3Params &P, long long n);
 
 // the same staging from the fp32 stash written by the summary pass of the generator form (gaps beyond the range --
 // the halo of the level walk in the last tile -- are drawn)
+// HALO: also stage the 256 gaps beyond the tile that the level walk (WANT_P) reads; otherwise only the one gap that the
+// last job's x needs
+template <bool HALO>
 __device__ __forceinline__ void stage_tile_stash(const K3Params &P, long long tile_base, double *smS, double *smA)
 {
     if (tile_base + K3_TILE + K3_HALO <= P.n) {
@@ -103,15 +106,16 @@ __device__ __forceinline__ void stage_tile_stash(const K3Params &P, long long ti
             vS[k] = __ldcs(V + k * K3_THREADS + threadIdx.x);
             vA[k] = __ldcs(G + k * K3_THREADS + threadIdx.x);
         }
-        const float h = __ldcs(G + K3_TILE + threadIdx.x);
+        float h = 0.0f;
+        if (HALO || threadIdx.x == 0) h = __ldcs(G + K3_TILE + threadIdx.x);
 #pragma unroll
         for (int k = 0; k < K3_L; ++k) {
             const int e = k * K3_THREADS + threadIdx.x;
             smS[k3_pad(e)] = (double)vS[k];
             smA[k3_pad(e)] = (double)vA[k];
         }
-        smA[k3_pad(K3_TILE + threadIdx.x)] = (double)h;
-        if (threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = (double)__ldcs(G + K3_TILE + K3_HALO);
+        if (HALO || threadIdx.x == 0) smA[k3_pad(K3_TILE + threadIdx.x)] = (double)h;
+        if (HALO && threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = (double)__ldcs(G + K3_TILE + K3_HALO);
         __syncthreads();
         return;
     }
@@ -126,19 +130,19 @@ __device__ __forceinline__ void stage_tile_stash(const K3Params &P, long long ti
         smS[k3_pad(e)] = n < P.n ? (double)__ldcs(P.stV + n) : 0.0;
         smA[k3_pad(e)] = gap_at(n);
     }
-    {
+    if (HALO || threadIdx.x == 0) {
         const int e = K3_TILE + threadIdx.x;
         smA[k3_pad(e)] = gap_at(tile_base + e);
-        if (threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = gap_at(tile_base + K3_TILE + K3_HALO);
+        if (HALO && threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = gap_at(tile_base + K3_TILE + K3_HALO);
     }
     __syncthreads();
 }
 
-template <bool STASH = false>
+template <bool STASH = false, bool HALO = true>
 __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_base, double *smS, double *smA)
 {
     if (STASH) {
-        stage_tile_stash(P, tile_base, smS, smA);
+        stage_tile_stash<HALO>(P, tile_base, smS, smA);
         return;
     }
     const int vs = k3_valid(P.n, tile_base, K3_TILE);                                    // services in range
@@ -150,10 +154,10 @@ __device__ __forceinline__ void stage_tile(const K3Params &P, long long tile_bas
         smS[k3_pad(e)] = e < vs ? __ldcs(S + e) : 0.0;
         smA[k3_pad(e)] = e < va ? __ldcs(A + e) : 0.0;
     }
-    {   // one more gap for x of the last job, and the halo used by the level walk
+    if (HALO || threadIdx.x == 0) {   // one more gap for x of the last job, and the halo used by the level walk
         const int e = K3_TILE + threadIdx.x;
         smA[k3_pad(e)] = e < va ? __ldcs(A + e) : 0.0;
-        if (threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = K3_TILE + K3_HALO < va ? __ldcs(A + K3_TILE + K3_HALO) : 0.0;
+        if (HALO && threadIdx.x == 0) smA[k3_pad(K3_TILE + K3_HALO)] = K3_TILE + K3_HALO < va ? __ldcs(A + K3_TILE + K3_HALO) : 0.0;
     }
     __syncthreads();
 }
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
-        if (REPLAY) stage_tile(P, t * K3_TILE, smS, smA);
+        if (REPLAY) stage_tile<false, false>(P, t * K3_TILE, smS, smA);
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
         MP mine;
         if (!REPLAY) {
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(K3_THREADS, (MODE == 0 ? 1 : ((MODE == 2 && !W
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         double x[K3_L], s[K3_L];
-        if (REPLAY) stage_tile<MODE == 2>(P, t * K3_TILE, smS, smA);
+        if (REPLAY) stage_tile<MODE == 2, WANT_P>(P, t * K3_TILE, smS, smA);
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
         // staged forms (replay, stash): the tile sits in shared memory, so nothing is carried in registers across the
         // CTA scan -- the fold and the walk both read their operands from there (halves the register count of v1)
