@@ -292,12 +292,13 @@ def run_ours(args):
             "roofline": {"bound": "issue", "achieved": achieved, "peak": peak_issue, "unit": "Glane-instr/s",
                          "frac": achieved / peak_issue,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch
-                         # (profiles/r01_ncu_k2_v2_full.txt); valid for the default 1e6 x 1e5 configuration
-                         "traffic": 5.057e9 if (reps, jobs) == (1_000_000, 100_000) else None,
+                         # (profiles/r01_ncu_k2_full_traffic.csv, the final kernel: 0.82 GB read + 3.31 GB written); valid for
+                         # the default 1e6 x 1e5 configuration
+                         "traffic": 4.131e9 if (reps, jobs) == (1_000_000, 100_000) else None,
                          "kernel": "k2_fifo_gen<8,M,H2,infinite>",
                          "note": f"achieved = jobs/s/GPU x {I_ALG:.0f} algorithmic lane-instructions per job "
                                  f"(SURVEY 8d); peak = {sms} SMs x 128 lanes x {sm_max:.0f} MHz ({peak_src} clock); "
-                                 "traffic in bytes per launch (fp64 per-replication records, ~5 KB per replication incl. "
+                                 "traffic in bytes per launch (fp64 per-replication records, ~4 KB per replication incl. "
                                  "flushes): HBM is idle, the kernel is issue bound"},
             "moments": moment_err,
         }
@@ -368,8 +369,9 @@ def other_configs_leg():
         out["cfg3_replay_2p28"] = {
             "jobs_per_s": nr / t, "ms": t * 1e3, "w1": float(st[_lib.S_W] / st[_lib.S_TAKED]), "w1_theory_mm1": 0.7 * 0.7 / 0.3,
             "roofline": {"bound": "hbm", "achieved": 16.0 * nr / t / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": None,
-                         "note": "algorithmic bytes 16 B/job (A and S read once); the two passes move 34 B/job; peak " + peak_src}}
+                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": 33.75 * nr,
+                         "note": "algorithmic bytes 16 B/job (A and S read once); traffic = dram bytes of the summary and walk kernels from "
+                                 "profiles/r01_ncu_k3_replay_traffic.csv (2^26 jobs: 33.75 B/job, no over-read), scaled; peak " + peak_src}}
     except Exception as e:  # reported, never fatal for the headline line
         out["cfg3_replay_2p28"] = {"error": repr(e)[:200]}
     # cfg4: M/Gamma/4, two classes, NP and PR, 1e5 replications x 1e5 jobs
