@@ -75,6 +75,7 @@ constexpr int K3_PADDED = K3_TILE + K3_TILE / 16 + 2;
 constexpr int K3_PADDED_A = (K3_TILE + K3_HALO) + (K3_TILE + K3_HALO) / 16 + 2;
 constexpr int K3_PBL = 32;    // levels N >= 1..32 accumulated per lane in shared memory
 constexpr size_t K3_STAGE_BYTES = sizeof(double) * (K3_PADDED + K3_PADDED_A);
+constexpr size_t K3_XSTAGE_BYTES = sizeof(double) * K3_PADDED;  // summary pass, replay form: x = S - A' only
 constexpr size_t K3_LEVEL_BYTES = sizeof(float) * K3_PBL * K3_THREADS + sizeof(double) * (K3_THREADS / 32) * (K3_PBL + 1);
 
 __device__ __forceinline__ int k3_pad(int e) { return e + (e >> 4); }
@@ -265,28 +266,46 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
 }
 
 template <bool REPLAY, bool STASH_W = false>
-__global__ void __launch_bounds__(K3_THREADS) k3_summary(const K3Params P)
+__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? 4 : 1)) k3_summary(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
     extern __shared__ double stage[];
-    double *smS = stage, *smA = stage + K3_PADDED;
+    double *smS = stage;
     __shared__ float stash_stage[STASH_W ? 2 * K3_PADDED : 2];
     float *stg = stash_stage, *stv = stash_stage + (STASH_W ? K3_PADDED : 1);
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
-        double x[K3_L], s[K3_L];
-        if (REPLAY) stage_tile<false, false>(P, t * K3_TILE, smS, smA);
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
         MP mine;
         if (!REPLAY) {
             mine = full_tile ? gen_fold_segment<STASH_W, true>(P, n0, stg, stv)
                              : gen_fold_segment<STASH_W, false>(P, n0, stg, stv);
-        } else if (full_tile) {
-            load_segment<REPLAY, false, STASH_W, true>(P, n0, x, s, smS, smA, stg, stv);
-            mine = fold_segment<true>(P, n0, x);
         } else {
-            load_segment<REPLAY, false, STASH_W, false>(P, n0, x, s, smS, smA, stg, stv);
-            mine = fold_segment<false>(P, n0, x);
+            // replay form: the fold only needs x[n] = S[n] - A[n+1], formed while the coalesced loads arrive and staged
+            // as ONE array (35 KB instead of 72 KB per CTA: 6 resident CTAs instead of 3); jobs beyond the range are 0
+            const long long tb = t * K3_TILE;
+            const int vs = k3_valid(P.n, tb, K3_TILE);
+            const double *S = P.S + tb, *A = P.A + tb + 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // two batches of 16 loads: enough in flight, half the registers
+                double vS[K3_L / 2], vA[K3_L / 2];
+#pragma unroll
+                for (int k = 0; k < K3_L / 2; ++k) {
+                    const int e = (h * (K3_L / 2) + k) * K3_THREADS + threadIdx.x;
+                    vS[k] = e < vs ? __ldcs(S + e) : 0.0;
+                    vA[k] = e < vs ? __ldcs(A + e) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < K3_L / 2; ++k)
+                    smS[k3_pad((h * (K3_L / 2) + k) * K3_THREADS + threadIdx.x)] = __dsub_rn(vS[k], vA[k]);
+            }
+            __syncthreads();
+            const int e0 = threadIdx.x * K3_L;
+            const int valid = full_tile ? K3_L : k3_valid(P.n, n0, K3_L);
+            mine = mp_id();
+#pragma unroll
+            for (int j = 0; j < K3_L; ++j)
+                if (j < valid) mine = mp_step(mine, smS[k3_pad(e0 + j)]);
         }
         MP total;
         const MP ex_seg = cta_scan<K3_THREADS>(mine, smem, &total);  // its barriers also fence the stage reuse
@@ -629,9 +648,9 @@ cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
 {
     if (P.replay) {
         cudaError_t e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)K3_STAGE_BYTES);
+                                             (int)K3_XSTAGE_BYTES);
         if (e != cudaSuccess) return e;
-        k3_summary<true><<<grid, K3_THREADS, K3_STAGE_BYTES, st>>>(P);
+        k3_summary<true><<<grid, K3_THREADS, K3_XSTAGE_BYTES, st>>>(P);
     } else if (P.stG) {
         k3_summary<false, true><<<grid, K3_THREADS, 0, st>>>(P);
     } else {
@@ -699,9 +718,9 @@ cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_bloc
     const int mode = replay ? 1 : (stash ? 2 : 0);
     const size_t wsm = k3_walk_smem(mode != 0, want_p);
     if (replay) {
-        e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_STAGE_BYTES);
+        e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_XSTAGE_BYTES);
         if (e == cudaSuccess)
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_STAGE_BYTES);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_XSTAGE_BYTES);
     } else if (stash) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false, true>, K3_THREADS, 0);
     } else {
