@@ -75,6 +75,9 @@ constexpr int K3_PADDED = K3_TILE + K3_TILE / 16 + 2;
 constexpr int K3_PADDED_A = (K3_TILE + K3_HALO) + (K3_TILE + K3_HALO) / 16 + 2;
 constexpr int K3_PBL = 32;    // levels N >= 1..32 accumulated per lane in shared memory
 constexpr size_t K3_STAGE_BYTES = sizeof(double) * (K3_PADDED + K3_PADDED_A);
+#ifndef K3_SUM_MINB
+#define K3_SUM_MINB 4
+#endif
 constexpr size_t K3_XSTAGE_BYTES = sizeof(double) * K3_PADDED;  // summary pass, replay form: x = S - A' only
 constexpr size_t K3_LEVEL_BYTES = sizeof(float) * K3_PBL * K3_THREADS + sizeof(double) * (K3_THREADS / 32) * (K3_PBL + 1);
 
@@ -266,7 +269,7 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
 }
 
 template <bool REPLAY, bool STASH_W = false>
-__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? 4 : 1)) k3_summary(const K3Params P)
+__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 1)) k3_summary(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
     extern __shared__ double stage[];
