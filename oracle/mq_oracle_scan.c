@@ -68,7 +68,7 @@ static void finish(const double *A, const double *S, int64_t N, const double *W,
 
 int mqo_lindley_seq(const double *A, const double *S, int64_t N, double w_in, double *W, mqo_lindley_out *out)
 {
-    double *buf = W ? W : (double *)malloc((size_t)(N > 0 ? N : 1) * sizeof(double));
+    double *buf = W ? W : (double *)calloc((size_t)(N > 0 ? N : 1), sizeof(double));
     if (!buf) return -3;
     double w = w_in;
     mp f = MP_ID;
@@ -124,7 +124,7 @@ int mqo_lindley_tree(const double *A, const double *S, int64_t N, double w_in, i
     if (L < 1 || N < 0) return -2;
     const int64_t tile = (int64_t)TILE_THREADS * L;
     const int64_t ntiles = (N + tile - 1) / tile;
-    double *buf = W ? W : (double *)malloc((size_t)(N > 0 ? N : 1) * sizeof(double));
+    double *buf = W ? W : (double *)calloc((size_t)(N > 0 ? N : 1), sizeof(double));
     mp *tsum = (mp *)malloc((size_t)(ntiles > 0 ? ntiles : 1) * sizeof(mp));
     mp *tex = (mp *)malloc((size_t)(ntiles > 0 ? ntiles : 1) * sizeof(mp));
     if (!buf || !tsum || !tex) return -3;
