@@ -269,7 +269,7 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
 }
 
 template <bool REPLAY, bool STASH_W = false>
-__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 1)) k3_summary(const K3Params P)
+__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 6)) k3_summary(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
     extern __shared__ double stage[];
