@@ -88,9 +88,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(seconds_target: float, jobs: int, threads: int | None = None):
-    """Times the oracle port (CPU restatement of QsSim.run, fp64, libm) on a bounded sample of the
-    same workload: `reps` replications of `jobs` jobs spread over all host threads."""
+def cpu_port(seconds_target: float, jobs: int, threads: int | None = None):
+    """Times the oracle port (oracle/mq_oracle.c: the builder's C restatement of QsSim.run, fp64, libm) on a bounded
+    sample of the same workload: `reps` replications of `jobs` jobs spread over all host threads.  A second, clearly
+    labelled CPU figure (`cpu_port`): ~190x faster per core than the reference class, so the conservative one."""
     from oracle import oracle
 
     threads = threads or os.cpu_count() or 1
@@ -115,34 +116,120 @@ def cpu_baseline(seconds_target: float, jobs: int, threads: int | None = None):
             "seconds": dt, "w1": float(np.mean([r.w_sum[0] / r.taked for r in res]))}
 
 
+def _reference_worker(task):
+    """One process = one unmodified reference `QsSim(8, seed=s).run(jobs)` (most_queue/sim/base.py:29,488) imported
+    from baseline/_ref; stdout / stderr (tqdm, colour banners) go to /dev/null."""
+    seed, jobs = task
+    import contextlib
+    import io
+
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    from most_queue.random.utils.params import H2Params
+    from most_queue.sim.base import QsSim
+
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        qs = QsSim(C_SERVERS, verbose=False, seed=seed)
+        qs.set_sources(ARRIVAL_RATE, "M")
+        qs.set_servers(H2Params(**H2), "H")
+        t0 = time.perf_counter()
+        r = qs.run(jobs)
+        dt = time.perf_counter() - t0
+    return qs.served, dt, float(r.w[0]), float(r.v[0])
+
+
+class ReferencePool:
+    """All host cores running the unmodified reference class, one process per core, distinct seeds."""
+
+    def __init__(self, cores: int | None = None):
+        import multiprocessing as mp
+
+        self.cores = cores or os.cpu_count() or 1
+        # bench.py's reference arm never initialises CUDA, so fork is safe (and the GPU arm calls it in a subprocess)
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.seed = 1000
+
+    def step(self, jobs: int, rounds: int = 1):
+        tasks = [(self.seed + i, jobs) for i in range(self.cores * rounds)]
+        self.seed += len(tasks)
+        t0 = time.perf_counter()
+        rows = self.pool.map(_reference_worker, tasks, chunksize=1)
+        dt = time.perf_counter() - t0
+        return {"served": sum(r[0] for r in rows), "seconds": dt,
+                "per_core": float(np.mean([r[0] / r[1] for r in rows])),
+                "w1": float(np.mean([r[2] for r in rows])), "v1": float(np.mean([r[3] for r in rows])),
+                "replications": len(rows)}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "most_queue"))
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path -- the unmodified pure-Python `QsSim`
+    (baseline/_ref, installed by baseline/install_reference.py) -- on all host cores, one process per core, each step a
+    bounded sample of the cfg2 workload (one replication of `--ref-jobs` jobs per core).  If baseline/_ref is missing the
+    C port is timed instead and the line says so (`kind: "port"`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU arm runs on rank 0 only
-    jobs = args.jobs
-    base = None
-    vals = []
-    for i in range(args.warmup + args.steps):
-        b = cpu_baseline(args.ref_seconds, jobs)
-        if i >= args.warmup:
-            vals.append(b)
-        base = b
-    total_jobs = sum(b["value"] * b["seconds"] for b in vals)
-    total_s = sum(b["seconds"] for b in vals)
-    value = total_jobs / total_s
-    base = dict(base, value=value)
-    base.pop("seconds", None)
+    jobs = args.ref_jobs
+    if reference_available() and not args.ref_port:
+        pool = ReferencePool()
+        rows = []
+        for i in range(args.warmup + args.steps):
+            r = pool.step(jobs)
+            if i >= args.warmup:
+                rows.append(r)
+        pool.close()
+        total_jobs = sum(r["served"] for r in rows)
+        total_s = sum(r["seconds"] for r in rows)
+        value = total_jobs / total_s
+        base = {"value": value, "unit": "jobs/s", "cores": pool.cores, "kind": "reference",
+                "per_core": float(np.mean([r["per_core"] for r in rows])),
+                "sample": f"per step {pool.cores} replications x {jobs} jobs of the same M/H2/8 workload: the unmodified "
+                          f"most_queue.sim.base.QsSim (baseline/_ref), one process per host core, distinct seeds",
+                "w1": float(np.mean([r["w1"] for r in rows])), "v1": float(np.mean([r["v1"] for r in rows]))}
+        dtype, gen = "f64", "numpy PCG64 (the reference's own generator)"
+    else:
+        vals = []
+        for i in range(args.warmup + args.steps):
+            b = cpu_port(args.ref_seconds, args.jobs)
+            if i >= args.warmup:
+                vals.append(b)
+        total_jobs = sum(b["value"] * b["seconds"] for b in vals)
+        total_s = sum(b["seconds"] for b in vals)
+        value = total_jobs / total_s
+        base = dict(vals[-1], value=value)
+        base.pop("seconds", None)
+        rows = vals
+        dtype, gen = "f64", "Philox2x32-10"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "jobs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(len(vals), 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"M/H2/{C_SERVERS} FIFO rho=0.7 CV=1.5, {jobs} jobs per replication (cfg2), "
-                               "bounded sample per step", "generator": "Philox2x32-10"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(len(rows), 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": f"M/H2/{C_SERVERS} FIFO rho=0.7 CV=1.5 (BASELINE cfg2), bounded sample per step: "
+                               f"{base['cores']} replications x {jobs} jobs", "generator": gen},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "jobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_subprocess(jobs: int, steps: int, warmup: int, port: bool = False, timeout: float = 600.0):
+    """Runs the reference arm in a fresh interpreter (no CUDA context to fork) and returns its `cpu_baseline`."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup",
+           str(warmup), "--ref-jobs", str(jobs)] + (["--ref-port"] if port else [])
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError(f"reference arm failed: {out.stderr[-400:]}")
 
 
 def run_ours(args):
@@ -303,9 +390,17 @@ def run_ours(args):
             "moments": moment_err,
         }
         if world == 1 and not args.no_cpu:
-            base = cpu_baseline(args.cpu_seconds, jobs)
-            base.pop("seconds", None)
-            line["cpu_baseline"] = base
+            # the reference's own class on all host cores (bounded sample), and the C port as a second figure
+            try:
+                if reference_available():
+                    line["cpu_baseline"] = reference_subprocess(args.ref_jobs, steps=3, warmup=1)
+            except Exception as e:
+                line["cpu_baseline_error"] = repr(e)[:300]
+            port = cpu_port(args.cpu_seconds, jobs)
+            port.pop("seconds", None)
+            line["cpu_port"] = port
+            if "cpu_baseline" not in line:
+                line["cpu_baseline"] = port
         if world == 1 and not args.no_replay:
             try:
                 line["replay"] = replay_leg(ctx, peaks, peak_src)
@@ -440,6 +535,9 @@ def main():
     ap.add_argument("--jobs", type=int, default=100_000, help="jobs per replication (cfg2: 1e5)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=8.0)
+    ap.add_argument("--ref-jobs", type=int, default=100_000,
+                    help="jobs per replication of the reference class (one replication per core and step)")
+    ap.add_argument("--ref-port", action="store_true", help="time the C port instead of the reference class")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-replay", action="store_true")

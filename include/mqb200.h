@@ -98,7 +98,7 @@ typedef struct {
     int64_t replications; /* replications simulated by THIS call (this rank's shard)    */
     int64_t rep0;         /* global id of the first one: Philox counter word            */
     uint64_t seed;        /* QsSim(seed=...) -> Philox key                 base_core.py:23 */
-    int32_t flags;        /* MQ_FIFO_V_AT_START or 0                                    */
+    int32_t flags;        /* MQ_FIFO_V_AT_START | MQ_FIFO_FP64 | MQ_FIFO_BUSY or 0      */
     int32_t warmup;       /* additive (0 = the reference's behaviour): statistics restart at the     */
                           /* instant of the warmup-th start of service; w / v then cover the jobs     */
                           /* started after it (rows TAKED / SERVED hold those sample counts) and      */
@@ -109,6 +109,18 @@ typedef struct {
  * then) instead of only the jobs that left, which removes the right-censoring bias of the reference's
  * stop rule (the <= c jobs in service at the stop are long ones); SERVED then equals TAKED */
 #define MQ_FIFO_V_AT_START 1
+/* additive: run the same loop in fp64 (clocks, variates via the CUDA double math library, power sums) on the same
+ * Philox words -- the A/B tier that measures what the fp32 production arithmetic costs against the reference's
+ * Python floats; several times slower */
+#define MQ_FIFO_FP64 2
+/* also gather QsSim.busy, the busy-period raw moments (base.py:179-184, 274-281, 297-298).  The per-replication
+ * record then has MQ_FIFO_BUSY_ROWS more rows behind MQ_REC_ROWS(p_bins) and the aggregate MQ_AGG_BUSY_LEN more
+ * entries behind MQ_AGG_LEN(p_bins): [0..2] sum over replications of sum(b^k)/n, [3] sum of n, [4..7] their squares */
+#define MQ_FIFO_BUSY 4
+#define MQ_FB_BUSY 0     /* 3 rows: sum of (busy period)^k, k = 1..3 */
+#define MQ_FB_BUSYN 3    /* number of busy periods (QsSim.busy_moments) */
+#define MQ_FIFO_BUSY_ROWS 4
+#define MQ_AGG_BUSY_LEN 8
 
 #define MQ_MAX_PBINS 1024
 #define MQ_MAX_CHANNELS 32

@@ -27,6 +27,8 @@ A_REPS, A_W, A_W2, A_V, A_V2 = 0, 1, 5, 9, 13
 A_ARRIVED, A_TAKED, A_SERVED, A_DROPPED, A_TTEK, A_WPOOL, A_VPOOL, A_FLAGGED, A_POVER, A_P = 17, 18, 19, 20, 21, 22, 26, 30, 31, 32
 RF_WRUN, RF_VRUN, RF_BUSYRUN, RF_BUSYN, RF_INSYS, RF_QUEUED, RF_AUSED, RF_SUSED, REPLAY_EXTRA = 0, 4, 8, 11, 12, 13, 14, 15, 16
 MAX_PBINS = 1024
+FIFO_V_AT_START, FIFO_FP64, FIFO_BUSY = 1, 2, 4  # mq_fifo_cfg.flags
+FB_BUSY, FB_BUSYN, FIFO_BUSY_ROWS, AGG_BUSY_LEN = 0, 3, 4, 8
 
 
 def rec_rows(p_bins: int) -> int:
@@ -436,7 +438,9 @@ class Context:
 
     # ---- K2 ----
     def sim_fifo(self, c, buffer, src: MqDist, srv: MqDist, total_served, replications, rep0, seed,
-                 p_bins=128, per_replication=False, warmup=0, v_at_start=False):
+                 p_bins=128, per_replication=False, warmup=0, v_at_start=False, fp64=False, busy=False):
+        """busy=True: the aggregate has AGG_BUSY_LEN more entries behind agg_len(p_bins) and the record
+        FIFO_BUSY_ROWS more rows behind rec_rows(p_bins) (mqb200.h MQ_FIFO_BUSY)."""
         cfg = MqFifoCfg()
         cfg.c, cfg.p_bins = int(c), int(p_bins)
         cfg.buffer = -1 if buffer is None else int(buffer)
@@ -444,9 +448,10 @@ class Context:
         cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.warmup = int(warmup)
-        cfg.flags = 1 if v_at_start else 0  # MQ_FIFO_V_AT_START
-        agg = np.zeros(agg_len(p_bins))
-        rec = np.empty((rec_rows(p_bins), int(replications))) if per_replication else None
+        cfg.flags = (FIFO_V_AT_START if v_at_start else 0) | (FIFO_FP64 if fp64 else 0) | (FIFO_BUSY if busy else 0)
+        agg = np.zeros(agg_len(p_bins) + (AGG_BUSY_LEN if busy else 0))
+        rows = rec_rows(p_bins) + (FIFO_BUSY_ROWS if busy else 0)
+        rec = np.empty((rows, int(replications))) if per_replication else None
         check(self._L.mq_sim_fifo(
             self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
             rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))

@@ -41,9 +41,69 @@ constexpr int MQ_BLOCK = 128;    // lanes per CTA
 constexpr int MQ_BF = 32;        // histogram states kept in shared memory
 constexpr int MQ_EV = 32;        // events between epoch re-bases
 constexpr int MQ_FLUSH = 64;     // re-bases between fp32 -> fp64 flushes
-constexpr uint32_t MQ_KEY_GONE = 0xfe800000u;  // -8.5e37: server free "since ever" (plus slot id)
-constexpr uint32_t MQ_KEY_OFF = 0x7e800000u;   // +8.5e37: slot not used (c < CT): always busy, never departs
-constexpr float MQ_KEY_LIM = 1.0e30f;          // |key| below this is a real time
+// Arithmetic type of the kernel.  float is the production tier (fp32 clocks relative to an epoch, MUFU samplers);
+// double is the A/B tier (MQ_FIFO_FP64): the same loop, the same Philox words, fp64 clocks, fp64 libm-grade samplers and
+// fp64 power sums -- the precision the reference's Python floats have.  It exists to MEASURE what fp32 costs.
+template <typename Real>
+struct RT;
+
+template <>
+struct RT<float> {
+    using U = uint32_t;
+    using Ring = float2;
+    static constexpr U KEY_GONE = 0xfe800000u;  // -8.5e37: server free "since ever" (plus slot id)
+    static constexpr U KEY_OFF = 0x7e800000u;   // +8.5e37: slot not used (c < CT): always busy, never departs
+    static constexpr float LIM = 1.0e30f;       // |key| below this is a real time
+    static constexpr float HUGE_T = 3.0e38f;
+    static __device__ __forceinline__ U bits(float x) { return __float_as_uint(x); }
+    static __device__ __forceinline__ float real(U b) { return __uint_as_float(b); }
+    static __device__ __forceinline__ float rcp(float x) { return fast_rcp(x); }
+    static __device__ __forceinline__ float sat(float x) { return __saturatef(x); }
+    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float abs_(float a) { return fabsf(a); }
+    static __device__ __forceinline__ Ring ring(float a, float b) { return make_float2(a, b); }
+    static __device__ __forceinline__ float ld(uint32_t addr)
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+        return v;
+    }
+    static __device__ __forceinline__ void st(uint32_t addr, float v)
+    {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+    }
+};
+
+template <>
+struct RT<double> {
+    using U = unsigned long long;
+    using Ring = double2;
+    static constexpr U KEY_GONE = 0xC7D0000000000000ull;  // -2^126
+    static constexpr U KEY_OFF = 0x47D0000000000000ull;   // +2^126
+    static constexpr double LIM = 1.0e30;
+    static constexpr double HUGE_T = 1.0e300;
+    static __device__ __forceinline__ U bits(double x) { return (U)__double_as_longlong(x); }
+    static __device__ __forceinline__ double real(U b) { return __longlong_as_double((long long)b); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double sat(double x) { return fmin(fmax(x, 0.0), 1.0); }
+    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+    static __device__ __forceinline__ double abs_(double a) { return fabs(a); }
+    static __device__ __forceinline__ Ring ring(double a, double b) { return make_double2(a, b); }
+    static __device__ __forceinline__ double ld(uint32_t addr)
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+        return v;
+    }
+    static __device__ __forceinline__ void st(uint32_t addr, double v)
+    {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+    }
+};
 
 struct K2Params {
     int c;
@@ -57,97 +117,92 @@ struct K2Params {
     uint32_t warm;     // statistics restart at the warm-th start of service (0: never)
     int v_at_start;    // MQ_FIFO_V_AT_START: keep the v of the jobs still in service at the stop
     DistF src, srv;
+    DistD srcd, srvd; // the same laws with fp64 constants (MQ_FIFO_FP64 tier only)
     double *rec;      // [MQ_REC_ROWS(p_bins)][reps], zeroed by the caller
-    float2 *ring;     // finite buffer: [buffer][total lanes]
+    void *ring;       // finite buffer: [buffer][total lanes] of (gap, service) pairs in the kernel's real type
     long long lanes;  // gridDim.x * MQ_BLOCK
 };
-
-__device__ __forceinline__ float ld_shared(uint32_t addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ void st_shared(uint32_t addr, float v)
-{
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 
 template <int CT>
 struct Tag {
     static constexpr int TB = CT <= 1 ? 0 : CT <= 2 ? 1 : CT <= 4 ? 2 : CT <= 8 ? 3 : CT <= 16 ? 4 : 5;
     static constexpr uint32_t MASK = (1u << TB) - 1u;
     static constexpr uint32_t HALF = TB ? (1u << (TB - 1)) : 0u;
+    template <typename Real>
+    static __device__ __forceinline__ uint32_t of(Real x)  // slot id carried by a key
+    {
+        return (uint32_t)RT<Real>::bits(x) & MASK;
+    }
 };
 
 // round the key to the tag grid (nearest) and stamp the slot id into its low bits
-template <int CT>
-__device__ __forceinline__ float stamp(float x, uint32_t tag)
+template <int CT, typename Real>
+__device__ __forceinline__ Real stamp(Real x, uint32_t tag)
 {
     if (Tag<CT>::TB == 0) return x;
-    uint32_t b = __float_as_uint(x);
-    return __uint_as_float(((b + Tag<CT>::HALF) & ~Tag<CT>::MASK) | tag);
+    using U = typename RT<Real>::U;
+    const U b = RT<Real>::bits(x);
+    return RT<Real>::real(((b + (U)Tag<CT>::HALF) & ~(U)Tag<CT>::MASK) | (U)tag);
 }
 
 // L[0..CT-1] sorted ascending.  new L = sorted(L[0..CT-2] + {y}); the old maximum is dropped.
-template <int CT>
-__device__ __forceinline__ void insert_drop_last(float (&L)[CT], float y)
+template <int CT, typename Real>
+__device__ __forceinline__ void insert_drop_last(Real (&L)[CT], Real y)
 {
-    float prev = L[0];
-    L[0] = fminf(prev, y);
+    Real prev = L[0];
+    L[0] = RT<Real>::mn(prev, y);
 #pragma unroll
     for (int j = 1; j < CT; ++j) {
-        float cur = L[j];
-        float up = fmaxf(prev, y);
-        L[j] = (j == CT - 1) ? up : fminf(cur, up);
+        Real cur = L[j];
+        Real up = RT<Real>::mx(prev, y);
+        L[j] = (j == CT - 1) ? up : RT<Real>::mn(cur, up);
         prev = cur;
     }
     if (CT == 1) L[0] = y;
 }
 
 // new L = sorted(L[1..CT-1] + {y}); the old minimum is dropped.
-template <int CT>
-__device__ __forceinline__ void insert_drop_first(float (&L)[CT], float y)
+template <int CT, typename Real>
+__device__ __forceinline__ void insert_drop_first(Real (&L)[CT], Real y)
 {
     if (CT == 1) {
         L[0] = y;
         return;
     }
-    float prev = L[1];
-    L[0] = fminf(prev, y);
+    Real prev = L[1];
+    L[0] = RT<Real>::mn(prev, y);
 #pragma unroll
     for (int j = 1; j < CT - 1; ++j) {
-        float cur = L[j + 1];
-        L[j] = fminf(cur, fmaxf(prev, y));
+        Real cur = L[j + 1];
+        L[j] = RT<Real>::mn(cur, RT<Real>::mx(prev, y));
         prev = cur;
     }
-    L[CT - 1] = fmaxf(prev, y);
+    L[CT - 1] = RT<Real>::mx(prev, y);
 }
 
 // One wiring for both event kinds: an arrival keeps L[0..CT-2] (the old maximum -- a free slot, or
 // y itself when nothing starts -- is dropped), a departure drops L[0]; y is inserted in order.
-template <int CT>
-__device__ __forceinline__ void unified_insert(float (&L)[CT], float y, bool is_arr)
+template <int CT, typename Real>
+__device__ __forceinline__ void unified_insert(Real (&L)[CT], Real y, bool is_arr)
 {
     if (CT == 1) {
         L[0] = y;
         return;
     }
-    float M[CT > 1 ? CT - 1 : 1];
+    Real M[CT > 1 ? CT - 1 : 1];
 #pragma unroll
     for (int j = 0; j < CT - 1; ++j) M[j] = is_arr ? L[j] : L[j + 1];
-    L[0] = fminf(M[0], y);
+    L[0] = RT<Real>::mn(M[0], y);
 #pragma unroll
-    for (int j = 1; j < CT - 1; ++j) L[j] = fminf(M[j], fmaxf(M[j - 1], y));
-    L[CT - 1] = fmaxf(M[CT - 2], y);
+    for (int j = 1; j < CT - 1; ++j) L[j] = RT<Real>::mn(M[j], RT<Real>::mx(M[j - 1], y));
+    L[CT - 1] = RT<Real>::mx(M[CT - 2], y);
 }
 
 // After a re-base two keys can land on the same grid point and then differ only by their slot
 // ids, which may invert an adjacent pair.  Restore strict order (odd-even transposition until
 // clean; almost always the check alone).
-template <int CT>
-__device__ __forceinline__ void restore_order(float (&L)[CT])
+template <int CT, typename Real>
+__device__ __forceinline__ void restore_order(Real (&L)[CT])
 {
     if (CT == 1) return;
     bool bad = false;
@@ -159,7 +214,7 @@ __device__ __forceinline__ void restore_order(float (&L)[CT])
         for (int par = 0; par < 2; ++par) {
 #pragma unroll
             for (int j = par; j + 1 < CT; j += 2) {
-                const float lo = fminf(L[j], L[j + 1]), hi = fmaxf(L[j], L[j + 1]);
+                const Real lo = RT<Real>::mn(L[j], L[j + 1]), hi = RT<Real>::mx(L[j], L[j + 1]);
                 bad |= lo != L[j];
                 L[j] = lo;
                 L[j + 1] = hi;
@@ -179,16 +234,29 @@ __device__ __forceinline__ void restore_order(float (&L)[CT])
 #endif
 constexpr int K2_UNROLL = MQ_K2_UNROLL;
 
-template <int CT, int SRCK, int SRVK, bool FINITE>
-__global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_gen(const K2Params P)
+template <typename Real, int CT>
+constexpr int k2_min_blocks()
 {
-    extern __shared__ float smem[];
+    return sizeof(Real) == 4 ? (CT <= 8 ? MQ_K2_MINB : 2) : (CT <= 8 ? 3 : 1);
+}
+
+// BUSY: also gather QsSim.busy, the reference's busy-period moments (base.py:179-184, 274-281, 297-298): the time from
+// the last start of service that left no channel free to the first departure that finds the waiting line empty.  Extra
+// rows MQ_FB_* behind the record; off by default so that the production loop does not pay for it.
+template <typename Real, int CT, int SRCK, int SRVK, bool FINITE, bool BUSY>
+__global__ void __launch_bounds__(MQ_BLOCK, (k2_min_blocks<Real, CT>())) k2_fifo_gen(const K2Params P)
+{
+    using T = RT<Real>;
+    using Ring = typename T::Ring;
+    extern __shared__ double smem_raw[];
+    Real *smem = reinterpret_cast<Real *>(smem_raw);
     const int tid = threadIdx.x;
-    float *hist = smem + tid;                           // [MQ_BF][MQ_BLOCK]: states c+1 .. c+MQ_BF
-    float *vslot = smem + MQ_BF * MQ_BLOCK + tid;       // [CT][MQ_BLOCK]
+    Real *hist = smem + tid;                           // [MQ_BF][MQ_BLOCK]: states c+1 .. c+MQ_BF
+    Real *vslot = smem + MQ_BF * MQ_BLOCK + tid;       // [CT][MQ_BLOCK]
     // 32-bit shared-window addresses of this lane's columns (keeps the address math out of the loop)
     const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
     const uint32_t vslot_sa = (uint32_t)__cvta_generic_to_shared(vslot);
+    constexpr uint32_t COL = MQ_BLOCK * (uint32_t)sizeof(Real);  // bytes between two rows of a [row][lane] array
     const long long gtid = (long long)blockIdx.x * MQ_BLOCK + tid;
     const int c = P.c;
     const uint32_t key0 = P.key0;
@@ -196,44 +264,69 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
     const uint32_t N = (uint32_t)P.jobs;
     const uint32_t cap = FINITE ? (uint32_t)P.buffer : 0u;
     const int off = CT - c;  // register hs[m] holds state m - off
+    Ring *ring = reinterpret_cast<Ring *>(P.ring);
+    const Real ZERO = (Real)0;
 
     for (long long rl = gtid; rl < R; rl += P.lanes) {
         const uint32_t rep = P.rep0 + (uint32_t)rl;
         double *rec = P.rec + rl;
+        auto draw_a = [&](uint32_t w, uint32_t idx) -> Real {
+            if constexpr (sizeof(Real) == 4)
+                return sample<SRCK>(P.src, w, idx, rep, key0, 0);
+            else
+                return sample_d(P.srcd, w, idx, rep, key0, 0);
+        };
+        auto draw_s = [&](uint32_t w, uint32_t idx) -> Real {
+            if constexpr (sizeof(Real) == 4)
+                return sample<SRVK>(P.srv, w, idx, rep, key0, 1);
+            else
+                return sample_d(P.srvd, w, idx, rep, key0, 1);
+        };
 
         // ---- state ----
-        float L[CT];
+        Real L[CT];
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
             // ascending: the c real slots, free since ever (more negative = larger slot id), then unused
-            L[j] = __uint_as_float(j < c ? (MQ_KEY_GONE | (uint32_t)(c - 1 - j)) : (MQ_KEY_OFF | (uint32_t)j));
+            L[j] = T::real(j < c ? (T::KEY_GONE | (typename T::U)(c - 1 - j)) : (T::KEY_OFF | (typename T::U)j));
         }
-        float hs[CT + 1];
+        Real hs[CT + 1];
 #pragma unroll
-        for (int m = 0; m <= CT; ++m) hs[m] = 0.0f;
+        for (int m = 0; m <= CT; ++m) hs[m] = ZERO;
 #pragma unroll
-        for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
+        for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = ZERO;
 
-        float t = 0.0f;
+        Real t = ZERO;
         double tbase = 0.0;
-        float sw[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+        Real sw[4] = {ZERO, ZERO, ZERO, ZERO}, sv[4] = {ZERO, ZERO, ZERO, ZERO};
         // nxt = index of the arrival scheduled at tA (= number of arrivals so far); q = waiting jobs.
         // Infinite buffer: the waiting jobs are the last q arrivals, so the head of the queue is nxt - q.
         uint32_t nxt = 0, taked = 0, dropped = 0, q = 0;
-        float a_h = 0.0f, S_h = 0.0f;  // infinite buffer: arrival time and service time of the queue head
-        uint32_t head = 0;             // finite buffer: ring bookkeeping
-        float a_anchor = 0.0f, a_lastq = 0.0f;
+        Real a_h = ZERO, S_h = ZERO;  // infinite buffer: arrival time and service time of the queue head
+        uint32_t head = 0;            // finite buffer: ring bookkeeping
+        Real a_anchor = ZERO, a_lastq = ZERO;
         uint32_t flags = 0;
         double t_warm = 0.0;
         bool warm_done = false;
         uint32_t next_stop = (P.warm != 0u && P.warm < N) ? P.warm : N;
+        // busy periods (BUSY): power sums of the samples, their number, start of the current one
+        Real sb[3] = {ZERO, ZERO, ZERO};
+        uint32_t nbusy = 0;
+        Real start_busy = ZERO;
+        auto busy_sample = [&](Real x) {
+            const Real x2 = x * x;
+            sb[0] += x;
+            sb[1] += x2;
+            sb[2] = T::fma_(x2, x, sb[2]);
+            nbusy++;
+        };
 
         // first arrival: the draw set_sources makes (base.py:112)
-        float tA, S_pend;
+        Real tA, S_pend;
         {
             uint2 w = philox2x32_10(0u, rep, key0);
-            tA = sample<SRCK>(P.src, w.x, 0u, rep, key0, 0);
-            S_pend = sample<SRVK>(P.srv, w.y, 0u, rep, key0, 1);
+            tA = draw_a(w.x, 0u);
+            S_pend = draw_s(w.y, 0u);
         }
 
         auto flush = [&]() {
@@ -241,43 +334,51 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
             for (int k = 0; k < 4; ++k) {
                 rec[(long long)(MQ_F_W + k) * R] += (double)sw[k];
                 rec[(long long)(MQ_F_V + k) * R] += (double)sv[k];
-                sw[k] = 0.0f;
-                sv[k] = 0.0f;
+                sw[k] = ZERO;
+                sv[k] = ZERO;
+            }
+            if (BUSY) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    rec[(long long)(MQ_REC_ROWS(P.p_bins) + MQ_FB_BUSY + k) * R] += (double)sb[k];
+                    sb[k] = ZERO;
+                }
             }
 #pragma unroll
             for (int m = 0; m <= CT; ++m) {
                 const int k = m - off;
                 if (k >= 0) {
                     rec[(long long)(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)hs[m];
-                    hs[m] = 0.0f;
+                    hs[m] = ZERO;
                 }
             }
             for (int b = 0; b < MQ_BF; ++b) {
                 const int k = c + 1 + b;
                 rec[(long long)(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)hist[b * MQ_BLOCK];
-                hist[b * MQ_BLOCK] = 0.0f;
+                hist[b * MQ_BLOCK] = ZERO;
             }
         };
         auto rebase = [&]() {
-            const float base = t;
+            const Real base = t;
             tbase += (double)base;
-            t = 0.0f;
+            t = ZERO;
             tA -= base;
             a_h -= base;
             a_anchor -= base;
             a_lastq -= base;
+            if (BUSY) start_busy -= base;
 #pragma unroll
             for (int j = 0; j < CT; ++j) {
-                const float moved = stamp<CT>(L[j] - base, __float_as_uint(L[j]) & Tag<CT>::MASK);
-                L[j] = fabsf(L[j]) < MQ_KEY_LIM ? moved : L[j];
+                const Real moved = stamp<CT, Real>(L[j] - base, Tag<CT>::of(L[j]));
+                L[j] = T::abs_(L[j]) < T::LIM ? moved : L[j];
             }
-            restore_order<CT>(L);
+            restore_order<CT, Real>(L);
         };
         // time with c + qq jobs in the system, qq >= 1
-        auto add_q_state = [&](uint32_t qq, float dt) {
+        auto add_q_state = [&](uint32_t qq, Real dt) {
             if (qq <= (uint32_t)MQ_BF) {
-                const uint32_t ha = hist_sa + (qq - 1u) * (MQ_BLOCK * 4u);
-                st_shared(ha, ld_shared(ha) + dt);
+                const uint32_t ha = hist_sa + (qq - 1u) * COL;
+                T::st(ha, T::ld(ha) + dt);
             } else {
                 const long long k = (long long)c + qq;
                 rec[(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)dt;
@@ -289,39 +390,42 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
         while (taked < N) {
 #pragma unroll K2_UNROLL
             for (int ev = 0; ev < MQ_EV; ++ev) {
-                const float d0 = L[0];
+                const Real d0 = L[0];
                 const bool q0 = q == 0u;
                 // nobody waits: the next event is the arrival (departures are settled lazily);
                 // otherwise arrival or departure, arrival wins ties (base.py:442-454)
                 const bool is_arr = q0 || tA <= d0;
-                const float te = is_arr ? tA : d0;
+                const Real te = is_arr ? tA : d0;
                 // _update_state_probs (base.py:327-340)
-                const float dt = te - t;
+                const Real dt = te - t;
                 {
                     // nobody waits: between t and te the c servers finish in key order, state (c - j) lasts
                     // until key j.  With r_j = saturate((key_j - t) / dt) the time in state (c - j) is
                     // (r_j - r_{j-1}) dt: one FFMA.SAT per key on the FMA pipe instead of two FMNMX clamps.
                     // Lanes with waiting jobs run the same code with a zero weight (no divergent arm).
-                    const float inv = (q0 && dt > 0.0f) ? fast_rcp(dt) : 0.0f;
-                    const float wgt = q0 ? dt : 0.0f;
-                    const float nt = -t * inv;
-                    float prev = 0.0f;
+                    const Real inv = (q0 && dt > ZERO) ? T::rcp(dt) : ZERO;
+                    const Real wgt = q0 ? dt : ZERO;
+                    const Real nt = -t * inv;
+                    Real prev = ZERO;
 #pragma unroll
                     for (int j = 0; j < CT; ++j) {
-                        const float r = __saturatef(fmaf(L[j], inv, nt));
-                        hs[CT - j] = fmaf(r - prev, wgt, hs[CT - j]);
+                        const Real r = T::sat(T::fma_(L[j], inv, nt));
+                        hs[CT - j] = T::fma_(r - prev, wgt, hs[CT - j]);
                         prev = r;
                     }
-                    hs[0] = fmaf(1.0f - prev, wgt, hs[0]);
+                    hs[0] = T::fma_((Real)1 - prev, wgt, hs[0]);
                     // somebody waits: all servers are busy, the state is c + q (q = 0 adds 0 to the first bin)
-                    add_q_state(q0 ? 1u : q, q0 ? 0.0f : dt);
+                    add_q_state(q0 ? 1u : q, q0 ? ZERO : dt);
                 }
+                // a busy period ends at the first departure that finds the line empty while every channel was
+                // taken (base.py:274-281): with nobody waiting that is key 0, if it lies inside (t, te)
+                if (BUSY && q0 && d0 > t && d0 < te) busy_sample(d0 - start_busy);
                 t = te;
 
                 // one generator site per event: the arrival after this one (lead cursor) or, on a
                 // departure that leaves jobs waiting, the next head of the queue (lag cursor)
                 const bool pop_more = !FINITE && !is_arr && q > 1u;
-                float gx = 0.0f, sx = 0.0f;
+                Real gx = ZERO, sx = ZERO;
                 if (is_arr || pop_more) {
                     const uint32_t ridx = (is_arr ? nxt : nxt - q) + 1u;
 #if MQ_K2_RK
@@ -329,19 +433,19 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
 #else
                     uint2 w = philox2x32_10(ridx, rep, key0);
 #endif
-                    gx = sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
-                    sx = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
+                    gx = draw_a(w.x, ridx);
+                    sx = draw_s(w.y, ridx);
                 }
 
                 // a job starts service: the arriving one if a server is free (send_task_to_channel
                 // base.py:155-184), or the head of the queue on a departure (base.py:288-310)
                 const bool start = is_arr ? (q0 && d0 <= te) : true;
-                float a_q = a_h, S_q = S_h;
+                Real a_q = a_h, S_q = S_h;
                 if (FINITE) {
-                    a_q = 0.0f;
-                    S_q = 0.0f;
+                    a_q = ZERO;
+                    S_q = ZERO;
                     if (!is_arr) {
-                        const float2 e = P.ring[(long long)head * P.lanes + gtid];
+                        const Ring e = ring[(long long)head * P.lanes + gtid];
                         a_q = a_anchor + e.x;
                         S_q = e.y;
                         a_anchor = a_q;
@@ -349,27 +453,28 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                         if (head >= cap) head = 0u;
                     }
                 }
-                const float S_st = is_arr ? S_pend : S_q;
-                const float w = is_arr ? 0.0f : fmaxf(t - a_q, 0.0f);
-                const float vv = w + S_st;
-                const uint32_t tag = __float_as_uint(d0) & Tag<CT>::MASK;
-                const float y = start ? stamp<CT>(t + S_st, tag) : d0;  // d0 back in = no change
-                insert_drop_first<CT>(L, y);
-                if (start) st_shared(vslot_sa + tag * (MQ_BLOCK * 4u), vv);
-                acc4(sw, start ? w : 0.0f);
-                acc4(sv, start ? vv : 0.0f);
+                const Real S_st = is_arr ? S_pend : S_q;
+                const Real w = is_arr ? ZERO : T::mx(t - a_q, ZERO);
+                const Real vv = w + S_st;
+                const uint32_t tag = Tag<CT>::of(d0);
+                const Real y = start ? stamp<CT, Real>(t + S_st, tag) : d0;  // d0 back in = no change
+                insert_drop_first<CT, Real>(L, y);
+                if (start) T::st(vslot_sa + tag * COL, vv);
+                if (BUSY) start_busy = start ? t : start_busy;  // the last start before all channels are taken counts
+                acc4(sw, start ? w : ZERO);
+                acc4(sv, start ? vv : ZERO);
                 taked += start ? 1u : 0u;
                 // ---- queue ----
                 const bool accept = start || !FINITE || q < cap;  // base.py:204-212
                 const bool enq = is_arr && !start && accept;
                 if (FINITE) {
                     if (enq) {
-                        float gap = 0.0f;
+                        Real gap = ZERO;
                         if (q0) a_anchor = t; else gap = t - a_lastq;
                         a_lastq = t;
                         uint32_t slot = head + q;
                         if (slot >= cap) slot -= cap;
-                        P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_pend);
+                        ring[(long long)slot * P.lanes + gtid] = T::ring(gap, S_pend);
                     }
                 } else {
                     const bool enq_first = enq && q0;  // the arriving job becomes the head
@@ -392,17 +497,24 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                 next_stop = N;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    sw[k] = 0.0f;
-                    sv[k] = 0.0f;
+                    sw[k] = ZERO;
+                    sv[k] = ZERO;
                     rec[(long long)(MQ_F_W + k) * R] = 0.0;
                     rec[(long long)(MQ_F_V + k) * R] = 0.0;
                 }
+                if (BUSY) {
+                    for (int k = 0; k < 3; ++k) {
+                        sb[k] = ZERO;
+                        rec[(long long)(MQ_REC_ROWS(P.p_bins) + MQ_FB_BUSY + k) * R] = 0.0;
+                    }
+                    nbusy = 0;
+                }
 #pragma unroll
-                for (int m = 0; m <= CT; ++m) hs[m] = 0.0f;
-                for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = 0.0f;
+                for (int m = 0; m <= CT; ++m) hs[m] = ZERO;
+                for (int b = 0; b < MQ_BF; ++b) hist[b * MQ_BLOCK] = ZERO;
                 for (int k = 0; k < P.p_bins; ++k) rec[(long long)(MQ_F_P + k) * R] = 0.0;
                 rec[(long long)MQ_F_POVER * R] = 0.0;
-                for (int j = 0; j < CT; ++j) vslot[j * MQ_BLOCK] = -1.0f;
+                for (int j = 0; j < CT; ++j) vslot[j * MQ_BLOCK] = (Real)-1;
                 t_warm = tbase;
             }
             if ((++epoch % MQ_FLUSH) == 0) flush();
@@ -414,19 +526,19 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
             int busy = 0;
 #pragma unroll
             for (int j = 0; j < CT; ++j) {
-                const uint32_t tg = __float_as_uint(L[j]) & Tag<CT>::MASK;
-                const bool real = L[j] < MQ_KEY_LIM;     // not an unused slot
+                const uint32_t tg = Tag<CT>::of(L[j]);
+                const bool real = L[j] < T::LIM;         // not an unused slot
                 const bool gone = L[j] <= t;             // departed (settled lazily) or never used
-                L[j] = (real && gone) ? __uint_as_float(MQ_KEY_GONE | tg) : L[j];
+                L[j] = (real && gone) ? T::real(T::KEY_GONE | (typename T::U)tg) : L[j];
                 busy += (real && !gone) ? 1 : 0;
             }
             uint32_t served = taked - (uint32_t)busy;
             while (served < N) {
-                float dmin = 3.0e38f;
+                Real dmin = T::HUGE_T;
 #pragma unroll
-                for (int j = 0; j < CT; ++j) dmin = L[j] > -MQ_KEY_LIM ? fminf(dmin, L[j]) : dmin;
+                for (int j = 0; j < CT; ++j) dmin = L[j] > -T::LIM ? T::mn(dmin, L[j]) : dmin;
                 const bool is_arr = busy == 0 || tA <= dmin;
-                const float te = is_arr ? tA : dmin;
+                const Real te = is_arr ? tA : dmin;
                 {
                     const long long k = (long long)busy + q;
                     rec[(k < P.p_bins ? MQ_F_P + k : MQ_F_POVER) * R] += (double)(te - t);
@@ -436,25 +548,26 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                     const uint32_t idx1 = nxt + 1u;
                     nxt++;
                     uint2 w = philox2x32_10(idx1, rep, key0);
-                    const float gx = sample<SRCK>(P.src, w.x, idx1, rep, key0, 0);
-                    const float sx = sample<SRVK>(P.srv, w.y, idx1, rep, key0, 1);
-                    const float S_i = S_pend;
+                    const Real gx = draw_a(w.x, idx1);
+                    const Real sx = draw_s(w.y, idx1);
+                    const Real S_i = S_pend;
                     tA = t + gx;
                     S_pend = sx;
                     if (busy < c) {
                         bool placed = false;
 #pragma unroll
                         for (int j = 0; j < CT; ++j) {
-                            if (!placed && L[j] < -MQ_KEY_LIM) {
-                                const uint32_t tg = __float_as_uint(L[j]) & Tag<CT>::MASK;
-                                L[j] = stamp<CT>(t + S_i, tg);
-                                st_shared(vslot_sa + tg * (MQ_BLOCK * 4u), S_i);
+                            if (!placed && L[j] < -T::LIM) {
+                                const uint32_t tg = Tag<CT>::of(L[j]);
+                                L[j] = stamp<CT, Real>(t + S_i, tg);
+                                T::st(vslot_sa + tg * COL, S_i);
                                 placed = true;
                             }
                         }
                         busy++;
                         taked++;
                         acc4(sv, S_i);
+                        if (BUSY) start_busy = t;
                     } else if (!FINITE || q < cap) {
                         if (!FINITE) {
                             if (q == 0u) {
@@ -462,12 +575,12 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                                 S_h = S_i;
                             }
                         } else {
-                            float gap = 0.0f;
+                            Real gap = ZERO;
                             if (q == 0u) a_anchor = t; else gap = t - a_lastq;
                             a_lastq = t;
                             uint32_t slot = head + q;
                             if (slot >= cap) slot -= cap;
-                            P.ring[(long long)slot * P.lanes + gtid] = make_float2(gap, S_i);
+                            ring[(long long)slot * P.lanes + gtid] = T::ring(gap, S_i);
                         }
                         q++;
                     } else {
@@ -475,7 +588,7 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                     }
                 } else {
                     served++;
-                    float a = 0.0f, S = 0.0f;
+                    Real a = ZERO, S = ZERO;
                     const bool pop = q > 0u;
                     if (pop) {
                         if (!FINITE) {
@@ -484,11 +597,11 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                             if (q > 1u) {
                                 const uint32_t ridx = nxt - q + 1u;
                                 uint2 w = philox2x32_10(ridx, rep, key0);
-                                a_h += sample<SRCK>(P.src, w.x, ridx, rep, key0, 0);
-                                S_h = sample<SRVK>(P.srv, w.y, ridx, rep, key0, 1);
+                                a_h += draw_a(w.x, ridx);
+                                S_h = draw_s(w.y, ridx);
                             }
                         } else {
-                            const float2 e = P.ring[(long long)head * P.lanes + gtid];
+                            const Ring e = ring[(long long)head * P.lanes + gtid];
                             a = a_anchor + e.x;
                             a_anchor = a;
                             S = e.y;
@@ -497,17 +610,19 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
                         }
                         q--;
                         taked++;
+                        if (BUSY) start_busy = t;
                     } else {
+                        if (BUSY && busy == c) busy_sample(t - start_busy);
                         busy--;
                     }
-                    const float w = fmaxf(t - a, 0.0f);
-                    const float vv = w + S;
+                    const Real w = T::mx(t - a, ZERO);
+                    const Real vv = w + S;
 #pragma unroll
                     for (int j = 0; j < CT; ++j) {
                         if (L[j] == dmin) {
-                            const uint32_t tg = __float_as_uint(L[j]) & Tag<CT>::MASK;
-                            L[j] = pop ? stamp<CT>(t + S, tg) : __uint_as_float(MQ_KEY_GONE | tg);
-                            if (pop) st_shared(vslot_sa + tg * (MQ_BLOCK * 4u), vv);
+                            const uint32_t tg = Tag<CT>::of(L[j]);
+                            L[j] = pop ? stamp<CT, Real>(t + S, tg) : T::real(T::KEY_GONE | (typename T::U)tg);
+                            if (pop) T::st(vslot_sa + tg * COL, vv);
                         }
                     }
                     if (pop) {
@@ -525,8 +640,8 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
         uint32_t in_service = 0;
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
-            const float xs = fabsf(L[j]) < MQ_KEY_LIM ? vslot[(__float_as_uint(L[j]) & Tag<CT>::MASK) * MQ_BLOCK] : -1.0f;
-            if (xs >= 0.0f && !P.v_at_start) {  // in service and started after the warm-up
+            const Real xs = T::abs_(L[j]) < T::LIM ? vslot[Tag<CT>::of(L[j]) * MQ_BLOCK] : (Real)-1;
+            if (xs >= ZERO && !P.v_at_start) {  // in service and started after the warm-up
                 in_service++;
                 const double x = (double)xs;
                 const double x2 = x * x;
@@ -545,6 +660,7 @@ __global__ void __launch_bounds__(MQ_BLOCK, (CT <= 8 ? MQ_K2_MINB : 2)) k2_fifo_
         rec[(long long)MQ_F_DROPPED * R] = (double)dropped;
         rec[(long long)MQ_F_TTEK * R] = tbase - t_warm;
         rec[(long long)MQ_F_FLAGS * R] = (double)flags;
+        if (BUSY) rec[(long long)(MQ_REC_ROWS(P.p_bins) + MQ_FB_BUSYN) * R] = (double)nbusy;
     }
 }
 

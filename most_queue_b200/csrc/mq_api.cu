@@ -8,7 +8,7 @@
 namespace mq {
 
 #define MQ_DECL_K2(n) \
-    cudaError_t k2_dispatch_ct##n(const K2Params &, int, bool, int, size_t, cudaStream_t, int *);
+    cudaError_t k2_dispatch_ct##n(const K2Params &, int, bool, bool, int, size_t, cudaStream_t, int *);
 #define MQ_DECL_K1(n) cudaError_t k1_dispatch_ct##n(const K1Params &, bool, cudaStream_t);
 MQ_DECL_K2(1) MQ_DECL_K2(2) MQ_DECL_K2(3) MQ_DECL_K2(4) MQ_DECL_K2(5) MQ_DECL_K2(6) MQ_DECL_K2(7)
 MQ_DECL_K2(8) MQ_DECL_K2(16) MQ_DECL_K2(32)
@@ -133,6 +133,58 @@ DistF make_distf(const mq_dist &d)
     return f;
 }
 
+DistD make_distd(const mq_dist &d)
+{
+    DistD f;
+    std::memset(&f, 0, sizeof(f));
+    f.kind = d.kind;
+    const double *p = d.p;
+    switch (d.kind) {
+    case MQ_M:
+        f.a = 1.0 / p[0];
+        break;
+    case MQ_H2:
+    case MQ_C2:
+        f.T = branch_threshold(p[0]);
+        f.a = 1.0 / p[1];
+        f.b = 1.0 / p[2];
+        break;
+    case MQ_E:
+        f.r = (int)p[0];
+        f.a = 1.0 / p[1];
+        break;
+    case MQ_GAMMA: {
+        const double alpha = p[1], a = alpha >= 1.0 ? alpha : alpha + 1.0;
+        f.a = a - 1.0 / 3.0;
+        f.b = 1.0 / std::sqrt(9.0 * f.a);
+        f.c = 1.0 / p[0];
+        f.d = 1.0 / alpha;
+        f.r = alpha < 1.0 ? 1 : 0;
+        break;
+    }
+    case MQ_PA:
+        f.a = -1.0 / p[0];
+        f.b = p[1];
+        break;
+    case MQ_D:
+        f.a = p[0];
+        break;
+    case MQ_UNIFORM:
+        f.a = p[0] - p[1];
+        f.b = 2.0 * p[1];
+        break;
+    case MQ_NORM:
+        f.a = p[0];
+        f.b = p[1];
+        break;
+    case MQ_WEIBULL:
+        f.a = p[1];
+        f.b = -1.0 / p[0];
+        break;
+    }
+    return f;
+}
+
 // 64-bit user seed -> 32-bit Philox key (splitmix64 finaliser)
 uint32_t seed_to_key(uint64_t s)
 {
@@ -143,13 +195,13 @@ uint32_t seed_to_key(uint64_t s)
     return (uint32_t)(s ^ (s >> 32));
 }
 
-static cudaError_t k2_dispatch(int ct, const K2Params &P, int pc, bool fin, int grid, size_t smem,
+static cudaError_t k2_dispatch(int ct, const K2Params &P, int pc, bool fin, bool busy, int grid, size_t smem,
                                cudaStream_t st, int *occ)
 {
     switch (ct) {
 #define MQ_CASE(n) \
     case n:        \
-        return k2_dispatch_ct##n(P, pc, fin, grid, smem, st, occ);
+        return k2_dispatch_ct##n(P, pc, fin, busy, grid, smem, st, occ);
         MQ_CASE(1) MQ_CASE(2) MQ_CASE(3) MQ_CASE(4) MQ_CASE(5) MQ_CASE(6) MQ_CASE(7) MQ_CASE(8)
         MQ_CASE(16) MQ_CASE(32)
 #undef MQ_CASE
@@ -269,9 +321,12 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     CU(cudaSetDevice(ctx->device));
 
     const long long R = cfg->replications;
-    const int rows = MQ_REC_ROWS(cfg->p_bins);
+    const bool fp64 = (cfg->flags & MQ_FIFO_FP64) != 0;
+    const bool busy = (cfg->flags & MQ_FIFO_BUSY) != 0;
+    const int rows = MQ_REC_ROWS(cfg->p_bins) + (busy ? MQ_FIFO_BUSY_ROWS : 0);
+    const int agg_len = MQ_AGG_LEN(cfg->p_bins) + (busy ? MQ_AGG_BUSY_LEN : 0);
     if (int rc = ensure(ctx->rec, sizeof(double) * (size_t)rows * (size_t)R)) return rc;
-    if (int rc = stage_agg(ctx, cfg->p_bins)) return rc;
+    if (int rc = ensure_host_agg(ctx, sizeof(double) * (size_t)agg_len)) return rc;
 
     K2Params P;
     std::memset(&P, 0, sizeof(P));
@@ -287,46 +342,63 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     P.v_at_start = (cfg->flags & MQ_FIFO_V_AT_START) ? 1 : 0;
     P.src = make_distf(cfg->src);
     P.srv = make_distf(cfg->srv);
+    P.srcd = make_distd(cfg->src);
+    P.srvd = make_distd(cfg->srv);
     P.rec = (double *)ctx->rec.p;
 
     const bool finite = cfg->buffer >= 0;
     int pc = 0;
     if (cfg->src.kind == MQ_M && cfg->srv.kind == MQ_M) pc = 1;
     if (cfg->src.kind == MQ_M && cfg->srv.kind == MQ_H2) pc = 2;
-    const size_t smem = sizeof(float) * (size_t)(MQ_BF + ct) * MQ_BLOCK;
+    if (busy) pc = 0;  // the busy-period variant exists for the generic class only
+    if (fp64) pc = 3;
+    const size_t real_b = fp64 ? sizeof(double) : sizeof(float);
+    const size_t smem = real_b * (size_t)(MQ_BF + ct) * MQ_BLOCK;
     int occ = 0;
-    CU(k2_dispatch(ct, P, pc, finite, 0, smem, nullptr, &occ));
+    CU(k2_dispatch(ct, P, pc, finite, busy, 0, smem, nullptr, &occ));
     if (occ < 1) return fail(MQ_E_CUDA, "mq_sim_fifo: kernel does not fit on an SM");
     long long blocks_needed = (R + MQ_BLOCK - 1) / MQ_BLOCK;
     long long grid = (long long)occ * ctx->sms;
     if (grid > blocks_needed) grid = blocks_needed;
     P.lanes = grid * MQ_BLOCK;
     if (finite && cfg->buffer > 0) {
-        const size_t bytes = sizeof(float2) * (size_t)cfg->buffer * (size_t)P.lanes;
+        const size_t bytes = 2 * real_b * (size_t)cfg->buffer * (size_t)P.lanes;
         if (bytes > (size_t)48 << 30)
             return fail(MQ_E_UNSUPPORTED, "mq_sim_fifo: buffer=%lld needs %.1f GiB of queue scratch",
                         (long long)cfg->buffer, bytes / 1073741824.0);
         if (int rc = ensure(ctx->ring, bytes)) return rc;
-        P.ring = (float2 *)ctx->ring.p;
+        P.ring = ctx->ring.p;
+    }
+    if (busy) {
+        const int B = MQ_REC_ROWS(cfg->p_bins);
+        const RatioDesc d[4] = {{B + MQ_FB_BUSY, B + MQ_FB_BUSYN}, {B + MQ_FB_BUSY + 1, B + MQ_FB_BUSYN},
+                                {B + MQ_FB_BUSY + 2, B + MQ_FB_BUSYN}, {B + MQ_FB_BUSYN, -1}};
+        if (int rc = ensure(ctx->desc, sizeof(d))) return rc;
+        CU(cudaMemcpyAsync(ctx->desc.p, d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // d is a stack array
     }
 
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(cudaMemsetAsync(ctx->rec.p, 0, sizeof(double) * (size_t)rows * (size_t)R, ctx->stream));
-    CU(k2_dispatch(ct, P, pc, finite, (int)grid, smem, ctx->stream, nullptr));
+    CU(k2_dispatch(ct, P, pc, finite, busy, (int)grid, smem, ctx->stream, nullptr));
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(launch_reduce_records((const double *)ctx->rec.p, R, cfg->p_bins, (double *)ctx->agg.p, ctx->stream));
     ctx->launches++;
+    if (busy) {
+        CU(launch_reduce_ratio((const double *)ctx->rec.p, R, (const RatioDesc *)ctx->desc.p, 4,
+                               (double *)ctx->agg.p + MQ_AGG_LEN(cfg->p_bins), ctx->stream));
+        ctx->launches++;
+    }
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_agg, ctx->agg.p, sizeof(double) * MQ_AGG_LEN(cfg->p_bins),
-                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_agg, ctx->agg.p, sizeof(double) * (size_t)agg_len, cudaMemcpyDeviceToHost, ctx->stream));
     if (rep_out)
         CU(cudaMemcpyAsync(rep_out, ctx->rec.p, sizeof(double) * (size_t)rows * (size_t)R,
                            cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(agg, ctx->h_agg, sizeof(double) * MQ_AGG_LEN(cfg->p_bins));
+    std::memcpy(agg, ctx->h_agg, sizeof(double) * (size_t)agg_len);
     return finish_timing(ctx);
 }
 

@@ -202,6 +202,83 @@ __device__ __forceinline__ float sample(const DistF &d, uint32_t w0, uint32_t id
     }
 }
 
+// -------------------------------------------------------------------------------------
+// fp64 tier of the same samplers (MQ_FIFO_FP64: the A/B kernel that measures what the fp32 production tier costs in
+// accuracy).  Same words, same formulas, evaluated with the CUDA math library's double log / exp / cos / sqrt -- the
+// generator specification of DESIGN.md section 3 as oracle/mq_oracle.c states it in fp64.
+// -------------------------------------------------------------------------------------
+struct DistD {
+    int kind;
+    int r;
+    uint32_t T;
+    uint32_t pad;
+    double a, b, c, d;
+};
+
+__device__ __forceinline__ double u01d(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
+
+static __device__ __noinline__ double sample_d(int kind, int r, uint32_t T, double a, double b, double c, double d,
+                                               uint32_t w0, uint32_t idx, uint32_t rep, uint32_t key0, int which)
+{
+    switch (kind) {
+    case MQ_M:  // a = 1/mu
+        return -log(u01d(w0)) * a;
+    case MQ_H2:  // a = 1/mu1, b = 1/mu2 (distributions.py:407-429; one word, see sample_h2)
+        if (w0 < T) return -log(((double)w0 + 0.5) / (double)T) * a;
+        return -log(((double)(w0 - T) + 0.5) / (4294967296.0 - (double)T)) * b;
+    case MQ_E: {  // a = 1/mu
+        double acc = log(u01d(w0));
+        uint2 e = make_uint2(0u, 0u);
+        for (int k = 1; k < r; ++k) {
+            if (k & 1) e = ext_words(idx, rep, key0, which, (uint32_t)(k + 1) >> 1);
+            acc += log(u01d((k & 1) ? e.x : e.y));
+        }
+        return -acc * a;
+    }
+    case MQ_GAMMA: {  // a = dd, b = cc, c = 1/mu, d = 1/alpha, r = (alpha < 1)
+        double x = a;
+        for (uint32_t t = 0; t < 15; ++t) {
+            uint2 e0 = ext_words(idx, rep, key0, which, 2 * t + 1);
+            const double z = sqrt(-2.0 * log(u01d(e0.x))) * cos(6.283185307179586 * u01d(e0.y));
+            double v = 1.0 + b * z;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            x = a * v;
+            const uint32_t wa = (t == 0 && !r) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
+            if (log(u01d(wa)) < 0.5 * z * z + a - a * v + a * log(v)) break;
+        }
+        if (r) x *= exp(log(u01d(w0)) * d);
+        return x * c;
+    }
+    case MQ_PA:  // a = -1/alpha, b = K
+        return b * exp(log(u01d(w0)) * a);
+    case MQ_D:
+        return a;
+    case MQ_C2: {  // a = 1/mu1, b = 1/mu2
+        uint2 e = ext_words(idx, rep, key0, which, 1);
+        double res = -log(u01d(w0)) * a;
+        if (e.x < T) res -= log(u01d(e.y)) * b;
+        return res;
+    }
+    case MQ_UNIFORM:  // a = mean - half, b = 2 half
+        return fma(b, u01d(w0), a);
+    case MQ_NORM: {  // a = mean, b = std
+        uint2 e = ext_words(idx, rep, key0, which, 1);
+        return fma(b * sqrt(-2.0 * log(u01d(w0))), cos(6.283185307179586 * u01d(e.x)), a);
+    }
+    case MQ_WEIBULL:  // a = W, b = -1/k
+        return exp(log(-log(u01d(w0)) * a) * b);
+    default:
+        return 0.0;
+    }
+}
+
+__device__ __forceinline__ double sample_d(const DistD &q, uint32_t w0, uint32_t idx, uint32_t rep, uint32_t key0,
+                                           int which)
+{
+    return sample_d(q.kind, q.r, q.T, q.a, q.b, q.c, q.d, w0, idx, rep, key0, which);
+}
+
 // sum of x^k, k = 1..4 (5 issue slots)
 __device__ __forceinline__ void acc4(float (&s)[4], float x)
 {
@@ -210,6 +287,15 @@ __device__ __forceinline__ void acc4(float (&s)[4], float x)
     s[1] += x2;
     s[2] = fmaf(x2, x, s[2]);
     s[3] = fmaf(x2, x2, s[3]);
+}
+
+__device__ __forceinline__ void acc4(double (&s)[4], double x)
+{
+    double x2 = x * x;
+    s[0] += x;
+    s[1] += x2;
+    s[2] = fma(x2, x, s[2]);
+    s[3] = fma(x2, x2, s[3]);
 }
 
 }  // namespace mq

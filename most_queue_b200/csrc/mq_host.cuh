@@ -97,6 +97,7 @@ cudaError_t launch_reduce_ratio(const double *rec, long long R, const RatioDesc 
 
 int check_dist(const mq_dist &d, const char *what);
 DistF make_distf(const mq_dist &d);
+DistD make_distd(const mq_dist &d);
 uint32_t seed_to_key(uint64_t s);
 
 }  // namespace mq

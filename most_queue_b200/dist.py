@@ -38,17 +38,56 @@ def shard(replications: int, rank: int | None = None, world_size: int | None = N
     return lo, hi - lo
 
 
+_dev_buf = {}  # (device index, length) -> (device tensor, pinned host tensor): allocated once, reused by every call
+
+
+def _buffers(n: int):
+    import torch
+
+    key = (torch.cuda.current_device(), n)
+    if key not in _dev_buf:
+        _dev_buf[key] = (torch.empty(n, dtype=torch.float64, device="cuda"),
+                         torch.empty(n, dtype=torch.float64).pin_memory())
+    return _dev_buf[key]
+
+
 def allreduce_sum(vec: np.ndarray) -> np.ndarray:
-    """Sum a small fp64 vector over all ranks (identity when not distributed)."""
+    """Sum a small fp64 vector over all ranks (identity when not distributed).  With NCCL the vector goes through a
+    persistent device buffer and a pinned host buffer (no allocation, no pageable copy per call)."""
     d = _dist()
     if d is None or d.get_world_size() == 1:
         return vec
     import torch
 
     if d.get_backend() == "nccl":
-        t = torch.from_numpy(np.ascontiguousarray(vec)).cuda()
-        d.all_reduce(t, op=d.ReduceOp.SUM)
-        return t.cpu().numpy()
+        dev, host = _buffers(len(vec))
+        host.numpy()[:] = vec
+        dev.copy_(host, non_blocking=True)
+        d.all_reduce(dev, op=d.ReduceOp.SUM)
+        host.copy_(dev)
+        return host.numpy().copy()
     t = torch.from_numpy(np.ascontiguousarray(vec).copy())
     d.all_reduce(t, op=d.ReduceOp.SUM)
     return t.numpy()
+
+
+def common_seed(seed) -> int:
+    """The Philox seed of a run.  An explicit seed is used as is (every rank was given the same one).  seed=None means
+    non-deterministic like numpy.random.default_rng(None) (base_core.py:23): rank 0 draws one from os.urandom and
+    broadcasts it, because a run sharded over ranks must use ONE key -- otherwise the result would depend on the
+    number of ranks, and the ranges of one chain would be generated from different streams."""
+    if seed is not None:
+        return int(seed)
+    import os
+
+    seed = int.from_bytes(os.urandom(8), "little") & 0x7FFFFFFFFFFFFFFF
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return seed
+    import torch
+
+    t = torch.tensor([seed], dtype=torch.int64)
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    d.broadcast(t, src=0)
+    return int(t.item())

@@ -30,7 +30,8 @@ class QsSim:
     """Queueing system GI/G/n/r and GI/G/n (FIFO), batched over replications on one B200."""
 
     def __init__(self, num_of_channels, buffer=None, verbose=True, buffer_type="list", seed=None,
-                 replications=1, p_bins=128, device=None, warmup=0, v_at_start=False):
+                 replications=1, p_bins=128, device=None, warmup=0, v_at_start=False, precision="f32",
+                 busy=False):
         if buffer_type not in ("list", "deque"):
             raise ValueError("Unknown queue type")  # base.py:73
         self.n = int(num_of_channels)
@@ -45,6 +46,17 @@ class QsSim:
         self.warmup = int(warmup)
         # additive: sample v for every job that started service before the stop (no right-censoring)
         self.v_at_start = bool(v_at_start)
+        # additive: "f32" = the production kernel (fp32 clocks relative to an epoch, MUFU samplers); "f64" = the same
+        # loop on the same Philox words in fp64 (MQ_FIFO_FP64), the precision of the reference's Python floats
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        self.precision = precision
+        # busy-period moments (QsSim.busy, base.py:274-281) cost a few instructions per event: they are gathered when
+        # busy=True, or on first access of `.busy` after a run (the run is repeated with the same seed)
+        self.want_busy = bool(busy)
+        self._busy = None
+        self._last_run = None
+        self.busy_moments = 0
 
         self.num_of_states = DEFAULT_NUM_STATES
         self.w = [0, 0, 0, 0]
@@ -86,23 +98,41 @@ class QsSim:
         R = int(self.replications if replications is None else replications)
         if R < 1:
             raise ValueError("replications must be >= 1")
-        seed = self.seed
-        if seed is None:  # non-deterministic like numpy.random.default_rng(None), base_core.py:23
-            seed = int.from_bytes(os.urandom(8), "little")
+        seed = dist.common_seed(self.seed)  # seed=None: drawn on rank 0 and broadcast
+        self._busy = None
+        self._last_run = (int(total_served), R, seed)
+        agg, rec = self._launch(total_served, R, seed, keep_replications, self.want_busy)
+        self._publish(agg, rec)
+        self.time_spent = time.process_time() - start
+        return QueueResults(v=self.get_v(), w=self.get_w(), p=self.get_p(), duration=self.time_spent,
+                            utilization=self.calc_load(), replications=R, ci=self.ci)
+
+    def _launch(self, total_served, R, seed, keep_replications, busy):
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         if count > 0:
             agg, rec = ctx.sim_fifo(self.n, self.buffer, self._src, self._srv, total_served, count, rep0, seed,
                                     p_bins=self.p_bins, per_replication=keep_replications, warmup=self.warmup,
-                                    v_at_start=self.v_at_start)
+                                    v_at_start=self.v_at_start, fp64=self.precision == "f64", busy=busy)
             self.timing = ctx.last_timing()
         else:
-            agg, rec = np.zeros(_lib.agg_len(self.p_bins)), None
-        agg = dist.allreduce_sum(agg)
-        self._publish(agg, rec)
-        self.time_spent = time.process_time() - start
-        return QueueResults(v=self.get_v(), w=self.get_w(), p=self.get_p(), duration=self.time_spent,
-                            utilization=self.calc_load(), replications=R, ci=self.ci)
+            agg, rec = np.zeros(_lib.agg_len(self.p_bins) + (_lib.AGG_BUSY_LEN if busy else 0)), None
+        return dist.allreduce_sum(agg), rec
+
+    @property
+    def busy(self):
+        """Raw moments 1..3 of the busy period (QsSim.busy, base.py:274-281), mean over replications."""
+        if self._busy is None and self._last_run is not None:
+            n, R, seed = self._last_run
+            agg, _ = self._launch(n, R, seed, False, True)
+            self._set_busy(agg)
+        return self._busy if self._busy is not None else [0, 0, 0]
+
+    def _set_busy(self, agg):
+        b = agg[_lib.agg_len(self.p_bins):]
+        R = agg[_lib.A_REPS]
+        self._busy = [float(x) / R for x in b[0:3]]
+        self.busy_moments = int(round(b[3])) if R == 1 else float(b[3]) / R
 
     def _publish(self, agg: np.ndarray, rec):
         L = _lib
@@ -110,6 +140,8 @@ class QsSim:
         P = self.p_bins
         self.agg = agg
         self.per_replication = rec
+        if len(agg) > L.agg_len(P):
+            self._set_busy(agg)
         if agg[L.A_FLAGGED] > 0:
             raise _lib.MqError(_lib.MQ_E_OVERFLOW, f"{int(agg[L.A_FLAGGED])} replications hit a library limit")
 

@@ -64,8 +64,7 @@ def run_chain(source, server, total_served: int, seed=None, chain: int = 0, devi
     start = time.process_time()
     L = _lib
     src, srv = L.make_dist(source[0], source[1]), L.make_dist(server[0], server[1])
-    if seed is None:
-        seed = int.from_bytes(os.urandom(8), "little")
+    seed = dist.common_seed(seed)  # one key for every range of the chain (seed=None: drawn on rank 0, broadcast)
     rank, world = dist.world()
     job0, count = dist.shard(int(total_served))
     ctx = L.default_context(device)

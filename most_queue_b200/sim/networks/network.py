@@ -69,7 +69,7 @@ class NetworkSimulator:
         start = time.process_time()
         self._check_sources_and_nodes_is_set()
         R = int(self.replications if replications is None else replications)
-        seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
+        seed = dist.common_seed(self.seed)
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         m = self.n_num

@@ -51,7 +51,7 @@ class TandemBlockingSim:
         if not (self.is_sources_set and self.is_nodes_set):
             raise RuntimeError("set sources and nodes before run()")
         R = int(self.replications if replications is None else replications)
-        seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
+        seed = dist.common_seed(self.seed)
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         m = self.m

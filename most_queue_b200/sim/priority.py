@@ -75,7 +75,7 @@ class PriorityQueueSimulator:
             raise RuntimeError("set_sources() and set_servers() must be called before run()")
         start = time.process_time()
         R = int(self.replications if replications is None else replications)
-        seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
+        seed = dist.common_seed(self.seed)
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         if count > 0:

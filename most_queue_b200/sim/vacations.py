@@ -62,7 +62,7 @@ class VacationQueueingSystemSimulator(QsSim):
         R = int(self.replications if replications is None else replications)
         if R < 1:
             raise ValueError("replications must be >= 1")
-        seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
+        seed = dist.common_seed(self.seed)
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         if count > 0:

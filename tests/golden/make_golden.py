@@ -620,6 +620,62 @@ def make_tandem():
 
 
 # --------------------------------------------------------------------------- theory
+def _priority_and_network_theory():
+    """Calculators SURVEY 8(d) names for BASELINE cfg4 / cfg5: the exact truncated-CTMC M/M/k preemptive-resume solver
+    (theory/priority/preemptive/mmk_prty_exact.py:24), the invariant-relations approximation for M/G/n priorities
+    (theory/priority/mgn_invar_approx.py:21), the exact Jackson product form (theory/networks/jackson_network.py:25)
+    and the decomposition approximation (theory/networks/open_network.py:17)."""
+    from most_queue.random.distributions import GammaDistribution, H2Distribution
+    from most_queue.theory.networks.jackson_network import JacksonNetworkCalc
+    from most_queue.theory.networks.open_network import OpenNetworkCalc
+    from most_queue.theory.priority.mgn_invar_approx import MGnInvarApproximation
+    from most_queue.theory.priority.preemptive.mmk_prty_exact import MMkPriorityExact
+
+    out = {}
+    lam, mu = [0.3, 0.5], [0.5, 0.25]
+    with quiet():
+        c = MMkPriorityExact(n=4, with_variance=True)
+        c.set_sources(lam)
+        c.set_servers(mu)
+        r = c.run()
+    out["cfg4_mm4_pr_exact"] = {"n": 4, "lam": lam, "mu": mu, "v": [list(map(float, x)) for x in r.v],
+                                "w": [list(map(float, x)) for x in r.w], "utilization": float(r.utilization),
+                                "boundary_mass": float(np.max(c.boundary_mass)) if c.boundary_mass is not None else None}
+    g = [GammaDistribution.get_params_by_mean_and_cv(m, 1.2) for m in (2.0, 4.0)]
+    b = [list(map(float, GammaDistribution.calc_theory_moments(x, 4))) for x in g]
+    for prty in ("NP", "PR"):
+        with quiet():
+            c = MGnInvarApproximation(n=4, priority=prty)
+            c.set_sources(lam)
+            c.set_servers(b)
+            v = c.get_v()
+        out[f"cfg4_mg4_{prty.lower()}_invar"] = {"n": 4, "lam": lam, "b": b, "approximate": True,
+                                                 "v": [list(map(float, np.real(x))) for x in v]}
+    R = np.matrix([[1, 0, 0, 0, 0, 0], [0, 0.4, 0.6, 0, 0, 0], [0, 0, 0.2, 0.4, 0.4, 0], [0, 0, 0, 0, 1, 0],
+                   [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 0, 1]], dtype=float)
+    ch = [3, 2, 3, 4, 3]
+    with quiet():
+        c = JacksonNetworkCalc()
+        c.set_sources(arrival_rate=1.0, R=R)
+        lam_i = [float(x) for x in c.solve_intensities()]
+        mus = [lam_i[i] / (0.7 * ch[i]) for i in range(5)]
+        c.set_nodes(mu=mus, n=ch)
+        r = c.run()
+    out["cfg5_jackson"] = {"n": ch, "mu": mus, "intensities": lam_i, "loads": list(map(float, r.loads)),
+                           "v1": float(r.v[0])}
+    hs = [H2Distribution.get_params_by_mean_and_cv(0.7 * c_, 1.2) for c_ in ch]
+    bh = [list(map(float, np.real(H2Distribution.calc_theory_moments(h, 4)))) for h in hs]
+    with quiet():
+        c = OpenNetworkCalc()
+        c.set_sources(R=R, arrival_rate=1.0)
+        c.set_nodes(b=bh, n=ch)
+        r = c.run()
+    out["cfg5_open_network_h2"] = {"n": ch, "approximate": True, "h2": [[float(h.p1), float(h.mu1), float(h.mu2)] for h in hs],
+                                   "intensities": list(map(float, r.intensities)), "loads": list(map(float, r.loads)),
+                                   "v": list(map(float, np.real(r.v)))}
+    return out
+
+
 def make_theory():
     """Analytical values used by the generator-mode (statistical) tests."""
     from most_queue.random.distributions import GammaDistribution, H2Distribution, ParetoDistribution
@@ -694,6 +750,7 @@ def make_theory():
                    "moments": list(map(float, ErlangDistribution.calc_theory_moments(e, 3)))},
         "exp": {"params": 0.8, "moments": list(map(float, ExpDistribution.calc_theory_moments(0.8, 3)))},
     }
+    out.update(_priority_and_network_theory())
     with open(os.path.join(OUT, "theory.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("theory.json written")

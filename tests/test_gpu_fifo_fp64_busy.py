@@ -1,0 +1,158 @@
+"""K2 additions of round 2: the fp64 A/B tier (MQ_FIFO_FP64) and the busy-period moments (MQ_FIFO_BUSY, QsSim.busy).
+
+The fp64 tier runs the same loop on the same Philox words in fp64, so per replication it must follow the oracle's
+sample path (oracle/mq_oracle.c, fp64 / libm) to double-precision rounding, and the fp32 production tier must agree
+with it to fp32 accuracy -- which is the direct measurement of what fp32 costs (bench.py reports it at R = 1e6).
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H2 = dict(p1=0.447586, mu1=0.0950716, mu2=0.619214)
+
+
+def _h2():
+    from most_queue_b200.random.utils.params import H2Params
+
+    return H2Params(**H2)
+
+
+CASES = [
+    (8, None, ("M", 1.0), ("H", None), 3000),
+    (3, 30, ("M", 1.0), ("M", 1.0 / 2.1), 3000),
+    (3, 0, ("M", 2.0), ("M", 1.0), 2000),
+    (1, None, ("Gamma", "g"), ("Pa", "p"), 3000),
+    (5, 4, ("E", "e"), ("Gamma", "g2"), 2500),
+    (2, None, ("M", 1.0), ("D", 1.4), 2500),
+]
+
+
+def _params(x):
+    from most_queue_b200.random.distributions import GammaDistribution, ParetoDistribution
+    from most_queue_b200.random.utils.params import ErlangParams
+
+    if x is None:
+        return _h2()
+    if x == "g":
+        return GammaDistribution.get_params_by_mean_and_cv(1.0, 0.56)
+    if x == "g2":
+        return GammaDistribution.get_params_by_mean_and_cv(3.5, 1.3)
+    if x == "p":
+        return ParetoDistribution.get_params_by_mean_and_cv(0.7, 1.2)
+    if x == "e":
+        return ErlangParams(r=3, mu=3.0)
+    return x
+
+
+@pytest.mark.parametrize("c,buffer,src,srv,n", CASES)
+def test_fp64_tier_follows_the_oracle_path(c, buffer, src, srv, n):
+    from most_queue_b200 import _lib
+    from oracle import oracle
+
+    src, srv = (src[0], _params(src[1])), (srv[0], _params(srv[1]))
+    ctx = _lib.default_context()
+    seed, reps = 11, 64
+    agg, rec = ctx.sim_fifo(c, buffer, _lib.make_dist(*src), _lib.make_dist(*srv), n, reps, 5, seed, p_bins=48,
+                            per_replication=True, fp64=True, busy=True)
+    ref = oracle.fifo_generate(c, buffer, src, srv, n, _lib.seed_to_key(seed), 5, reps, p_bins=48,
+                               threads=os.cpu_count() or 1)
+    B = _lib.rec_rows(48)
+    same = 0
+    for r, o in enumerate(ref):
+        if (int(rec[_lib.F_ARRIVED, r]), int(rec[_lib.F_TAKED, r]), int(rec[_lib.F_DROPPED, r])) != (o.arrived, o.taked, o.dropped):
+            continue  # an exact tie resolved the other way (CUDA log vs libm log differ by an ulp): a different path
+        same += 1
+        np.testing.assert_allclose(rec[_lib.F_TTEK, r], o.ttek, rtol=1e-12)
+        np.testing.assert_allclose(rec[_lib.F_W:_lib.F_W + 4, r], o.w_sum, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(rec[_lib.F_V:_lib.F_V + 4, r], o.v_sum, rtol=1e-9)
+        np.testing.assert_allclose(rec[_lib.F_P:_lib.F_P + 48, r], o.p_time, rtol=1e-9, atol=1e-9 * o.ttek)
+        # busy periods: the oracle keeps the reference's running means (base.py:274-281)
+        assert int(rec[B + _lib.FB_BUSYN, r]) == o.busy_n
+        if o.busy_n:
+            np.testing.assert_allclose(rec[B + _lib.FB_BUSY:B + _lib.FB_BUSY + 3, r] / o.busy_n, o.busy, rtol=1e-9)
+    assert same >= reps - 2, same
+
+
+@pytest.mark.parametrize("c,buffer,src,srv,n", CASES[:3])
+def test_busy_moments_of_the_production_tier(c, buffer, src, srv, n):
+    """fp32 tier with MQ_FIFO_BUSY against the oracle: same count of busy periods on replications that follow the same
+    path, moments to fp32 accuracy."""
+    from most_queue_b200 import _lib
+    from oracle import oracle
+
+    src, srv = (src[0], _params(src[1])), (srv[0], _params(srv[1]))
+    ctx = _lib.default_context()
+    seed, reps = 12, 64
+    agg, rec = ctx.sim_fifo(c, buffer, _lib.make_dist(*src), _lib.make_dist(*srv), n, reps, 0, seed, p_bins=48,
+                            per_replication=True, busy=True)
+    ref = oracle.fifo_generate(c, buffer, src, srv, n, _lib.seed_to_key(seed), 0, reps, p_bins=48,
+                               threads=os.cpu_count() or 1)
+    B = _lib.rec_rows(48)
+    same = 0
+    for r, o in enumerate(ref):
+        if (int(rec[_lib.F_ARRIVED, r]), int(rec[_lib.F_TAKED, r]), int(rec[_lib.F_DROPPED, r])) != (o.arrived, o.taked, o.dropped):
+            continue
+        if int(rec[B + _lib.FB_BUSYN, r]) != o.busy_n:
+            continue  # an fp32 near-tie between an arrival and the departure that ends a busy period
+        same += 1
+        if o.busy_n:
+            np.testing.assert_allclose(rec[B + _lib.FB_BUSY:B + _lib.FB_BUSY + 3, r] / o.busy_n, o.busy, rtol=2e-4)
+    assert same >= reps * 3 // 4, same
+    # aggregate extension: mean over replications of the per-replication moments
+    n_b = rec[B + _lib.FB_BUSYN]
+    m1 = np.where(n_b > 0, rec[B + _lib.FB_BUSY] / np.maximum(n_b, 1), 0.0)
+    np.testing.assert_allclose(agg[_lib.agg_len(48)], m1.sum(), rtol=1e-12)
+    np.testing.assert_allclose(agg[_lib.agg_len(48) + 3], n_b.sum(), rtol=1e-12)
+
+
+def test_qssim_busy_attribute_and_precision_switch():
+    """QsSim.busy (base.py:58 / base_core.py:27) through the public API: gathered on demand (the run is repeated with
+    the same seed), equal to the explicit busy=True run; precision='f64' reproduces the f32 moments to fp32 accuracy."""
+    from most_queue_b200.sim.base import QsSim
+
+    def make(**kw):
+        qs = QsSim(3, buffer=30, seed=5, replications=4096, p_bins=48, **kw)
+        qs.set_sources(1.0, "M")
+        qs.set_servers(1.0 / 2.1, "M")
+        return qs
+
+    a = make()
+    ra = a.run(20_000)
+    busy_lazy = list(a.busy)
+    b = make(busy=True)
+    rb = b.run(20_000)
+    assert busy_lazy == list(b.busy) and a.busy_moments == b.busy_moments > 0
+    np.testing.assert_allclose(ra.w, rb.w, rtol=1e-12)  # the flag does not change the sample path
+    # M/M/3 all-busy period until the first departure with an empty line: at least one Exp(3 mu) stage
+    assert busy_lazy[0] > 1.0 / (3 * (1.0 / 2.1)) * 0.99
+    c = make(precision="f64")
+    rc = c.run(20_000)
+    np.testing.assert_allclose(rc.w, ra.w, rtol=2e-4)
+    np.testing.assert_allclose(rc.v, ra.v, rtol=2e-4)
+    np.testing.assert_allclose(rc.p[:12], ra.p[:12], rtol=0, atol=2e-5)
+    with pytest.raises(ValueError):
+        QsSim(3, precision="f16")
+
+
+def test_fp32_minus_fp64_on_cfg2_is_far_inside_the_confidence_interval():
+    """The direct measurement of the fp32 contribution (VERDICT r1 'nothing measures it'): cfg2 shape, same seed, same
+    words, R = 20 000 x 1e5 jobs in both precisions.  The paired difference of every raw moment of w and v must be below
+    1e-4 relative -- far below the 99 % CI half-width of the run itself."""
+    from most_queue_b200.sim.base import QsSim
+
+    out = {}
+    for prec in ("f32", "f64"):
+        qs = QsSim(8, seed=99, replications=20_000, precision=prec)
+        qs.set_sources(1.0, "M")
+        qs.set_servers(_h2(), "H")
+        out[prec] = (qs.run(100_000), qs.ci)
+    r32, r64 = out["f32"][0], out["f64"][0]
+    for k in range(4):
+        assert abs(r32.w[k] - r64.w[k]) <= 1e-4 * r64.w[k], (k, r32.w[k], r64.w[k])
+        assert abs(r32.v[k] - r64.v[k]) <= 1e-4 * r64.v[k], (k, r32.v[k], r64.v[k])
+        assert abs(r32.w[k] - r64.w[k]) < 0.1 * out["f64"][1]["w"][k]
+    np.testing.assert_allclose(r32.p[:16], r64.p[:16], rtol=0, atol=2e-6)
