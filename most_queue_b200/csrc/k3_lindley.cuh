@@ -43,6 +43,19 @@ struct K3Params {
     float *stG, *stV;
 };
 
+// number of valid entries among [base, base + span) when the valid ones are [0, limit)
+__host__ __device__ __forceinline__ int k3_valid_count(long long limit, long long base, int span)
+{
+    const long long r = limit - base;
+    return r <= 0 ? 0 : (r >= span ? span : (int)r);
+}
+
+// k3_onepass.cu: the replay form in one pass over A and S (TMA-staged tiles, decoupled look-back); same tree, same values
+bool k3_onepass_usable(const K3Params &P);
+size_t k3_onepass_scratch_bytes(long long ntiles);
+cudaError_t k3_onepass_occupancy(int *blocks);
+cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaStream_t st);
+
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);

@@ -1,0 +1,806 @@
+// k3_onepass.cu -- K3 replay form with ONE read of A and S from HBM: a persistent, warp-specialised decoupled look-back scan.
+//
+// Same specification as k3_lindley.cu (and oracle/mq_oracle_scan.c): the max-plus Lindley recursion of QsSim.run() with
+// one channel (most_queue/sim/base.py:488-528, wait sample base.py:302, sojourn base.py:272) evaluated with the FIXED
+// association tree "16-job segments folded sequentially -> Kogge-Stone over the 32 lanes of a warp -> sequential over the
+// 8 warps of a 4096-job tile -> tile level: chunks of ceil(ntiles/1024) tiles folded sequentially, Kogge-Stone over 32
+// chunks, sequential over the 32 groups".  Every value this kernel produces is the value the three-launch path produces,
+// bit for bit; only the schedule differs.
+//
+// One CTA per SM, co-resident (cooperative launch), static tile order t = blockIdx.x + k * gridDim.x, 24 warps, two
+// TMA-fed pipelines that meet on mbarriers only:
+//   FOLD side   warp 22 (one lane) brings tile k from HBM with two TMA tensor copies (S and A as [rows][16] fp64 boxes of
+//               256 x 16 with the 128-byte swizzle: thread r reads ITS row -- its 16-job segment -- with conflict-free
+//               LDS.128) + one 16-byte bulk copy for the gap that follows the tile.  Warps 0-7 pull their rows into
+//               registers (the single stage is refilled while they compute), fold them (x = S - A'), scan the 256 segment
+//               summaries, park every segment's exclusive prefix in an L2-resident ring and publish the tile summary.
+//   look-back   warps 16-18 (A, tile k on warp 16 + k % 3) publish what OTHER tiles wait for: the fold of the tile's chunk from the identity up to the
+//               tile (needs published summaries only), the exclusive prefix of a chunk (first tile of the chunk:
+//               Kogge-Stone over the earlier chunk folds of the group + the group carry) and the carry into the next group.
+//               warps 19-21 (B) resolve the tile's own exclusive prefix: they continue from the nearest predecessor that has
+//               published its inclusive prefix, else from the chunk's exclusive prefix, folding the summaries in between
+//               (the sequential association makes every such route give the same bits).
+//   WALK side   once a tile is folded, warp 23 (one lane) brings it in AGAIN -- from L2, where it still sits: the fold side
+//               runs only OP_RING tiles ahead -- into one of two stages; warps 8-15 walk their segment from its carry and
+//               accumulate the power sums of w and v.
+// The look-back latency (three dependent L2 round trips of ~0.7 us under load and two folds of up to a chunk of summaries)
+// is hidden by the lead of the fold side, not by shared-memory stages.  Published words carry their own "ready" flag
+// (see publish()): no fences anywhere on the look-back path.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "k3_lindley.cuh"
+
+namespace mq {
+
+namespace {
+
+constexpr int OP_WSTAGES = 2;                    // walk-side stages
+constexpr int OP_RING = 12;                      // tiles the fold side may lead the walk side by (ring of hand-off slots)
+constexpr int OP_TILE = K3_THREADS * K3_L;       // 4096 jobs
+constexpr int OP_ROWS = K3_THREADS;              // 256 rows of 16 doubles
+constexpr int OP_ARR_BYTES = OP_TILE * 8;        // 32 KB per array per stage
+constexpr int OP_NLB = 3;                         // look-back warps of each kind (tile k goes to warp k % OP_NLB)
+constexpr int OP_THREADS = 768;                  // 24 warps: 8 fold, 8 walk, 3 + 3 look-back, 2 producers
+constexpr int OP_LB = 128;                       // look-back window kept in shared memory (summaries), per look-back warp
+constexpr uint32_t OP_TX = 2u * OP_ARR_BYTES + 16u;
+constexpr uint32_t OP_SPIN_LIMIT = 4000000u;     // wait iterations (each sleeps 20 ns .. 20 us) before a protocol bug traps instead of hanging
+
+struct OpStage {
+    // 1024-byte aligned (the swizzle pattern is a function of the shared-memory address bits 4-9)
+    unsigned char S[OP_ARR_BYTES];
+    unsigned char A[OP_ARR_BYTES];
+};
+
+struct OpShared {
+    OpStage fold;                                 // fold-side stage (single: its rows go to registers at once)
+    OpStage walk[OP_WSTAGES];                     // walk-side stages
+    double f_anext[2];                            // A[tile_base + 4096], A[tile_base + 4097] of the fold-side tile
+    double w_anext[OP_WSTAGES][2];
+    MP tile_total[OP_RING];                       // the tile's summary (fold group -> look-back warps)
+    MP tile_ex[OP_RING];                          // the tile's exclusive prefix (look-back B -> walk group)
+    MP lbA[OP_NLB][OP_LB], lbB[OP_NLB][OP_LB];    // summaries gathered by the look-back warps, newest first
+    MP warp_tot[K3_THREADS / 32];
+    MP ks_left[OP_NLB][5];                        // left operands of the late Kogge-Stone lane (look-back A)
+    double red[16][K3_NSTAT];
+    unsigned long long f_full, f_empty, w_full[OP_WSTAGES], w_empty[OP_WSTAGES];
+    unsigned long long folded[OP_RING], prefix[OP_RING], slot_free[OP_RING];
+};
+
+__device__ __forceinline__ MP mp_id() { return MP{-INFINITY, 0.0}; }
+__device__ __forceinline__ MP mp_then(MP earlier, MP later)
+{
+    return MP{fmax(later.a, __dadd_rn(earlier.a, later.b)), __dadd_rn(earlier.b, later.b)};
+}
+__device__ __forceinline__ MP mp_step(MP f, double x)
+{
+    return MP{fmax(0.0, __dadd_rn(f.a, x)), __dadd_rn(f.b, x)};
+}
+__device__ __forceinline__ double mp_apply(MP f, double w) { return fmax(f.a, __dadd_rn(w, f.b)); }
+__device__ __forceinline__ MP mp_shfl(MP v, int src)
+{
+    return MP{__shfl_sync(0xffffffffu, v.a, src), __shfl_sync(0xffffffffu, v.b, src)};
+}
+__device__ __forceinline__ MP mp_shfl_up(MP v, int d)
+{
+    return MP{__shfl_up_sync(0xffffffffu, v.a, d), __shfl_up_sync(0xffffffffu, v.b, d)};
+}
+// Kogge-Stone inclusive scan over the 32 lanes (the association of cta_scan in k3_lindley.cu)
+__device__ __forceinline__ MP warp_inclusive(MP v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        MP up = mp_shfl_up(v, d);
+        if (lane >= d) v = mp_then(up, v);
+    }
+    return v;
+}
+
+// ---- mbarrier / TMA primitives (PTX) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~the hint has passed, so a
+// waiting warp costs a handful of issue slots per microsecond instead of spinning (a spin loop with a clock read per
+// iteration took more than half of all issue slots of the SM in the first version of this kernel)
+__device__ __forceinline__ bool mbar_try(unsigned long long *b, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity), "r"(20000u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity, int *err)
+{
+    for (uint32_t it = 0; !mbar_try(b, parity); ++it) {
+        if (it > OP_SPIN_LIMIT) {  // seconds: a protocol bug traps instead of hanging the GPU
+            *err = 1;
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_tile_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// the same copy with an L2 eviction-priority hint (createpolicy): the first fetch of a tile asks the L2 to keep it
+// (evict_last) until the walk side has read it again, and that second read releases it (evict_first)
+__device__ __forceinline__ void tma_tile_2d_hint(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar,
+                                                 unsigned long long policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_copy_16(void *dst, const void *src, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ long long gtime()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void named_bar(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- publication through L2 without fences: a published (a, b) pair is ONE 16-byte word; "not yet" is the all-ones
+// pattern (a NaN in b, which a sum of finite draws never is) that the launch memsets the arrays to.  128-bit relaxed
+// loads / stores at GPU scope are single-copy atomic (PTX b128), so the word itself is the flag: no release fence on the
+// writer, no acquire (and no L1 invalidation) on the reader, one L2 round trip per hop. ----
+__device__ __forceinline__ void publish(MP *p, MP v)
+{
+    asm volatile(
+        "{\n\t.reg .b128 q;\n\t"
+        "mov.b128 q, {%1, %2};\n\t"
+        "st.relaxed.gpu.global.b128 [%0], q;\n\t}"
+        ::"l"(p), "l"(__double_as_longlong(v.a)), "l"(__double_as_longlong(v.b))
+        : "memory");
+}
+__device__ __forceinline__ bool try_mp(const MP *p, MP &v)
+{
+    long long lo, hi;
+    asm volatile(
+        "{\n\t.reg .b128 q;\n\t"
+        "ld.relaxed.gpu.global.b128 q, [%2];\n\t"
+        "mov.b128 {%0, %1}, q;\n\t}"
+        : "=l"(lo), "=l"(hi)
+        : "l"(p)
+        : "memory");
+    v = MP{__longlong_as_double(lo), __longlong_as_double(hi)};
+    return hi != -1ll;
+}
+__device__ __forceinline__ MP wait_mp(const MP *p, int *err)
+{
+    MP v;
+    if (try_mp(p, v)) return v;
+    for (uint32_t it = 0;; ++it) {
+        __nanosleep(it < 8 ? 32 : 128);
+        if (try_mp(p, v)) return v;
+        if (it > OP_SPIN_LIMIT) {
+            *err = 2;
+            __trap();
+        }
+    }
+}
+
+// element (row r, column col) of a swizzled [256][16] fp64 box: 16-byte chunk q = col / 2 sits at chunk q ^ (r & 7)
+__device__ __forceinline__ const double2 *sw_chunk(const unsigned char *box, int r, int q)
+{
+    return reinterpret_cast<const double2 *>(box + r * 128 + ((q ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ double *sw_elem(unsigned char *box, int e)
+{
+    const int r = e >> 4, col = e & 15;
+    return reinterpret_cast<double *>(box + r * 128 + (((col >> 1) ^ (r & 7)) << 4) + ((col & 1) << 3));
+}
+
+// half h (8 jobs) of row r of a staged tile: S[16 r + 8 h ..] and the 9 gaps A[16 r + 8 h .. 16 r + 8 h + 8]
+constexpr int OP_H = K3_L / 2;
+__device__ __forceinline__ void load_half(const OpStage &st, const double *a_next, int r, int h, double (&sv)[OP_H],
+                                          double (&av)[OP_H + 1])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double2 x = *sw_chunk(st.S, r, 4 * h + q);
+        const double2 y = *sw_chunk(st.A, r, 4 * h + q);
+        sv[2 * q] = x.x;
+        sv[2 * q + 1] = x.y;
+        av[2 * q] = y.x;
+        av[2 * q + 1] = y.y;
+    }
+    if (h == 0)
+        av[OP_H] = sw_chunk(st.A, r, 4)->x;
+    else
+        av[OP_H] = r + 1 < OP_ROWS ? sw_chunk(st.A, r + 1, 0)->x : a_next[0];
+}
+
+// the last tile of the range is staged with plain loads: services beyond the range and gaps beyond the chain are 0
+__device__ __forceinline__ void stage_ragged(const K3Params &P, long long tb, OpStage &st, double *a_next, int r)
+{
+    const int vs = k3_valid_count(P.n, tb, OP_TILE);
+    const int va = k3_valid_count(P.n + P.n_ahead + 1, tb, OP_TILE + 2);
+    for (int e = r; e < OP_TILE; e += K3_THREADS) {
+        *sw_elem(st.S, e) = e < vs ? __ldcs(P.S + tb + e) : 0.0;
+        *sw_elem(st.A, e) = e < va ? __ldcs(P.A + tb + e) : 0.0;
+    }
+    if (r < 2) a_next[r] = OP_TILE + r < va ? __ldcs(P.A + tb + OP_TILE + r) : 0.0;
+}
+
+}  // namespace
+
+struct K3OnePassParams {
+    K3Params P;            // n, A, S, w_in, partial, tail, total, W
+    CUtensorMap mapS, mapA;
+    // published words, all-ones until written (see publish()):
+    MP *t_sum;             // [ntiles] tile summaries
+    MP *t_incf;            // [ntiles] fold of the tile's chunk from the identity up to and including the tile
+    MP *t_inc;             // [ntiles] inclusive prefix of the tile
+    MP *chunk_ex;          // [K3_TOP] exclusive prefix of a chunk (published when chunks have more than one tile)
+    MP *carry;             // [40]     carry into group g
+    MP *seg_ring;          // [grid][OP_RING][256] exclusive prefix of every segment inside its tile (fold -> walk hand-off)
+    long long chunk;       // tiles per chunk
+    int hints;             // 1: L2 eviction-priority hints on the two fetches of a tile
+    int lead;              // tiles the fold side may lead the walk side by (1..OP_RING): bounds the L2 footprint
+    int *err;
+    long long *trace;      // optional [grid][OP_TRACE_TILES][16] SM clocks of the pipeline events (MQ_SCAN_TRACE)
+};
+
+constexpr int OP_TRACE_TILES = 64;
+#define OP_TRACE(ev, val)                                                                             \
+    do {                                                                                              \
+        if (Q.trace && k < OP_TRACE_TILES) Q.trace[((long long)blockIdx.x * OP_TRACE_TILES + k) * 24 + (ev)] = (val); \
+    } while (0)
+
+// f o lb[n-1] o ... o lb[0] (lb holds the newest summary first)
+__device__ __forceinline__ MP fold_newest_first(MP f, const MP *lb, int n)
+{
+#pragma unroll 1
+    for (int i = n - 1; i >= 0; --i) f = mp_then(f, lb[i]);
+    return f;
+}
+
+// Backward scan over the predecessors of tile t inside its chunk, 32 at a time (lane i looks at tile t - 1 - cnt - i).
+// `ready` is the array of published partial folds (t_incf or t_inc): the nearest predecessor that has one becomes the base
+// (idx = number of summaries to fold after it, newest first in lb[]); every nearer predecessor contributes its summary,
+// which the lane waits for.  idx stays -1 when the chunk start is reached first (all n_pred summaries are in lb[]).
+__device__ __forceinline__ void gather(const K3OnePassParams &Q, MP *lb, const MP *ready, long long t, long long n_pred,
+                                       int lane, long long &idx, MP &base)
+{
+    long long cnt = 0;
+    while (idx < 0 && cnt < n_pred) {
+        const long long i = cnt + lane;
+        const bool ok = i < n_pred;
+        const long long p = t - 1 - i;
+        MP v = mp_id(), sum = mp_id();
+        bool have = false, have_sum = false;
+        if (ok) {
+            have = try_mp(ready + p, v);          // both loads are in flight together: one L2 round trip
+            have_sum = try_mp(Q.t_sum + p, sum);
+            if (!have && i == OP_LB - 1) {  // the window is OP_LB summaries long: its last slot waits for a partial fold
+                v = wait_mp(ready + p, Q.err);
+                have = true;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, have);
+        const int j = m ? __ffs(m) - 1 : 32;
+        if (ok && lane < j) lb[i] = have_sum ? sum : wait_mp(Q.t_sum + p, Q.err);
+        if (m) {
+            base = mp_shfl(v, j);
+            idx = cnt + j;
+        }
+        cnt += 32;
+    }
+    __syncwarp();
+}
+
+__global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassParams Q)
+{
+    extern __shared__ __align__(1024) unsigned char op_raw[];
+    OpShared &sm = *reinterpret_cast<OpShared *>(op_raw);
+    if (threadIdx.x == 0 && (smem_u32(op_raw) & 1023u)) {  // the swizzle pattern assumes 1024-byte aligned boxes
+        *Q.err = 3;
+        __trap();
+    }
+    const K3Params &P = Q.P;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = P.ntiles;
+    const int LEAD = Q.lead;
+    const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+    MP *ring = Q.seg_ring + (long long)blockIdx.x * OP_RING * K3_THREADS;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.f_full, 1);
+        mbar_init(&sm.f_empty, K3_THREADS);
+        for (int s = 0; s < OP_WSTAGES; ++s) {
+            mbar_init(&sm.w_full[s], 1);
+            mbar_init(&sm.w_empty[s], K3_THREADS);
+        }
+        for (int d = 0; d < OP_RING; ++d) {
+            mbar_init(&sm.folded[d], K3_THREADS);
+            mbar_init(&sm.prefix[d], 1);
+            mbar_init(&sm.slot_free[d], K3_THREADS + 2);  // the walk group and both look-back warps are done with the slot
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 22) {
+        // ------------------------------------------------------------------ fold-side producer (HBM -> shared memory)
+        if (lane == 0) {
+            const unsigned long long keep = policy_evict_last();
+            for (int k = 0; k < my_tiles; ++k) {
+                const long long t = blockIdx.x + (long long)k * gridDim.x;
+                mbar_wait(&sm.f_empty, (uint32_t)(k & 1) ^ 1u, Q.err);
+                OP_TRACE(0, clock64());
+                OP_TRACE(21, gtime());
+                if ((t + 1) * (long long)OP_TILE < P.n) {
+                    mbar_expect_tx(&sm.f_full, OP_TX);
+                    if (Q.hints) {
+                        tma_tile_2d_hint(sm.fold.S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.f_full, keep);
+                        tma_tile_2d_hint(sm.fold.A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.f_full, keep);
+                    } else {
+                        tma_tile_2d(sm.fold.S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.f_full);
+                        tma_tile_2d(sm.fold.A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.f_full);
+                    }
+                    bulk_copy_16(sm.f_anext, P.A + (t + 1) * OP_TILE, &sm.f_full);
+                } else {
+                    mbar_arrive(&sm.f_full);  // the last tile is staged by the fold group itself (bounds checks)
+                }
+            }
+        }
+    } else if (warp == 23) {
+        // ------------------------------------------------------------------ walk-side producer (L2 -> shared memory)
+        if (lane == 0) {
+            const unsigned long long drop = policy_evict_first();
+            for (int k = 0; k < my_tiles; ++k) {
+                const int s = (int)(k % OP_WSTAGES), d = (int)(k % LEAD);
+                const long long t = blockIdx.x + (long long)k * gridDim.x;
+                mbar_wait(&sm.w_empty[s], (uint32_t)((k / OP_WSTAGES) & 1) ^ 1u, Q.err);
+                mbar_wait(&sm.folded[d], (uint32_t)((k / LEAD) & 1), Q.err);  // the fold side has had it: it is in L2
+                OP_TRACE(1, clock64());
+                if ((t + 1) * (long long)OP_TILE < P.n) {
+                    mbar_expect_tx(&sm.w_full[s], OP_TX);
+                    if (Q.hints) {
+                        tma_tile_2d_hint(sm.walk[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.w_full[s], drop);
+                        tma_tile_2d_hint(sm.walk[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.w_full[s], drop);
+                    } else {
+                        tma_tile_2d(sm.walk[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.w_full[s]);
+                        tma_tile_2d(sm.walk[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.w_full[s]);
+                    }
+                    bulk_copy_16(sm.w_anext[s], P.A + (t + 1) * OP_TILE, &sm.w_full[s]);
+                } else {
+                    mbar_arrive(&sm.w_full[s]);
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------------------------ fold group
+        const int r = threadIdx.x;
+        double sum_a = 0.0, sum_s = 0.0;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int d = (int)(k % LEAD);
+            const long long t = blockIdx.x + (long long)k * gridDim.x;
+            const long long tb = t * OP_TILE;
+            mbar_wait(&sm.slot_free[d], (uint32_t)((k / LEAD) & 1) ^ 1u, Q.err);  // at most OP_RING tiles ahead
+            mbar_wait(&sm.f_full, (uint32_t)(k & 1), Q.err);
+            const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
+            int valid = K3_L;
+            if (!full_tile) {
+                stage_ragged(P, tb, sm.fold, sm.f_anext, r);
+                named_bar(1, K3_THREADS);
+                valid = k3_valid_count(P.n, tb + (long long)r * K3_L, K3_L);
+            }
+            // the whole row goes to registers so that the stage can be refilled while this tile is folded
+            double s0[OP_H], a0[OP_H + 1], s1[OP_H], a1[OP_H + 1];
+            load_half(sm.fold, sm.f_anext, r, 0, s0, a0);
+            load_half(sm.fold, sm.f_anext, r, 1, s1, a1);
+            mbar_arrive(&sm.f_empty);
+            MP mine = mp_id();
+#pragma unroll
+            for (int j = 0; j < OP_H; ++j) {
+                if (full_tile || j < valid) {
+                    mine = mp_step(mine, __dsub_rn(s0[j], a0[j + 1]));
+                    sum_a += a0[j];
+                    sum_s += s0[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < OP_H; ++j) {
+                if (full_tile || OP_H + j < valid) {
+                    mine = mp_step(mine, __dsub_rn(s1[j], a1[j + 1]));
+                    sum_a += a1[j];
+                    sum_s += s1[j];
+                }
+            }
+            // CTA scan of the 256 segment summaries (Kogge-Stone per warp, sequential over the 8 warps)
+            const MP inc = warp_inclusive(mine, lane);
+            MP within = mp_shfl_up(inc, 1);
+            if (lane == 0) within = mp_id();
+            if (lane == 31) sm.warp_tot[warp] = inc;
+            named_bar(1, K3_THREADS);
+            MP carry = mp_id(), tot = mp_id();
+#pragma unroll
+            for (int g = 0; g < K3_THREADS / 32; ++g) {
+                if (g == warp) carry = tot;
+                tot = mp_then(tot, sm.warp_tot[g]);
+            }
+            const MP ex = mp_then(carry, within);
+            __stcg(reinterpret_cast<double2 *>(ring + d * K3_THREADS + r), make_double2(ex.a, ex.b));
+            if (r == 0) {
+                OP_TRACE(2, clock64());
+                sm.tile_total[d] = tot;
+                publish(Q.t_sum + t, tot);
+                OP_TRACE(3, clock64());
+                OP_TRACE(16, gtime());
+            }
+            mbar_arrive(&sm.folded[d]);  // (release, CTA scope) the ring slot and tile_total are visible to the waiters
+            named_bar(1, K3_THREADS);    // warp_tot is reused by the next tile
+        }
+        // sum(A), sum(S) of this CTA: statistics 8 and 9
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            sum_a += __shfl_down_sync(0xffffffffu, sum_a, dd);
+            sum_s += __shfl_down_sync(0xffffffffu, sum_s, dd);
+        }
+        if (lane == 0) {
+            sm.red[warp][8] = sum_a;
+            sm.red[warp][9] = sum_s;
+        }
+    } else if (warp >= 16 && warp < 16 + OP_NLB) {
+        // ------------------------------------------------------------------ look-back A: everything other tiles wait for
+        // (1) the chunk fold from the identity up to this tile -- depends on published SUMMARIES only; (2) for the first
+        // tile of a chunk, the chunk's exclusive prefix: Kogge-Stone over the folds of the earlier chunks of the group
+        // (products of step 1 of other tiles) and the group carry; (3) at the end of a group, the carry into the next one.
+        // Step 1 of an iteration never waits for a step 2 / 3 of the same or a later iteration of any CTA, so waits do not
+        // chain from CTA to CTA.
+        const long long chunk = Q.chunk;
+        MP *lb = sm.lbA[warp - 16];
+        for (int k = warp - 16; k < my_tiles; k += OP_NLB) {
+            const int d = (int)(k % LEAD);
+            const long long t = blockIdx.x + (long long)k * gridDim.x;
+            mbar_wait(&sm.folded[d], (uint32_t)((k / LEAD) & 1), Q.err);
+            if (lane == 0) OP_TRACE(4, clock64());
+            const MP own = sm.tile_total[d];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.slot_free[d]);  // tile_total[d] has been read
+            const long long c = t / chunk, lo = c * chunk, n_pred = t - lo;
+            const int g = (int)(c >> 5), l = (int)(c & 31);
+            long long idx = -1;
+            MP base = mp_id();
+            gather(Q, lb, Q.t_incf, t, n_pred, lane, idx, base);
+            if (idx < 0) idx = n_pred;  // fold from the identity at the chunk start
+            MP f = base;
+            if (lane == 0) {
+                OP_TRACE(5, clock64());
+                OP_TRACE(11, idx);
+                f = fold_newest_first(f, lb, (int)idx);
+                f = mp_then(f, own);
+                publish(Q.t_incf + t, f);
+                OP_TRACE(6, clock64());
+                OP_TRACE(17, gtime());
+            }
+            const long long group_hi = ((long long)(g + 1) * 32 * chunk < ntiles ? (long long)(g + 1) * 32 * chunk : ntiles);
+            const bool group_end = t == group_hi - 1;
+            if (n_pred == 0 || group_end) {
+                f = mp_shfl(f, 0);
+                MP cg = mp_id();
+                if (g > 0) {
+                    if (lane == 0) cg = wait_mp(Q.carry + g, Q.err);  // published a whole group ago (or about to be)
+                    cg = mp_shfl(cg, 0);
+                }
+                if (n_pred == 0) {
+                    // The chunk's exclusive prefix = group carry, then the Kogge-Stone inclusive value at lane l - 1 over
+                    // the folds of the earlier chunks of the group.  All of those but the LAST (the chunk that ends at
+                    // tile t - 1) were published long ago.  Kogge-Stone only looks to the left, so the five left operands
+                    // lane l - 1 meets do not depend on its own value: the scan runs first without that lane and records
+                    // them; the late fold then needs five dependent steps on one lane instead of five shuffle rounds.
+                    const int last = l - 1;
+                    MP v = mp_id();
+                    if (lane < last) v = wait_mp(Q.t_incf + ((long long)g * 32 + lane + 1) * chunk - 1, Q.err);
+                    MP *left = sm.ks_left[warp - 16];
+#pragma unroll
+                    for (int sft = 0; sft < 5; ++sft) {
+                        const MP up = mp_shfl_up(v, 1 << sft);
+                        if (lane == last) left[sft] = up;
+                        if (lane >= (1 << sft) && lane != last) v = mp_then(up, v);
+                    }
+                    if (l == 0) {
+                        if (lane == 0) publish(Q.chunk_ex + c, mp_then(cg, mp_id()));
+                    } else if (lane == last) {
+                        MP x = wait_mp(Q.t_incf + t - 1, Q.err);
+#pragma unroll
+                        for (int sft = 0; sft < 5; ++sft)
+                            if (last >= (1 << sft)) x = mp_then(left[sft], x);
+                        publish(Q.chunk_ex + c, mp_then(cg, x));
+                    }
+                    if (lane == 0) OP_TRACE(18, gtime());
+                }
+                if (group_end) {
+                    // the group total is the Kogge-Stone value at lane 31 (a different association from lane l's when the
+                    // range ends inside the group, so the full scan it is; one tile in 32 chunks comes here)
+                    MP v = mp_id();
+                    if (lane < l)
+                        v = wait_mp(Q.t_incf + ((long long)g * 32 + lane + 1) * chunk - 1, Q.err);
+                    else if (lane == l)
+                        v = f;
+                    const MP total_g = mp_shfl(warp_inclusive(v, lane), 31);
+                    if (lane == 0) {
+                        const MP next = mp_then(cg, total_g);
+                        if (t == ntiles - 1)
+                            *P.total = next;  // the groups after the last tile hold the identity
+                        else
+                            publish(Q.carry + g + 1, next);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 16 + OP_NLB && warp < 16 + 2 * OP_NLB) {
+        // ------------------------------------------------------------------ look-back B: the tile's exclusive prefix
+        const long long chunk = Q.chunk;
+        MP *lb = sm.lbB[warp - 16 - OP_NLB];
+        for (int k = warp - 16 - OP_NLB; k < my_tiles; k += OP_NLB) {
+            const int d = (int)(k % LEAD);
+            const long long t = blockIdx.x + (long long)k * gridDim.x;
+            mbar_wait(&sm.folded[d], (uint32_t)((k / LEAD) & 1), Q.err);
+            const MP own = sm.tile_total[d];
+            const long long c = t / chunk, n_pred = t - c * chunk;
+            long long idx = -1;
+            MP base = mp_id();
+            gather(Q, lb, Q.t_inc, t, n_pred, lane, idx, base);
+            if (lane == 0) {
+                OP_TRACE(12, idx);
+                OP_TRACE(20, gtime());
+            }
+            if (idx < 0) {
+                // reached the chunk start: continue from the chunk's exclusive prefix (look-back A of its first tile)
+                idx = n_pred;
+                if (lane == 0) base = wait_mp(Q.chunk_ex + c, Q.err);
+                base = mp_shfl(base, 0);
+            }
+            if (lane == 0) {
+                const MP ex = fold_newest_first(base, lb, (int)idx);
+                sm.tile_ex[d] = ex;
+                mbar_arrive(&sm.prefix[d]);
+                OP_TRACE(7, clock64());
+                OP_TRACE(19, gtime());
+                publish(Q.t_inc + t, mp_then(ex, own));
+                OP_TRACE(8, clock64());
+                mbar_arrive(&sm.slot_free[d]);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 8 && warp < 16) {
+        // ------------------------------------------------------------------ walk group (warps 8-15)
+        const int r = threadIdx.x - 256;
+        double acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int s = (int)(k % OP_WSTAGES), d = (int)(k % LEAD);
+            const long long t = blockIdx.x + (long long)k * gridDim.x;
+            const long long tb = t * OP_TILE, n0 = tb + (long long)r * K3_L;
+            mbar_wait(&sm.prefix[d], (uint32_t)((k / LEAD) & 1), Q.err);  // implies folded[d]: the ring slot is written
+            const double2 sx = __ldcg(reinterpret_cast<const double2 *>(ring + d * K3_THREADS + r));
+            const double w_tile = mp_apply(sm.tile_ex[d], P.w_in);
+            mbar_wait(&sm.w_full[s], (uint32_t)((k / OP_WSTAGES) & 1), Q.err);
+            if (r == 0) OP_TRACE(9, clock64());
+            const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
+            if (!full_tile) {
+                stage_ragged(P, tb, sm.walk[s], sm.w_anext[s], r);
+                named_bar(2, K3_THREADS);
+            }
+            const int valid = full_tile ? K3_L : k3_valid_count(P.n, n0, K3_L);
+            double w = mp_apply(MP{sx.x, sx.y}, w_tile);
+            const int last_j = (!full_tile && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
+            double *Wp = P.W ? P.W + n0 : nullptr;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                double sv[OP_H], av[OP_H + 1];
+                load_half(sm.walk[s], sm.w_anext[s], r, h, sv, av);
+#pragma unroll
+                for (int jj = 0; jj < OP_H; ++jj) {
+                    const int j = h * OP_H + jj;
+                    if (full_tile || j < valid) {
+                        if (Wp) Wp[j] = w;
+                        const double v = __dadd_rn(w, sv[jj]);
+                        const double w2 = w * w, v2 = v * v;
+                        acc[0] += w;
+                        acc[1] += w2;
+                        acc[2] += w2 * w;
+                        acc[3] += w2 * w2;
+                        acc[4] += v;
+                        acc[5] += v2;
+                        acc[6] += v2 * v;
+                        acc[7] += v2 * v2;
+                        const double raw = __dadd_rn(w, __dsub_rn(sv[jj], av[jj + 1]));
+                        if (!full_tile && j == last_j) {
+                            P.tail[0] = raw;
+                            P.tail[1] = v;
+                        }
+                        w = fmax(0.0, raw);
+                    }
+                }
+            }
+            if (r == 0) {
+                OP_TRACE(10, clock64());
+                OP_TRACE(22, gtime());
+            }
+            mbar_arrive(&sm.w_empty[s]);
+            mbar_arrive(&sm.slot_free[d]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = acc[i];
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_down_sync(0xffffffffu, v, dd);
+            if (lane == 0) sm.red[warp][i] = v;
+        }
+    }
+    __syncthreads();
+    // fixed-order CTA reduction: statistics 0-7 from the walk warps, 8-9 from the fold warps
+    if (threadIdx.x < K3_NSTAT) {
+        const int i = threadIdx.x;
+        double v = 0.0;
+        if (i < 8)
+            for (int wv = 8; wv < 16; ++wv) v += sm.red[wv][i];
+        else if (i < 10)
+            for (int wv = 0; wv < 8; ++wv) v += sm.red[wv][i];
+        P.partial[(long long)blockIdx.x * K3_NSTAT + i] = v;
+    }
+}
+
+size_t k3_onepass_smem() { return sizeof(OpShared); }
+
+size_t k3_onepass_scratch_bytes(long long ntiles)
+{
+    // t_sum, t_incf, t_inc [ntiles], chunk_ex [K3_TOP], carry [40] (all memset to ones before every launch), err, and the
+    // hand-off ring of segment prefixes (at most 256 CTAs)
+    return sizeof(MP) * (3 * (size_t)ntiles + K3_TOP + 40) + 256 + sizeof(MP) * (size_t)256 * OP_RING * K3_THREADS;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// rows of 16 doubles, box of 256 rows, 128-byte swizzle
+static bool make_map(CUtensorMap *map, const double *base, long long rows)
+{
+    auto enc = tensor_map_encoder();
+    if (!enc || rows < 1) return false;
+    cuuint64_t dims[2] = {16, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {16, (cuuint32_t)OP_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool k3_onepass_usable(const K3Params &P)
+{
+    if (!P.replay || P.level_partial) return false;
+    if ((reinterpret_cast<uintptr_t>(P.A) | reinterpret_cast<uintptr_t>(P.S)) & 15) return false;  // TMA: 16-byte aligned
+    if (P.ntiles * (long long)OP_ROWS >= (1ll << 31)) return false;                                 // 32-bit box coordinate
+    return tensor_map_encoder() != nullptr;
+}
+
+// `scratch` = k3_onepass_scratch_bytes(ntiles) bytes of device memory; grid <= resident CTAs (one per SM)
+cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaStream_t st)
+{
+    static bool attr_set = false;
+    const size_t smem = k3_onepass_smem();
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k3_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    K3OnePassParams Q;
+    Q.P = P;
+    // full tiles only go through TMA: rows that are completely inside the arrays
+    if (!make_map(&Q.mapS, P.S, P.n / 16 > 0 ? P.n / 16 : 1) || !make_map(&Q.mapA, P.A, (P.n + 1) / 16 > 0 ? (P.n + 1) / 16 : 1))
+        return cudaErrorInvalidValue;
+    MP *mp = (MP *)scratch;
+    const size_t words = 3 * (size_t)P.ntiles + K3_TOP + 40;
+    Q.t_sum = mp;
+    Q.t_incf = Q.t_sum + P.ntiles;
+    Q.t_inc = Q.t_incf + P.ntiles;
+    Q.chunk_ex = Q.t_inc + P.ntiles;
+    Q.carry = Q.chunk_ex + K3_TOP;
+    Q.err = (int *)(mp + words);
+    Q.seg_ring = (MP *)((char *)(mp + words) + 256);
+    if (grid > 256) return cudaErrorInvalidValue;
+    Q.chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
+    // the walk side re-reads a tile from L2 `lead` tiles after the fold side fetched it from HBM: lead x grid x 64 KB must
+    // stay well inside the L2 (4 x 148 x 64 KB = 38 MB); MQ_SCAN_LEAD overrides (3..8)
+    Q.lead = 4;
+    if (const char *ev = std::getenv("MQ_SCAN_LEAD")) Q.lead = std::atoi(ev);
+    if (Q.lead < OP_NLB) Q.lead = OP_NLB;  // a look-back warp moves OP_NLB tiles at a time: a shorter ring would alias phases
+    if (Q.lead > OP_RING) Q.lead = OP_RING;
+    Q.hints = 0;
+    if (const char *ev = std::getenv("MQ_SCAN_HINTS")) Q.hints = std::atoi(ev) != 0;
+    cudaError_t e = cudaMemsetAsync(scratch, 0xFF, sizeof(MP) * words, st);
+    if (e != cudaSuccess) return e;
+    // MQ_SCAN_TRACE=<file>: SM clocks of every pipeline event of the first 64 tiles of each CTA (a development aid)
+    Q.trace = nullptr;
+    const char *trace_path = std::getenv("MQ_SCAN_TRACE");
+    const size_t trace_bytes = sizeof(long long) * (size_t)grid * OP_TRACE_TILES * 24;
+    if (trace_path) {
+        if (cudaMalloc(&Q.trace, trace_bytes) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(Q.trace, 0, trace_bytes, st);
+    }
+    void *args[] = {(void *)&Q};
+    e = cudaLaunchCooperativeKernel((const void *)k3_onepass, dim3(grid), dim3(OP_THREADS), args, smem, st);
+    if (trace_path) {
+        std::vector<long long> h((size_t)grid * OP_TRACE_TILES * 24);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), Q.trace, trace_bytes, cudaMemcpyDeviceToHost);
+        cudaFree(Q.trace);
+        if (FILE *f = std::fopen(trace_path, "wb")) {
+            std::fwrite(h.data(), 1, trace_bytes, f);
+            std::fclose(f);
+        }
+    }
+    return e;
+}
+
+cudaError_t k3_onepass_occupancy(int *blocks)
+{
+    const size_t smem = k3_onepass_smem();
+    cudaError_t e = cudaFuncSetAttribute(k3_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, k3_onepass, OP_THREADS, smem);
+}
+
+}  // namespace mq

@@ -286,7 +286,7 @@ int mq_destroy(mq_ctx *ctx)
 {
     if (!ctx) return MQ_OK;
     cudaSetDevice(ctx->device);
-    for (Buf *b : {&ctx->rec, &ctx->agg, &ctx->ring, &ctx->in_a, &ctx->in_s, &ctx->desc})
+    for (Buf *b : {&ctx->rec, &ctx->agg, &ctx->ring, &ctx->in_a, &ctx->in_s, &ctx->desc, &ctx->lookback})
         if (b->p) cudaFree(b->p);
     if (ctx->h_agg) cudaFreeHost(ctx->h_agg);
     for (auto &e : ctx->ev)

@@ -12,7 +12,12 @@ struct ScanRun {
     K3Params P;
     int grid_sum = 0, grid_walk = 0;
     bool staged_inputs = false;
+    bool onepass = false;  // replay form in one pass (k3_onepass.cu): no summary launches, the walk is the fused kernel
 };
+
+// gaps past the range that a host-pointer replay stages for the time-in-state level walk (a job's sojourn would have to
+// span more than this many later arrivals to notice)
+constexpr long long SCAN_AHEAD_STAGED = 1ll << 22;
 
 int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, ScanRun &run, const char *who,
                  bool will_walk = false)
@@ -35,6 +40,39 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     for (int r = 0; r < 10; ++r) P.rk[r] = P.key + (uint32_t)r * MQ_PHILOX_W;
     const long long tile = (long long)K3_THREADS * K3_L;
     P.ntiles = (P.n + tile - 1) / tile;
+
+    const bool want_p = (cfg->flags & MQ_SCAN_WANT_P) != 0;
+    P.n_ahead = cfg->jobs_ahead > 0 ? cfg->jobs_ahead : 0;
+    if (replay) {
+        if (cfg->device_ptrs) {
+            P.A = A;
+            P.S = S;
+        } else {
+            // host arrays: the walk reads gaps past A[jobs] only for the time-in-state levels; stage what it may read and
+            // tell the kernels how much that is (reading past the staged buffer was an out-of-bounds read)
+            const long long ahead = want_p ? std::min<long long>(P.n_ahead, SCAN_AHEAD_STAGED) : 0;
+            P.n_ahead = ahead;
+            const size_t na = (size_t)(P.n + 1 + ahead);
+            if (int rc = ensure(ctx->in_a, sizeof(double) * na)) return rc;
+            if (int rc = ensure(ctx->in_s, sizeof(double) * (size_t)P.n)) return rc;
+            CU(cudaMemcpyAsync(ctx->in_a.p, A, sizeof(double) * na, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->in_s.p, S, sizeof(double) * (size_t)P.n, cudaMemcpyHostToDevice, ctx->stream));
+            P.A = (const double *)ctx->in_a.p;
+            P.S = (const double *)ctx->in_s.p;
+        }
+    } else {
+        P.src = make_distf(cfg->src);
+        P.srv = make_distf(cfg->srv);
+    }
+    // replay form followed by a walk: one pass over A and S when the arrays can be fetched by TMA (16-byte aligned) and
+    // no time-in-state levels are wanted; MQ_SCAN_TWO_PASS=1 keeps the three-launch path (the checker of the fused one)
+    if (replay && will_walk && !want_p && P.ntiles >= 2 && !std::getenv("MQ_SCAN_TWO_PASS")) {
+        K3Params probe = P;
+        probe.level_partial = nullptr;
+        int occ1 = 0;
+        run.onepass = k3_onepass_usable(probe) && k3_onepass_occupancy(&occ1) == cudaSuccess && occ1 >= 1;
+        cudaGetLastError();
+    }
 
     // generator form followed by a walk: stash the fp32 draws of the summary pass (8 B per job) when they fit, so the
     // walk does not draw everything a second time.  MQ_SCAN_NO_STASH=1 turns it off.
@@ -59,7 +97,7 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     }
     // the summary pass can keep every segment's exclusive prefix (4 KB per tile) so that the walk skips its own fold and
     // CTA scan; MQ_SCAN_NO_PREFIX=1 turns it off
-    if (will_walk && !std::getenv("MQ_SCAN_NO_PREFIX")) {
+    if (will_walk && !run.onepass && !std::getenv("MQ_SCAN_NO_PREFIX")) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t need = sizeof(MP) * (size_t)K3_THREADS * (size_t)P.ntiles;
@@ -71,8 +109,11 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
         }
     }
     int occ_s = 0, occ_w = 0;
-    const bool want_p = (cfg->flags & MQ_SCAN_WANT_P) != 0;
     CU(k3_occupancy(replay, stash, want_p, &occ_s, &occ_w));
+    if (run.onepass) {
+        occ_w = 1;  // one CTA per SM by design
+        if (int rc = ensure(ctx->lookback, k3_onepass_scratch_bytes(P.ntiles))) return rc;
+    }
     if (occ_s < 1 || occ_w < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     run.grid_sum = (int)std::min<long long>(P.ntiles, (long long)occ_s * ctx->sms);
     run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
@@ -90,30 +131,13 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     P.tail = (double *)(P.chunk_ex + K3_TOP);
     P.partial = P.tail + 2;
     P.level_partial = want_p ? P.partial + (size_t)run.grid_walk * K3_NSTAT + K3_NSTAT + K3_NLEVEL : nullptr;
-    P.n_ahead = cfg->jobs_ahead > 0 ? cfg->jobs_ahead : 0;
     if (int rc = ensure_host_agg(ctx, sizeof(double) * 64)) return rc;
-
-    if (replay) {
-        if (cfg->device_ptrs) {
-            P.A = A;
-            P.S = S;
-        } else {
-            if (int rc = ensure(ctx->in_a, sizeof(double) * (size_t)(P.n + 1))) return rc;
-            if (int rc = ensure(ctx->in_s, sizeof(double) * (size_t)P.n)) return rc;
-            CU(cudaMemcpyAsync(ctx->in_a.p, A, sizeof(double) * (size_t)(P.n + 1), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->in_s.p, S, sizeof(double) * (size_t)P.n, cudaMemcpyHostToDevice, ctx->stream));
-            P.A = (const double *)ctx->in_a.p;
-            P.S = (const double *)ctx->in_s.p;
-        }
-    } else {
-        P.src = make_distf(cfg->src);
-        P.srv = make_distf(cfg->srv);
-    }
     return MQ_OK;
 }
 
 int scan_summary(mq_ctx *ctx, ScanRun &run)
 {
+    if (run.onepass) return MQ_OK;  // the fused kernel forms and consumes the summaries itself
     CU(k3_launch_summary(run.P, run.grid_sum, ctx->stream));
     CU(k3_launch_top(run.P, ctx->stream));
     ctx->launches += 4;
@@ -135,7 +159,10 @@ int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, d
     }
     P.W = dW;
     double *d_stats = P.partial + (size_t)run.grid_walk * K3_NSTAT;
-    CU(k3_launch_walk(P, run.grid_walk, ctx->stream));
+    if (run.onepass)
+        CU(k3_launch_onepass(P, ctx->lookback.p, run.grid_walk, ctx->stream));
+    else
+        CU(k3_launch_walk(P, run.grid_walk, ctx->stream));
     CU(k3_launch_final(P.partial, P.level_partial, run.grid_walk, d_stats, ctx->stream));
     ctx->launches += 2;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));

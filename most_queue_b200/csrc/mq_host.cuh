@@ -43,7 +43,7 @@ struct mq_ctx {
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, sim done, reduce done, end
-    mq::Buf rec, agg, ring, in_a, in_s, desc;
+    mq::Buf rec, agg, ring, in_a, in_s, desc, lookback;
     double *h_agg = nullptr;  // pinned staging
     size_t h_agg_cap = 0;
     double sim_ms = 0, reduce_ms = 0, total_ms = 0;

@@ -123,6 +123,7 @@ def replay_chain(A, S, total_served: int | None = None, ranges: int = 1, want_w:
     tot = np.zeros(L.S_A)
     levels = np.zeros(L.SCAN_NLEVEL)
     Ws, tail_v, tail_raw, sim_ms = [], 0.0, 0.0, 0.0
+    pairs_apply = []  # the range summaries as the apply call reports them (the one-pass kernel forms its own)
     for g in range(ranges):
         n = bounds[g + 1] - bounds[g]
         stats, W = ctx.scan_apply(n, carries[g], job0=bounds[g], A=A[bounds[g]:], S=S[bounds[g]:],
@@ -131,12 +132,13 @@ def replay_chain(A, S, total_served: int | None = None, ranges: int = 1, want_w:
         levels += stats[L.S_LEVELS:L.S_LEVELS + L.SCAN_NLEVEL]
         sim_ms += ctx.last_timing()["sim_ms"]
         tot += stats[:L.S_A]
+        pairs_apply.append((float(stats[L.S_A]), float(stats[L.S_B])))
         if want_w:
             Ws.append(W)
         tail_v, tail_raw = stats[L.S_TAILV], stats[L.S_TAILRAW]
     out = {"w_sum": tot[L.S_W:L.S_W + 4], "v_sum": tot[L.S_V:L.S_V + 4], "taked": int(tot[L.S_TAKED]),
            "served": int(tot[L.S_SERVED]), "sum_a": tot[L.S_SUMA], "sum_s": tot[L.S_SUMS], "pairs": pairs,
-           "carries": carries, "w_out": w_out, "tail_raw": tail_raw, "ttek": tot[L.S_SUMA] + tail_v,
+           "pairs_apply": pairs_apply, "carries": carries, "w_out": w_out, "tail_raw": tail_raw, "ttek": tot[L.S_SUMA] + tail_v,
            "sim_ms": sim_ms, "levels": levels}
     if want_p:
         out["p"], out["p_tail"] = levels_to_p(levels, out["ttek"])

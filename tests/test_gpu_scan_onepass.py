@@ -1,0 +1,99 @@
+"""K3 replay form in one pass (csrc/k3_onepass.cu: TMA-staged tiles, mbarrier pipeline, decoupled look-back) against
+the three-launch path (MQ_SCAN_TWO_PASS=1) and the oracle: the association tree is the specification, so per-job waits,
+range summaries and the tail are equal BIT FOR BIT; the power sums agree to rounding (different partition into CTAs)."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(A, S, N, **kw):
+    from most_queue_b200.sim.lindley import replay_chain
+
+    os.environ.pop("MQ_SCAN_TWO_PASS", None)
+    one = replay_chain(A, S, N, **kw)
+    os.environ["MQ_SCAN_TWO_PASS"] = "1"
+    try:
+        two = replay_chain(A, S, N, **kw)
+    finally:
+        os.environ.pop("MQ_SCAN_TWO_PASS", None)
+    return one, two
+
+
+# 2 tiles; ragged last tile; exactly full last tile; > 1024 tiles (chunks of 2, 3 and 10 tiles); a partial last group
+@pytest.mark.parametrize("N", [4097, 8192, 70_001, (1 << 20) + 5, 4096 * 1500 + 77, 4096 * 2500, 40_000_000])
+def test_one_pass_equals_three_launch_path_bitwise(N):
+    rng = np.random.default_rng(N % 1000)
+    A = rng.exponential(1.0, N + 1)
+    S = rng.exponential(0.9, N)
+    (o1, W1), (o2, W2) = _both(A, S, N)
+    assert np.array_equal(W1, W2)
+    assert o1["pairs_apply"] == o2["pairs_apply"] == o2["pairs"]
+    assert o1["tail_raw"] == o2["tail_raw"] and o1["ttek"] == pytest.approx(o2["ttek"], rel=1e-14)
+    assert (o1["taked"], o1["served"]) == (o2["taked"], o2["served"])
+    np.testing.assert_allclose(o1["w_sum"], o2["w_sum"], rtol=1e-11)
+    np.testing.assert_allclose(o1["v_sum"], o2["v_sum"], rtol=1e-11)
+    np.testing.assert_allclose([o1["sum_a"], o1["sum_s"]], [A[:N].sum(), S.sum()], rtol=1e-12)
+
+
+@pytest.mark.parametrize("N", [4097, 300_000, 4096 * 1100 + 9])
+def test_one_pass_waits_bitwise_vs_oracle_tree(N):
+    from most_queue_b200.sim.lindley import replay_chain
+    from oracle import oracle
+
+    rng = np.random.default_rng(N)
+    A = rng.gamma(3.18878, 1 / 3.18878, N + 1)
+    S = 0.395878 * rng.random(N) ** (-1 / 2.30171)
+    out, W = replay_chain(A, S, N)
+    Wt, ot = oracle.lindley(A, S, N, tree=True)
+    assert np.array_equal(W, Wt)
+    assert out["pairs_apply"][0] == (ot.a, ot.b)
+    assert out["tail_raw"] == ot.w_last_raw
+    np.testing.assert_allclose(out["w_sum"], ot.w_sum, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(out["v_sum"], ot.v_sum, rtol=1e-11)
+
+
+def test_one_pass_ranges_with_carries():
+    """Ranges with carried waits (the multi-GPU form): every range goes through the fused kernel with w_in != 0."""
+    rng = np.random.default_rng(7)
+    N = 3_000_000
+    A = rng.exponential(1.0, N + 1)
+    S = rng.exponential(0.95, N)
+    (o1, W1), (o2, W2) = _both(A, S, N, ranges=4)
+    assert np.array_equal(W1, W2)
+    assert o1["pairs_apply"] == o2["pairs_apply"] == o1["pairs"]
+    assert max(o1["carries"]) > 1.0
+    (o3, W3), _ = _both(A, S, N, ranges=1)
+    np.testing.assert_allclose(W1, W3, rtol=0, atol=1e-8)
+
+
+def test_one_pass_device_pointers_and_misaligned_fallback():
+    """Device-resident arrays (the bench's form); an 8-byte-aligned (not 16) pointer cannot be fetched by TMA and must
+    fall back to the three-launch path with the same result."""
+    import torch
+
+    from most_queue_b200 import _lib
+
+    ctx = _lib.default_context()
+    n = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.empty(n + 3, device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
+    S = torch.empty(n + 2, device="cuda", dtype=torch.float64).exponential_(1.0 / 0.8, generator=g)
+    torch.cuda.synchronize()
+    st1, _ = ctx.scan_apply(n, 0.0, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)
+    os.environ["MQ_SCAN_TWO_PASS"] = "1"
+    try:
+        st2, _ = ctx.scan_apply(n, 0.0, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)
+    finally:
+        os.environ.pop("MQ_SCAN_TWO_PASS", None)
+    assert st1[_lib.S_A] == st2[_lib.S_A] and st1[_lib.S_B] == st2[_lib.S_B]
+    assert st1[_lib.S_TAILRAW] == st2[_lib.S_TAILRAW]
+    np.testing.assert_allclose(st1[:10], st2[:10], rtol=1e-11)
+    # odd element offset: 8-byte aligned only
+    st3, _ = ctx.scan_apply(n, 0.0, A=A.data_ptr() + 8, S=S.data_ptr() + 8, device_ptrs=True)
+    Ah, Sh = A[1:n + 2].cpu().numpy(), S[1:n + 1].cpu().numpy()
+    np.testing.assert_allclose(st3[_lib.S_SUMS], Sh.sum(), rtol=1e-12)
+    np.testing.assert_allclose(st3[_lib.S_SUMA], Ah[:n].sum(), rtol=1e-12)

@@ -142,13 +142,21 @@ def test_cfg4_mm4_preemptive_against_exact_ctmc():
     res = ps.run(100_000)
     ref = np.load(os.path.join(G, "stat_cfg4_mm4_PR.npz"))
     for k in range(2):
-        for j in range(2):  # the solver returns the first two moments of v, the first of w
+        # E[v] of both classes, E[v^2] of the top class (never pre-empted), E[w]
+        for j in range(2 if k == 0 else 1):
             t = th["v"][k][j]
             assert abs(res.v[k][j] - t) <= res.ci["v"][k][j] + 2e-3 * t, (k, j, res.v[k][j], t)
             se = ref["v"][:, k, j].std(ddof=1) / 16.0
             assert abs(ref["v"][:, k, j].mean() - t) <= 3.3 * se + 2e-3 * t
         t = th["w"][k][0]
         assert abs(res.w[k][0] - t) <= res.ci["w"][k][0] + 2e-3 * max(t, 1.0), (k, res.w[k][0], t)
+    # E[v^2] of the pre-empted class: the solver's tagged-job model keeps a pre-empted job at its FCFS position, the
+    # reference's SIMULATOR sends it to the tail of its class line (priority.py:413-433), which changes the second
+    # moment (not the mean): solver 49.31, reference simulator 52.29 +- 0.2, this engine follows the simulator
+    t2 = th["v"][1][1]
+    m_ref, se_ref = ref["v"][:, 1, 1].mean(), ref["v"][:, 1, 1].std(ddof=1) / 16.0
+    assert abs(res.v[1][1] - m_ref) <= 3.3 * se_ref + res.ci["v"][1][1]
+    assert res.v[1][1] > 1.04 * t2 and m_ref > 1.04 * t2
 
 
 @pytest.mark.parametrize("prty", ["NP", "PR"])
