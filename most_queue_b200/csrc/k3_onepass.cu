@@ -50,6 +50,13 @@ constexpr int OP_LB = 128;                       // look-back window kept in sha
 constexpr uint32_t OP_TX = 2u * OP_ARR_BYTES + 16u;
 constexpr uint32_t OP_SPIN_LIMIT = 4000000u;     // wait iterations (each sleeps 20 ns .. 20 us) before a protocol bug traps instead of hanging
 
+struct OpTrue {
+    static constexpr bool value = true;
+};
+struct OpFalse {
+    static constexpr bool value = false;
+};
+
 struct OpStage {
     // 1024-byte aligned (the swizzle pattern is a function of the shared-memory address bits 4-9)
     unsigned char S[OP_ARR_BYTES];
@@ -109,6 +116,16 @@ __device__ __forceinline__ void mbar_init(unsigned long long *b, uint32_t count)
 __device__ __forceinline__ void mbar_arrive(unsigned long long *b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// arrive that may only be issued once `token` exists.  An mbarrier arrive does NOT wait for the data of earlier
+// shared-memory LOADS of the thread to have come back (measured: a stage handed back right after its LDS were issued was
+// overwritten by the next TMA copy before the loads had read it).  The caller folds one word of every loaded register
+// into `token`; the instructions that do so cannot issue before the loads have returned.
+// `zero_mask` is a kernel parameter that is 0 at run time: neither the compiler nor ptxas can fold token & zero_mask, so
+// the address of the arrive really depends on every loaded register that went into the token.
+__device__ __forceinline__ void mbar_arrive_after(unsigned long long *b, uint32_t token, uint32_t zero_mask)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b) + (token & zero_mask)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, uint32_t bytes)
 {
@@ -281,6 +298,7 @@ struct K3OnePassParams {
     MP *carry;             // [40]     carry into group g
     MP *seg_ring;          // [grid][OP_RING][256] exclusive prefix of every segment inside its tile (fold -> walk hand-off)
     long long chunk;       // tiles per chunk
+    uint32_t zero_mask;    // 0 (see mbar_arrive_after)
     int hints;             // 1: L2 eviction-priority hints on the two fetches of a tile
     int lead;              // tiles the fold side may lead the walk side by (1..OP_RING): bounds the L2 footprint
     int *err;
@@ -436,24 +454,41 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             double s0[OP_H], a0[OP_H + 1], s1[OP_H], a1[OP_H + 1];
             load_half(sm.fold, sm.f_anext, r, 0, s0, a0);
             load_half(sm.fold, sm.f_anext, r, 1, s1, a1);
-            mbar_arrive(&sm.f_empty);
+            {
+                // the rows must have been READ before the stage is handed back to the TMA producer (see mbar_arrive_after):
+                // one word of every 16-byte load goes into the token
+                uint32_t token = (uint32_t)__double2hiint(a0[OP_H]) | (uint32_t)__double2hiint(a1[OP_H]);
+#pragma unroll
+                for (int q = 0; q < OP_H; q += 2)
+                    token |= (uint32_t)__double2hiint(s0[q]) | (uint32_t)__double2hiint(a0[q]) |
+                             (uint32_t)__double2hiint(s1[q]) | (uint32_t)__double2hiint(a1[q]);
+                mbar_arrive_after(&sm.f_empty, token, Q.zero_mask);
+            }
+            // tile-uniform fast path: every tile but the last one of the range has no per-job bounds logic
             MP mine = mp_id();
+            auto fold_row = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-            for (int j = 0; j < OP_H; ++j) {
-                if (full_tile || j < valid) {
-                    mine = mp_step(mine, __dsub_rn(s0[j], a0[j + 1]));
-                    sum_a += a0[j];
-                    sum_s += s0[j];
+                for (int j = 0; j < OP_H; ++j) {
+                    if (FULL || j < valid) {
+                        mine = mp_step(mine, __dsub_rn(s0[j], a0[j + 1]));
+                        sum_a += a0[j];
+                        sum_s += s0[j];
+                    }
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < OP_H; ++j) {
-                if (full_tile || OP_H + j < valid) {
-                    mine = mp_step(mine, __dsub_rn(s1[j], a1[j + 1]));
-                    sum_a += a1[j];
-                    sum_s += s1[j];
+                for (int j = 0; j < OP_H; ++j) {
+                    if (FULL || OP_H + j < valid) {
+                        mine = mp_step(mine, __dsub_rn(s1[j], a1[j + 1]));
+                        sum_a += a1[j];
+                        sum_s += s1[j];
+                    }
                 }
-            }
+            };
+            if (full_tile)
+                fold_row(OpTrue{});
+            else
+                fold_row(OpFalse{});
             // CTA scan of the 256 segment summaries (Kogge-Stone per warp, sequential over the 8 warps)
             const MP inc = warp_inclusive(mine, lane);
             MP within = mp_shfl_up(inc, 1);
@@ -504,7 +539,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             if (lane == 0) OP_TRACE(4, clock64());
             const MP own = sm.tile_total[d];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.slot_free[d]);  // tile_total[d] has been read
+            if (lane == 0) mbar_arrive_after(&sm.slot_free[d], (uint32_t)__double2hiint(own.b), Q.zero_mask);  // tile_total[d] has been read
             const long long c = t / chunk, lo = c * chunk, n_pred = t - lo;
             const int g = (int)(c >> 5), l = (int)(c & 31);
             long long idx = -1;
@@ -636,33 +671,50 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             double w = mp_apply(MP{sx.x, sx.y}, w_tile);
             const int last_j = (!full_tile && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
             double *Wp = P.W ? P.W + n0 : nullptr;
+            // tile-uniform fast path (all tiles but the last): no bounds, no tail; the per-job wait store is a second
+            // compile-time switch
+            auto walk_row = [&](auto full_tag, auto w_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                constexpr bool STORE_W = decltype(w_tag)::value;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                double sv[OP_H], av[OP_H + 1];
-                load_half(sm.walk[s], sm.w_anext[s], r, h, sv, av);
+                for (int h = 0; h < 2; ++h) {
+                    double sv[OP_H], av[OP_H + 1];
+                    load_half(sm.walk[s], sm.w_anext[s], r, h, sv, av);
 #pragma unroll
-                for (int jj = 0; jj < OP_H; ++jj) {
-                    const int j = h * OP_H + jj;
-                    if (full_tile || j < valid) {
-                        if (Wp) Wp[j] = w;
-                        const double v = __dadd_rn(w, sv[jj]);
-                        const double w2 = w * w, v2 = v * v;
-                        acc[0] += w;
-                        acc[1] += w2;
-                        acc[2] += w2 * w;
-                        acc[3] += w2 * w2;
-                        acc[4] += v;
-                        acc[5] += v2;
-                        acc[6] += v2 * v;
-                        acc[7] += v2 * v2;
-                        const double raw = __dadd_rn(w, __dsub_rn(sv[jj], av[jj + 1]));
-                        if (!full_tile && j == last_j) {
-                            P.tail[0] = raw;
-                            P.tail[1] = v;
+                    for (int jj = 0; jj < OP_H; ++jj) {
+                        const int j = h * OP_H + jj;
+                        if (FULL || j < valid) {
+                            if (STORE_W) Wp[j] = w;
+                            const double v = __dadd_rn(w, sv[jj]);
+                            const double w2 = w * w, v2 = v * v;
+                            acc[0] += w;
+                            acc[1] += w2;
+                            acc[2] += w2 * w;
+                            acc[3] += w2 * w2;
+                            acc[4] += v;
+                            acc[5] += v2;
+                            acc[6] += v2 * v;
+                            acc[7] += v2 * v2;
+                            const double raw = __dadd_rn(w, __dsub_rn(sv[jj], av[jj + 1]));
+                            if (!FULL && j == last_j) {
+                                P.tail[0] = raw;
+                                P.tail[1] = v;
+                            }
+                            w = fmax(0.0, raw);
                         }
-                        w = fmax(0.0, raw);
                     }
                 }
+            };
+            if (full_tile) {
+                if (Wp)
+                    walk_row(OpTrue{}, OpTrue{});
+                else
+                    walk_row(OpTrue{}, OpFalse{});
+            } else {
+                if (Wp)
+                    walk_row(OpFalse{}, OpTrue{});
+                else
+                    walk_row(OpFalse{}, OpFalse{});
             }
             if (r == 0) {
                 OP_TRACE(10, clock64());
@@ -763,12 +815,13 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     if (grid > 256) return cudaErrorInvalidValue;
     Q.chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
     // the walk side re-reads a tile from L2 `lead` tiles after the fold side fetched it from HBM: lead x grid x 64 KB must
-    // stay well inside the L2 (4 x 148 x 64 KB = 38 MB); MQ_SCAN_LEAD overrides (3..8)
-    Q.lead = 4;
+    // stay inside the L2 (6 x 148 x 64 KB = 58 MB, kept there by the eviction hints); MQ_SCAN_LEAD overrides (3..12)
+    Q.lead = 6;
     if (const char *ev = std::getenv("MQ_SCAN_LEAD")) Q.lead = std::atoi(ev);
     if (Q.lead < OP_NLB) Q.lead = OP_NLB;  // a look-back warp moves OP_NLB tiles at a time: a shorter ring would alias phases
     if (Q.lead > OP_RING) Q.lead = OP_RING;
-    Q.hints = 0;
+    Q.hints = 1;
+    Q.zero_mask = 0;
     if (const char *ev = std::getenv("MQ_SCAN_HINTS")) Q.hints = std::atoi(ev) != 0;
     cudaError_t e = cudaMemsetAsync(scratch, 0xFF, sizeof(MP) * words, st);
     if (e != cudaSuccess) return e;
