@@ -7,6 +7,14 @@
 One "step" = one pass of QsSim.run(): `replications` independent M/H2/8 replications of
 `total_served` jobs each, per GPU (weak scaling: every rank simulates the full configuration with
 its own global replication ids).  Rank 0 prints ONE JSON line.
+
+    --config cfg2|cfg3|cfg5   cfg2 (default, the headline): M/H2/8; cfg3: one Gamma/Pareto/1 chain of 1e10 jobs cut into
+                              one contiguous range per GPU (summary -> all-gather of (a, b) -> carried walk); cfg5: the
+                              5-node H2 network, replications sharded
+    --scaling weak|strong     weak (default): every GPU gets the full configuration; strong: the configuration's total
+                              (cfg2: 1e6 replications, cfg5: 1e5 replications, cfg3: always the one 1e10-job chain) is
+                              split over the GPUs
+The reference arm (--impl reference) times the UNMODIFIED reference class (baseline/_ref) on all host cores.
 """
 
 from __future__ import annotations
@@ -31,6 +39,27 @@ C_SERVERS = 8
 ARRIVAL_RATE = 1.0
 I_ALG = 160.0  # planning lane-instructions per job for cfg2: the issue roofline's work unit
 METRIC = "simulated jobs/sec (M/H2/8 FIFO)"
+# planning budgets of SURVEY 8(d), lane-instructions per job, and what ncu measured (profiles/, issue-lane-slots per job
+# = warp instructions x 32 / jobs)
+I_ALG_OTHER = {"cfg3": 120.0, "cfg4": 220.0, "cfg5": 520.0}
+I_MEASURED = {"cfg2": 227.0, "cfg4": 53.0 * 32.0, "cfg5": None, "cfg3": None}
+NET_R = [[1, 0, 0, 0, 0, 0], [0, 0.4, 0.6, 0, 0, 0], [0, 0, 0.2, 0.4, 0.4, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 1, 0],
+         [0, 0, 0, 0, 0, 1]]
+NET_CH = [3, 2, 3, 4, 3]
+
+
+def issue_roofline(jobs_per_s_per_gpu, i_alg, kernel, peaks, peak_src, sms=148, extra=None):
+    """Issue roofline of a generate-and-simulate kernel: achieved = jobs/s/GPU x planning lane-instructions per job."""
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    peak = sms * 128 * sm_max * 1e6 / 1e9
+    achieved = jobs_per_s_per_gpu * i_alg / 1e9
+    r = {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "Glane-instr/s", "frac": achieved / peak,
+         "traffic": None, "kernel": kernel,
+         "note": f"achieved = jobs/s/GPU x {i_alg:.0f} planning lane-instructions per job (SURVEY 8d); peak = {sms} SMs x "
+                 f"128 lanes x {sm_max:.0f} MHz ({peak_src} clock)"}
+    if extra:
+        r.update(extra)
+    return r
 
 
 def _peaks():
@@ -269,9 +298,15 @@ def run_ours(args):
     src, srv = _lib.make_dist("M", ARRIVAL_RATE), _lib.make_dist("H", h2)
 
     # ---- device-resident throughput: the C-ABI call, timed with CUDA events on its stream ----
+    strong = args.scaling == "strong"
+    if strong:  # the configuration's 1e6 replications in total, this rank's contiguous share
+        from most_queue_b200 import dist as mqdist
+        rep0_rank, reps_rank = mqdist.shard(reps, rank, world)
+    else:       # every rank simulates `reps` replications with its own global ids
+        rep0_rank, reps_rank = rank * reps, reps
+
     def step(i):
-        # every rank simulates `reps` replications with its own global ids (weak scaling)
-        agg, _ = ctx.sim_fifo(C_SERVERS, None, src, srv, jobs, reps, rank * reps, 20260101 + i, p_bins=p_bins)
+        agg, _ = ctx.sim_fifo(C_SERVERS, None, src, srv, jobs, reps_rank, rep0_rank, 20260101 + i, p_bins=p_bins)
         return agg, ctx.last_timing()
 
     for i in range(args.warmup):
@@ -308,7 +343,7 @@ def run_ours(args):
         qs.set_sources(ARRIVAL_RATE, "M")
         qs.set_servers(h2, "H")
         # under torchrun QsSim shards `replications` over the ranks and allreduces the aggregate
-        res = qs.run(jobs, replications=reps * world)
+        res = qs.run(jobs, replications=reps if strong else reps * world)
         return qs, res
 
     api_step(0)
@@ -365,9 +400,10 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "jobs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"M/H2/{C_SERVERS} FIFO rho=0.7 CV=1.5 (BASELINE cfg2): {reps} replications x "
-                                   f"{jobs} jobs per GPU", "replications_per_gpu": reps, "jobs_per_replication": jobs,
+                                   f"{jobs} jobs " + ("in total (strong scaling)" if strong else "per GPU"),
+                       "replications_per_gpu": reps_rank, "jobs_per_replication": jobs,
                        "p_bins": p_bins, "generator": "Philox2x32-10, counter=(arrival index, global replication id)",
                        "cache": "generator mode has no input arrays; per-replication records "
                                 f"({8 * _lib.rec_rows(p_bins) * reps / 1e6:.0f} MB) exceed L2",
@@ -408,17 +444,48 @@ def run_ours(args):
                 line["replay"] = {"error": repr(e)}
         if world == 1 and not args.no_others:
             try:
-                line["other_configs"] = other_configs_leg()
+                line["other_configs"] = other_configs_leg(peaks, peak_src, sms)
             except Exception as e:
                 line["other_configs"] = {"error": repr(e)}
+        if world == 1 and not args.no_fp64:
+            try:
+                line["k2_fp64"] = fp64_leg(ctx, src, srv, jobs, reps, p_bins, agg, args.warmup + args.steps - 1)
+            except Exception as e:
+                line["k2_fp64"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
 
 
-def other_configs_leg():
+def fp64_leg(ctx, src, srv, jobs, reps, p_bins, agg32, step_index):
+    """The same loop in fp64 (MQ_FIFO_FP64: fp64 clocks, CUDA double-precision log, fp64 power sums) on the SAME seed and
+    replication ids as the last timed fp32 step: throughput of the fp64 tier and the paired difference of every raw
+    moment -- the measured cost of the fp32 production arithmetic ('nothing measures it directly')."""
+    from most_queue_b200 import _lib
+
+    agg64, _ = ctx.sim_fifo(C_SERVERS, None, src, srv, jobs, reps, 0, 20260101 + step_index, p_bins=p_bins, fp64=True)
+    tm = ctx.last_timing()
+    R = agg64[_lib.A_REPS]
+    out = {"jobs_per_s": float(agg64[_lib.A_SERVED]) / (tm["sim_ms"] * 1e-3), "ms": tm["sim_ms"], "replications": int(R),
+           "kernel": "k2_fifo_gen<double,8,runtime kinds,infinite>", "same_seed_as_step": step_index}
+    for name, a, a2 in (("w", _lib.A_W, _lib.A_W2), ("v", _lib.A_V, _lib.A_V2)):
+        m64 = agg64[a:a + 4] / R
+        m32 = agg32[a:a + 4] / agg32[_lib.A_REPS]
+        ci = 2.5758 * np.sqrt(np.maximum(agg64[a2:a2 + 4] / R - m64 * m64, 0.0) / R)
+        out[name + "_f64"] = [float(x) for x in m64]
+        out[name + "_f32_minus_f64"] = [float(x) for x in (m32 - m64)]
+        out[name + "_rel_diff"] = [float(x) for x in (m32 - m64) / m64]
+        out[name + "_ci99_of_the_run"] = [float(x) for x in ci]
+    p64 = agg64[_lib.A_P:_lib.A_P + 16] / R
+    p32 = agg32[_lib.A_P:_lib.A_P + 16] / agg32[_lib.A_REPS]
+    out["p_max_abs_diff"] = float(np.max(np.abs(p32 - p64)))
+    return out
+
+
+def other_configs_leg(peaks, peak_src, sms):
     """The other BASELINE.json configurations through the public API (parity-test cases, reported for reference:
-    device time of the simulation kernels from the library's CUDA events, one run each after a small warm-up)."""
+    device time of the simulation kernels from the library's CUDA events, one run each after a small warm-up), each with
+    the roofline object SURVEY 8(d) defines for it."""
     from most_queue_b200.random.distributions import GammaDistribution, H2Distribution, ParetoDistribution
     from most_queue_b200.sim.base import QsSim
     from most_queue_b200.sim.lindley import run_chain
@@ -438,8 +505,10 @@ def other_configs_leg():
     par = ParetoDistribution.get_params_by_mean_and_cv(0.7, 1.2)
     run_chain(("Gamma", gam), ("Pa", par), 1 << 24, seed=3, want_p=False)
     c3 = run_chain(("Gamma", gam), ("Pa", par), 10_000_000_000, seed=3, want_p=False)
-    out["cfg3_gamma_pareto_1_chain"] = {"jobs_per_s": 1e10 / (c3.timing["sim_ms"] * 1e-3), "w1": c3.w[0],
-                                        "utilization": c3.utilization}
+    j3 = 1e10 / (c3.timing["sim_ms"] * 1e-3)
+    out["cfg3_gamma_pareto_1_chain"] = {"jobs_per_s": j3, "w1": c3.w[0], "utilization": c3.utilization,
+                                        "roofline": issue_roofline(j3, I_ALG_OTHER["cfg3"], "k3_summary + k3_walk (generator form, "
+                                                                   "fp32 draw stash)", peaks, peak_src, sms)}
     # cfg3, replay form (2^28 jobs = 4 GiB of fp64 A, S resident in HBM, 16 B/job): the HBM-bound kernel of the set
     try:
         import torch
@@ -464,9 +533,11 @@ def other_configs_leg():
         out["cfg3_replay_2p28"] = {
             "jobs_per_s": nr / t, "ms": t * 1e3, "w1": float(st[_lib.S_W] / st[_lib.S_TAKED]), "w1_theory_mm1": 0.7 * 0.7 / 0.3,
             "roofline": {"bound": "hbm", "achieved": 16.0 * nr / t / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": 33.75 * nr,
-                         "note": "algorithmic bytes 16 B/job (A and S read once); traffic = dram bytes of the summary and walk kernels from "
-                                 "profiles/r01_ncu_k3_replay_traffic.csv (2^26 jobs: 33.75 B/job, no over-read), scaled; peak " + peak_src}}
+                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": 16.04 * nr,
+                         "kernel": "k3_onepass (TMA + decoupled look-back, one HBM read)",
+                         "note": "algorithmic bytes 16 B/job (A and S read once); traffic = dram__bytes_read + write of k3_onepass from "
+                                 "profiles/r02_ncu_k3_onepass_traffic.csv (2^26 jobs: 16.04 B/job), scaled; the three-launch "
+                                 "path (MQ_SCAN_TWO_PASS=1) moves 33.75 B/job; peak " + peak_src}}
     except Exception as e:  # reported, never fatal for the headline line
         out["cfg3_replay_2p28"] = {"error": repr(e)[:200]}
     # cfg4: M/Gamma/4, two classes, NP and PR, 1e5 replications x 1e5 jobs
@@ -478,8 +549,10 @@ def other_configs_leg():
         ps.set_servers([{"type": "Gamma", "params": g0}, {"type": "Gamma", "params": g1}])
         ps.run(1000, replications=4096)
         r = ps.run(100_000)
-        out[f"cfg4_mg4_2class_{prty}"] = {"jobs_per_s": 1e5 * 1e5 / (ps.timing["sim_ms"] * 1e-3),
-                                         "v1": [r.v[0][0], r.v[1][0]]}
+        j4 = 1e5 * 1e5 / (ps.timing["sim_ms"] * 1e-3)
+        out[f"cfg4_mg4_2class_{prty}"] = {"jobs_per_s": j4, "v1": [r.v[0][0], r.v[1][0]],
+                                         "roofline": issue_roofline(j4, I_ALG_OTHER["cfg4"], "k4v2_prio<4 slots,2 classes,generator>",
+                                                                    peaks, peak_src, sms)}
     # cfg5: 5-node open network of H2 nodes, 1e5 replications x 1e4 network jobs
     R = [[1, 0, 0, 0, 0, 0], [0, 0.4, 0.6, 0, 0, 0], [0, 0, 0.2, 0.4, 0.4, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 1, 0],
          [0, 0, 0, 0, 0, 1]]
@@ -489,7 +562,10 @@ def other_configs_leg():
     net.set_nodes([{"type": "H", "params": H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2)} for c in ch], ch)
     net.run(500, replications=4096)
     r = net.run(10_000)
-    out["cfg5_network_5_nodes"] = {"network_jobs_per_s": 1e5 * 1e4 / (net.timing["sim_ms"] * 1e-3), "v1": r.v[0]}
+    j5 = 1e5 * 1e4 / (net.timing["sim_ms"] * 1e-3)
+    out["cfg5_network_5_nodes"] = {"network_jobs_per_s": j5, "v1": r.v[0],
+                                   "roofline": issue_roofline(j5, I_ALG_OTHER["cfg5"], "k5v2_net<16 server slots,generator>",
+                                                              peaks, peak_src, sms)}
     return out
 
 
@@ -525,6 +601,109 @@ def replay_leg(ctx, peaks, peak_src, reps=65536, rows=4096, steps=3):
                          "note": f"algorithmic bytes = 8 B x variates consumed (16 B/job); peak {peak_src}"}}
 
 
+def run_other_config(args):
+    """--config cfg3 | cfg5 under the same launch contract (one rank per GPU, barrier + synchronize around exactly K timed
+    steps, max over ranks, rank 0 prints one JSON line).  cfg3: ONE Gamma/Pareto/1 chain of --chain-jobs jobs (1e10) cut
+    into one contiguous range per rank: local max-plus summary -> all-gather of the (a, b) pairs -> carries folded in rank
+    order -> walk from the carry -> allreduce of the sums (always strong scaling: it is one chain).  cfg5: the 5-node
+    H2 network, 1e5 replications x 1e4 network jobs, sharded (strong) or per GPU (weak)."""
+    import torch
+    import torch.distributed as tdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from most_queue_b200 import _lib
+    from most_queue_b200.random.distributions import GammaDistribution, H2Distribution, ParetoDistribution
+    from most_queue_b200.sim.lindley import run_chain
+    from most_queue_b200.sim.networks.network import NetworkSimulator
+
+    peaks, peak_src = _peaks()
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.config == "cfg3":
+        gam = GammaDistribution.get_params_by_mean_and_cv(1.0, 0.56)
+        par = ParetoDistribution.get_params_by_mean_and_cv(0.7, 1.2)
+        n = int(args.chain_jobs)
+
+        def step(i):
+            r = run_chain(("Gamma", gam), ("Pa", par), n, seed=300 + i, want_p=False)
+            return r, (r.timing["sim_ms"] if r.timing else 0.0), n
+
+        metric, unit = "simulated jobs/sec (GI/G/1 Gamma/Pareto chain, max-plus Lindley scan)", "jobs/s"
+        workload = f"Gamma/Pareto/1 rho=0.7, ONE chain of {n} jobs cut into {world} contiguous range(s) (BASELINE cfg3)"
+        scaling, i_alg, kernel = "strong", I_ALG_OTHER["cfg3"], "k3_summary + k3_walk (generator form)"
+        h2d, d2h = 0, 8 * 56
+    else:
+        strong = args.scaling == "strong"
+        reps = 100_000 if strong else 100_000 * world
+        jobs = 10_000
+
+        def step(i):
+            net = NetworkSimulator(seed=500 + i, replications=reps)
+            net.set_sources(1.0, np.array(NET_R, dtype=float))
+            net.set_nodes([{"type": "H", "params": H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2)} for c in NET_CH], NET_CH)
+            r = net.run(jobs)
+            return r, (net.timing["sim_ms"] if net.timing else 0.0), reps * jobs
+
+        metric, unit = "simulated network jobs/sec (5-node open network of M/H2/c nodes)", "network jobs/s"
+        workload = (f"5-node open network, H2 nodes c={NET_CH}, {reps} replications x {jobs} network jobs "
+                    + ("in total, sharded" if strong else "(100000 per GPU)") + " (BASELINE cfg5)")
+        scaling, i_alg, kernel = args.scaling, I_ALG_OTHER["cfg5"], "k5v2_net<16 server slots,generator>"
+        h2d, d2h = int(__import__("ctypes").sizeof(_lib.MqNetCfg)), 8 * _lib.net_agg_len(5)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    dev_ms, units, res = 0.0, 0, None
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            res, ms, u = step(args.warmup + i)
+            dev_ms += ms
+            units += u
+        barrier()
+        wall_s = time.perf_counter() - t0
+    clocks = clk.summary()
+    dev_ms = maxreduce(dev_ms)
+    wall_s = maxreduce(wall_s)
+    if rank == 0:
+        value = units / (dev_ms * 1e-3)       # units are whole-job counts (every rank returns the same total)
+        e2e = units / wall_s
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "f32 variates, f64 recursion" if args.config == "cfg3" else "f64", "data": "synthetic",
+                "config": {"workload": workload, "generator": "Philox2x32-10",
+                           "cache": "generator mode: no input arrays",
+                           "parallelism": (f"{world} contiguous job ranges, all-gather of {world} (a, b) pairs + one allreduce"
+                                           if args.config == "cfg3" else f"replications sharded over {world} GPU(s), one allreduce")},
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "run_chain(source, server, n)" if args.config == "cfg3" else "NetworkSimulator().run(job_served, replications=)"},
+                "gpu_launches": args.steps * (7 if args.config == "cfg3" and world > 1 else (6 if args.config == "cfg3" else 2)),
+                "roofline": issue_roofline(value / world, i_alg, kernel, peaks, peak_src, sms),
+                "result": {"w1": float(res.w[0]), "v1": float(res.v[0])} if args.config == "cfg3" else {"v1": float(res.v[0])}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -541,11 +720,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-replay", action="store_true")
+    ap.add_argument("--no-fp64", action="store_true", help="skip the fp64 A/B run of K2")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--chain-jobs", type=float, default=1e10, help="--config cfg3: jobs of the one chain")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.config == "cfg2":
         run_ours(args)
+    else:
+        run_other_config(args)
 
 
 if __name__ == "__main__":

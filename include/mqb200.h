@@ -125,6 +125,13 @@ typedef struct {
 #define MQ_MAX_PBINS 1024
 #define MQ_MAX_CHANNELS 32
 
+/* The same call on SEVERAL GPUs from one host thread: the replications of cfg (global ids rep0 .. rep0 + replications)
+ * are cut into one contiguous share per context, every context (one per device, mq_create) simulates its share on its
+ * own host thread, and the aggregates -- sums over replications -- are added.  This is what a single-process caller of
+ * qs.run(n, replications=R) uses to fill a box without torchrun; results do not depend on the number of contexts
+ * (Philox counters carry the global replication id).  rep_out is not available in this form. */
+int mq_sim_fifo_multi(mq_ctx *const *ctxs, int n_ctx, const mq_fifo_cfg *cfg, double *agg);
+
 /* GI/G/c/r FIFO, replay mode: variates come from caller arrays instead of the generator.
  * A[i * replications + r] is the i-th interarrival draw of replication r (A[0][r] is the
  * draw set_sources makes, base.py:112); S[j * replications + r] the j-th service draw

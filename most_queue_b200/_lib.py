@@ -344,6 +344,8 @@ def load():
         L.mq_sim_size.argtypes = [vp, C.POINTER(MqSizeCfg), dp, dp]
         L.mq_replay_size.restype = C.c_int
         L.mq_replay_size.argtypes = [vp, C.POINTER(MqSizeCfg), vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, dp, dp]
+        L.mq_sim_fifo_multi.restype = C.c_int
+        L.mq_sim_fifo_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(MqFifoCfg), dp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -456,6 +458,23 @@ class Context:
             self._h, C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double)),
             rec.ctypes.data_as(C.POINTER(C.c_double)) if rec is not None else None))
         return agg, rec
+
+    def sim_fifo_multi(self, others, c, buffer, src, srv, total_served, replications, rep0, seed, p_bins=128,
+                       warmup=0, v_at_start=False, fp64=False, busy=False):
+        """mq_sim_fifo_multi: this context and `others` (one per GPU) share the replications of one call."""
+        cfg = MqFifoCfg()
+        cfg.c, cfg.p_bins = int(c), int(p_bins)
+        cfg.buffer = -1 if buffer is None else int(buffer)
+        cfg.src, cfg.srv = src, srv
+        cfg.total_served, cfg.replications, cfg.rep0 = int(total_served), int(replications), int(rep0)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.warmup = int(warmup)
+        cfg.flags = (FIFO_V_AT_START if v_at_start else 0) | (FIFO_FP64 if fp64 else 0) | (FIFO_BUSY if busy else 0)
+        agg = np.zeros(agg_len(p_bins) + (AGG_BUSY_LEN if busy else 0))
+        ctxs = [self] + list(others)
+        arr = (C.c_void_p * len(ctxs))(*[x._h for x in ctxs])
+        check(self._L.mq_sim_fifo_multi(arr, len(ctxs), C.byref(cfg), agg.ctypes.data_as(C.POINTER(C.c_double))))
+        return agg, None
 
     # ---- K1 ----
     def replay_fifo(self, c, buffer, A: np.ndarray, S: np.ndarray, total_served, p_bins=128, want_agg=True):
@@ -865,6 +884,13 @@ def default_context(device: int | None = None) -> Context:
     if key not in _default_ctx:
         _default_ctx[key] = Context(device)
     return _default_ctx[key]
+
+
+def device_contexts(devices) -> list:
+    """Contexts of several GPUs for single-process use: devices = "all" or a list of device indices."""
+    if devices == "all":
+        devices = list(range(load().mq_device_count()))
+    return [default_context(int(d)) for d in devices]
 
 
 def seed_to_key(seed: int) -> int:

@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(MQ_K1_BLOCK) k1_fifo_replay(const K1Params P)
             const bool more = is_pstart && q > 1;
             h += more;
             a_h = more ? __dadd_rn(a_h, a_lag) : a_h;
-            if (first || more) a_lag = A[(long long)(h + 1u) * R];  // h + 1 <= ia - 1 < n_a while somebody waits
+            // h + 1 <= ia - 1 < n_a while somebody waits; on the input-short path (ia >= n_a, status set at the end of the
+            // trip) the row does not exist: the load is skipped instead of reading one row past the caller's array
+            if ((first || more) && h + 1u < n_a) a_lag = A[(long long)(h + 1u) * R];
             q += (uint32_t)arr_q - (uint32_t)is_pstart;
         } else {
             const bool accept = arr_q && q < cap;

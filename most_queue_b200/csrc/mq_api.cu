@@ -5,6 +5,10 @@
 #include "k1_fifo_replay.cuh"
 #include "k2_fifo_gen.cuh"
 
+#include <string>
+#include <thread>
+#include <vector>
+
 namespace mq {
 
 #define MQ_DECL_K2(n) \
@@ -400,6 +404,55 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
     CU(cudaStreamSynchronize(ctx->stream));
     std::memcpy(agg, ctx->h_agg, sizeof(double) * (size_t)agg_len);
     return finish_timing(ctx);
+}
+
+int mq_sim_fifo_multi(mq_ctx *const *ctxs, int n_ctx, const mq_fifo_cfg *cfg, double *agg)
+{
+    if (!ctxs || n_ctx < 1 || !cfg || !agg) return fail(MQ_E_INVALID, "mq_sim_fifo_multi: NULL argument");
+    for (int i = 0; i < n_ctx; ++i)
+        if (!ctxs[i]) return fail(MQ_E_INVALID, "mq_sim_fifo_multi: context %d is NULL", i);
+    if (n_ctx == 1) return mq_sim_fifo(ctxs[0], cfg, agg, nullptr);
+    if (cfg->p_bins < 1 || cfg->p_bins > MQ_MAX_PBINS)
+        return fail(MQ_E_INVALID, "mq_sim_fifo_multi: p_bins must be in 1..%d", MQ_MAX_PBINS);
+    const int len = MQ_AGG_LEN(cfg->p_bins) + ((cfg->flags & MQ_FIFO_BUSY) ? MQ_AGG_BUSY_LEN : 0);
+    std::vector<std::vector<double>> part(n_ctx, std::vector<double>(len, 0.0));
+    std::vector<int> rc(n_ctx, MQ_OK);
+    std::vector<std::string> msg(n_ctx);
+    std::vector<std::thread> th;
+    const long long R = cfg->replications;
+    for (int i = 0; i < n_ctx; ++i) {
+        const long long lo = R * i / n_ctx, hi = R * (i + 1) / n_ctx;
+        if (hi <= lo) continue;
+        th.emplace_back([&, i, lo, hi]() {
+            mq_fifo_cfg c = *cfg;
+            c.rep0 = cfg->rep0 + lo;
+            c.replications = hi - lo;
+            rc[i] = mq_sim_fifo(ctxs[i], &c, part[i].data(), nullptr);
+            if (rc[i] != MQ_OK) msg[i] = g_err;  // the message is thread-local
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n_ctx; ++i)
+        if (rc[i] != MQ_OK) return fail(rc[i], "mq_sim_fifo_multi: device %d: %s", ctxs[i]->device, msg[i].c_str());
+    for (int q = 0; q < len; ++q) {
+        double s = 0.0;
+        for (int i = 0; i < n_ctx; ++i) s += part[i][q];  // fixed order: the sum does not depend on thread timing
+        agg[q] = s;
+    }
+    // the timing of the call = the slowest device
+    double sim = 0, red = 0, tot = 0;
+    int launches = 0;
+    for (int i = 0; i < n_ctx; ++i) {
+        sim = std::fmax(sim, ctxs[i]->sim_ms);
+        red = std::fmax(red, ctxs[i]->reduce_ms);
+        tot = std::fmax(tot, ctxs[i]->total_ms);
+        launches += ctxs[i]->launches;
+    }
+    ctxs[0]->sim_ms = sim;
+    ctxs[0]->reduce_ms = red;
+    ctxs[0]->total_ms = tot;
+    ctxs[0]->launches = launches;
+    return MQ_OK;
 }
 
 int mq_replay_fifo(mq_ctx *ctx, const mq_replay_cfg *cfg, const double *A, const double *S, double *agg,

@@ -91,3 +91,50 @@ def common_seed(seed) -> int:
         t = t.cuda()
     d.broadcast(t, src=0)
     return int(t.item())
+
+
+def local_devices(devices=None):
+    """Devices a single-process run spreads over: an explicit list, "all", or the MQ_DEVICES environment variable
+    ("all" or "0,1,2"); None (the default) means one GPU, as before.  Ignored under torch.distributed, where every
+    rank owns one GPU."""
+    import os
+
+    if _dist() is not None and _dist().get_world_size() > 1:
+        return None
+    if devices is None:
+        devices = os.environ.get("MQ_DEVICES")
+        if not devices:
+            return None
+        devices = "all" if devices == "all" else [int(x) for x in devices.split(",")]
+    return devices
+
+
+def run_on_devices(contexts, replications: int, fn):
+    """Single-process multi-GPU: fn(ctx, rep0, count) -> aggregate vector runs on one host thread per context (the
+    library call releases the GIL) on a contiguous share of the replications; the aggregates -- sums over
+    replications -- are added in device order."""
+    import threading
+
+    n = len(contexts)
+    out, err = [None] * n, [None] * n
+
+    def work(i):
+        lo, hi = replications * i // n, replications * (i + 1) // n
+        try:
+            out[i] = fn(contexts[i], lo, hi - lo) if hi > lo else None
+        except BaseException as e:  # re-raised in the caller's thread
+            err[i] = e
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    parts = [x for x in out if x is not None]
+    total = parts[0].copy()
+    for x in parts[1:]:
+        total += x
+    return total

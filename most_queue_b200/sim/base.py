@@ -31,7 +31,7 @@ class QsSim:
 
     def __init__(self, num_of_channels, buffer=None, verbose=True, buffer_type="list", seed=None,
                  replications=1, p_bins=128, device=None, warmup=0, v_at_start=False, precision="f32",
-                 busy=False):
+                 busy=False, devices=None):
         if buffer_type not in ("list", "deque"):
             raise ValueError("Unknown queue type")  # base.py:73
         self.n = int(num_of_channels)
@@ -41,6 +41,10 @@ class QsSim:
         self.replications = int(replications)
         self.p_bins = int(p_bins)
         self.device = device
+        # additive: devices="all" (or a list of indices, or MQ_DEVICES=all in the environment) spreads the replications
+        # of ONE run() call over several GPUs from this single process (one host thread per GPU inside the library,
+        # mq_sim_fifo_multi); under torchrun every rank keeps its one GPU
+        self.devices = devices
         # additive: discard the statistics of the first `warmup` jobs that start service (the reference
         # starts empty and keeps everything, base.py:488-528, which biases every replication by O(1/N))
         self.warmup = int(warmup)
@@ -108,6 +112,15 @@ class QsSim:
                             utilization=self.calc_load(), replications=R, ci=self.ci)
 
     def _launch(self, total_served, R, seed, keep_replications, busy):
+        devs = dist.local_devices(self.devices)
+        if devs is not None and not keep_replications:
+            ctxs = _lib.device_contexts(devs)
+            if len(ctxs) > 1:
+                agg, _ = ctxs[0].sim_fifo_multi(ctxs[1:], self.n, self.buffer, self._src, self._srv, total_served, R, 0,
+                                                seed, p_bins=self.p_bins, warmup=self.warmup, v_at_start=self.v_at_start,
+                                                fp64=self.precision == "f64", busy=busy)
+                self.timing = ctxs[0].last_timing()
+                return agg, None
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         if count > 0:

@@ -68,16 +68,20 @@ def run_chain(source, server, total_served: int, seed=None, chain: int = 0, devi
     rank, world = dist.world()
     job0, count = dist.shard(int(total_served))
     ctx = L.default_context(device)
+    summary_ms = 0.0
     if world == 1:
         carries = [0.0]  # one range: no summary exchange, the apply call computes its own tile prefixes
     else:
         ab = ctx.scan_summary(count, job0=job0, src=src, srv=srv, seed=seed, chain=chain) if count > 0 else (-np.inf, 0.0)
+        summary_ms = ctx.last_timing()["sim_ms"] if count > 0 else 0.0
         carries, _ = fold_carries(_gather_pairs(ab))
     if count > 0:
         stats, _ = ctx.scan_apply(count, carries[rank], job0=job0, src=src, srv=srv, seed=seed, chain=chain,
                                   last_range=(rank == world - 1), want_p=want_p,
                                   jobs_ahead=int(total_served) - (job0 + count))
-        timing = ctx.last_timing()
+        timing = dict(ctx.last_timing())
+        timing["summary_ms"] = summary_ms      # the range summary exchanged before the walk (multi-rank runs)
+        timing["sim_ms"] += summary_ms
     else:
         stats, timing = np.zeros(L.SCAN_LEN), None
     # everything that sums; the tail belongs to the last range only

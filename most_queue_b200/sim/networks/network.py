@@ -23,11 +23,12 @@ Z99 = 2.5758293035489004
 
 
 class NetworkSimulator:
-    def __init__(self, seed=None, replications=1, queue_cap=0, device=None):
+    def __init__(self, seed=None, replications=1, queue_cap=0, device=None, devices=None):
         self.seed = seed
         self.replications = int(replications)
         self.queue_cap = int(queue_cap)
         self.device = device
+        self.devices = devices  # "all" / list of GPU indices: one process, several GPUs (see QsSim)
         self.R = None
         self.n_num = None
         self.nodes = None
@@ -73,7 +74,15 @@ class NetworkSimulator:
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
         m = self.n_num
-        if count > 0:
+        devs = dist.local_devices(self.devices)
+        if devs is not None and not keep_replications and len(_lib.device_contexts(devs)) > 1:
+            # single process, several GPUs: one host thread per device, aggregates added (dist.run_on_devices)
+            ctxs = _lib.device_contexts(devs)
+            agg = dist.run_on_devices(ctxs, R, lambda cx, r0, n: cx.sim_net(
+                self.R, self.nodes, self._src, self._srv, job_served, n, r0, seed, queue_cap=self.queue_cap)[0])
+            rec = None
+            self.timing = max((cx.last_timing() for cx in ctxs), key=lambda t: t["sim_ms"])
+        elif count > 0:
             agg, rec = ctx.sim_net(self.R, self.nodes, self._src, self._srv, job_served, count, rep0, seed,
                                    queue_cap=self.queue_cap, per_replication=keep_replications)
             self.timing = ctx.last_timing()

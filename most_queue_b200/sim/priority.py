@@ -24,7 +24,7 @@ Z99 = 2.5758293035489004
 
 class PriorityQueueSimulator:
     def __init__(self, num_of_channels, num_of_classes, prty_type="No", buffer=None, seed=None, replications=1,
-                 p_bins=64, queue_cap=0, device=None):
+                 p_bins=64, queue_cap=0, device=None, devices=None):
         self.n = int(num_of_channels)
         self.k = int(num_of_classes)
         self.prty_type = prty_type
@@ -34,6 +34,7 @@ class PriorityQueueSimulator:
         self.p_bins = int(p_bins)
         self.queue_cap = int(queue_cap)
         self.device = device
+        self.devices = devices  # "all" / list of GPU indices: one process, several GPUs (see QsSim)
         self.num_of_states = DEFAULT_NUM_STATES
         self.w = [[0, 0, 0, 0] for _ in range(self.k)]
         self.v = [[0, 0, 0, 0] for _ in range(self.k)]
@@ -78,7 +79,16 @@ class PriorityQueueSimulator:
         seed = dist.common_seed(self.seed)
         rep0, count = dist.shard(R)
         ctx = _lib.default_context(self.device)
-        if count > 0:
+        devs = dist.local_devices(self.devices)
+        if devs is not None and not keep_replications and len(_lib.device_contexts(devs)) > 1:
+            # single process, several GPUs: one host thread per device, aggregates added (dist.run_on_devices)
+            ctxs = _lib.device_contexts(devs)
+            agg = dist.run_on_devices(ctxs, R, lambda cx, r0, n: cx.sim_prio(
+                self.n, self.k, self.prty_type, self.buffer, self._src, self._srv, total_served, n, r0, seed,
+                p_bins=self.p_bins, queue_cap=self.queue_cap)[0])
+            rec = None
+            self.timing = max((cx.last_timing() for cx in ctxs), key=lambda t: t["sim_ms"])
+        elif count > 0:
             agg, rec = ctx.sim_prio(self.n, self.k, self.prty_type, self.buffer, self._src, self._srv, total_served,
                                     count, rep0, seed, p_bins=self.p_bins, queue_cap=self.queue_cap,
                                     per_replication=keep_replications)

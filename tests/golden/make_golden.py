@@ -152,10 +152,10 @@ class LowestFirstSet(set):
         return iter(sorted(set.__iter__(self)))
 
 
-def prio_case(name, c, K, prty, A, S, total_served, nprobs=64):
+def prio_case(name, c, K, prty, A, S, total_served, nprobs=64, buffer=None):
     from most_queue.sim.priority import PriorityQueueSimulator
 
-    qs = PriorityQueueSimulator(c, K, prty)
+    qs = PriorityQueueSimulator(c, K, prty, buffer=buffer)
     qs.set_sources([{"type": "M", "params": 1.0} for _ in range(K)])
     qs.set_servers([{"type": "M", "params": 1.0} for _ in range(K)])
     ia = [[0] for _ in range(K)]
@@ -170,6 +170,8 @@ def prio_case(name, c, K, prty, A, S, total_served, nprobs=64):
         while sum(qs.served) < total_served:  # run() minus tqdm (priority.py:636-637)
             qs.run_one_step()
     out = dict(c=c, K=K, prty=prty, total_served=total_served, ttek=float(qs.ttek))
+    if buffer is not None:
+        out["buffer"] = buffer
     for k in range(K):
         out[f"A{k}"] = np.asarray(A[k])
         out[f"S{k}"] = np.asarray(S[k])
@@ -204,6 +206,13 @@ def make_prio():
         A = [rng.exponential(5.0, n), rng.exponential(4.0, n), rng.exponential(3.0, n)]
         S = [rng.exponential(0.8, 2 * n), rng.exponential(1.0, 2 * n), rng.exponential(0.9, 2 * n)]
         prio_case(f"c1k3_{prty}", 1, 3, prty, A, S, n)
+    # finite total buffer (priority.py:437-455: it only bounds the pre-emptive disciplines, when no weaker job can be
+    # thrown off a server); its own generator so that the fixtures above keep their streams
+    rng = np.random.default_rng(20261020)
+    for prty, buf in (("PR", 3), ("RS", 5), ("RW", 2), ("PR", 1)):
+        A = [rng.exponential(1.6, 2 * n), rng.exponential(1.1, 2 * n), rng.exponential(1.3, 2 * n)]
+        S = [rng.exponential(1.0, 3 * n), gam(1.4, 0.8, 3 * n), rng.exponential(1.6, 3 * n)]
+        prio_case(f"c2k3_{prty}_buffer{buf}", 2, 3, prty, A, S, n, buffer=buf)
 
 
 # --------------------------------------------------------------------------- network

@@ -49,6 +49,39 @@ def main():
     assert multi.served == Nj
     np.testing.assert_allclose(multi.w[0], w1, rtol=1e-10)
     np.testing.assert_allclose(multi.v[0], v1, rtol=1e-10)
+    # priority (cfg4 shape) and network (cfg5 shape): replications sharded over the ranks == one process
+    from most_queue_b200.random.distributions import GammaDistribution, H2Distribution
+    from most_queue_b200.sim.networks.network import NetworkSimulator
+    from most_queue_b200.sim.priority import PriorityQueueSimulator
+
+    g = [GammaDistribution.get_params_by_mean_and_cv(m, 1.2) for m in (2.0, 4.0)]
+    ps = PriorityQueueSimulator(4, 2, "PR", seed=17, replications=2048, p_bins=32)
+    ps.set_sources([{"type": "M", "params": 0.3}, {"type": "M", "params": 0.5}])
+    ps.set_servers([{"type": "Gamma", "params": x} for x in g])
+    ps.run(2000)
+    pa = ctx.sim_prio(4, 2, "PR", None, [_lib.make_dist("M", 0.3), _lib.make_dist("M", 0.5)],
+                      [_lib.make_dist("Gamma", x) for x in g], 2000, 2048, 0, 17, p_bins=32)[0]
+    np.testing.assert_allclose(ps.agg, pa, rtol=1e-12, atol=1e-9)
+    Rm = [[1, 0, 0, 0, 0, 0], [0, 0.4, 0.6, 0, 0, 0], [0, 0, 0.2, 0.4, 0.4, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 1, 0],
+          [0, 0, 0, 0, 0, 1]]
+    ch = [3, 2, 3, 4, 3]
+    net = NetworkSimulator(seed=23, replications=2048)
+    net.set_sources(1.0, np.array(Rm, dtype=float))
+    hs = [H2Distribution.get_params_by_mean_and_cv(0.7 * c, 1.2) for c in ch]
+    net.set_nodes([{"type": "H", "params": h} for h in hs], ch)
+    net.run(1000)
+    na = ctx.sim_net(Rm, ch, _lib.make_dist("M", 1.0), [_lib.make_dist("H", h) for h in hs], 1000, 2048, 0, 23)[0]
+    np.testing.assert_allclose(net.agg, na, rtol=1e-12, atol=1e-9)
+    # seed=None: rank 0's seed is broadcast, so every rank reports the SAME result
+    q2 = QsSim(3, seed=None, p_bins=16)
+    q2.set_sources(2.0, "M")
+    q2.set_servers(1.0, "M")
+    r2 = q2.run(500, replications=256)
+    t = torch.tensor([r2.w[0]], dtype=torch.float64, device="cuda")
+    lo_, hi_ = t.clone(), t.clone()
+    tdist.all_reduce(lo_, op=tdist.ReduceOp.MIN)
+    tdist.all_reduce(hi_, op=tdist.ReduceOp.MAX)
+    assert float(lo_) == float(hi_)
     tdist.barrier()
     if rank == 0:
         print(f"MGPU_CHECK_OK world={world} w1={multi.w[0]:.6f} v1={multi.v[0]:.6f}")

@@ -26,7 +26,8 @@ def test_replay_matches_reference_bitwise(path):
     nb = g["p_time"].shape[1]
     A = [np.repeat(g[f"A{k}"][:, None], 2, axis=1) for k in range(K)]
     S = [np.repeat(g[f"S{k}"][:, None], 2, axis=1) for k in range(K)]
-    out = replay(int(g["c"]), K, str(g["prty"]), A, S, int(g["total_served"]), p_bins=nb)
+    buffer = int(g["buffer"]) if "buffer" in g.files else None  # finite total buffer (priority.py:437-455)
+    out = replay(int(g["c"]), K, str(g["prty"]), A, S, int(g["total_served"]), buffer=buffer, p_bins=nb)
     for r in range(2):
         assert out["ttek"][r] == float(g["ttek"])
         for name in ("arrived", "served", "taked", "dropped", "in_sys", "a_used", "s_used"):

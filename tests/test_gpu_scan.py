@@ -161,3 +161,33 @@ def test_generator_chain_sums_equal_the_sums_of_the_variates():
     for row in (L.S_W, L.S_W + 1, L.S_V, L.S_V + 1):
         np.testing.assert_allclose(two[row], one[row], rtol=1e-11)
         np.testing.assert_allclose(p1[row] + p2[row], one[row], rtol=1e-10)
+
+
+def test_levels_of_ranges_equal_single_range_on_a_fresh_context():
+    """ADVICE r1: with host pointers the walk of a non-last range reads gaps past A[jobs] for the time-in-state levels;
+    the staged copy must hold them.  A FRESH context (nothing left in the staging buffer by an earlier call) and three
+    ranges must give the levels of the single range to rounding."""
+    from most_queue_b200 import _lib
+    from most_queue_b200.sim import lindley
+
+    rng = np.random.default_rng(11)
+    N = 180_000
+    A = rng.exponential(1.0, N + 1)
+    S = rng.exponential(0.85, N)
+
+    def run(ranges):
+        ctx = _lib.Context()
+        old = _lib._default_ctx.copy()
+        _lib._default_ctx.clear()
+        _lib._default_ctx[-1] = ctx
+        try:
+            out, _ = lindley.replay_chain(A, S, N, ranges=ranges, want_w=False, want_p=True)
+        finally:
+            _lib._default_ctx.clear()
+            _lib._default_ctx.update(old)
+            ctx.close()
+        return out
+
+    one, three = run(1), run(3)
+    np.testing.assert_allclose(three["levels"], one["levels"], rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(three["p"][:24], one["p"][:24], rtol=0, atol=1e-12)

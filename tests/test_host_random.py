@@ -65,3 +65,22 @@ def test_kendall_codes_are_validated_like_the_reference():
     assert list(d.p)[:2] == [5.0, 1.0]
     d = _lib.make_dist("E", ErlangParams(r=3, mu=2.0))
     assert list(d.p)[:2] == [3.0, 2.0]
+
+
+def test_create_distribution_factory_mirrors_the_reference():
+    """random/utils/create.py:19-80: one class per Kendall code, ValueError for an unknown code."""
+    from most_queue_b200.random.utils.create import create_distribution
+    from most_queue_b200.random.utils.params import GammaParams, H2Params, ParetoParams
+
+    cases = [("M", 1.5, D.ExpDistribution), ("H", H2Params(p1=0.4, mu1=1.0, mu2=3.0), D.H2Distribution),
+             ("E", ErlangParams(r=3, mu=2.0), D.ErlangDistribution), ("Gamma", GammaParams(mu=2.0, alpha=1.5), D.GammaDistribution),
+             ("C", Cox2Params(p1=0.7, mu1=2.0, mu2=0.5), D.CoxDistribution), ("Pa", ParetoParams(alpha=2.5, K=1.0), D.ParetoDistribution),
+             ("Uniform", UniformParams(mean=2.0, half_interval=0.5), D.UniformDistribution),
+             ("Norm", GaussianParams(mean=5.0, std_dev=1.0), D.NormalDistribution), ("D", 1.7, D.DeterministicDistribution)]
+    for code, prm, cls in cases:
+        d = create_distribution(prm, code, None)
+        assert type(d) is cls and d.params is prm and d.type == code
+    with pytest.raises(ValueError):
+        create_distribution(1.0, "Q", None)
+    with pytest.raises(NotImplementedError):
+        create_distribution(None, "MAP", None)

@@ -14,15 +14,19 @@ CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "prio
 
 
 def test_fixtures_present():
-    assert len(CASES) >= 8
+    assert len(CASES) >= 12
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])
 def test_oracle_matches_reference_bitwise(path):
     g = np.load(path)
     K = int(g["K"])
+    buffer = int(g["buffer"]) if "buffer" in g.files else None  # finite total buffer (priority.py:437-455)
     r = oracle.prio_replay(int(g["c"]), K, str(g["prty"]), [g[f"A{k}"] for k in range(K)],
-                           [g[f"S{k}"] for k in range(K)], int(g["total_served"]), p_bins=g["p_time"].shape[1])
+                           [g[f"S{k}"] for k in range(K)], int(g["total_served"]), buffer=buffer,
+                           p_bins=g["p_time"].shape[1])
+    if buffer is not None:
+        assert int(np.sum(g["dropped"])) > 0  # the fixture really exercises the drop branch
     assert r.ttek == float(g["ttek"])
     for name in ("arrived", "served", "taked", "dropped", "in_sys", "a_used", "s_used"):
         assert np.array_equal(getattr(r, name), g[name]), name
