@@ -442,6 +442,10 @@ def run_ours(args):
                 line["replay"] = replay_leg(ctx, peaks, peak_src)
             except Exception as e:  # the headline must not be lost to the secondary measurement
                 line["replay"] = {"error": repr(e)}
+            try:
+                line["replay_jobs"] = replay_jobs_leg(ctx, peaks, peak_src)
+            except Exception as e:
+                line["replay_jobs"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_others:
             try:
                 line["other_configs"] = other_configs_leg(peaks, peak_src, sms)
@@ -702,6 +706,39 @@ def run_other_config(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
+
+
+def replay_jobs_leg(ctx, peaks, peak_src, reps=65536, rows=4096, steps=3):
+    """cfg 2r through K1b, the job-indexed replay kernel (csrc/k1b_fifo_jobs.cu): fp64 A, S of `reps` replications x
+    `rows` jobs resident in HBM ([job][replication], 2 x 2 GiB), every row read exactly once; HBM roofline."""
+    import torch
+
+    from most_queue_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = -torch.log(1.0 - torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64))
+    br = torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64) < H2["p1"]
+    S = -torch.log(1.0 - torch.rand((rows, reps), generator=g, device="cuda", dtype=torch.float64))
+    S = S / torch.where(br, H2["mu1"], H2["mu2"])
+    del br
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(steps + 1):
+        agg = ctx.replay_fifo_jobs_device(C_SERVERS, A.data_ptr(), S.data_ptr(), rows, reps)
+        if i:
+            ms.append(ctx.last_timing()["sim_ms"])
+    t = float(np.mean(ms)) * 1e-3
+    jobs = float(rows) * reps
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = 16.0 * jobs / t / 1e9
+    return {"kernel": "k1b_fifo_jobs<8>", "jobs_per_s": jobs / t, "ms": t * 1e3,
+            "workload": f"{reps} replications x {rows} jobs, fp64 A,S resident in HBM ([job][replication]), M/H2/8 draws",
+            "w1": float(agg[0] / reps), "v1": float(agg[4] / reps),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": 16.0 * jobs * 1.0,
+                         "note": "algorithmic bytes 16 B/job (one gap and one service time, each read once; rows are "
+                                 "consumed by all lanes of a warp at the same step: 256 contiguous bytes per row and array); "
+                                 "traffic: dram bytes of one launch, profiles/r02_ncu_k1b_traffic.csv; peak " + peak_src}}
 
 
 def main():

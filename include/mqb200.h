@@ -148,6 +148,38 @@ typedef struct {
     int32_t flags;
 } mq_replay_cfg;
 
+/* GI/G/c FIFO with an INFINITE buffer, replay mode, job-indexed (csrc/k1b_fifo_jobs.cu): the HBM-roofline tier of the
+ * replay.  Jobs n = 0..jobs-1 of every replication in arrival order (Kiefer-Wolfowitz recursion): arrival time
+ * t_n = t_{n-1} + A[n] (base.py:230-236), the job takes the server that frees first, wait w_n = max(t_n, m) - t_n
+ * (base.py:300-303), sojourn v_n = (max(t_n, m) + S[n]) - t_n (servers.py:88-90, base.py:269-272).  Every w_n, v_n equals
+ * the sample QsSim produces for that job bit for bit; the sums run over the first `jobs` ARRIVALS in arrival order
+ * (QsSim.run stops at the jobs-th DEPARTURE, which leaves out the <= c-1 jobs then in service), and no time-in-state
+ * histogram is kept.  A[n * replications + r], S[n * replications + r]: `jobs` rows each. */
+typedef struct {
+    int32_t c;            /* num_of_channels                                             base.py:29 */
+    int32_t device_ptrs;  /* 1: A, S (and rep_out, W, V when given) are device pointers              */
+    int64_t jobs;
+    int64_t replications;
+    int32_t flags;
+    int32_t reserved;
+} mq_jobs_cfg;
+
+/* per-replication record rows of mq_replay_fifo_jobs */
+#define MQ_JB_W 0      /* 4: sum of w^k in arrival order: s1 += w, s2 += w*w, s3 = fma(w*w, w, s3), s4 = fma(w*w, w*w, s4) */
+#define MQ_JB_V 4      /* 4: the same for v                                                        */
+#define MQ_JB_JOBS 8   /* number of samples (= jobs)                                               */
+#define MQ_JB_TLAST 9  /* arrival time of the last job                                             */
+#define MQ_JB_DMAX 10  /* largest completion time: the clock when the last of the jobs has left    */
+#define MQ_JB_WAITED 11 /* jobs with w > 0                                                         */
+#define MQ_JB_ROWS 12
+/* aggregate: for each of the 12 rows the sum over replications (rows 0-7 divided by jobs first: the per-replication
+ * moment estimates), then the 12 sums of squares */
+#define MQ_JB_AGG_LEN 24
+
+/* agg, rep_out, W, V may be NULL.  W / V: [jobs][replications] per-job waits / sojourn times. */
+int mq_replay_fifo_jobs(mq_ctx *ctx, const mq_jobs_cfg *cfg, const double *A, const double *S, double *agg,
+                        double *rep_out, double *W, double *V);
+
 /* extra rows appended to the replay record after MQ_REC_ROWS(p_bins): the reference's own
  * running-mean moments (stats_update.py:6-22), bit-exact */
 #define MQ_RF_WRUN 0    /* 4 */

@@ -56,6 +56,14 @@ class MqFifoCfg(C.Structure):
     ]
 
 
+class MqJobsCfg(C.Structure):
+    _fields_ = [("c", C.c_int32), ("device_ptrs", C.c_int32), ("jobs", C.c_int64), ("replications", C.c_int64),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+JB_W, JB_V, JB_JOBS, JB_TLAST, JB_DMAX, JB_WAITED, JB_ROWS, JB_AGG_LEN = 0, 4, 8, 9, 10, 11, 12, 24
+
+
 class MqReplayCfg(C.Structure):
     _fields_ = [
         ("c", C.c_int32), ("p_bins", C.c_int32), ("buffer", C.c_int64), ("total_served", C.c_int64),
@@ -346,6 +354,8 @@ def load():
         L.mq_replay_size.argtypes = [vp, C.POINTER(MqSizeCfg), vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, dp, dp]
         L.mq_sim_fifo_multi.restype = C.c_int
         L.mq_sim_fifo_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(MqFifoCfg), dp]
+        L.mq_replay_fifo_jobs.restype = C.c_int
+        L.mq_replay_fifo_jobs.argtypes = [vp, C.POINTER(MqJobsCfg), vp, vp, dp, vp, vp, vp]
         L.mq_last_timing.restype = C.c_int
         L.mq_last_timing.argtypes = [vp, dp, dp, dp]
         L.mq_last_launches.restype = C.c_int
@@ -507,6 +517,38 @@ class Context:
         agg = np.zeros(agg_len(p_bins))
         check(self._L.mq_replay_fifo(self._h, C.byref(cfg), a_ptr, s_ptr,
                                      agg.ctypes.data_as(C.POINTER(C.c_double)), rec_ptr))
+        return agg
+
+    # ---- K1b ----
+    def replay_fifo_jobs(self, c, A, S, jobs=None, want_samples=False):
+        """Job-indexed replay, infinite buffer (mq_replay_fifo_jobs).  A, S: [jobs, R] float64 host arrays.
+        Returns (agg, rec, W, V); W, V are None unless want_samples."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        if A.ndim != 2 or S.ndim != 2 or A.shape[1] != S.shape[1]:
+            raise ValueError("A and S must be 2-D [job][replication] with equal replication counts")
+        n = int(min(A.shape[0], S.shape[0]) if jobs is None else jobs)
+        if n < 1 or n > A.shape[0] or n > S.shape[0]:
+            raise ValueError("jobs must be in 1..rows of A and S")
+        R = A.shape[1]
+        A, S = np.ascontiguousarray(A[:n]), np.ascontiguousarray(S[:n])
+        cfg = MqJobsCfg()
+        cfg.c, cfg.device_ptrs, cfg.jobs, cfg.replications = int(c), 0, n, R
+        agg, rec = np.zeros(JB_AGG_LEN), np.empty((JB_ROWS, R))
+        W = np.empty((n, R)) if want_samples else None
+        V = np.empty((n, R)) if want_samples else None
+        check(self._L.mq_replay_fifo_jobs(self._h, C.byref(cfg), A.ctypes.data, S.ctypes.data,
+                                          agg.ctypes.data_as(C.POINTER(C.c_double)), rec.ctypes.data,
+                                          W.ctypes.data if want_samples else None, V.ctypes.data if want_samples else None))
+        return agg, rec, W, V
+
+    def replay_fifo_jobs_device(self, c, a_ptr: int, s_ptr: int, jobs, replications, rec_ptr: int = 0):
+        """Device-pointer form (arrays resident in HBM); rec_ptr: optional JB_ROWS x R doubles on the device."""
+        cfg = MqJobsCfg()
+        cfg.c, cfg.device_ptrs, cfg.jobs, cfg.replications = int(c), 1, int(jobs), int(replications)
+        agg = np.zeros(JB_AGG_LEN)
+        check(self._L.mq_replay_fifo_jobs(self._h, C.byref(cfg), a_ptr, s_ptr, agg.ctypes.data_as(C.POINTER(C.c_double)),
+                                          rec_ptr or None, None, None))
         return agg
 
     # ---- K4 ----

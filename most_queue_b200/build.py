@@ -40,7 +40,7 @@ def _units():
     for n in SLOT_COUNTS:
         units.append(("k2_inst.cu", [f"-DMQ_CT={n}"], f"k2_ct{n}.o"))
         units.append(("k1_inst.cu", [f"-DMQ_CT={n}"], f"k1_ct{n}.o"))
-    for extra in ("mq_api_prio.cu", "mq_api_net.cu", "mq_api_scan.cu", "mq_api_tandem.cu", "mq_api_prionet.cu", "mq_api_vacation.cu", "mq_api_negatives.cu", "mq_api_size.cu", "k3_lindley.cu", "k3_onepass.cu",
+    for extra in ("mq_api_prio.cu", "mq_api_net.cu", "mq_api_scan.cu", "mq_api_tandem.cu", "mq_api_prionet.cu", "mq_api_vacation.cu", "mq_api_negatives.cu", "mq_api_size.cu", "k3_lindley.cu", "k3_onepass.cu", "k1b_fifo_jobs.cu",
                   "k4_prio.cu", "k4v2_prio.cu", "k5_net.cu", "k5v2_net.cu", "k6_tandem.cu", "k6v2_tandem.cu", "k7_prionet.cu", "k7v2_prionet.cu", "k8_vacation.cu", "k9_negatives.cu", "k10_size.cu"):
         if os.path.exists(os.path.join(CSRC, extra)):
             units.append((extra, [], extra[:-3] + ".o"))

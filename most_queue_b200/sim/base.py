@@ -247,3 +247,23 @@ def replay(num_of_channels: int, buffer, A, S, total_served: int, p_bins: int = 
     }
     out["p"] = out["p_time"] / ttek[:, None]
     return out
+
+
+def replay_jobs(num_of_channels: int, A, S, jobs: int | None = None, want_samples: bool = False, device=None):
+    """Job-indexed replay tier for an infinite buffer (csrc/k1b_fifo_jobs.cu): jobs 0..jobs-1 of every replication in
+    arrival order.  A[n, r] is the gap before job n of replication r, S[n, r] its service time.  Every per-job wait and
+    sojourn time equals the sample QsSim produces for that job bit for bit (base.py:230-236, 269-272, 300-303,
+    servers.py:88-90); the moments are over the first `jobs` ARRIVALS (QsSim.run stops at the jobs-th departure).
+    Returns a dict: w, v [R, 4] raw moments per replication, w_sum, v_sum, waited, t_last, d_max, and W, V [jobs, R]
+    when want_samples."""
+    L = _lib
+    ctx = L.default_context(device)
+    agg, rec, W, V = ctx.replay_fifo_jobs(num_of_channels, A, S, jobs, want_samples)
+    n = rec[L.JB_JOBS]
+    out = {"w_sum": rec[L.JB_W:L.JB_W + 4].T.copy(), "v_sum": rec[L.JB_V:L.JB_V + 4].T.copy(),
+           "w": (rec[L.JB_W:L.JB_W + 4] / n).T.copy(), "v": (rec[L.JB_V:L.JB_V + 4] / n).T.copy(),
+           "jobs": n.astype(np.int64), "t_last": rec[L.JB_TLAST].copy(), "d_max": rec[L.JB_DMAX].copy(),
+           "waited": rec[L.JB_WAITED].astype(np.int64), "agg": agg, "timing": ctx.last_timing()}
+    if want_samples:
+        out["W"], out["V"] = W, V
+    return out

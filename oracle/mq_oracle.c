@@ -447,6 +447,52 @@ int mqo_fifo_replay(int c, int64_t buffer, const double *A, int64_t nA, int64_t 
                      w_samples, w_cap, v_samples, v_cap);
 }
 
+/* Job-indexed form of the same simulator for an infinite buffer (the checker of csrc/k1b_fifo_jobs.cu): jobs 0..n-1 in
+ * arrival order.  With FIFO and an unbounded line a job takes the server that frees first, so
+ *   t_n = t_{n-1} + A[n]            (sim/base.py:230-236)      start = max(t_n, min completion)
+ *   w_n = start - t_n               (base.py:300-303)          d = start + S[n]   (sim/utils/servers.py:88-90)
+ *   v_n = d - t_n                   (base.py:269-272)
+ * are the operations QsSim performs for job n on the same operands: w[n] / v[n] equal its samples bit for bit
+ * (tests/test_oracle_fifo_jobs.py checks that against the reference's own fixtures).  Sums in arrival order with the
+ * kernel's association: s1 += x, s2 += x*x, s3 = fma(x*x, x, s3), s4 = fma(x*x, x*x, s4). */
+int mqo_fifo_jobs(int c, const double *A, int64_t strideA, const double *S, int64_t strideS, int64_t n,
+                  double *w, double *v, double *w_sum, double *v_sum, double *t_last, double *d_max, int64_t *waited)
+{
+    if (c < 1 || c > 64 || n < 0) return -1;
+    double L[64];
+    for (int j = 0; j < c; ++j) L[j] = 0.0;
+    double t = 0.0, dm = 0.0;
+    int64_t nw = 0;
+    for (int k = 0; k < 4; ++k) { w_sum[k] = 0.0; v_sum[k] = 0.0; }
+    for (int64_t i = 0; i < n; ++i) {
+        t = t + A[i * strideA];
+        int jm = 0;
+        for (int j = 1; j < c; ++j) if (L[j] < L[jm]) jm = j;
+        const double start = L[jm] > t ? L[jm] : t;
+        const double wi = start - t;
+        const double d = start + S[i * strideS];
+        const double vi = d - t;
+        L[jm] = d;
+        if (d > dm) dm = d;
+        if (wi > 0.0) nw++;
+        if (w) w[i] = wi;
+        if (v) v[i] = vi;
+        const double w2 = wi * wi, v2 = vi * vi;
+        w_sum[0] = w_sum[0] + wi;
+        w_sum[1] = w_sum[1] + w2;
+        w_sum[2] = fma(w2, wi, w_sum[2]);
+        w_sum[3] = fma(w2, w2, w_sum[3]);
+        v_sum[0] = v_sum[0] + vi;
+        v_sum[1] = v_sum[1] + v2;
+        v_sum[2] = fma(v2, vi, v_sum[2]);
+        v_sum[3] = fma(v2, v2, v_sum[3]);
+    }
+    *t_last = t;
+    *d_max = dm;
+    *waited = nw;
+    return 0;
+}
+
 typedef struct {
     int c;
     int64_t warm;

@@ -65,6 +65,10 @@ typedef struct {
  * (time-in-state sums, NOT normalised).  w_samples / v_samples may be NULL; when given
  * they receive up to cap samples in the reference's sample order.
  * Returns 0, or -1 when the arrays ran out before total_served departures. */
+/* job-indexed replay, infinite buffer: per-job waits / sojourn times (may be NULL) and power sums in arrival order */
+int mqo_fifo_jobs(int c, const double *A, int64_t strideA, const double *S, int64_t strideS, int64_t n,
+                  double *w, double *v, double *w_sum, double *v_sum, double *t_last, double *d_max, int64_t *waited);
+
 int mqo_fifo_replay(int c, int64_t buffer, const double *A, int64_t nA, int64_t strideA,
                     const double *S, int64_t nS, int64_t strideS, int64_t total_served,
                     double *p, int64_t p_bins, mqo_fifo_out *out,

@@ -295,6 +295,26 @@ def fifo_replay(c: int, buffer, A: np.ndarray, S: np.ndarray, total_served: int,
     return _unpack(out, p, ws, vs)
 
 
+def fifo_jobs(c: int, A: np.ndarray, S: np.ndarray, n: int | None = None):
+    """Job-indexed replay (infinite buffer): dict with per-job `w`, `v` and the sums of the kernel's association."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    n = int(min(len(A), len(S)) if n is None else n)
+    w, v = np.zeros(n), np.zeros(n)
+    ws, vs = np.zeros(4), np.zeros(4)
+    tl, dm, nw = C.c_double(), C.c_double(), C.c_int64()
+    L = lib()
+    L.mqo_fifo_jobs.restype = C.c_int
+    L.mqo_fifo_jobs.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_int64, C.c_int64,
+                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_int64)]
+    rc = L.mqo_fifo_jobs(c, _dp(A), 1, _dp(S), 1, n, _dp(w), _dp(v), _dp(ws), _dp(vs), C.byref(tl), C.byref(dm), C.byref(nw))
+    if rc != 0:
+        raise RuntimeError(f"oracle fifo_jobs failed rc={rc}")
+    return {"w": w, "v": v, "w_sum": ws, "v_sum": vs, "t_last": tl.value, "d_max": dm.value, "waited": nw.value}
+
+
 def fifo_generate(c: int, buffer, src, srv, total_served: int, seed: int, rep0: int, reps: int,
                   p_bins: int = 64, threads: int = 1, warmup: int = 0) -> list[FifoResult]:
     """Generator-mode oracle: src/srv are (kendall code, params) tuples."""
