@@ -330,7 +330,7 @@ typedef struct {
     uint32_t chain;       /* chain id (generator stream)                                     */
     int32_t device_ptrs;  /* replay form: A, S (and W) are device pointers                   */
     int32_t last_range;   /* 1: this range ends the chain (apply the stop rule, base.py:505) */
-    int32_t flags;        /* MQ_SCAN_WANT_P or 0                                             */
+    int32_t flags;        /* MQ_SCAN_WANT_P | MQ_SCAN_KEEP or 0                              */
     int64_t jobs_ahead;   /* jobs of the chain after this range (0 for the last range); in   */
                           /* the replay form A must then hold jobs + 1 + jobs_ahead gaps     */
 } mq_scan_cfg;
@@ -340,6 +340,11 @@ typedef struct {
  * p[0] = 1 - T[>=1]/ttek, p[m] = (T[>=m] - T[>=m+1]) / ttek.  Only jobs 0..N-1 are counted (the
  * reference also counts the few arrivals between the last arrival and the stop). */
 #define MQ_SCAN_WANT_P 1
+/* mq_scan_gg1_summary only: keep the range's intermediate results on the device; if the NEXT call on the context is
+ * mq_scan_gg1_apply with the same range description (jobs, job0, seed, chain, laws / array pointers, jobs_ahead,
+ * MQ_SCAN_WANT_P), it walks from them instead of forming them again.  This is the multi-GPU sequence: summary ->
+ * all-gather of the (a, b) pairs -> apply from the carry. */
+#define MQ_SCAN_KEEP 2
 
 #define MQ_S_W 0       /* 4: sum of W^k over the jobs of the range (+ job N when last_range and it  */
                        /*    was already waiting at the N-th departure, base.py:300-305)            */

@@ -642,9 +642,10 @@ class Context:
         return agg, rec
 
     # ---- K3 ----
-    def _scan_cfg(self, src, srv, jobs, job0, seed, chain, device_ptrs, last_range, want_p=False, jobs_ahead=0):
+    def _scan_cfg(self, src, srv, jobs, job0, seed, chain, device_ptrs, last_range, want_p=False, jobs_ahead=0,
+                  keep=False):
         cfg = MqScanCfg()
-        cfg.flags = 1 if want_p else 0  # MQ_SCAN_WANT_P
+        cfg.flags = (1 if want_p else 0) | (2 if keep else 0)  # MQ_SCAN_WANT_P | MQ_SCAN_KEEP
         cfg.jobs_ahead = int(jobs_ahead)
         if src is not None:
             cfg.src, cfg.srv = src, srv
@@ -653,9 +654,12 @@ class Context:
         cfg.chain, cfg.device_ptrs, cfg.last_range = int(chain), int(device_ptrs), int(last_range)
         return cfg
 
-    def scan_summary(self, jobs, job0=0, src=None, srv=None, seed=0, chain=0, A=None, S=None, device_ptrs=False):
-        """(a, b) of the range: W_out = max(a, W_in + b).  A, S: numpy arrays or device pointers (ints)."""
-        cfg = self._scan_cfg(src, srv, jobs, job0, seed, chain, device_ptrs, 0)
+    def scan_summary(self, jobs, job0=0, src=None, srv=None, seed=0, chain=0, A=None, S=None, device_ptrs=False,
+                     keep=False, want_p=False, jobs_ahead=0):
+        """(a, b) of the range: W_out = max(a, W_in + b).  A, S: numpy arrays or device pointers (ints).
+        keep=True (MQ_SCAN_KEEP): the next scan_apply of the same range on this context walks from what this call left
+        on the device (pass the same want_p / jobs_ahead)."""
+        cfg = self._scan_cfg(src, srv, jobs, job0, seed, chain, device_ptrs, 0, want_p, jobs_ahead, keep)
         pa, ps, _keep = _scan_ptrs(A, S, jobs, device_ptrs)
         ab = (C.c_double * 2)()
         check(self._L.mq_scan_gg1_summary(self._h, C.byref(cfg), pa, ps, ab))

@@ -183,7 +183,7 @@ extern "C" int mq_replay_fifo_jobs(mq_ctx *ctx, const mq_jobs_cfg *cfg, const do
         return fail(cfg->c < 1 ? MQ_E_INVALID : MQ_E_UNSUPPORTED, "mq_replay_fifo_jobs: num_of_channels must be in 1..%d",
                     MQ_MAX_CHANNELS);
     if (cfg->jobs < 1 || cfg->replications < 1) return fail(MQ_E_INVALID, "mq_replay_fifo_jobs: bad sizes");
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
     const long long R = cfg->replications, N = cfg->jobs;
     const size_t arr = sizeof(double) * (size_t)N * (size_t)R;
     const size_t rec_bytes = sizeof(double) * (size_t)MQ_JB_ROWS * (size_t)R;

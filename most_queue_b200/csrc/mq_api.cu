@@ -322,7 +322,7 @@ int mq_sim_fifo(mq_ctx *ctx, const mq_fifo_cfg *cfg, double *agg, double *rep_ou
         return fail(MQ_E_INVALID, "mq_sim_fifo: warmup must be in 0..total_served-1");
     if (int rc = check_dist(cfg->src, "set_sources")) return rc;
     if (int rc = check_dist(cfg->srv, "set_servers")) return rc;
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const bool fp64 = (cfg->flags & MQ_FIFO_FP64) != 0;
@@ -470,7 +470,7 @@ int mq_replay_fifo(mq_ctx *ctx, const mq_replay_cfg *cfg, const double *A, const
     if (cfg->total_served >= (1ll << 31) || cfg->n_a >= (1ll << 31) || cfg->n_s >= (1ll << 31) ||
         cfg->buffer >= (1ll << 31))
         return fail(MQ_E_UNSUPPORTED, "mq_replay_fifo: total_served, n_a, n_s and buffer must be < 2^31");
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int rows = MQ_REPLAY_ROWS(cfg->p_bins);
@@ -545,7 +545,7 @@ int mq_last_launches(mq_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int mq_debug_philox2x32(mq_ctx *ctx, uint32_t c0, uint32_t c1, uint32_t key, uint32_t out[2])
 {
     if (!ctx || !out) return fail(MQ_E_INVALID, "mq_debug_philox2x32: NULL argument");
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, 8));
     debug_philox_kernel<<<1, 1, 0, ctx->stream>>>(c0, c1, key, d);
@@ -562,7 +562,7 @@ int mq_debug_variates(mq_ctx *ctx, const mq_dist *d, uint64_t seed, uint32_t rep
 {
     if (!ctx || !d || !out || n < 1) return fail(MQ_E_INVALID, "mq_debug_variates: bad argument");
     if (int rc = check_dist(*d, "mq_debug_variates")) return rc;
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
     float *dev = nullptr;
     CU(cudaMalloc(&dev, sizeof(float) * (size_t)n));
     debug_variates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(make_distf(*d), seed_to_key(seed),

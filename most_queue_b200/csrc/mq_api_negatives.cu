@@ -26,7 +26,7 @@ static int negatives_common(mq_ctx *ctx, const mq_neg_cfg *cfg, bool replay, con
     } else if (!X || !n) {
         return fail(MQ_E_INVALID, "%s: NULL arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int pb = cfg->p_bins;

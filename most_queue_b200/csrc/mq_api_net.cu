@@ -47,7 +47,7 @@ static int net_common(mq_ctx *ctx, const mq_net_cfg *cfg, bool replay, const dou
     } else if (!A || !U || !S || !n_s || n_a < 1 || n_u < 1) {
         return fail(MQ_E_INVALID, "%s: NULL or empty arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int rows = MQ_NET_REC_ROWS(m);

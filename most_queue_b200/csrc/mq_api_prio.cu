@@ -35,7 +35,7 @@ static int prio_common(mq_ctx *ctx, const mq_prio_cfg *cfg, bool replay, const d
     } else if (!A || !S || !n_a || !n_s) {
         return fail(MQ_E_INVALID, "%s: NULL arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int rows = MQ_PRIO_REC_ROWS(K, cfg->p_bins);

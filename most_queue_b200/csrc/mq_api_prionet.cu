@@ -58,7 +58,7 @@ static int prionet_common(mq_ctx *ctx, const mq_prionet_cfg *cfg, bool replay, c
     } else if (!A || !n_a || !U || n_u < 1 || !S || !n_s) {
         return fail(MQ_E_INVALID, "%s: NULL or empty arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int rows = MQ_PN_REC_ROWS(m, K);

@@ -19,6 +19,36 @@ struct ScanRun {
 // span more than this many later arrivals to notice)
 constexpr long long SCAN_AHEAD_STAGED = 1ll << 22;
 
+struct ScanKey {
+    long long jobs, job0, jobs_ahead;
+    unsigned long long seed;
+    unsigned chain;
+    int device_ptrs, flags;
+    mq_dist src, srv;
+    const double *A, *S;
+};
+static_assert(sizeof(ScanKey) <= 256, "ScanKey must fit mq_ctx::scan_key");
+
+ScanKey make_key(const mq_scan_cfg *cfg, const double *A, const double *S)
+{
+    ScanKey k;
+    std::memset(&k, 0, sizeof(k));
+    k.jobs = cfg->jobs;
+    k.job0 = cfg->job0;
+    k.jobs_ahead = cfg->jobs_ahead;
+    k.seed = cfg->seed;
+    k.chain = cfg->chain;
+    k.device_ptrs = cfg->device_ptrs;
+    k.flags = cfg->flags & ~MQ_SCAN_KEEP;
+    if (!A && !S) {
+        k.src = cfg->src;
+        k.srv = cfg->srv;
+    }
+    k.A = A;
+    k.S = S;
+    return k;
+}
+
 int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, ScanRun &run, const char *who,
                  bool will_walk = false)
 {
@@ -30,7 +60,7 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
         if (int rc = check_dist(cfg->src, "set_sources")) return rc;
         if (int rc = check_dist(cfg->srv, "set_servers")) return rc;
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
     K3Params &P = run.P;
     std::memset(&P, 0, sizeof(P));
     P.n = cfg->jobs;
@@ -212,7 +242,9 @@ int mq_scan_gg1_summary(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, co
 {
     if (!ab) return fail(MQ_E_INVALID, "mq_scan_gg1_summary: NULL output");
     ScanRun run;
-    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_summary")) return rc;
+    // generator form only: a replayed range is read once by the summary and once by the (one-pass) apply either way
+    const bool keep = cfg && (cfg->flags & MQ_SCAN_KEEP) != 0 && !A && !S;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_summary", keep)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (int rc = scan_summary(ctx, run)) return rc;
@@ -223,6 +255,13 @@ int mq_scan_gg1_summary(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, co
     CU(cudaStreamSynchronize(ctx->stream));
     ab[0] = ctx->h_agg[0];
     ab[1] = ctx->h_agg[1];
+    if (keep) {
+        static_assert(sizeof(ScanRun) <= sizeof(ctx->scan_cache), "ScanRun must fit mq_ctx::scan_cache");
+        const ScanKey key = make_key(cfg, A, S);
+        std::memcpy(ctx->scan_cache, &run, sizeof(run));
+        std::memcpy(ctx->scan_key, &key, sizeof(key));
+        ctx->scan_valid = true;
+    }
     return finish_timing(ctx);
 }
 
@@ -231,6 +270,18 @@ int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, cons
 {
     if (!stats) return fail(MQ_E_INVALID, "mq_scan_gg1_apply: NULL output");
     ScanRun run;
+    if (ctx && cfg && ctx->scan_valid) {
+        // the previous call on this context was the summary of this very range with MQ_SCAN_KEEP: walk from what it left
+        const ScanKey key = make_key(cfg, A, S);
+        if (std::memcmp(ctx->scan_key, &key, sizeof(key)) == 0) {
+            std::memcpy(&run, ctx->scan_cache, sizeof(run));
+            ctx->scan_valid = false;
+            CU(cudaSetDevice(ctx->device));
+            ctx->launches = 0;
+            CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+            return scan_apply(ctx, cfg, run, w_in, stats, W);
+        }
+    }
     if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_apply", true)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));

@@ -26,7 +26,7 @@ static int size_common(mq_ctx *ctx, const mq_size_cfg *cfg, bool replay, const d
     } else if (!A || !S || n_a < 1 || n_s < 1) {
         return fail(MQ_E_INVALID, "%s: NULL or empty arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int pb = cfg->p_bins;

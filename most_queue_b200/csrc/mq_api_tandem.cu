@@ -25,7 +25,7 @@ static int tandem_common(mq_ctx *ctx, const mq_tandem_cfg *cfg, bool replay, con
     } else if (!A || !S || !n_s || n_a < 1) {
         return fail(MQ_E_INVALID, "%s: NULL or empty arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int rows = MQ_TANDEM_REC_ROWS(m);

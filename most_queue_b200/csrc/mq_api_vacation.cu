@@ -38,7 +38,7 @@ static int vacation_common(mq_ctx *ctx, const mq_vac_cfg *cfg, bool replay, cons
     } else if (!X || !n) {
         return fail(MQ_E_INVALID, "%s: NULL arrays", who);
     }
-    CU(cudaSetDevice(ctx->device));
+    CU(use_device(ctx));
 
     const long long R = cfg->replications;
     const int pb = cfg->p_bins;

@@ -48,9 +48,22 @@ struct mq_ctx {
     size_t h_agg_cap = 0;
     double sim_ms = 0, reduce_ms = 0, total_ms = 0;
     int launches = 0;
+    // mq_scan_gg1_summary(MQ_SCAN_KEEP) leaves the range's intermediate results (tile prefixes, segment prefixes, the
+    // fp32 draw stash) in the scratch buffers; the next call on the context, if it is the matching mq_scan_gg1_apply,
+    // walks from them instead of forming them again.  Any other entry point clears the flag (use_device).
+    bool scan_valid = false;
+    alignas(16) unsigned char scan_cache[1024];
+    unsigned char scan_key[256];
 };
 
 namespace mq {
+
+// every entry point that is about to use the context's scratch buffers starts with this
+inline cudaError_t use_device(mq_ctx *ctx)
+{
+    ctx->scan_valid = false;
+    return cudaSetDevice(ctx->device);
+}
 
 inline int ensure(Buf &b, size_t bytes)
 {

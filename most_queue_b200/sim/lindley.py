@@ -72,7 +72,9 @@ def run_chain(source, server, total_served: int, seed=None, chain: int = 0, devi
     if world == 1:
         carries = [0.0]  # one range: no summary exchange, the apply call computes its own tile prefixes
     else:
-        ab = ctx.scan_summary(count, job0=job0, src=src, srv=srv, seed=seed, chain=chain) if count > 0 else (-np.inf, 0.0)
+        # the summary keeps its draws and prefixes on the device: the apply below only walks (MQ_SCAN_KEEP)
+        ab = (ctx.scan_summary(count, job0=job0, src=src, srv=srv, seed=seed, chain=chain, keep=True, want_p=want_p,
+                               jobs_ahead=int(total_served) - (job0 + count)) if count > 0 else (-np.inf, 0.0))
         summary_ms = ctx.last_timing()["sim_ms"] if count > 0 else 0.0
         carries, _ = fold_carries(_gather_pairs(ab))
     if count > 0:

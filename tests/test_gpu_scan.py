@@ -191,3 +191,31 @@ def test_levels_of_ranges_equal_single_range_on_a_fresh_context():
     one, three = run(1), run(3)
     np.testing.assert_allclose(three["levels"], one["levels"], rtol=1e-11, atol=1e-9)
     np.testing.assert_allclose(three["p"][:24], one["p"][:24], rtol=0, atol=1e-12)
+
+
+def test_summary_keep_then_apply_walks_from_the_kept_state():
+    """MQ_SCAN_KEEP (the multi-GPU sequence summary -> exchange -> apply on one context): the apply that follows the kept
+    summary gives the statistics of the stand-alone apply bit for bit, and a call in between invalidates the kept state
+    without changing the answer."""
+    from most_queue_b200 import _lib
+
+    ctx = _lib.default_context()
+    src, srv = _lib.make_dist("Gamma", GAMMA), _lib.make_dist("Pa", PARETO)
+    n, j0, ahead = 3_000_017, 1_000_000, 5_000
+    alone, _ = ctx.scan_apply(n, 0.37, job0=j0, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead)
+    t_alone = ctx.last_timing()["sim_ms"]
+    ab = ctx.scan_summary(n, job0=j0, src=src, srv=srv, seed=9, keep=True, jobs_ahead=ahead)
+    kept, _ = ctx.scan_apply(n, 0.37, job0=j0, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead)
+    t_kept = ctx.last_timing()["sim_ms"]
+    assert np.array_equal(kept, alone)
+    assert (kept[_lib.S_A], kept[_lib.S_B]) == ab
+    assert t_kept < 0.8 * t_alone           # it only walked
+    # something else uses the context in between: the kept state must not be trusted
+    ctx.scan_summary(n, job0=j0, src=src, srv=srv, seed=9, keep=True, jobs_ahead=ahead)
+    ctx.sim_fifo(2, None, _lib.make_dist("M", 1.0), _lib.make_dist("M", 0.8), 200, 64, 0, 1, p_bins=8)
+    again, _ = ctx.scan_apply(n, 0.37, job0=j0, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead)
+    assert np.array_equal(again, alone)
+    # a different range description does not match the key
+    ctx.scan_summary(n, job0=j0, src=src, srv=srv, seed=9, keep=True, jobs_ahead=ahead)
+    other, _ = ctx.scan_apply(n, 0.37, job0=j0 + 16, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead)
+    assert not np.array_equal(other[:8], alone[:8])
