@@ -1,31 +1,40 @@
-// k3_onepass.cu -- K3 replay form with ONE read of A and S from HBM: a persistent, warp-specialised decoupled look-back scan.
+// k3_onepass.cu -- K3 replay form with ONE read of A and S from HBM: a persistent, warp-specialised scan that WALKS EVERY
+// TILE SPECULATIVELY while it is in shared memory and repairs the few jobs that depended on the carry afterwards.
 //
 // Same specification as k3_lindley.cu (and oracle/mq_oracle_scan.c): the max-plus Lindley recursion of QsSim.run() with
 // one channel (most_queue/sim/base.py:488-528, wait sample base.py:302, sojourn base.py:272) evaluated with the FIXED
 // association tree "16-job segments folded sequentially -> Kogge-Stone over the 32 lanes of a warp -> sequential over the
 // 8 warps of a 4096-job tile -> tile level: chunks of ceil(ntiles/1024) tiles folded sequentially, Kogge-Stone over 32
-// chunks, sequential over the 32 groups".  Every value this kernel produces is the value the three-launch path produces,
-// bit for bit; only the schedule differs.
+// chunks, sequential over the 32 groups".  Every per-job wait, range summary and tail this kernel produces is the value
+// the three-launch path produces, bit for bit; the power sums agree to rounding (another order of addition).
 //
-// One CTA per SM, co-resident (cooperative launch), static tile order t = blockIdx.x + k * gridDim.x, 24 warps, two
-// TMA-fed pipelines that meet on mbarriers only:
-//   FOLD side   warp 22 (one lane) brings tile k from HBM with two TMA tensor copies (S and A as [rows][16] fp64 boxes of
-//               256 x 16 with the 128-byte swizzle: thread r reads ITS row -- its 16-job segment -- with conflict-free
-//               LDS.128) + one 16-byte bulk copy for the gap that follows the tile.  Warps 0-7 pull their rows into
-//               registers (the single stage is refilled while they compute), fold them (x = S - A'), scan the 256 segment
-//               summaries, park every segment's exclusive prefix in an L2-resident ring and publish the tile summary.
-//   look-back   warps 16-18 (A, tile k on warp 16 + k % 3) publish what OTHER tiles wait for: the fold of the tile's chunk from the identity up to the
-//               tile (needs published summaries only), the exclusive prefix of a chunk (first tile of the chunk:
-//               Kogge-Stone over the earlier chunk folds of the group + the group carry) and the carry into the next group.
-//               warps 19-21 (B) resolve the tile's own exclusive prefix: they continue from the nearest predecessor that has
-//               published its inclusive prefix, else from the chunk's exclusive prefix, folding the summaries in between
-//               (the sequential association makes every such route give the same bits).
-//   WALK side   once a tile is folded, warp 23 (one lane) brings it in AGAIN -- from L2, where it still sits: the fold side
-//               runs only OP_RING tiles ahead -- into one of two stages; warps 8-15 walk their segment from its carry and
-//               accumulate the power sums of w and v.
-// The look-back latency (three dependent L2 round trips of ~0.7 us under load and two folds of up to a chunk of summaries)
-// is hidden by the lead of the fold side, not by shared-memory stages.  Published words carry their own "ready" flag
-// (see publish()): no fences anywhere on the look-back path.
+// The idea that removes the second read.  The wait at the start of segment s of a tile is max(a_s, w_tile + b_s), where
+// (a_s, b_s) is the segment's exclusive prefix INSIDE the tile and w_tile the wait carried into the tile.  a_s is known as
+// soon as the tile itself has been scanned; w_tile needs the look-back over all earlier tiles (microseconds).  But a
+// queue forgets: after the first idle period inside the tile the carry no longer matters, and then max(.) == a_s exactly.
+// At rho = 0.7 that holds for all but 1.2 of the 256 segments of a tile on average (6 at rho = 0.9, 24 at rho = 0.95).
+// So the compute warps walk every segment from a_s at once, while the tile is still in shared memory, and a look-back
+// warp -- when w_tile finally arrives -- tests max(a_s, w_tile + b_s) != a_s for all 256 segments and re-walks exactly
+// those (from global memory: a few hundred bytes, usually still in L2), adding (true - provisional) to the sums and
+// overwriting their stored waits.  The look-back latency is off the critical path altogether: nothing waits for it but a
+// 4 KB ring slot of segment prefixes.
+//
+// One CTA per SM, co-resident (cooperative launch), static tile order t = blockIdx.x + k * gridDim.x, 23 warps:
+//   producer    warp 22 (one lane) brings tile k from HBM into one of three 64 KB stages with two TMA tensor copies (S and
+//               A as [rows][16] fp64 boxes of 256 x 16 with the 128-byte swizzle: thread r reads ITS row -- its 16-job
+//               segment -- with conflict-free LDS.128) + one 16-byte bulk copy for the gap that follows the tile.
+//   compute     two groups of 8 warps (tile k goes to group k % 2): fold the rows (x = S - A'), scan the 256 segment
+//               summaries, park every segment's exclusive prefix in an L2-resident ring, publish the tile summary, then
+//               walk the segment from a_s out of the same stage and hand the stage back.
+//   look-back A warps 16-18 (tile k on warp 16 + k % 3) publish what OTHER tiles wait for: the fold of the tile's chunk from
+//               the identity up to the tile (needs published summaries only), the exclusive prefix of a chunk (first tile
+//               of the chunk: Kogge-Stone over the earlier chunk folds of the group + the group carry) and the carry into
+//               the next group.
+//   look-back B warps 19-21 resolve the tile's own exclusive prefix (from the nearest predecessor that has published its
+//               inclusive prefix, else from the chunk's exclusive prefix; the sequential association makes every such
+//               route give the same bits), publish the inclusive one, and do the repair described above.  The last tile
+//               of the range (bounds checks, the tail sample of base.py:300-305) is walked here only.
+// Published words carry their own "ready" flag (see publish()): no fences anywhere on the look-back path.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -39,13 +48,19 @@ namespace mq {
 
 namespace {
 
-constexpr int OP_WSTAGES = 2;                    // walk-side stages
-constexpr int OP_RING = 12;                      // tiles the fold side may lead the walk side by (ring of hand-off slots)
+constexpr int OP_STAGES = 3;                     // 64 KB stages: two being computed on, one in flight
+constexpr int OP_GROUPS = 2;                     // compute groups of 8 warps (tile k -> group k % OP_GROUPS)
+constexpr int OP_RING = 24;                      // tiles whose repair may be pending (ring of hand-off slots)
 constexpr int OP_TILE = K3_THREADS * K3_L;       // 4096 jobs
 constexpr int OP_ROWS = K3_THREADS;              // 256 rows of 16 doubles
 constexpr int OP_ARR_BYTES = OP_TILE * 8;        // 32 KB per array per stage
-constexpr int OP_NLB = 3;                         // look-back warps of each kind (tile k goes to warp k % OP_NLB)
-constexpr int OP_THREADS = 768;                  // 24 warps: 8 fold, 8 walk, 3 + 3 look-back, 2 producers
+constexpr int OP_NLA = 3;                        // look-back A warps (tile k goes to warp k % OP_NLA)
+constexpr int OP_NLB = 4;                        // look-back B / repair warps (tile k goes to warp k % OP_NLB)
+constexpr int OP_CWARPS = OP_GROUPS * (K3_THREADS / 32);
+constexpr int OP_WARP_A = OP_CWARPS;             // 16..18
+constexpr int OP_WARP_B = OP_WARP_A + OP_NLA;    // 19..22
+constexpr int OP_WARP_P = OP_WARP_B + OP_NLB;    // 23
+constexpr int OP_THREADS = (OP_WARP_P + 1) * 32; // 768: 6 warps of 80 registers per scheduler
 constexpr int OP_LB = 128;                       // look-back window kept in shared memory (summaries), per look-back warp
 constexpr uint32_t OP_TX = 2u * OP_ARR_BYTES + 16u;
 constexpr uint32_t OP_SPIN_LIMIT = 4000000u;     // wait iterations (each sleeps 20 ns .. 20 us) before a protocol bug traps instead of hanging
@@ -64,30 +79,39 @@ struct OpStage {
 };
 
 struct OpShared {
-    OpStage fold;                                 // fold-side stage (single: its rows go to registers at once)
-    OpStage walk[OP_WSTAGES];                     // walk-side stages
-    double f_anext[2];                            // A[tile_base + 4096], A[tile_base + 4097] of the fold-side tile
-    double w_anext[OP_WSTAGES][2];
-    MP tile_total[OP_RING];                       // the tile's summary (fold group -> look-back warps)
-    MP tile_ex[OP_RING];                          // the tile's exclusive prefix (look-back B -> walk group)
-    MP lbA[OP_NLB][OP_LB], lbB[OP_NLB][OP_LB];    // summaries gathered by the look-back warps, newest first
-    MP warp_tot[K3_THREADS / 32];
-    MP ks_left[OP_NLB][5];                        // left operands of the late Kogge-Stone lane (look-back A)
-    double red[16][K3_NSTAT];
-    unsigned long long f_full, f_empty, w_full[OP_WSTAGES], w_empty[OP_WSTAGES];
-    unsigned long long folded[OP_RING], prefix[OP_RING], slot_free[OP_RING];
+    OpStage st[OP_STAGES];
+    double anext[OP_STAGES][2];                   // A[tile_base + 4096], A[tile_base + 4097] of the staged tile
+    MP tile_total[OP_RING];                       // the tile's summary (compute group -> look-back warps)
+    MP lbA[OP_NLA][OP_LB], lbB[OP_NLB][OP_LB];    // summaries gathered by the look-back warps, newest first
+    MP warp_tot[OP_GROUPS][2][K3_THREADS / 32];   // double-buffered by tile: one barrier per tile
+    MP ks_left[OP_NLA][5];                        // left operands of the late Kogge-Stone lane (look-back A)
+    double seg0[OP_RING][2 * K3_L + 2];           // S[0..15], A[0..16] of the tile's first segment (always repaired)
+    double red[OP_WARP_P][K3_NSTAT];
+    unsigned long long full[OP_STAGES], empty[OP_STAGES];
+    unsigned long long folded[OP_RING], walked[OP_RING], slot_free[OP_RING];
 };
 
+// The two maxima of the recursion without fmax's NaN handling (no operand is ever a NaN: sums of finite draws and
+// -inf): every wait of this kernel sits on a chain of dependent "add, max" steps, and fmax(double) is a seven-instruction
+// sequence (DSETP.MAX, FSEL, LOP3, SEL, SEL, two moves) where these are a shift and two ANDs, or DSETP.GT and two selects.
+// Same values bit for bit (a -0.0 result would need a -0.0 operand, which max(0, .) never produces).
+__device__ __forceinline__ double max0(double x)
+{
+    const int hi = __double2hiint(x);
+    const int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
+__device__ __forceinline__ double max2(double a, double s) { return s > a ? s : a; }
 __device__ __forceinline__ MP mp_id() { return MP{-INFINITY, 0.0}; }
 __device__ __forceinline__ MP mp_then(MP earlier, MP later)
 {
-    return MP{fmax(later.a, __dadd_rn(earlier.a, later.b)), __dadd_rn(earlier.b, later.b)};
+    return MP{max2(later.a, __dadd_rn(earlier.a, later.b)), __dadd_rn(earlier.b, later.b)};
 }
 __device__ __forceinline__ MP mp_step(MP f, double x)
 {
-    return MP{fmax(0.0, __dadd_rn(f.a, x)), __dadd_rn(f.b, x)};
+    return MP{max0(__dadd_rn(f.a, x)), __dadd_rn(f.b, x)};
 }
-__device__ __forceinline__ double mp_apply(MP f, double w) { return fmax(f.a, __dadd_rn(w, f.b)); }
+__device__ __forceinline__ double mp_apply(MP f, double w) { return max2(f.a, __dadd_rn(w, f.b)); }
 __device__ __forceinline__ MP mp_shfl(MP v, int src)
 {
     return MP{__shfl_sync(0xffffffffu, v.a, src), __shfl_sync(0xffffffffu, v.b, src)};
@@ -162,8 +186,7 @@ __device__ __forceinline__ void tma_tile_2d(void *dst, const CUtensorMap *map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
-// the same copy with an L2 eviction-priority hint (createpolicy): the first fetch of a tile asks the L2 to keep it
-// (evict_last) until the walk side has read it again, and that second read releases it (evict_first)
+// the same copy with an L2 eviction-priority hint (createpolicy): a tile is read once, so it is fetched evict_first
 __device__ __forceinline__ void tma_tile_2d_hint(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar,
                                                  unsigned long long policy)
 {
@@ -172,12 +195,6 @@ __device__ __forceinline__ void tma_tile_2d_hint(void *dst, const CUtensorMap *m
         " [%0], [%1, {%2, %3}], [%4], %5;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
-}
-__device__ __forceinline__ unsigned long long policy_evict_last()
-{
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
 }
 __device__ __forceinline__ unsigned long long policy_evict_first()
 {
@@ -296,13 +313,13 @@ struct K3OnePassParams {
     MP *t_inc;             // [ntiles] inclusive prefix of the tile
     MP *chunk_ex;          // [K3_TOP] exclusive prefix of a chunk (published when chunks have more than one tile)
     MP *carry;             // [40]     carry into group g
-    MP *seg_ring;          // [grid][OP_RING][256] exclusive prefix of every segment inside its tile (fold -> walk hand-off)
+    MP *seg_ring;          // [grid][OP_RING][256] exclusive prefix of every segment inside its tile (compute -> repair)
     long long chunk;       // tiles per chunk
     uint32_t zero_mask;    // 0 (see mbar_arrive_after)
-    int hints;             // 1: L2 eviction-priority hints on the two fetches of a tile
-    int lead;              // tiles the fold side may lead the walk side by (1..OP_RING): bounds the L2 footprint
+    int hints;             // 1: the tile fetch carries the L2 evict_first hint (MQ_SCAN_HINTS=1; off: the repair finds its lines in L2)
+    int ring;              // hand-off slots in use (OP_NLB..OP_RING): tiles whose look-back / repair may be pending
     int *err;
-    long long *trace;      // optional [grid][OP_TRACE_TILES][16] SM clocks of the pipeline events (MQ_SCAN_TRACE)
+    long long *trace;      // optional [grid][OP_TRACE_TILES][24] SM clocks of the pipeline events (MQ_SCAN_TRACE)
 };
 
 constexpr int OP_TRACE_TILES = 64;
@@ -353,6 +370,54 @@ __device__ __forceinline__ void gather(const K3OnePassParams &Q, MP *lb, const M
     __syncwarp();
 }
 
+
+// One segment walked by one lane of a look-back warp: the repair of a segment whose start wait depends on the carry into
+// the tile (FULL: adds true - provisional to acc), or the only walk of a segment of the last tile of the range (bounds,
+// tail sample; nothing provisional was accumulated).  Sp[j] = S[n0 + j], Ap[j] = A[n0 + 1 + j]: the shared-memory copy
+// of the tile's first segment, or global memory (prefetched into L1 by the caller: the loop then runs at L1 latency).
+template <bool FULL>
+__device__ __forceinline__ void repair_segment(const K3Params &P, long long n0, const double *Sp, const double *Ap,
+                                               double w_true, double w_prov, bool prov, double (&acc)[8])
+{
+    double *Wp = P.W ? P.W + n0 : nullptr;
+    const int valid = FULL ? K3_L : k3_valid_count(P.n, n0, K3_L);
+    const int last_j = (!FULL && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
+    double w = w_true, wp = w_prov;
+#pragma unroll 4
+    for (int j = 0; j < K3_L; ++j) {
+        if (FULL || j < valid) {
+            const double s = Sp[j], a1 = Ap[j];
+            if (Wp) Wp[j] = w;
+            const double x = __dsub_rn(s, a1);
+            const double v = __dadd_rn(w, s);
+            const double w2 = w * w, v2 = v * v;
+            double t[8] = {w, w2, w2 * w, w2 * w2, v, v2, v2 * v, v2 * v2};
+            if (FULL && prov) {
+                const double vp = __dadd_rn(wp, s);
+                const double p2 = wp * wp, q2 = vp * vp;
+                t[0] -= wp;
+                t[1] -= p2;
+                t[2] -= p2 * wp;
+                t[3] -= p2 * p2;
+                t[4] -= vp;
+                t[5] -= q2;
+                t[6] -= q2 * vp;
+                t[7] -= q2 * q2;
+                wp = max0(__dadd_rn(wp, x));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += t[i];
+            const double raw = __dadd_rn(w, x);
+            if (!FULL && j == last_j) {
+                P.tail[0] = raw;
+                P.tail[1] = v;
+            }
+            w = max0(raw);
+        }
+    }
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassParams Q)
 {
     extern __shared__ __align__(1024) unsigned char op_raw[];
@@ -364,124 +429,89 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
     const K3Params &P = Q.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = P.ntiles;
-    const int LEAD = Q.lead;
+    const int RING = Q.ring;
     const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
     MP *ring = Q.seg_ring + (long long)blockIdx.x * OP_RING * K3_THREADS;
 
     if (threadIdx.x == 0) {
-        mbar_init(&sm.f_full, 1);
-        mbar_init(&sm.f_empty, K3_THREADS);
-        for (int s = 0; s < OP_WSTAGES; ++s) {
-            mbar_init(&sm.w_full[s], 1);
-            mbar_init(&sm.w_empty[s], K3_THREADS);
+        for (int s = 0; s < OP_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], K3_THREADS);
         }
         for (int d = 0; d < OP_RING; ++d) {
             mbar_init(&sm.folded[d], K3_THREADS);
-            mbar_init(&sm.prefix[d], 1);
-            mbar_init(&sm.slot_free[d], K3_THREADS + 2);  // the walk group and both look-back warps are done with the slot
+            mbar_init(&sm.walked[d], K3_THREADS);
+            mbar_init(&sm.slot_free[d], 2);  // both look-back warps of the tile are done with the slot
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == 22) {
-        // ------------------------------------------------------------------ fold-side producer (HBM -> shared memory)
+    if (warp == OP_WARP_P) {
+        // ------------------------------------------------------------------ producer (HBM -> shared memory)
         if (lane == 0) {
-            const unsigned long long keep = policy_evict_last();
+            const unsigned long long once = policy_evict_first();
             for (int k = 0; k < my_tiles; ++k) {
+                const int s = k % OP_STAGES;
                 const long long t = blockIdx.x + (long long)k * gridDim.x;
-                mbar_wait(&sm.f_empty, (uint32_t)(k & 1) ^ 1u, Q.err);
+                mbar_wait(&sm.empty[s], (uint32_t)((k / OP_STAGES) & 1) ^ 1u, Q.err);
                 OP_TRACE(0, clock64());
                 OP_TRACE(21, gtime());
                 if ((t + 1) * (long long)OP_TILE < P.n) {
-                    mbar_expect_tx(&sm.f_full, OP_TX);
+                    mbar_expect_tx(&sm.full[s], OP_TX);
                     if (Q.hints) {
-                        tma_tile_2d_hint(sm.fold.S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.f_full, keep);
-                        tma_tile_2d_hint(sm.fold.A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.f_full, keep);
+                        tma_tile_2d_hint(sm.st[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.full[s], once);
+                        tma_tile_2d_hint(sm.st[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.full[s], once);
                     } else {
-                        tma_tile_2d(sm.fold.S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.f_full);
-                        tma_tile_2d(sm.fold.A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.f_full);
+                        tma_tile_2d(sm.st[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.full[s]);
+                        tma_tile_2d(sm.st[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.full[s]);
                     }
-                    bulk_copy_16(sm.f_anext, P.A + (t + 1) * OP_TILE, &sm.f_full);
+                    bulk_copy_16(sm.anext[s], P.A + (t + 1) * OP_TILE, &sm.full[s]);
                 } else {
-                    mbar_arrive(&sm.f_full);  // the last tile is staged by the fold group itself (bounds checks)
+                    mbar_arrive(&sm.full[s]);  // the last tile is staged by the compute group itself (bounds checks)
                 }
             }
         }
-    } else if (warp == 23) {
-        // ------------------------------------------------------------------ walk-side producer (L2 -> shared memory)
-        if (lane == 0) {
-            const unsigned long long drop = policy_evict_first();
-            for (int k = 0; k < my_tiles; ++k) {
-                const int s = (int)(k % OP_WSTAGES), d = (int)(k % LEAD);
-                const long long t = blockIdx.x + (long long)k * gridDim.x;
-                mbar_wait(&sm.w_empty[s], (uint32_t)((k / OP_WSTAGES) & 1) ^ 1u, Q.err);
-                mbar_wait(&sm.folded[d], (uint32_t)((k / LEAD) & 1), Q.err);  // the fold side has had it: it is in L2
-                OP_TRACE(1, clock64());
-                if ((t + 1) * (long long)OP_TILE < P.n) {
-                    mbar_expect_tx(&sm.w_full[s], OP_TX);
-                    if (Q.hints) {
-                        tma_tile_2d_hint(sm.walk[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.w_full[s], drop);
-                        tma_tile_2d_hint(sm.walk[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.w_full[s], drop);
-                    } else {
-                        tma_tile_2d(sm.walk[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.w_full[s]);
-                        tma_tile_2d(sm.walk[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.w_full[s]);
-                    }
-                    bulk_copy_16(sm.w_anext[s], P.A + (t + 1) * OP_TILE, &sm.w_full[s]);
-                } else {
-                    mbar_arrive(&sm.w_full[s]);
-                }
-            }
-        }
-    } else if (warp < 8) {
-        // ------------------------------------------------------------------ fold group
-        const int r = threadIdx.x;
+    } else if (warp < OP_CWARPS) {
+        // ------------------------------------------------------------------ compute groups: fold, scan, provisional walk
+        const int grp = warp / (K3_THREADS / 32), gw = warp % (K3_THREADS / 32);
+        const int r = threadIdx.x % K3_THREADS;
+        const int bar_id = 1 + grp;
+        double acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
         double sum_a = 0.0, sum_s = 0.0;
-        for (int k = 0; k < my_tiles; ++k) {
-            const int d = (int)(k % LEAD);
+        for (int k = grp; k < my_tiles; k += OP_GROUPS) {
+            const int s = k % OP_STAGES, d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
             const long long tb = t * OP_TILE;
-            mbar_wait(&sm.slot_free[d], (uint32_t)((k / LEAD) & 1) ^ 1u, Q.err);  // at most OP_RING tiles ahead
-            mbar_wait(&sm.f_full, (uint32_t)(k & 1), Q.err);
+            OpStage &stg = sm.st[s];
+            const double *a_next = sm.anext[s];
+            mbar_wait(&sm.slot_free[d], (uint32_t)((k / RING) & 1) ^ 1u, Q.err);  // at most RING tiles await their repair
+            mbar_wait(&sm.full[s], (uint32_t)((k / OP_STAGES) & 1), Q.err);
+            if (r == 0) OP_TRACE(9, clock64());
             const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
             int valid = K3_L;
             if (!full_tile) {
-                stage_ragged(P, tb, sm.fold, sm.f_anext, r);
-                named_bar(1, K3_THREADS);
+                stage_ragged(P, tb, stg, sm.anext[s], r);
+                named_bar(bar_id, K3_THREADS);
                 valid = k3_valid_count(P.n, tb + (long long)r * K3_L, K3_L);
             }
-            // the whole row goes to registers so that the stage can be refilled while this tile is folded
-            double s0[OP_H], a0[OP_H + 1], s1[OP_H], a1[OP_H + 1];
-            load_half(sm.fold, sm.f_anext, r, 0, s0, a0);
-            load_half(sm.fold, sm.f_anext, r, 1, s1, a1);
-            {
-                // the rows must have been READ before the stage is handed back to the TMA producer (see mbar_arrive_after):
-                // one word of every 16-byte load goes into the token
-                uint32_t token = (uint32_t)__double2hiint(a0[OP_H]) | (uint32_t)__double2hiint(a1[OP_H]);
-#pragma unroll
-                for (int q = 0; q < OP_H; q += 2)
-                    token |= (uint32_t)__double2hiint(s0[q]) | (uint32_t)__double2hiint(a0[q]) |
-                             (uint32_t)__double2hiint(s1[q]) | (uint32_t)__double2hiint(a1[q]);
-                mbar_arrive_after(&sm.f_empty, token, Q.zero_mask);
-            }
-            // tile-uniform fast path: every tile but the last one of the range has no per-job bounds logic
+            // ---- fold the row (tile-uniform fast path: every tile but the last one has no per-job bounds logic)
             MP mine = mp_id();
             auto fold_row = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-                for (int j = 0; j < OP_H; ++j) {
-                    if (FULL || j < valid) {
-                        mine = mp_step(mine, __dsub_rn(s0[j], a0[j + 1]));
-                        sum_a += a0[j];
-                        sum_s += s0[j];
-                    }
-                }
+                for (int h = 0; h < 2; ++h) {
+                    double sv[OP_H], av[OP_H + 1];
+                    load_half(stg, a_next, r, h, sv, av);
 #pragma unroll
-                for (int j = 0; j < OP_H; ++j) {
-                    if (FULL || OP_H + j < valid) {
-                        mine = mp_step(mine, __dsub_rn(s1[j], a1[j + 1]));
-                        sum_a += a1[j];
-                        sum_s += s1[j];
+                    for (int j = 0; j < OP_H; ++j) {
+                        if (FULL || h * OP_H + j < valid) {
+                            mine = mp_step(mine, __dsub_rn(sv[j], av[j + 1]));
+                            sum_a += av[j];
+                            sum_s += sv[j];
+                        }
                     }
                 }
             };
@@ -489,17 +519,18 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
                 fold_row(OpTrue{});
             else
                 fold_row(OpFalse{});
-            // CTA scan of the 256 segment summaries (Kogge-Stone per warp, sequential over the 8 warps)
+            // ---- scan of the 256 segment summaries (Kogge-Stone per warp, sequential over the 8 warps)
             const MP inc = warp_inclusive(mine, lane);
             MP within = mp_shfl_up(inc, 1);
             if (lane == 0) within = mp_id();
-            if (lane == 31) sm.warp_tot[warp] = inc;
-            named_bar(1, K3_THREADS);
+            MP *wt = sm.warp_tot[grp][(k / OP_GROUPS) & 1];
+            if (lane == 31) wt[gw] = inc;
+            named_bar(bar_id, K3_THREADS);
             MP carry = mp_id(), tot = mp_id();
 #pragma unroll
             for (int g = 0; g < K3_THREADS / 32; ++g) {
-                if (g == warp) carry = tot;
-                tot = mp_then(tot, sm.warp_tot[g]);
+                if (g == gw) carry = tot;
+                tot = mp_then(tot, wt[g]);
             }
             const MP ex = mp_then(carry, within);
             __stcg(reinterpret_cast<double2 *>(ring + d * K3_THREADS + r), make_double2(ex.a, ex.b));
@@ -511,9 +542,63 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
                 OP_TRACE(16, gtime());
             }
             mbar_arrive(&sm.folded[d]);  // (release, CTA scope) the ring slot and tile_total are visible to the waiters
-            named_bar(1, K3_THREADS);    // warp_tot is reused by the next tile
+            // ---- provisional walk from a_s (the first segment has no a_s: it is always repaired; the last tile of the
+            // range is walked by the repair only)
+            uint32_t token = (uint32_t)__double2hiint(mine.b);
+            if (full_tile && r != 0) {
+                double w = ex.a;
+                double *Wp = P.W ? P.W + tb + (long long)r * K3_L : nullptr;
+                auto walk_row = [&](auto w_tag) {
+                    constexpr bool STORE_W = decltype(w_tag)::value;
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        double sv[OP_H], av[OP_H + 1];
+                        load_half(stg, a_next, r, h, sv, av);
+#pragma unroll
+                        for (int jj = 0; jj < OP_H; ++jj) {
+                            if (STORE_W) Wp[h * OP_H + jj] = w;
+                            const double v = __dadd_rn(w, sv[jj]);
+                            const double w2 = w * w, v2 = v * v;
+                            acc[0] += w;
+                            acc[1] += w2;
+                            acc[2] += w2 * w;
+                            acc[3] += w2 * w2;
+                            acc[4] += v;
+                            acc[5] += v2;
+                            acc[6] += v2 * v;
+                            acc[7] += v2 * v2;
+                            w = max0(__dadd_rn(w, __dsub_rn(sv[jj], av[jj + 1])));
+                        }
+                    }
+                };
+                if (Wp)
+                    walk_row(OpTrue{});
+                else
+                    walk_row(OpFalse{});
+                token |= (uint32_t)__double2hiint(w);  // w depends on every word the walk loaded
+            } else if (full_tile) {
+                // r == 0: the first segment is walked by the repair alone; leave it a copy of the row
+                double *c0 = sm.seg0[d];
+#pragma unroll
+                for (int j = 0; j < K3_L; ++j) c0[j] = *sw_elem(stg.S, j);
+#pragma unroll
+                for (int j = 0; j <= K3_L; ++j) c0[K3_L + j] = *sw_elem(stg.A, j);
+            }
+            // the rows must have been READ before the stage goes back to the TMA producer (see mbar_arrive_after)
+            mbar_arrive_after(&sm.empty[s], token, Q.zero_mask);
+            mbar_arrive(&sm.walked[d]);
+            if (r == 0) {
+                OP_TRACE(10, clock64());
+                OP_TRACE(22, gtime());
+            }
         }
-        // sum(A), sum(S) of this CTA: statistics 8 and 9
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = acc[i];
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_down_sync(0xffffffffu, v, dd);
+            if (lane == 0) sm.red[warp][i] = v;
+        }
 #pragma unroll
         for (int dd = 16; dd > 0; dd >>= 1) {
             sum_a += __shfl_down_sync(0xffffffffu, sum_a, dd);
@@ -523,7 +608,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             sm.red[warp][8] = sum_a;
             sm.red[warp][9] = sum_s;
         }
-    } else if (warp >= 16 && warp < 16 + OP_NLB) {
+    } else if (warp >= OP_WARP_A && warp < OP_WARP_A + OP_NLA) {
         // ------------------------------------------------------------------ look-back A: everything other tiles wait for
         // (1) the chunk fold from the identity up to this tile -- depends on published SUMMARIES only; (2) for the first
         // tile of a chunk, the chunk's exclusive prefix: Kogge-Stone over the folds of the earlier chunks of the group
@@ -531,11 +616,11 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
         // Step 1 of an iteration never waits for a step 2 / 3 of the same or a later iteration of any CTA, so waits do not
         // chain from CTA to CTA.
         const long long chunk = Q.chunk;
-        MP *lb = sm.lbA[warp - 16];
-        for (int k = warp - 16; k < my_tiles; k += OP_NLB) {
-            const int d = (int)(k % LEAD);
+        MP *lb = sm.lbA[warp - OP_WARP_A];
+        for (int k = warp - OP_WARP_A; k < my_tiles; k += OP_NLA) {
+            const int d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
-            mbar_wait(&sm.folded[d], (uint32_t)((k / LEAD) & 1), Q.err);
+            mbar_wait(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
             if (lane == 0) OP_TRACE(4, clock64());
             const MP own = sm.tile_total[d];
             __syncwarp();
@@ -574,7 +659,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
                     const int last = l - 1;
                     MP v = mp_id();
                     if (lane < last) v = wait_mp(Q.t_incf + ((long long)g * 32 + lane + 1) * chunk - 1, Q.err);
-                    MP *left = sm.ks_left[warp - 16];
+                    MP *left = sm.ks_left[warp - OP_WARP_A];
 #pragma unroll
                     for (int sft = 0; sft < 5; ++sft) {
                         const MP up = mp_shfl_up(v, 1 << sft);
@@ -612,14 +697,19 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             }
             __syncwarp();
         }
-    } else if (warp >= 16 + OP_NLB && warp < 16 + 2 * OP_NLB) {
-        // ------------------------------------------------------------------ look-back B: the tile's exclusive prefix
+    } else if (warp >= OP_WARP_B && warp < OP_WARP_B + OP_NLB) {
+        // ------------------------------------------------------------------ look-back B: the tile's exclusive prefix, then
+        // the repair of the segments whose start wait depends on it
         const long long chunk = Q.chunk;
-        MP *lb = sm.lbB[warp - 16 - OP_NLB];
-        for (int k = warp - 16 - OP_NLB; k < my_tiles; k += OP_NLB) {
-            const int d = (int)(k % LEAD);
+        MP *lb = sm.lbB[warp - OP_WARP_B];
+        double acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+        for (int k = warp - OP_WARP_B; k < my_tiles; k += OP_NLB) {
+            const int d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
-            mbar_wait(&sm.folded[d], (uint32_t)((k / LEAD) & 1), Q.err);
+            const long long tb = t * OP_TILE;
+            mbar_wait(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
             const MP own = sm.tile_total[d];
             const long long c = t / chunk, n_pred = t - c * chunk;
             long long idx = -1;
@@ -635,93 +725,55 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
                 if (lane == 0) base = wait_mp(Q.chunk_ex + c, Q.err);
                 base = mp_shfl(base, 0);
             }
+            MP ex = mp_id();
             if (lane == 0) {
-                const MP ex = fold_newest_first(base, lb, (int)idx);
-                sm.tile_ex[d] = ex;
-                mbar_arrive(&sm.prefix[d]);
+                ex = fold_newest_first(base, lb, (int)idx);
                 OP_TRACE(7, clock64());
                 OP_TRACE(19, gtime());
                 publish(Q.t_inc + t, mp_then(ex, own));
                 OP_TRACE(8, clock64());
-                mbar_arrive(&sm.slot_free[d]);
+            }
+            ex = mp_shfl(ex, 0);
+            const double w_tile = mp_apply(ex, P.w_in);
+            // ---- repair.  The provisional walk (and its wait stores, which the repair overwrites) must be over.
+            mbar_wait(&sm.walked[d], (uint32_t)((k / RING) & 1), Q.err);
+            const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
+            double2 sx[K3_THREADS / 32];
+#pragma unroll
+            for (int q = 0; q < K3_THREADS / 32; ++q)
+                sx[q] = __ldcg(reinterpret_cast<const double2 *>(ring + d * K3_THREADS + q * 32 + lane));
+            int repaired = 0;
+#pragma unroll 1
+            for (int q = 0; q < K3_THREADS / 32; ++q) {
+                const int sg = q * 32 + lane;
+                const double w0 = mp_apply(MP{sx[q].x, sx[q].y}, w_tile);
+                const long long n0 = tb + (long long)sg * K3_L;
+                const double *Sp = P.S + n0, *Ap = P.A + n0 + 1;
+                if (full_tile) {
+                    if (sg == 0) {
+                        repair_segment<true>(P, n0, sm.seg0[d], sm.seg0[d] + K3_L + 1, w0, 0.0, false, acc);
+                        ++repaired;
+                    } else if (w0 != sx[q].x) {
+                        prefetch_l1(Sp);
+                        prefetch_l1(Sp + K3_L - 1);
+                        prefetch_l1(Ap);
+                        prefetch_l1(Ap + K3_L - 1);
+                        repair_segment<true>(P, n0, Sp, Ap, w0, sx[q].x, true, acc);
+                        ++repaired;
+                    }
+                } else {
+                    repair_segment<false>(P, n0, Sp, Ap, w0, 0.0, false, acc);
+                }
+            }
+            if (Q.trace) {
+                repaired = __reduce_add_sync(0xffffffffu, repaired);
+                if (lane == 0) OP_TRACE(13, repaired);
             }
             __syncwarp();
-        }
-    } else if (warp >= 8 && warp < 16) {
-        // ------------------------------------------------------------------ walk group (warps 8-15)
-        const int r = threadIdx.x - 256;
-        double acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-        for (int k = 0; k < my_tiles; ++k) {
-            const int s = (int)(k % OP_WSTAGES), d = (int)(k % LEAD);
-            const long long t = blockIdx.x + (long long)k * gridDim.x;
-            const long long tb = t * OP_TILE, n0 = tb + (long long)r * K3_L;
-            mbar_wait(&sm.prefix[d], (uint32_t)((k / LEAD) & 1), Q.err);  // implies folded[d]: the ring slot is written
-            const double2 sx = __ldcg(reinterpret_cast<const double2 *>(ring + d * K3_THREADS + r));
-            const double w_tile = mp_apply(sm.tile_ex[d], P.w_in);
-            mbar_wait(&sm.w_full[s], (uint32_t)((k / OP_WSTAGES) & 1), Q.err);
-            if (r == 0) OP_TRACE(9, clock64());
-            const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
-            if (!full_tile) {
-                stage_ragged(P, tb, sm.walk[s], sm.w_anext[s], r);
-                named_bar(2, K3_THREADS);
+            if (lane == 0) {
+                OP_TRACE(14, clock64());
+                mbar_arrive_after(&sm.slot_free[d], (uint32_t)__double2hiint(sx[0].y), Q.zero_mask);
             }
-            const int valid = full_tile ? K3_L : k3_valid_count(P.n, n0, K3_L);
-            double w = mp_apply(MP{sx.x, sx.y}, w_tile);
-            const int last_j = (!full_tile && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
-            double *Wp = P.W ? P.W + n0 : nullptr;
-            // tile-uniform fast path (all tiles but the last): no bounds, no tail; the per-job wait store is a second
-            // compile-time switch
-            auto walk_row = [&](auto full_tag, auto w_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-                constexpr bool STORE_W = decltype(w_tag)::value;
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    double sv[OP_H], av[OP_H + 1];
-                    load_half(sm.walk[s], sm.w_anext[s], r, h, sv, av);
-#pragma unroll
-                    for (int jj = 0; jj < OP_H; ++jj) {
-                        const int j = h * OP_H + jj;
-                        if (FULL || j < valid) {
-                            if (STORE_W) Wp[j] = w;
-                            const double v = __dadd_rn(w, sv[jj]);
-                            const double w2 = w * w, v2 = v * v;
-                            acc[0] += w;
-                            acc[1] += w2;
-                            acc[2] += w2 * w;
-                            acc[3] += w2 * w2;
-                            acc[4] += v;
-                            acc[5] += v2;
-                            acc[6] += v2 * v;
-                            acc[7] += v2 * v2;
-                            const double raw = __dadd_rn(w, __dsub_rn(sv[jj], av[jj + 1]));
-                            if (!FULL && j == last_j) {
-                                P.tail[0] = raw;
-                                P.tail[1] = v;
-                            }
-                            w = fmax(0.0, raw);
-                        }
-                    }
-                }
-            };
-            if (full_tile) {
-                if (Wp)
-                    walk_row(OpTrue{}, OpTrue{});
-                else
-                    walk_row(OpTrue{}, OpFalse{});
-            } else {
-                if (Wp)
-                    walk_row(OpFalse{}, OpTrue{});
-                else
-                    walk_row(OpFalse{}, OpFalse{});
-            }
-            if (r == 0) {
-                OP_TRACE(10, clock64());
-                OP_TRACE(22, gtime());
-            }
-            mbar_arrive(&sm.w_empty[s]);
-            mbar_arrive(&sm.slot_free[d]);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -732,14 +784,16 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
         }
     }
     __syncthreads();
-    // fixed-order CTA reduction: statistics 0-7 from the walk warps, 8-9 from the fold warps
+    // fixed-order CTA reduction: statistics 0-7 from the compute warps and the repairs, 8-9 from the compute warps
     if (threadIdx.x < K3_NSTAT) {
         const int i = threadIdx.x;
         double v = 0.0;
-        if (i < 8)
-            for (int wv = 8; wv < 16; ++wv) v += sm.red[wv][i];
-        else if (i < 10)
-            for (int wv = 0; wv < 8; ++wv) v += sm.red[wv][i];
+        if (i < 8) {
+            for (int wv = 0; wv < OP_CWARPS; ++wv) v += sm.red[wv][i];
+            for (int wv = OP_WARP_B; wv < OP_WARP_B + OP_NLB; ++wv) v += sm.red[wv][i];
+        } else if (i < 10) {
+            for (int wv = 0; wv < OP_CWARPS; ++wv) v += sm.red[wv][i];
+        }
         P.partial[(long long)blockIdx.x * K3_NSTAT + i] = v;
     }
 }
@@ -789,6 +843,8 @@ bool k3_onepass_usable(const K3Params &P)
 }
 
 // `scratch` = k3_onepass_scratch_bytes(ntiles) bytes of device memory; grid <= resident CTAs (one per SM)
+
+// `scratch` = k3_onepass_scratch_bytes(ntiles) bytes of device memory; grid <= resident CTAs (one per SM)
 cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaStream_t st)
 {
     static bool attr_set = false;
@@ -814,13 +870,13 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     Q.seg_ring = (MP *)((char *)(mp + words) + 256);
     if (grid > 256) return cudaErrorInvalidValue;
     Q.chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
-    // the walk side re-reads a tile from L2 `lead` tiles after the fold side fetched it from HBM: lead x grid x 64 KB must
-    // stay inside the L2 (6 x 148 x 64 KB = 58 MB, kept there by the eviction hints); MQ_SCAN_LEAD overrides (3..12)
-    Q.lead = 6;
-    if (const char *ev = std::getenv("MQ_SCAN_LEAD")) Q.lead = std::atoi(ev);
-    if (Q.lead < OP_NLB) Q.lead = OP_NLB;  // a look-back warp moves OP_NLB tiles at a time: a shorter ring would alias phases
-    if (Q.lead > OP_RING) Q.lead = OP_RING;
-    Q.hints = 1;
+    // hand-off slots: a tile's slot (4 KB of segment prefixes in L2) is held until its look-back and repair are done, so
+    // the ring depth x the tile period is the look-back latency the pipeline tolerates; MQ_SCAN_LEAD overrides (3..24)
+    Q.ring = 16;
+    if (const char *ev = std::getenv("MQ_SCAN_LEAD")) Q.ring = std::atoi(ev);
+    if (Q.ring < OP_NLB) Q.ring = OP_NLB;  // a look-back warp moves OP_NLB tiles at a time: a shorter ring would alias phases
+    if (Q.ring > OP_RING) Q.ring = OP_RING;
+    Q.hints = 0;
     Q.zero_mask = 0;
     if (const char *ev = std::getenv("MQ_SCAN_HINTS")) Q.hints = std::atoi(ev) != 0;
     cudaError_t e = cudaMemsetAsync(scratch, 0xFF, sizeof(MP) * words, st);

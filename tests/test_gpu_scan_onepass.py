@@ -84,6 +84,7 @@ def test_one_pass_device_pointers_and_misaligned_fallback():
     S = torch.empty(n + 2, device="cuda", dtype=torch.float64).exponential_(1.0 / 0.8, generator=g)
     torch.cuda.synchronize()
     st1, _ = ctx.scan_apply(n, 0.0, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)
+    assert ctx.last_timing()["launches"] == 2  # the fused kernel + the reduction: no silent fall-back to three launches
     os.environ["MQ_SCAN_TWO_PASS"] = "1"
     try:
         st2, _ = ctx.scan_apply(n, 0.0, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)

@@ -30,13 +30,13 @@ def run(nr, two_pass, reps=5):
             ms.append(ctx.last_timing()["sim_ms"])
     os.environ.pop("MQ_SCAN_TWO_PASS", None)
     t = float(np.median(ms)) * 1e-3
-    return {"jobs": nr, "two_pass": two_pass, "ms": t * 1e3, "ms_all": ms, "jobs_per_s": nr / t, "GBps_algorithmic": 16.0 * nr / t / 1e9,
+    return {"jobs": nr, "two_pass": two_pass, "launches": ctx.last_timing()["launches"], "ms": t * 1e3, "ms_all": ms, "jobs_per_s": nr / t, "GBps_algorithmic": 16.0 * nr / t / 1e9,
             "w1": float(st[_lib.S_W] / st[_lib.S_TAKED])}
 
 
 if __name__ == "__main__":
     logs = [int(x) for x in sys.argv[1:]] or [26, 28]
-    leads = [int(x) for x in os.environ.get("LEADS", "4").split(",")]
+    leads = [int(x) for x in os.environ.get("LEADS", "16").split(",")]
     for lg in logs:
         for lead in leads:
             os.environ["MQ_SCAN_LEAD"] = str(lead)
