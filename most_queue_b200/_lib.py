@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmqb200.so")
+# MQB200_LIB: another build of the same library (A/B measurements of kernel variants, tools/ab_variants.sh)
+LIB_PATH = os.environ.get("MQB200_LIB") or os.path.join(HERE, "libmqb200.so")
 
 # distribution kinds (mqb200.h MQ_M ...)
 KINDS = {"M": 0, "H": 1, "E": 2, "Gamma": 3, "Pa": 4, "D": 5, "C": 6, "Uniform": 7, "Norm": 8, "Weibull": 9}

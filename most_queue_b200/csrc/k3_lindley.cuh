@@ -55,6 +55,7 @@ bool k3_onepass_usable(const K3Params &P);
 size_t k3_onepass_scratch_bytes(long long ntiles);
 cudaError_t k3_onepass_occupancy(int *blocks);
 cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaStream_t st);
+int k3_onepass_error();
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);

@@ -63,7 +63,16 @@ constexpr int OP_WARP_P = OP_WARP_B + OP_NLB;    // 23
 constexpr int OP_THREADS = (OP_WARP_P + 1) * 32; // 768: 6 warps of 80 registers per scheduler
 constexpr int OP_LB = 128;                       // look-back window kept in shared memory (summaries), per look-back warp
 constexpr uint32_t OP_TX = 2u * OP_ARR_BYTES + 16u;
-constexpr uint32_t OP_SPIN_LIMIT = 4000000u;     // wait iterations (each sleeps 20 ns .. 20 us) before a protocol bug traps instead of hanging
+#ifndef OP_V_CSLEEP
+#define OP_V_CSLEEP 0
+#endif
+#ifndef OP_V_LBIDLE
+#define OP_V_LBIDLE 0
+#endif
+#ifndef OP_V_SPIN_LIMIT
+#define OP_V_SPIN_LIMIT 4000000u
+#endif
+constexpr uint32_t OP_SPIN_LIMIT = OP_V_SPIN_LIMIT;     // wait iterations (each sleeps 20 ns .. 20 us) before a protocol bug traps instead of hanging
 
 struct OpTrue {
     static constexpr bool value = true;
@@ -170,13 +179,33 @@ __device__ __forceinline__ bool mbar_try(unsigned long long *b, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// A wait that ran out of patience (seconds: a protocol bug) leaves a code in MAPPED HOST memory and traps: the launch
+// fails instead of hanging the GPU, and the host can still read the code after the context is gone.  The reporter does
+// not return -- with a bail-out path instead of the trap the same kernel ran 6 % slower (the compiler keeps the state
+// of the exit alive across every wait).
+__device__ __noinline__ void op_give_up(int *err, int code)
+{
+    *(volatile int *)err = code;
+    __threadfence_system();
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity, int *err)
 {
     for (uint32_t it = 0; !mbar_try(b, parity); ++it) {
-        if (it > OP_SPIN_LIMIT) {  // seconds: a protocol bug traps instead of hanging the GPU
-            *err = 1;
-            __trap();
-        }
+#if OP_V_CSLEEP
+        __nanosleep(OP_V_CSLEEP);
+#endif
+        if (it > OP_SPIN_LIMIT) op_give_up(err, 0x100 | (int)(smem_u32(b) & 0xffff) << 12 | (int)parity);
+    }
+}
+// the look-back warps are off the critical path: they sleep between polls and leave the issue slots to the compute warps
+__device__ __forceinline__ void mbar_wait_idle(unsigned long long *b, uint32_t parity, int *err)
+{
+    for (uint32_t it = 0; !mbar_try(b, parity); ++it) {
+#if OP_V_LBIDLE
+        __nanosleep(OP_V_LBIDLE);
+#endif
+        if (it > OP_SPIN_LIMIT / 16) op_give_up(err, 0x200 | (int)(smem_u32(b) & 0xffff) << 12 | (int)parity);
     }
 }
 __device__ __forceinline__ void tma_tile_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
@@ -252,10 +281,7 @@ __device__ __forceinline__ MP wait_mp(const MP *p, int *err)
     for (uint32_t it = 0;; ++it) {
         __nanosleep(it < 8 ? 32 : 128);
         if (try_mp(p, v)) return v;
-        if (it > OP_SPIN_LIMIT) {
-            *err = 2;
-            __trap();
-        }
+        if (it > OP_SPIN_LIMIT) op_give_up(err, 0x300);
     }
 }
 
@@ -422,10 +448,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
 {
     extern __shared__ __align__(1024) unsigned char op_raw[];
     OpShared &sm = *reinterpret_cast<OpShared *>(op_raw);
-    if (threadIdx.x == 0 && (smem_u32(op_raw) & 1023u)) {  // the swizzle pattern assumes 1024-byte aligned boxes
-        *Q.err = 3;
-        __trap();
-    }
+    if (threadIdx.x == 0 && (smem_u32(op_raw) & 1023u)) op_give_up(Q.err, 3);  // the swizzle pattern assumes 1024-byte aligned boxes
     const K3Params &P = Q.P;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = P.ntiles;
@@ -620,7 +643,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
         for (int k = warp - OP_WARP_A; k < my_tiles; k += OP_NLA) {
             const int d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
-            mbar_wait(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
+            mbar_wait_idle(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
             if (lane == 0) OP_TRACE(4, clock64());
             const MP own = sm.tile_total[d];
             __syncwarp();
@@ -709,7 +732,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             const int d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
             const long long tb = t * OP_TILE;
-            mbar_wait(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
+            mbar_wait_idle(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
             const MP own = sm.tile_total[d];
             const long long c = t / chunk, n_pred = t - c * chunk;
             long long idx = -1;
@@ -736,7 +759,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             ex = mp_shfl(ex, 0);
             const double w_tile = mp_apply(ex, P.w_in);
             // ---- repair.  The provisional walk (and its wait stores, which the repair overwrites) must be over.
-            mbar_wait(&sm.walked[d], (uint32_t)((k / RING) & 1), Q.err);
+            mbar_wait_idle(&sm.walked[d], (uint32_t)((k / RING) & 1), Q.err);
             const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
             double2 sx[K3_THREADS / 32];
 #pragma unroll
@@ -842,7 +865,20 @@ bool k3_onepass_usable(const K3Params &P)
     return tensor_map_encoder() != nullptr;
 }
 
-// `scratch` = k3_onepass_scratch_bytes(ntiles) bytes of device memory; grid <= resident CTAs (one per SM)
+// one int of mapped pinned host memory per process: written by op_give_up(), readable by the host even after a trap
+static int *error_word(bool device_side)
+{
+    static int *h = nullptr, *d = nullptr;
+    if (!h) {
+        if (cudaHostAlloc((void **)&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            h = nullptr;
+            return nullptr;
+        }
+        *h = 0;
+        if (cudaHostGetDevicePointer((void **)&d, h, 0) != cudaSuccess) d = h;  // unified addressing: same pointer
+    }
+    return device_side ? d : h;
+}
 
 // `scratch` = k3_onepass_scratch_bytes(ntiles) bytes of device memory; grid <= resident CTAs (one per SM)
 cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaStream_t st)
@@ -866,7 +902,8 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     Q.t_inc = Q.t_incf + P.ntiles;
     Q.chunk_ex = Q.t_inc + P.ntiles;
     Q.carry = Q.chunk_ex + K3_TOP;
-    Q.err = (int *)(mp + words);
+    Q.err = error_word(true);
+    if (!Q.err) return cudaErrorMemoryAllocation;
     Q.seg_ring = (MP *)((char *)(mp + words) + 256);
     if (grid > 256) return cudaErrorInvalidValue;
     Q.chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
@@ -881,6 +918,7 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     if (const char *ev = std::getenv("MQ_SCAN_HINTS")) Q.hints = std::atoi(ev) != 0;
     cudaError_t e = cudaMemsetAsync(scratch, 0xFF, sizeof(MP) * words, st);
     if (e != cudaSuccess) return e;
+    *error_word(false) = 0;
     // MQ_SCAN_TRACE=<file>: SM clocks of every pipeline event of the first 64 tiles of each CTA (a development aid)
     Q.trace = nullptr;
     const char *trace_path = std::getenv("MQ_SCAN_TRACE");
@@ -902,6 +940,13 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
         }
     }
     return e;
+}
+
+// the code a wait that gave up left behind (0 = none); readable after a failed launch
+int k3_onepass_error()
+{
+    int *h = error_word(false);
+    return h ? *h : 0;
 }
 
 cudaError_t k3_onepass_occupancy(int *blocks)

@@ -204,7 +204,12 @@ int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, d
     if (W && !cfg->device_ptrs)
         CU(cudaMemcpyAsync(W, dW, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (cudaError_t e_sync = cudaStreamSynchronize(ctx->stream)) {
+        if (run.onepass && k3_onepass_error())
+            return fail(MQ_E_CUDA, "mq_scan_gg1: the one-pass scan kernel gave up on a wait (code 0x%x): %s; the CUDA context is "
+                        "lost, MQ_SCAN_TWO_PASS=1 selects the three-launch path", k3_onepass_error(), cudaGetErrorString(e_sync));
+        return fail(MQ_E_CUDA, "cudaStreamSynchronize failed: %s (%s:%d)", cudaGetErrorString(e_sync), __FILE__, __LINE__);
+    }
 
     for (int i = 0; i < MQ_SCAN_LEN; ++i) stats[i] = 0.0;
     for (int k = 0; k < 4; ++k) {
