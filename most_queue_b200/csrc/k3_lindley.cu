@@ -243,20 +243,60 @@ __device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, cons
 #define K3_GEN_UNROLL 1
 #endif
 constexpr int K3_GEN_UNROLL_N = K3_GEN_UNROLL;
-template <bool STASH_W, bool FULL>
+template <bool STASH_W, bool FULL, int SRCK, int SRVK>
 __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, float *stg, float *stv)
 {
     unsigned long long g = (unsigned long long)(P.job0 + n0);
     uint2 w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
-    float gap = sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+    float gap = sample<SRCK>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
     const int valid = FULL ? K3_L : k3_valid(P.n, n0, K3_L);
     MP f = mp_id();
-#pragma unroll K3_GEN_UNROLL_N
-    for (int j = 0; j < K3_L; ++j) {
-        const float sv = sample<-1>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
+    if (SRCK == MQ_GAMMA) {
+        // Gamma gaps: the rejection loop is the caller's.  A trip of this loop is ONE attempt at the gap that follows
+        // job j of the lane; a lane whose attempt is rejected (a few per cent) tries again in the next trip while its
+        // neighbours go on with their next job, so a warp makes 16 + (the most rejections of any of its lanes) trips
+        // instead of 16 x (attempts of its unluckiest lane per job).  Same draws, same fold order per lane.
+        const float dd = P.src.a, cc = P.src.b;
+        const int small_alpha = P.src.r;
+        int j = 0;
+        uint32_t t = 0;
+        float x = dd;
+        float sv = sample<SRVK>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
         ++g;
         w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
-        const float gnext = sample<-1>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+        while (__any_sync(0xffffffffu, j < K3_L)) {
+            if (j < K3_L) {
+                const bool ok = gamma_attempt(dd, cc, small_alpha, t, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0, x) || t == 14;
+                if (ok) {
+                    const float gnext = gamma_finish(x, P.src.c, P.src.d, small_alpha, w.x);
+                    if (FULL || j < valid) f = mp_step(f, __dsub_rn((double)sv, (double)gnext));
+                    if (STASH_W) {
+                        stg[k3_pad(threadIdx.x * K3_L + j)] = gap;
+                        stv[k3_pad(threadIdx.x * K3_L + j)] = sv;
+                        if (!FULL && n0 + j == P.n - 1) P.stG[P.n] = gnext;
+                    }
+                    gap = gnext;
+                    ++j;
+                    t = 0;
+                    x = dd;
+                    if (j < K3_L) {
+                        sv = sample<SRVK>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
+                        ++g;
+                        w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
+                    }
+                } else {
+                    ++t;
+                }
+            }
+        }
+        return f;
+    }
+#pragma unroll K3_GEN_UNROLL_N
+    for (int j = 0; j < K3_L; ++j) {
+        const float sv = sample<SRVK>(P.srv, w.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
+        ++g;
+        w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
+        const float gnext = sample<SRCK>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
         if (FULL || j < valid) f = mp_step(f, __dsub_rn((double)sv, (double)gnext));
         if (STASH_W) {
             stg[k3_pad(threadIdx.x * K3_L + j)] = gap;
@@ -268,7 +308,9 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
     return f;
 }
 
-template <bool REPLAY, bool STASH_W = false>
+// SRCK / SRVK: the laws of the gaps / services known at compile time (-1: switch on the kind at run time; the switch is
+// 9 % of the generator form's instructions, so the BASELINE shapes get their own instantiation)
+template <bool REPLAY, bool STASH_W = false, int SRCK = -1, int SRVK = -1>
 __global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 6)) k3_summary(const K3Params P)
 {
     __shared__ MP smem[K3_THREADS / 32];
@@ -281,8 +323,8 @@ __global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 6)) k3_sum
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
         MP mine;
         if (!REPLAY) {
-            mine = full_tile ? gen_fold_segment<STASH_W, true>(P, n0, stg, stv)
-                             : gen_fold_segment<STASH_W, false>(P, n0, stg, stv);
+            mine = full_tile ? gen_fold_segment<STASH_W, true, SRCK, SRVK>(P, n0, stg, stv)
+                             : gen_fold_segment<STASH_W, false, SRCK, SRVK>(P, n0, stg, stv);
         } else {
             // replay form: the fold only needs x[n] = S[n] - A[n+1], formed while the coalesced loads arrive and staged
             // as ONE array (35 KB instead of 72 KB per CTA: 6 resident CTAs instead of 3); jobs beyond the range are 0
@@ -647,6 +689,21 @@ __global__ void __launch_bounds__(32) k3_final(const double *partial, const doub
     if (lane == 0) stats[i] = v;
 }
 
+// the generator-form summary kernel for a pair of laws: own instantiations for the BASELINE chain (Gamma gaps, Pareto
+// services), Gamma gaps with any service law, and M/M; everything else switches on the kind at run time
+using SummaryKernel = void (*)(const K3Params);
+template <bool STASH_W>
+static SummaryKernel gen_summary_kernel_t(int src_kind, int srv_kind)
+{
+    if (src_kind == MQ_GAMMA) return srv_kind == MQ_PA ? k3_summary<false, STASH_W, MQ_GAMMA, MQ_PA> : k3_summary<false, STASH_W, MQ_GAMMA, -1>;
+    if (src_kind == MQ_M && srv_kind == MQ_M) return k3_summary<false, STASH_W, MQ_M, MQ_M>;
+    return k3_summary<false, STASH_W, -1, -1>;
+}
+static SummaryKernel gen_summary_kernel(bool stash, int src_kind, int srv_kind)
+{
+    return stash ? gen_summary_kernel_t<true>(src_kind, srv_kind) : gen_summary_kernel_t<false>(src_kind, srv_kind);
+}
+
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
 {
     if (P.replay) {
@@ -654,10 +711,8 @@ cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
                                              (int)K3_XSTAGE_BYTES);
         if (e != cudaSuccess) return e;
         k3_summary<true><<<grid, K3_THREADS, K3_XSTAGE_BYTES, st>>>(P);
-    } else if (P.stG) {
-        k3_summary<false, true><<<grid, K3_THREADS, 0, st>>>(P);
     } else {
-        k3_summary<false><<<grid, K3_THREADS, 0, st>>>(P);
+        gen_summary_kernel(P.stG != nullptr, P.src.kind, P.srv.kind)<<<grid, K3_THREADS, 0, st>>>(P);
     }
     return cudaGetLastError();
 }
@@ -714,7 +769,7 @@ static cudaError_t occ_walk_one(size_t smem, int *b)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, k3_walk<MODE, WANT_P>, K3_THREADS, smem);
 }
 
-cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_blocks, int *walk_blocks)
+cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int src_kind, int srv_kind, int *summary_blocks, int *walk_blocks)
 {
     int a = 0, b = 0;
     cudaError_t e;
@@ -724,10 +779,8 @@ cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_bloc
         e = cudaFuncSetAttribute(k3_summary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_XSTAGE_BYTES);
         if (e == cudaSuccess)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_XSTAGE_BYTES);
-    } else if (stash) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false, true>, K3_THREADS, 0);
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<false>, K3_THREADS, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gen_summary_kernel(stash, src_kind, srv_kind), K3_THREADS, 0);
     }
     if (e == cudaSuccess) {
         if (mode == 1)

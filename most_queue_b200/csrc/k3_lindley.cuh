@@ -62,7 +62,7 @@ cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_final(const double *partial, const double *level_partial, int grid, double *stats,
                             cudaStream_t st);
-cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int *summary_blocks, int *walk_blocks);
+cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int src_kind, int srv_kind, int *summary_blocks, int *walk_blocks);
 size_t k3_walk_smem(bool replay, bool want_p);
 
 }  // namespace mq

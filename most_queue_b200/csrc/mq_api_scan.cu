@@ -139,7 +139,7 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
         }
     }
     int occ_s = 0, occ_w = 0;
-    CU(k3_occupancy(replay, stash, want_p, &occ_s, &occ_w));
+    CU(k3_occupancy(replay, stash, want_p, P.src.kind, P.srv.kind, &occ_s, &occ_w));
     if (run.onepass) {
         occ_w = 1;  // one CTA per SM by design
         if (int rc = ensure(ctx->lookback, k3_onepass_scratch_bytes(P.ntiles))) return rc;

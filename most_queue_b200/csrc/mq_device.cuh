@@ -164,6 +164,31 @@ static __device__ __noinline__ float sample_gamma(float dd, float cc, float inv_
     return x * inv_mu;
 }
 
+// ONE attempt (number t) of sample_gamma's loop, for callers that keep the loop themselves so that a lane which rejects
+// retries in its next trip instead of holding its warp inside the sampler.  Same operations in the same order as the
+// loop body above, so `x` (start it at dd) ends up with the same bits; true = accepted (the caller also stops at t = 14).
+__device__ __forceinline__ bool gamma_attempt(float dd, float cc, int small_alpha, uint32_t t, uint32_t w0, uint32_t idx,
+                                              uint32_t rep, uint32_t key0, int which, float &x)
+{
+    uint2 e0 = ext_words(idx, rep, key0, which, 2 * t + 1);
+    float rad = sqrtf(-1.3862943611198906f * fast_lg2(u01(e0.x)));
+    float z = rad * fast_cos2pi(u01(e0.y));
+    float v = fmaf(cc, z, 1.0f);
+    if (v <= 0.0f) return false;
+    v = v * v * v;
+    x = dd * v;
+    const uint32_t wa = (t == 0 && !small_alpha) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
+    float lhs = 0.6931471805599453f * fast_lg2(u01(wa));
+    float rhs = 0.5f * z * z + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
+    return lhs < rhs;
+}
+// what sample_gamma does after its loop
+__device__ __forceinline__ float gamma_finish(float x, float inv_mu, float inv_alpha, int small_alpha, uint32_t w0)
+{
+    if (small_alpha) x *= fast_ex2(fast_lg2(u01(w0)) * inv_alpha);
+    return x * inv_mu;
+}
+
 template <int KIND>
 __device__ __forceinline__ float sample(const DistF &d, uint32_t w0, uint32_t idx, uint32_t rep,
                                         uint32_t key0, int which)

@@ -86,7 +86,7 @@ def test_generator_matches_oracle():
             same += 1
             np.testing.assert_allclose(rec[_lib.NG_VSUM, r], o.v_sum[0], rtol=2e-4)
             np.testing.assert_allclose(rec[_lib.NG_TTEK, r], o.ttek, rtol=1e-5)
-    assert same >= reps // 2
+    assert same >= reps * 3 // 4, same  # the rest: an fp32-draw near-tie resolved the other way (another sample path)
     np.testing.assert_allclose(agg[5] / reps, (rec[_lib.NG_VSUM] / rec[_lib.NG_SERVED]).mean(), rtol=1e-12)
 
 
@@ -95,7 +95,6 @@ def test_network_simulator_api_jackson_mean():
     node; mean sojourn = sum of visit ratios times M/M/c node sojourn times."""
     from most_queue_b200.sim.networks.network import NetworkSimulator
 
-    lam = [1.0, 1.0, 0.8, 0.32, 0.32 + 0.8 + 0.0]  # placeholder, replaced below by the traffic equations
     Rm = np.array(NET_R, dtype=float)
     m = 5
     P = Rm[1:, :m]

@@ -56,6 +56,24 @@ def test_one_pass_waits_bitwise_vs_oracle_tree(N):
     np.testing.assert_allclose(out["v_sum"], ot.v_sum, rtol=1e-11)
 
 
+@pytest.mark.parametrize("rho", [0.97, 1.25])
+def test_one_pass_when_the_carry_never_dies(rho):
+    """The fused kernel walks every segment speculatively from its in-tile prefix and repairs the segments whose start
+    wait depends on the carry into the tile.  Near and above saturation that is most or ALL of them (an unstable queue
+    never forgets): the repair then rewrites every wait and every sum, and must still give the three-launch values."""
+    rng = np.random.default_rng(11)
+    N = 1_500_000
+    A = rng.exponential(1.0, N + 1)
+    S = rng.exponential(rho, N)
+    (o1, W1), (o2, W2) = _both(A, S, N)
+    assert np.array_equal(W1, W2)
+    assert o1["pairs_apply"] == o2["pairs_apply"] and o1["tail_raw"] == o2["tail_raw"]
+    np.testing.assert_allclose(o1["w_sum"], o2["w_sum"], rtol=1e-10)
+    np.testing.assert_allclose(o1["v_sum"], o2["v_sum"], rtol=1e-10)
+    if rho > 1:
+        assert W1[-1] > 1e4  # the wait really grew without bound
+
+
 def test_one_pass_ranges_with_carries():
     """Ranges with carried waits (the multi-GPU form): every range goes through the fused kernel with w_in != 0."""
     rng = np.random.default_rng(7)
