@@ -909,7 +909,7 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     Q.chunk = (P.ntiles + K3_TOP - 1) / K3_TOP;
     // hand-off slots: a tile's slot (4 KB of segment prefixes in L2) is held until its look-back and repair are done, so
     // the ring depth x the tile period is the look-back latency the pipeline tolerates; MQ_SCAN_LEAD overrides (3..24)
-    Q.ring = 16;
+    Q.ring = 24;
     if (const char *ev = std::getenv("MQ_SCAN_LEAD")) Q.ring = std::atoi(ev);
     if (Q.ring < OP_NLB) Q.ring = OP_NLB;  // a look-back warp moves OP_NLB tiles at a time: a shorter ring would alias phases
     if (Q.ring > OP_RING) Q.ring = OP_RING;
