@@ -61,13 +61,14 @@ constexpr int OP_WARP_A = OP_CWARPS;             // 16..18
 constexpr int OP_WARP_B = OP_WARP_A + OP_NLA;    // 19..22
 constexpr int OP_WARP_P = OP_WARP_B + OP_NLB;    // 23
 constexpr int OP_THREADS = (OP_WARP_P + 1) * 32; // 768: 6 warps of 80 registers per scheduler
+static_assert(OP_RING % (OP_GROUPS * OP_NLA * OP_NLB) == 0, "every hand-off slot must keep the same waiters from phase to phase");
 constexpr int OP_LB = 128;                       // look-back window kept in shared memory (summaries), per look-back warp
 constexpr uint32_t OP_TX = 2u * OP_ARR_BYTES + 16u;
-#ifndef OP_V_CSLEEP
-#define OP_V_CSLEEP 0
+#ifndef OP_V_CHECK
+#define OP_V_CHECK 0
 #endif
-#ifndef OP_V_LBIDLE
-#define OP_V_LBIDLE 0
+#ifndef OP_V_PROGRESS
+#define OP_V_PROGRESS 0
 #endif
 #ifndef OP_V_SPIN_LIMIT
 #define OP_V_SPIN_LIMIT 4000000u
@@ -96,7 +97,12 @@ struct OpShared {
     MP ks_left[OP_NLA][5];                        // left operands of the late Kogge-Stone lane (look-back A)
     double seg0[OP_RING][2 * K3_L + 2];           // S[0..15], A[0..16] of the tile's first segment (always repaired)
     double red[OP_WARP_P][K3_NSTAT];
-    unsigned long long full[OP_STAGES], empty[OP_STAGES];
+    // full[s][g]: tile k lands in stage k % 3 for group k % 2 -- one "full" barrier per (stage, group), so that a barrier has
+    // ONE waiting group, which has seen every earlier phase itself.  With one barrier per stage the groups alternate on
+    // it, and a group that arrives while the OTHER group's tile is still in flight asks for the parity of a phase two
+    // ahead of the current one: try_wait.parity takes that for the preceding (completed) phase and lets it through onto
+    // stale data (measured: 1 launch in 100 with wrong sums, 1 in 2000 hung).
+    unsigned long long full[OP_STAGES][OP_GROUPS], empty[OP_STAGES];
     unsigned long long folded[OP_RING], walked[OP_RING], slot_free[OP_RING];
 };
 
@@ -192,19 +198,13 @@ __device__ __noinline__ void op_give_up(int *err, int code)
 __device__ __forceinline__ void mbar_wait(unsigned long long *b, uint32_t parity, int *err)
 {
     for (uint32_t it = 0; !mbar_try(b, parity); ++it) {
-#if OP_V_CSLEEP
-        __nanosleep(OP_V_CSLEEP);
-#endif
         if (it > OP_SPIN_LIMIT) op_give_up(err, 0x100 | (int)(smem_u32(b) & 0xffff) << 12 | (int)parity);
     }
 }
-// the look-back warps are off the critical path: they sleep between polls and leave the issue slots to the compute warps
+// the waits of the look-back warps (same loop, a shorter patience: they trap first and name the barrier that starved them)
 __device__ __forceinline__ void mbar_wait_idle(unsigned long long *b, uint32_t parity, int *err)
 {
     for (uint32_t it = 0; !mbar_try(b, parity); ++it) {
-#if OP_V_LBIDLE
-        __nanosleep(OP_V_LBIDLE);
-#endif
         if (it > OP_SPIN_LIMIT / 16) op_give_up(err, 0x200 | (int)(smem_u32(b) & 0xffff) << 12 | (int)parity);
     }
 }
@@ -348,6 +348,11 @@ struct K3OnePassParams {
     long long *trace;      // optional [grid][OP_TRACE_TILES][24] SM clocks of the pipeline events (MQ_SCAN_TRACE)
 };
 
+#if OP_V_PROGRESS
+#define OP_PROG(role, k_, code) (((volatile int *)Q.err)[16 + blockIdx.x * 16 + (role)] = (k_) * 16 + (code))
+#else
+#define OP_PROG(role, k_, code) ((void)0)
+#endif
 constexpr int OP_TRACE_TILES = 64;
 #define OP_TRACE(ev, val)                                                                             \
     do {                                                                                              \
@@ -458,7 +463,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < OP_STAGES; ++s) {
-            mbar_init(&sm.full[s], 1);
+            for (int g = 0; g < OP_GROUPS; ++g) mbar_init(&sm.full[s][g], 1);
             mbar_init(&sm.empty[s], K3_THREADS);
         }
         for (int d = 0; d < OP_RING; ++d) {
@@ -477,21 +482,24 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             for (int k = 0; k < my_tiles; ++k) {
                 const int s = k % OP_STAGES;
                 const long long t = blockIdx.x + (long long)k * gridDim.x;
+                OP_PROG(15, k, 1);
                 mbar_wait(&sm.empty[s], (uint32_t)((k / OP_STAGES) & 1) ^ 1u, Q.err);
+                OP_PROG(15, k, 2);
                 OP_TRACE(0, clock64());
                 OP_TRACE(21, gtime());
+                unsigned long long *fb = &sm.full[s][k % OP_GROUPS];
                 if ((t + 1) * (long long)OP_TILE < P.n) {
-                    mbar_expect_tx(&sm.full[s], OP_TX);
+                    mbar_expect_tx(fb, OP_TX);
                     if (Q.hints) {
-                        tma_tile_2d_hint(sm.st[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.full[s], once);
-                        tma_tile_2d_hint(sm.st[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.full[s], once);
+                        tma_tile_2d_hint(sm.st[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), fb, once);
+                        tma_tile_2d_hint(sm.st[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), fb, once);
                     } else {
-                        tma_tile_2d(sm.st[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), &sm.full[s]);
-                        tma_tile_2d(sm.st[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), &sm.full[s]);
+                        tma_tile_2d(sm.st[s].S, &Q.mapS, 0, (int)(t * OP_ROWS), fb);
+                        tma_tile_2d(sm.st[s].A, &Q.mapA, 0, (int)(t * OP_ROWS), fb);
                     }
-                    bulk_copy_16(sm.anext[s], P.A + (t + 1) * OP_TILE, &sm.full[s]);
+                    bulk_copy_16(sm.anext[s], P.A + (t + 1) * OP_TILE, fb);
                 } else {
-                    mbar_arrive(&sm.full[s]);  // the last tile is staged by the compute group itself (bounds checks)
+                    mbar_arrive(fb);  // the last tile is staged by the compute group itself (bounds checks)
                 }
             }
         }
@@ -510,10 +518,22 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             const long long tb = t * OP_TILE;
             OpStage &stg = sm.st[s];
             const double *a_next = sm.anext[s];
+            if (lane == 0 && gw < 4) OP_PROG(grp * 4 + gw, k, 1);
             mbar_wait(&sm.slot_free[d], (uint32_t)((k / RING) & 1) ^ 1u, Q.err);  // at most RING tiles await their repair
-            mbar_wait(&sm.full[s], (uint32_t)((k / OP_STAGES) & 1), Q.err);
+            if (lane == 0 && gw < 4) OP_PROG(grp * 4 + gw, k, 2);
+            mbar_wait(&sm.full[s][grp], (uint32_t)((k / (OP_STAGES * OP_GROUPS)) & 1), Q.err);
+            if (lane == 0 && gw < 4) OP_PROG(grp * 4 + gw, k, 3);
             if (r == 0) OP_TRACE(9, clock64());
             const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
+#if OP_V_CHECK
+            if (full_tile && (r & 31) == 5) {  // is the tile in the stage the tile we waited for?
+                const double got = *sw_elem(stg.S, r * K3_L + 3), want = P.S[tb + r * K3_L + 3];
+                if (got != want) {
+                    atomicAdd(Q.err + 4, 1);
+                    Q.err[6] = k * 1000 + blockIdx.x;
+                }
+            }
+#endif
             int valid = K3_L;
             if (!full_tile) {
                 stage_ragged(P, tb, stg, sm.anext[s], r);
@@ -548,7 +568,9 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             if (lane == 0) within = mp_id();
             MP *wt = sm.warp_tot[grp][(k / OP_GROUPS) & 1];
             if (lane == 31) wt[gw] = inc;
+            if (lane == 0 && gw < 4) OP_PROG(grp * 4 + gw, k, 4);
             named_bar(bar_id, K3_THREADS);
+            if (lane == 0 && gw < 4) OP_PROG(grp * 4 + gw, k, 5);
             MP carry = mp_id(), tot = mp_id();
 #pragma unroll
             for (int g = 0; g < K3_THREADS / 32; ++g) {
@@ -607,9 +629,20 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
 #pragma unroll
                 for (int j = 0; j <= K3_L; ++j) c0[K3_L + j] = *sw_elem(stg.A, j);
             }
+#if OP_V_CHECK
+            if (full_tile && (r & 31) == 7) {  // is it still there at the end of the walk?
+                const double got = *sw_elem(stg.A, r * K3_L + 9), want = P.A[tb + r * K3_L + 9];
+                if (got != want) {
+                    atomicAdd(Q.err + 5, 1);
+                    Q.err[7] = k * 1000 + blockIdx.x;
+                }
+                token |= (uint32_t)__double2hiint(got);
+            }
+#endif
             // the rows must have been READ before the stage goes back to the TMA producer (see mbar_arrive_after)
             mbar_arrive_after(&sm.empty[s], token, Q.zero_mask);
             mbar_arrive(&sm.walked[d]);
+            if (lane == 0 && gw < 4) OP_PROG(grp * 4 + gw, k, 6);
             if (r == 0) {
                 OP_TRACE(10, clock64());
                 OP_TRACE(22, gtime());
@@ -643,7 +676,9 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
         for (int k = warp - OP_WARP_A; k < my_tiles; k += OP_NLA) {
             const int d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
+            if (lane == 0) OP_PROG(warp - OP_WARP_A + 8, k, 1);
             mbar_wait_idle(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
+            if (lane == 0) OP_PROG(warp - OP_WARP_A + 8, k, 2);
             if (lane == 0) OP_TRACE(4, clock64());
             const MP own = sm.tile_total[d];
             __syncwarp();
@@ -654,6 +689,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             MP base = mp_id();
             gather(Q, lb, Q.t_incf, t, n_pred, lane, idx, base);
             if (idx < 0) idx = n_pred;  // fold from the identity at the chunk start
+            if (lane == 0) OP_PROG(warp - OP_WARP_A + 8, k, 3);
             MP f = base;
             if (lane == 0) {
                 OP_TRACE(5, clock64());
@@ -732,7 +768,9 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             const int d = k % RING;
             const long long t = blockIdx.x + (long long)k * gridDim.x;
             const long long tb = t * OP_TILE;
+            if (lane == 0) OP_PROG(warp - OP_WARP_B + 11, k, 1);
             mbar_wait_idle(&sm.folded[d], (uint32_t)((k / RING) & 1), Q.err);
+            if (lane == 0) OP_PROG(warp - OP_WARP_B + 11, k, 2);
             const MP own = sm.tile_total[d];
             const long long c = t / chunk, n_pred = t - c * chunk;
             long long idx = -1;
@@ -759,7 +797,9 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             ex = mp_shfl(ex, 0);
             const double w_tile = mp_apply(ex, P.w_in);
             // ---- repair.  The provisional walk (and its wait stores, which the repair overwrites) must be over.
+            if (lane == 0) OP_PROG(warp - OP_WARP_B + 11, k, 4);
             mbar_wait_idle(&sm.walked[d], (uint32_t)((k / RING) & 1), Q.err);
+            if (lane == 0) OP_PROG(warp - OP_WARP_B + 11, k, 5);
             const bool full_tile = (t + 1) * (long long)OP_TILE < P.n;
             double2 sx[K3_THREADS / 32];
 #pragma unroll
@@ -796,6 +836,7 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
             if (lane == 0) {
                 OP_TRACE(14, clock64());
                 mbar_arrive_after(&sm.slot_free[d], (uint32_t)__double2hiint(sx[0].y), Q.zero_mask);
+                OP_PROG(warp - OP_WARP_B + 11, k, 6);
             }
         }
 #pragma unroll
@@ -870,7 +911,7 @@ static int *error_word(bool device_side)
 {
     static int *h = nullptr, *d = nullptr;
     if (!h) {
-        if (cudaHostAlloc((void **)&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        if (cudaHostAlloc((void **)&h, 64 + 16 * 4 * 257, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
             h = nullptr;
             return nullptr;
         }
@@ -911,14 +952,18 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     // the ring depth x the tile period is the look-back latency the pipeline tolerates; MQ_SCAN_LEAD overrides (3..24)
     Q.ring = 24;
     if (const char *ev = std::getenv("MQ_SCAN_LEAD")) Q.ring = std::atoi(ev);
-    if (Q.ring < OP_NLB) Q.ring = OP_NLB;  // a look-back warp moves OP_NLB tiles at a time: a shorter ring would alias phases
-    if (Q.ring > OP_RING) Q.ring = OP_RING;
+    // a slot's barriers must have the SAME waiters in every phase (the compute group, the look-back A warp, the look-back
+    // B warp of the tile): the ring depth is a multiple of the two groups, the three A warps and the four B warps
+    Q.ring = Q.ring >= 24 ? 24 : 12;
     Q.hints = 0;
     Q.zero_mask = 0;
     if (const char *ev = std::getenv("MQ_SCAN_HINTS")) Q.hints = std::atoi(ev) != 0;
     cudaError_t e = cudaMemsetAsync(scratch, 0xFF, sizeof(MP) * words, st);
     if (e != cudaSuccess) return e;
     *error_word(false) = 0;
+#if OP_V_PROGRESS
+    for (int i = 16; i < 16 + 16 * 257; ++i) error_word(false)[i] = -1;
+#endif
     // MQ_SCAN_TRACE=<file>: SM clocks of every pipeline event of the first 64 tiles of each CTA (a development aid)
     Q.trace = nullptr;
     const char *trace_path = std::getenv("MQ_SCAN_TRACE");
@@ -946,6 +991,22 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
 int k3_onepass_error()
 {
     int *h = error_word(false);
+#if OP_V_CHECK
+    if (h && (h[4] || h[5])) {
+        std::fprintf(stderr, "k3_onepass stage check: %d wrong at fold start (last k*1000+cta %d), %d wrong at walk end (last %d)\n", h[4], h[6], h[5], h[7]);
+        h[4] = h[5] = 0;
+    }
+#endif
+#if OP_V_PROGRESS
+    if (h && *h) {
+        std::fprintf(stderr, "k3_onepass progress (tile * 16 + state) per CTA: compute warps 0-7 (group 0: 0-3? see code), A 8-10, B 11-14, producer 15\n");
+        for (int b = 0; b < 148; b += 21) {
+            std::fprintf(stderr, "  CTA %3d:", b);
+            for (int i = 0; i < 16; ++i) std::fprintf(stderr, " %d.%d", h[16 + b * 16 + i] / 16, h[16 + b * 16 + i] % 16);
+            std::fprintf(stderr, "\n");
+        }
+    }
+#endif
     return h ? *h : 0;
 }
 

@@ -211,6 +211,7 @@ int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, d
         return fail(MQ_E_CUDA, "cudaStreamSynchronize failed: %s (%s:%d)", cudaGetErrorString(e_sync), __FILE__, __LINE__);
     }
 
+    if (run.onepass) k3_onepass_error();  // (debug builds print their stage checks here)
     for (int i = 0; i < MQ_SCAN_LEN; ++i) stats[i] = 0.0;
     for (int k = 0; k < 4; ++k) {
         stats[MQ_S_W + k] = h[k];

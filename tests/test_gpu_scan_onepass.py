@@ -116,3 +116,31 @@ def test_one_pass_device_pointers_and_misaligned_fallback():
     Ah, Sh = A[1:n + 2].cpu().numpy(), S[1:n + 1].cpu().numpy()
     np.testing.assert_allclose(st3[_lib.S_SUMS], Sh.sum(), rtol=1e-12)
     np.testing.assert_allclose(st3[_lib.S_SUMA], Ah[:n].sum(), rtol=1e-12)
+
+
+def test_one_pass_is_reproducible_launch_after_launch():
+    """Every launch of the fused kernel on the same arrays gives the same bits (static tile order, fixed-order sums).
+    This is the test that would have caught the parity alias of round 2: with ONE "stage is full" mbarrier per stage and
+    two compute groups alternating on it, a group that arrived while the other group's tile was still in flight asked
+    try_wait.parity for a phase two ahead of the current one, was let through and folded stale data -- one launch in a
+    hundred with wrong sums (1e-6 relative: inside every statistical tolerance), one in two thousand hung.  Cheap enough
+    to keep: 1500 launches in about a second."""
+    import torch
+
+    from most_queue_b200 import _lib
+
+    ctx = _lib.default_context()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for n, launches in (((1 << 24) + 12345, 1000), ((1 << 26) + 777, 500)):
+        A = torch.empty(n + 1, device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
+        S = torch.empty(n, device="cuda", dtype=torch.float64).exponential_(1.0 / 0.8, generator=g)
+        torch.cuda.synchronize()
+        ref = None
+        for i in range(launches):
+            st, _ = ctx.scan_apply(n, 0.25, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)
+            assert ctx.last_timing()["launches"] == 2
+            key = tuple(st[:18])
+            if ref is None:
+                ref = key
+            assert key == ref, (n, i)
+        del A, S

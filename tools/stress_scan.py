@@ -1,0 +1,35 @@
+"""Launches the one-pass scan many times on the same arrays and checks every result against the first one bit for bit
+(range summary, tail, sums): catches rare hangs (reported by the kernel's bounded waits) and rare races."""
+import os, sys, time
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from most_queue_b200 import _lib
+
+ctx = _lib.default_context()
+g = torch.Generator(device="cuda").manual_seed(5)
+for lg, launches in [(int(a.split(":")[0]), int(a.split(":")[1])) for a in (sys.argv[1:] or ["26:3000", "28:600", "22:3000"])]:
+    nr = (1 << lg) + 12345
+    A = torch.empty(nr + 1, device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
+    S = torch.empty(nr, device="cuda", dtype=torch.float64).exponential_(1.0 / 0.8, generator=g)
+    torch.cuda.synchronize()
+    ref = None
+    t0 = time.time()
+    bad = 0
+    seen = {}
+    for i in range(launches):
+        try:
+            st, _ = ctx.scan_apply(nr, 0.25, A=A.data_ptr(), S=S.data_ptr(), device_ptrs=True)
+        except Exception as e:
+            print(f"2^{lg}: launch {i} FAILED: {e}", flush=True)
+            sys.exit(1)
+        key = tuple(st[:16])
+        seen[key] = seen.get(key, 0) + 1
+        if ref is None:
+            ref = key
+        elif key != ref:
+            bad += 1
+            if bad < 4:
+                print(f"2^{lg}: launch {i} differs from launch 0:", [(j, (key[j] - ref[j]) / (abs(ref[j]) + 1e-300)) for j in range(16) if key[j] != ref[j]], flush=True)
+    print(f"2^{lg}: {launches} launches, {bad} differ from launch 0, {len(seen)} distinct results with counts {sorted(seen.values(), reverse=True)[:6]}, {time.time() - t0:.1f} s", flush=True)
+    del A, S
