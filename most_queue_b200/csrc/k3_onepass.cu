@@ -225,6 +225,12 @@ __device__ __forceinline__ void tma_tile_2d_hint(void *dst, const CUtensorMap *m
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// L2 prefetch of a tile box: the HBM latency of a tile is paid while its stage is still busy with an earlier tile, and
+// the TMA copy that follows finds the lines in L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ unsigned long long policy_evict_first()
 {
     unsigned long long p;
@@ -342,7 +348,8 @@ struct K3OnePassParams {
     MP *seg_ring;          // [grid][OP_RING][256] exclusive prefix of every segment inside its tile (compute -> repair)
     long long chunk;       // tiles per chunk
     uint32_t zero_mask;    // 0 (see mbar_arrive_after)
-    int hints;             // 1: the tile fetch carries the L2 evict_first hint (MQ_SCAN_HINTS=1; off: the repair finds its lines in L2)
+    int hints;             // 1: the tile fetch carries the L2 evict_first hint (a tile is read once; MQ_SCAN_HINTS=0 turns it off)
+    int prefetch;          // tiles the producer prefetches into L2 ahead of the stage it is waiting for (0: none)
     int ring;              // hand-off slots in use (OP_NLB..OP_RING): tiles whose look-back / repair may be pending
     int *err;
     long long *trace;      // optional [grid][OP_TRACE_TILES][24] SM clocks of the pipeline events (MQ_SCAN_TRACE)
@@ -479,9 +486,18 @@ __global__ void __maxnreg__(80) k3_onepass(const __grid_constant__ K3OnePassPara
         // ------------------------------------------------------------------ producer (HBM -> shared memory)
         if (lane == 0) {
             const unsigned long long once = policy_evict_first();
+            const int PF = Q.prefetch;
+            int next_pf = OP_STAGES;  // tiles 0..2 go straight into the stages
             for (int k = 0; k < my_tiles; ++k) {
                 const int s = k % OP_STAGES;
                 const long long t = blockIdx.x + (long long)k * gridDim.x;
+                for (; PF > 0 && next_pf <= k + PF && next_pf < my_tiles; ++next_pf) {
+                    const long long tp = blockIdx.x + (long long)next_pf * gridDim.x;
+                    if (next_pf > k && (tp + 1) * (long long)OP_TILE < P.n) {
+                        tma_prefetch_2d(&Q.mapS, 0, (int)(tp * OP_ROWS));
+                        tma_prefetch_2d(&Q.mapA, 0, (int)(tp * OP_ROWS));
+                    }
+                }
                 OP_PROG(15, k, 1);
                 mbar_wait(&sm.empty[s], (uint32_t)((k / OP_STAGES) & 1) ^ 1u, Q.err);
                 OP_PROG(15, k, 2);
@@ -955,8 +971,10 @@ cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaSt
     // a slot's barriers must have the SAME waiters in every phase (the compute group, the look-back A warp, the look-back
     // B warp of the tile): the ring depth is a multiple of the two groups, the three A warps and the four B warps
     Q.ring = Q.ring >= 24 ? 24 : 12;
-    Q.hints = 0;
+    Q.hints = 1;
     Q.zero_mask = 0;
+    Q.prefetch = 1;
+    if (const char *ev = std::getenv("MQ_SCAN_PREFETCH")) Q.prefetch = std::atoi(ev) < 0 ? 0 : (std::atoi(ev) > 8 ? 8 : std::atoi(ev));
     if (const char *ev = std::getenv("MQ_SCAN_HINTS")) Q.hints = std::atoi(ev) != 0;
     cudaError_t e = cudaMemsetAsync(scratch, 0xFF, sizeof(MP) * words, st);
     if (e != cudaSuccess) return e;
