@@ -537,10 +537,10 @@ def other_configs_leg(peaks, peak_src, sms):
         out["cfg3_replay_2p28"] = {
             "jobs_per_s": nr / t, "ms": t * 1e3, "w1": float(st[_lib.S_W] / st[_lib.S_TAKED]), "w1_theory_mm1": 0.7 * 0.7 / 0.3,
             "roofline": {"bound": "hbm", "achieved": 16.0 * nr / t / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": 17.48 * nr,
+                         "frac": 16.0 * nr / t / 1e9 / peak, "traffic": 16.11 * nr,
                          "kernel": "k3_onepass (TMA stages, speculative walk in shared memory, decoupled look-back + repair: one HBM read)",
                          "note": "algorithmic bytes 16 B/job (A and S read once); traffic = dram__bytes_read + write of k3_onepass from "
-                                 "profiles/r02_ncu_k3_onepass_summary.csv (2^26 jobs: 16.49 B/job read + 0.98 written), scaled; the three-launch "
+                                 "profiles/r02_ncu_k3_onepass_summary.csv (2^26 jobs: 16.04 B/job read + 0.07 written), scaled; the three-launch "
                                  "path (MQ_SCAN_TWO_PASS=1) moves 33.75 B/job; peak " + peak_src}}
     except Exception as e:  # reported, never fatal for the headline line
         out["cfg3_replay_2p28"] = {"error": repr(e)[:200]}
