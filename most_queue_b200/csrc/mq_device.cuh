@@ -156,8 +156,12 @@ static __device__ __noinline__ float sample_gamma(float dd, float cc, float inv_
         // the acceptance uniform of the first attempt is the primary word itself when it is not needed for the
         // alpha < 1 boost: one extension call per draw in the common case instead of two
         const uint32_t wa = (t == 0 && !small_alpha) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
-        float lhs = 0.6931471805599453f * fast_lg2(u01(wa));
-        float rhs = 0.5f * z * z + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
+        const float u = u01(wa), z2 = z * z;
+        // Marsaglia-Tsang's squeeze: u < 1 - 0.0331 z^4 implies the logarithmic test below, so nine draws in ten are
+        // accepted without the two logarithms (the decision, hence the variate, is the same)
+        if (u < fmaf(-0.0331f * z2, z2, 1.0f)) break;
+        float lhs = 0.6931471805599453f * fast_lg2(u);
+        float rhs = 0.5f * z2 + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
         if (lhs < rhs) break;
     }
     if (small_alpha) x *= fast_ex2(fast_lg2(u01(w0)) * inv_alpha);
@@ -178,8 +182,10 @@ __device__ __forceinline__ bool gamma_attempt(float dd, float cc, int small_alph
     v = v * v * v;
     x = dd * v;
     const uint32_t wa = (t == 0 && !small_alpha) ? w0 : ext_words(idx, rep, key0, which, 2 * t + 2).x;
-    float lhs = 0.6931471805599453f * fast_lg2(u01(wa));
-    float rhs = 0.5f * z * z + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
+    const float u = u01(wa), z2 = z * z;
+    if (u < fmaf(-0.0331f * z2, z2, 1.0f)) return true;  // the squeeze, as in sample_gamma
+    float lhs = 0.6931471805599453f * fast_lg2(u);
+    float rhs = 0.5f * z2 + dd - dd * v + dd * 0.6931471805599453f * fast_lg2(v);
     return lhs < rhs;
 }
 // what sample_gamma does after its loop
