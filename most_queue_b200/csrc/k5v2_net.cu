@@ -35,8 +35,8 @@ template <bool REPLAY>
 struct K5VLayout {
     // doubles: 3 per server, then (replay) 16 per node + 12 for the network
     __host__ __device__ static int nd(int nserv, int m) { return 3 * nserv + (REPLAY ? 16 * m + 12 : 0); }
-    // ints per node: QHEAD, QSIZE, SIDX, SFILL (+ NTAKED, NSERVED in replay)
-    static constexpr int ISTR = REPLAY ? 6 : 4;
+    // ints per node: QHEAD, QSIZE, SIDX, SFILL, NSERVED (+ NTAKED in replay)
+    static constexpr int ISTR = REPLAY ? 6 : 5;
     __host__ __device__ static int ni(int m) { return ISTR * m; }
     __host__ __device__ static int nf(int m) { return REPLAY ? 0 : K5V_SB * m; }
     __host__ __device__ static size_t bytes(int nserv, int m)
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
 #define SD(w) smd[(w) * K5V_BLOCK]
 #define SI(w) smi[(w) * K5V_BLOCK]
 #define IN(node, f) SI((node) * LY::ISTR + (f))
-    enum { QHEAD = 0, QSIZE = 1, SIDX = 2, SFILL = 3, NTAKED = 4, NSERVED = 5 };
+    enum { QHEAD = 0, QSIZE = 1, SIDX = 2, SFILL = 3, NSERVED = 4, NTAKED = 5 };
     const int D_ARRN = 0, D_WAITN = nserv, D_ARRT = 2 * nserv, D_NODE = 3 * nserv, D_NET = 3 * nserv + 16 * m;
     // replay: per node VSUM 0..3, WSUM 4..7, VRUN 8..11, WRUN 12..15; network VSUM 0..2, WSUM 3..5, VRUN 6..8, WRUN 9..11
 
@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                     sum[i * K5V_BLOCK] = __dadd_rn(sum[i * K5V_BLOCK], pw);
                     pw = __dmul_rn(pw, x);
                 }
-            } else {
+            } else if (x != 0.0) {
+                // (a zero sample -- the wait of a job that finds a free server -- leaves the non-negative sums as they
+                // are, bit for bit: no atomics for it)
                 double *g = rnode0 + (long long)(node * MQ_NN_ROWS + row0) * R;
                 double pw = x;
 #pragma unroll
@@ -194,18 +196,17 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 }
             }
         };
-        auto node_count = [&](int node, int row, double d) {  // counters that are only reported
-            atomicAdd(rnode0 + (long long)(node * MQ_NN_ROWS + row) * R, d);
+        // counters that are only reported.  Replay tier: one atomic each.  Generator tier: only the departures of a
+        // node are counted (an int in shared memory); taken = served + jobs in service and arrived = taken + jobs
+        // waiting are derived when the replication ends
+        auto node_count = [&](int node, int row, double d) {
+            if (REPLAY) atomicAdd(rnode0 + (long long)(node * MQ_NN_ROWS + row) * R, d);
         };
 
         double arrival_time = next_gap();  // network.py:76
         double ttek = 0.0;
 
         while (served < P.jobs && status == 0) {
-            if (!REPLAY) refill_services();
-            // every trip consumes exactly one routing uniform and it depends on nothing else: start it first, so the
-            // Philox chain (or the load, in the replay tier) overlaps the event selection
-            const double pu = next_uniform();
             // ---- next event, base_network_sim.py:184-227: external arrival first, then the busy servers in
             // node-major, channel-minor order; the first minimum wins
             double mv[ST];
@@ -228,6 +229,21 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
             const int ev = mi[0];
             const bool is_dep = mt < 1e10 && mt < arrival_time;
             ttek = is_dep ? mt : arrival_time;
+            // the head of the departing node's waiting line is needed half a trip further down: load it NOW, before the
+            // draw-ahead refill and the Philox chain of the routing uniform, so that its L2 round trip hides behind them
+            const int dep_node = is_dep ? sh_nodeof[ev] : 0;
+            const int dep_qs = is_dep ? IN(dep_node, QSIZE) : 0;
+            const int dep_slot = is_dep ? IN(dep_node, QHEAD) : 0;
+            double q_arrn = 0.0, q_waitn = 0.0, q_arrt = 0.0;
+            if (dep_qs != 0) {
+                const double *qr = qrec(dep_node, dep_slot);
+                q_arrn = qr[0];
+                q_waitn = qr[QL];
+                q_arrt = qr[2 * QL];
+            }
+            if (!REPLAY) refill_services();
+            // every trip consumes exactly one routing uniform and it depends on nothing else
+            const double pu = next_uniform();
 
             // the job that moves in this trip, and where it is now (-1: the source)
             double j_arrn = ttek, j_waitn = 0.0;
@@ -241,29 +257,16 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 arrival_time = __dadd_rn(ttek, next_gap());
             } else {
                 // on_serving network.py:174-194: node.serving() first (base.py:249-310)
-                const int node = sh_nodeof[ev];
+                const int node = dep_node;
                 cur = node;
-                // the head of this node's waiting line is needed a dozen instructions further down: load it now, so
-                // the L2 round trip overlaps the node statistics
-                const int qs = IN(node, QSIZE);
-                const int slot = IN(node, QHEAD);
-                double q_arrn = 0.0, q_waitn = 0.0, q_arrt = 0.0;
-                if (qs != 0) {
-                    const double *qr = qrec(node, slot);
-                    q_arrn = qr[0];
-                    q_waitn = qr[QL];
-                    q_arrt = qr[2 * QL];
-                }
+                const int qs = dep_qs, slot = dep_slot;
                 j_arrn = SD(D_ARRN + ev);
                 j_waitn = SD(D_WAITN + ev);
                 const double a_t = SD(D_ARRT + ev);
                 busy &= ~(1u << ev);
                 wslot = ev;
-                int n_served = 0;
-                if (REPLAY) {
-                    n_served = IN(node, NSERVED) + 1;
-                    IN(node, NSERVED) = n_served;
-                }
+                const int n_served = IN(node, NSERVED) + 1;
+                IN(node, NSERVED) = n_served;
                 node_count(node, MQ_NN_SERVED, 1.0);
                 node_sample(node, MQ_NN_VSUM, __dsub_rn(ttek, a_t), n_served);
                 if (qs != 0) {
@@ -323,10 +326,11 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                     }
                 } else {
                     double pv = v, pw = j_waitn;
+                    const bool waited = j_waitn != 0.0;  // a zero sample leaves the sums as they are
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         atomicAdd(&rec[(long long)(MQ_NG_VSUM + i) * R], pv);
-                        atomicAdd(&rec[(long long)(MQ_NG_WSUM + i) * R], pw);
+                        if (waited) atomicAdd(&rec[(long long)(MQ_NG_WSUM + i) * R], pw);
                         pv = __dmul_rn(pv, v);
                         pw = __dmul_rn(pw, j_waitn);
                     }
@@ -396,8 +400,17 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                     rn[(long long)(MQ_NN_WRUN + k) * R] = SD(D_NODE + 16 * i + 12 + k);
                 }
             }
-            // jobs inside the node = arrived - served (this lane's own atomics on those two rows; exact small integers)
-            rn[(long long)MQ_NN_INSYS * R] = __dsub_rn(__ldcg(&rn[(long long)MQ_NN_ARRIVED * R]), __ldcg(&rn[(long long)MQ_NN_SERVED * R]));
+            if (REPLAY) {
+                // jobs inside the node = arrived - served (this lane's own atomics on those two rows; exact small integers)
+                rn[(long long)MQ_NN_INSYS * R] = __dsub_rn(__ldcg(&rn[(long long)MQ_NN_ARRIVED * R]), __ldcg(&rn[(long long)MQ_NN_SERVED * R]));
+            } else {
+                const int in_service = __popc((busy >> sh_base[i]) & ((1u << sh_ch[i]) - 1u));
+                const int n_served = IN(i, NSERVED), n_taked = n_served + in_service, n_arrived = n_taked + IN(i, QSIZE);
+                rn[(long long)MQ_NN_SERVED * R] = (double)n_served;
+                rn[(long long)MQ_NN_TAKED * R] = (double)n_taked;
+                rn[(long long)MQ_NN_ARRIVED * R] = (double)n_arrived;
+                rn[(long long)MQ_NN_INSYS * R] = (double)(n_arrived - n_served);
+            }
             rn[(long long)MQ_NN_SUSED * R] = (double)IN(i, SIDX);
             rn[(long long)MQ_NN_QUEUED * R] = (double)IN(i, QSIZE);
         }
