@@ -295,9 +295,14 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
             // choose_next_node network.py:102-114: first column whose running row sum exceeds the uniform
             int next = -1;
             {
+                // all columns are compared at once (independent loads and compares) and the first hit is picked from the
+                // bit mask: the same decision as the sequential scan without its chain of dependent selects
                 const double *row = sh_R + (cur + 1) * (m + 1);
-                for (int i = 0; i <= m; ++i) next = (next < 0 && row[i] > pu) ? i : next;
-                next = next < 0 ? 0 : next;
+                uint32_t hit = 0;
+#pragma unroll
+                for (int i = 0; i <= K5V_MAXN; ++i)
+                    if (i <= m) hit |= (row[i] > pu ? 1u : 0u) << i;
+                next = hit ? __ffs(hit) - 1 : 0;
             }
             if (status) break;
             if (!is_dep && next >= m) {

@@ -324,9 +324,13 @@ __global__ void __launch_bounds__(K7V_BLOCK) k7v2_prionet(const K7Params P)
             const double pu = next_uniform();
             int next = -1;
             {
+                // all columns at once, first hit from the bit mask (k5v2_net.cu): no chain of dependent selects
                 const double *row = sh_R + real * RS + (cur + 1) * (m + 1);
-                for (int i = 0; i <= m; ++i) next = (next < 0 && row[i] > pu) ? i : next;
-                next = next < 0 ? 0 : next;
+                uint32_t hit = 0;
+#pragma unroll
+                for (int i = 0; i <= 8; ++i)
+                    if (i <= m) hit |= (row[i] > pu ? 1u : 0u) << i;
+                next = hit ? __ffs(hit) - 1 : 0;
             }
             if (status) break;
             if (!is_dep && next >= m) {
