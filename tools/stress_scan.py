@@ -8,10 +8,11 @@ from most_queue_b200 import _lib
 
 ctx = _lib.default_context()
 g = torch.Generator(device="cuda").manual_seed(5)
+rho = float(os.environ.get("RHO", "0.8"))
 for lg, launches in [(int(a.split(":")[0]), int(a.split(":")[1])) for a in (sys.argv[1:] or ["26:3000", "28:600", "22:3000"])]:
     nr = (1 << lg) + 12345
     A = torch.empty(nr + 1, device="cuda", dtype=torch.float64).exponential_(1.0, generator=g)
-    S = torch.empty(nr, device="cuda", dtype=torch.float64).exponential_(1.0 / 0.8, generator=g)
+    S = torch.empty(nr, device="cuda", dtype=torch.float64).exponential_(1.0 / rho, generator=g)
     torch.cuda.synchronize()
     ref = None
     t0 = time.time()
