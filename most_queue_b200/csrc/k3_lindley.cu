@@ -253,7 +253,7 @@ __device__ __forceinline__ MP fold_segment(const K3Params &P, long long n0, cons
 #define K3_GEN_UNROLL 1
 #endif
 constexpr int K3_GEN_UNROLL_N = K3_GEN_UNROLL;
-template <bool STASH_W, bool FULL, int SRCK, int SRVK>
+template <int STAGE, bool FULL, int SRCK, int SRVK>
 __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, float *stg, float *stv)
 {
     unsigned long long g = (unsigned long long)(P.job0 + n0);
@@ -280,10 +280,10 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
                 if (ok) {
                     const float gnext = gamma_finish(x, P.src.c, P.src.d, small_alpha, w.x);
                     if (FULL || j < valid) f = mp_step(f, __dsub_rn((double)sv, (double)gnext));
-                    if (STASH_W) {
+                    if (STAGE) {
                         stg[k3_pad(threadIdx.x * K3_L + j)] = gap;
                         stv[k3_pad(threadIdx.x * K3_L + j)] = sv;
-                        if (!FULL && n0 + j == P.n - 1) P.stG[P.n] = gnext;
+                        if (STAGE == 1 && !FULL && n0 + j == P.n - 1) P.stG[P.n] = gnext;
                     }
                     gap = gnext;
                     ++j;
@@ -299,6 +299,7 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
                 }
             }
         }
+        if (STAGE == 2 && threadIdx.x == K3_THREADS - 1) stg[k3_pad(K3_TILE)] = gap;  // gap of the job after the tile
         return f;
     }
 #pragma unroll K3_GEN_UNROLL_N
@@ -308,33 +309,42 @@ __device__ __forceinline__ MP gen_fold_segment(const K3Params &P, long long n0, 
         w = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
         const float gnext = sample<SRCK>(P.src, w.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
         if (FULL || j < valid) f = mp_step(f, __dsub_rn((double)sv, (double)gnext));
-        if (STASH_W) {
+        if (STAGE) {
             stg[k3_pad(threadIdx.x * K3_L + j)] = gap;
             stv[k3_pad(threadIdx.x * K3_L + j)] = sv;
-            if (!FULL && n0 + j == P.n - 1) P.stG[P.n] = gnext;
+            if (STAGE == 1 && !FULL && n0 + j == P.n - 1) P.stG[P.n] = gnext;
         }
         gap = gnext;
     }
+    if (STAGE == 2 && threadIdx.x == K3_THREADS - 1) stg[k3_pad(K3_TILE)] = gap;
     return f;
 }
 
 // SRCK / SRVK: the laws of the gaps / services known at compile time (-1: switch on the kind at run time; the switch is
 // 9 % of the generator form's instructions, so the BASELINE shapes get their own instantiation)
-template <bool REPLAY, bool STASH_W = false, int SRCK = -1, int SRVK = -1>
-__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 6)) k3_summary(const K3Params P)
+#ifndef K3_SPEC_MINB
+#define K3_SPEC_MINB 5
+#endif
+// STAGE: 0 nothing kept of the draws; 1 stash them in HBM for the walk pass; 2 "speculative": keep them in shared memory,
+// walk every segment from its in-tile prefix right here and leave the repair of the carry-dependent segments to k3_repair
+template <bool REPLAY, int STAGE = 0, int SRCK = -1, int SRVK = -1>
+__global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : (STAGE == 2 ? K3_SPEC_MINB : 6))) k3_summary(const K3Params P)
 {
+    constexpr bool STASH_W = STAGE == 1;
     __shared__ MP smem[K3_THREADS / 32];
     extern __shared__ double stage[];
     double *smS = stage;
-    __shared__ float stash_stage[STASH_W ? 2 * K3_PADDED : 2];
-    float *stg = stash_stage, *stv = stash_stage + (STASH_W ? K3_PADDED : 1);
+    __shared__ float stash_stage[STAGE ? 2 * K3_PADDED : 2];
+    float *stg = stash_stage, *stv = stash_stage + (STAGE ? K3_PADDED : 1);
+    __shared__ double spec_red[STAGE == 2 ? K3_THREADS / 32 : 1][10];
+    if (STAGE == 2 && threadIdx.x < (K3_THREADS / 32) * 10) (&spec_red[0][0])[threadIdx.x] = 0.0;
     for (long long t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
         const long long n0 = (t * K3_THREADS + threadIdx.x) * K3_L;
         const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;  // uniform in the CTA
         MP mine;
         if (!REPLAY) {
-            mine = full_tile ? gen_fold_segment<STASH_W, true, SRCK, SRVK>(P, n0, stg, stv)
-                             : gen_fold_segment<STASH_W, false, SRCK, SRVK>(P, n0, stg, stv);
+            mine = full_tile ? gen_fold_segment<STAGE, true, SRCK, SRVK>(P, n0, stg, stv)
+                             : gen_fold_segment<STAGE, false, SRCK, SRVK>(P, n0, stg, stv);
         } else {
             // replay form: the fold only needs x[n] = S[n] - A[n+1], formed while the coalesced loads arrive and staged
             // as ONE array (35 KB instead of 72 KB per CTA: 6 resident CTAs instead of 3); jobs beyond the range are 0
@@ -379,7 +389,144 @@ __global__ void __launch_bounds__(K3_THREADS, (REPLAY ? K3_SUM_MINB : 6)) k3_sum
             }
             __syncthreads();  // before the next tile overwrites the staging arrays
         }
+        if (STAGE == 2) {
+            // (the scan's barriers have made the staged draws visible) speculative walk: the wait at the start of the
+            // segment is max(a_s, w_tile + b_s), and after the first idle period of the tile that is a_s whatever the
+            // carry w_tile is.  Segment 0 has no a_s and the last tile has bounds: both are walked by k3_repair alone.
+            if (full_tile) {
+                const int e0 = threadIdx.x * K3_L;
+                double acc[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+                if (threadIdx.x != 0) {
+                    double w = ex_seg.a;
+                    float g = stg[k3_pad(e0)];
+#pragma unroll 4
+                    for (int j = 0; j < K3_L; ++j) {
+                        const float sv = stv[k3_pad(e0 + j)];
+                        const float gn = stg[k3_pad(e0 + j + 1)];
+                        const double sd = (double)sv;
+                        const double v = __dadd_rn(w, sd);
+                        const double w2 = w * w, v2 = v * v;
+                        acc[0] += w;
+                        acc[1] += w2;
+                        acc[2] += w2 * w;
+                        acc[3] += w2 * w2;
+                        acc[4] += v;
+                        acc[5] += v2;
+                        acc[6] += v2 * v;
+                        acc[7] += v2 * v2;
+                        acc[8] += (double)g;
+                        acc[9] += sd;
+                        w = max0(__dadd_rn(w, __dsub_rn(sd, (double)gn)));
+                        g = gn;
+                    }
+                }
+                // the sums of the tile go to per-warp accumulators at once (fixed order): the kernel runs at 40 registers
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    double v = acc[i];
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+                    if (lane == 0) spec_red[warp][i] += v;
+                }
+            }
+            __syncthreads();  // before the next tile overwrites the staging arrays
+        }
         if (threadIdx.x == 0) P.tile_sum[t] = total;
+    }
+    if (STAGE == 2) {
+        __syncthreads();
+        if (threadIdx.x < K3_NSTAT) {
+            double v = 0.0;
+            if (threadIdx.x < 10)
+                for (int wv = 0; wv < K3_THREADS / 32; ++wv) v += spec_red[wv][threadIdx.x];
+            P.spec_partial[(long long)blockIdx.x * K3_NSTAT + threadIdx.x] = v;
+        }
+    }
+}
+
+// Speculative mode, second kernel: one warp per tile tests every segment's start wait max(a_s, w_tile + b_s) against the
+// a_s the summary pass walked it from and re-draws and re-walks the segments where they differ (1.2 of 256 at rho = 0.7),
+// adding (true - provisional) to the sums; segment 0 of every tile and the whole last tile are walked here only.
+__global__ void __launch_bounds__(K3_THREADS) k3_repair(const K3Params P)
+{
+    __shared__ double red[K3_THREADS / 32][K3_NSTAT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+    const long long warps = (long long)gridDim.x * (K3_THREADS / 32);
+    for (long long t = (long long)blockIdx.x * (K3_THREADS / 32) + warp; t < P.ntiles; t += warps) {
+        const bool full_tile = (t + 1) * (long long)K3_TILE < P.n;
+        const double w_tile = mp_apply(P.tile_ex[t], P.w_in);
+        const double2 *exs = reinterpret_cast<const double2 *>(P.thread_ex) + t * K3_THREADS;
+#pragma unroll 1
+        for (int q = 0; q < K3_THREADS / 32; ++q) {
+            const int seg = q * 32 + lane;
+            const double2 e = __ldcs(exs + seg);
+            const double w0 = mp_apply(MP{e.x, e.y}, w_tile);
+            const bool own = !full_tile || seg == 0;        // nothing provisional was accumulated for this segment
+            if (!own && w0 == e.x) continue;
+            const long long n0 = (t * K3_THREADS + seg) * K3_L;
+            const int valid = full_tile ? K3_L : k3_valid(P.n, n0, K3_L);
+            const int last_j = (!full_tile && P.n - 1 >= n0 && P.n - 1 < n0 + K3_L) ? (int)(P.n - 1 - n0) : -1;
+            unsigned long long g = (unsigned long long)(P.job0 + n0);
+            uint2 wd = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
+            float gap = sample<-1>(P.src, wd.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+            double w = w0, wp = e.x;
+#pragma unroll 1
+            for (int j = 0; j < valid; ++j) {
+                const float sv = sample<-1>(P.srv, wd.y, (uint32_t)g, (uint32_t)(g >> 32), P.key, 1);
+                ++g;
+                wd = philox2x32_10_rk((uint32_t)g, (uint32_t)(g >> 32), P.rk);
+                const float gn = sample<-1>(P.src, wd.x, (uint32_t)g, (uint32_t)(g >> 32), P.key, 0);
+                const double sd = (double)sv, x = __dsub_rn(sd, (double)gn);
+                const double v = __dadd_rn(w, sd);
+                const double w2 = w * w, v2 = v * v;
+                double tt[8] = {w, w2, w2 * w, w2 * w2, v, v2, v2 * v, v2 * v2};
+                if (own) {
+                    acc[8] += (double)gap;
+                    acc[9] += sd;
+                } else {
+                    const double vp = __dadd_rn(wp, sd);
+                    const double p2 = wp * wp, q2 = vp * vp;
+                    tt[0] -= wp;
+                    tt[1] -= p2;
+                    tt[2] -= p2 * wp;
+                    tt[3] -= p2 * p2;
+                    tt[4] -= vp;
+                    tt[5] -= q2;
+                    tt[6] -= q2 * vp;
+                    tt[7] -= q2 * q2;
+                    wp = max0(__dadd_rn(wp, x));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += tt[i];
+                const double raw = __dadd_rn(w, x);
+                if (j == last_j) {
+                    P.tail[0] = raw;
+                    P.tail[1] = v;
+                }
+                w = max0(raw);
+                gap = gn;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < K3_NSTAT) {
+        double v = 0.0;
+        if (threadIdx.x < 10)
+            for (int wv = 0; wv < K3_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        P.partial[(long long)blockIdx.x * K3_NSTAT + threadIdx.x] = v;
     }
 }
 
@@ -702,16 +849,17 @@ __global__ void __launch_bounds__(32) k3_final(const double *partial, const doub
 // the generator-form summary kernel for a pair of laws: own instantiations for the BASELINE chain (Gamma gaps, Pareto
 // services), Gamma gaps with any service law, and M/M; everything else switches on the kind at run time
 using SummaryKernel = void (*)(const K3Params);
-template <bool STASH_W>
+template <int STAGE>
 static SummaryKernel gen_summary_kernel_t(int src_kind, int srv_kind)
 {
-    if (src_kind == MQ_GAMMA) return srv_kind == MQ_PA ? k3_summary<false, STASH_W, MQ_GAMMA, MQ_PA> : k3_summary<false, STASH_W, MQ_GAMMA, -1>;
-    if (src_kind == MQ_M && srv_kind == MQ_M) return k3_summary<false, STASH_W, MQ_M, MQ_M>;
-    return k3_summary<false, STASH_W, -1, -1>;
+    if (src_kind == MQ_GAMMA) return srv_kind == MQ_PA ? k3_summary<false, STAGE, MQ_GAMMA, MQ_PA> : k3_summary<false, STAGE, MQ_GAMMA, -1>;
+    if (src_kind == MQ_M && srv_kind == MQ_M) return k3_summary<false, STAGE, MQ_M, MQ_M>;
+    return k3_summary<false, STAGE, -1, -1>;
 }
-static SummaryKernel gen_summary_kernel(bool stash, int src_kind, int srv_kind)
+static SummaryKernel gen_summary_kernel(int stage_mode, int src_kind, int srv_kind)
 {
-    return stash ? gen_summary_kernel_t<true>(src_kind, srv_kind) : gen_summary_kernel_t<false>(src_kind, srv_kind);
+    if (stage_mode == 2) return gen_summary_kernel_t<2>(src_kind, srv_kind);
+    return stage_mode == 1 ? gen_summary_kernel_t<1>(src_kind, srv_kind) : gen_summary_kernel_t<0>(src_kind, srv_kind);
 }
 
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
@@ -722,8 +870,20 @@ cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st)
         if (e != cudaSuccess) return e;
         k3_summary<true><<<grid, K3_THREADS, K3_XSTAGE_BYTES, st>>>(P);
     } else {
-        gen_summary_kernel(P.stG != nullptr, P.src.kind, P.srv.kind)<<<grid, K3_THREADS, 0, st>>>(P);
+        gen_summary_kernel(P.spec ? 2 : (P.stG != nullptr ? 1 : 0), P.src.kind, P.srv.kind)<<<grid, K3_THREADS, 0, st>>>(P);
     }
+    return cudaGetLastError();
+}
+
+int k3_repair_grid(long long ntiles, int sms)
+{
+    const long long want = (ntiles + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
+    return (int)(want < 4ll * sms ? (want < 1 ? 1 : want) : 4ll * sms);
+}
+
+cudaError_t k3_launch_repair(const K3Params &P, int grid, cudaStream_t st)
+{
+    k3_repair<<<grid, K3_THREADS, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -779,10 +939,11 @@ static cudaError_t occ_walk_one(size_t smem, int *b)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, k3_walk<MODE, WANT_P>, K3_THREADS, smem);
 }
 
-cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int src_kind, int srv_kind, int *summary_blocks, int *walk_blocks)
+cudaError_t k3_occupancy(bool replay, int stage_mode, bool want_p, int src_kind, int srv_kind, int *summary_blocks, int *walk_blocks)
 {
     int a = 0, b = 0;
     cudaError_t e;
+    const bool stash = stage_mode == 1;
     const int mode = replay ? 1 : (stash ? 2 : 0);
     const size_t wsm = k3_walk_smem(mode != 0, want_p);
     if (replay) {
@@ -790,7 +951,7 @@ cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int src_kind, int
         if (e == cudaSuccess)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k3_summary<true>, K3_THREADS, K3_XSTAGE_BYTES);
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gen_summary_kernel(stash, src_kind, srv_kind), K3_THREADS, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gen_summary_kernel(stage_mode, src_kind, srv_kind), K3_THREADS, 0);
     }
     if (e == cudaSuccess) {
         if (mode == 1)

@@ -41,6 +41,11 @@ struct K3Params {
     // generator form, optional: the summary pass stashes its fp32 draws (gap of job i in stG[i], i = 0..n; service in
     // stV[i]) and the walk pass reads them back instead of drawing everything a second time
     float *stG, *stV;
+    // generator form, "speculative" mode (spec != 0): the summary pass walks every segment at once from its in-tile
+    // prefix and leaves its power sums in spec_partial[grid_sum][K3_NSTAT]; k3_repair then re-draws and re-walks only the
+    // segments whose start wait depends on the carry into their tile (see k3_onepass.cu for the argument).  No stash.
+    int spec;
+    double *spec_partial;
 };
 
 // number of valid entries among [base, base + span) when the valid ones are [0, limit)
@@ -60,9 +65,11 @@ int k3_onepass_error();
 cudaError_t k3_launch_summary(const K3Params &P, int grid, cudaStream_t st);
 cudaError_t k3_launch_top(const K3Params &P, cudaStream_t st);
 cudaError_t k3_launch_walk(const K3Params &P, int grid, cudaStream_t st);
+cudaError_t k3_launch_repair(const K3Params &P, int grid, cudaStream_t st);
+int k3_repair_grid(long long ntiles, int sms);
 cudaError_t k3_launch_final(const double *partial, const double *level_partial, int grid, double *stats,
                             cudaStream_t st);
-cudaError_t k3_occupancy(bool replay, bool stash, bool want_p, int src_kind, int srv_kind, int *summary_blocks, int *walk_blocks);
+cudaError_t k3_occupancy(bool replay, int stage_mode, bool want_p, int src_kind, int srv_kind, int *summary_blocks, int *walk_blocks);
 size_t k3_walk_smem(bool replay, bool want_p);
 
 }  // namespace mq

@@ -10,8 +10,9 @@ namespace {
 
 struct ScanRun {
     K3Params P;
-    int grid_sum = 0, grid_walk = 0;
+    int grid_sum = 0, grid_walk = 0, grid_rep = 0;
     bool staged_inputs = false;
+    bool spec = false;     // generator form, speculative walk inside the summary pass + k3_repair (no stash, no walk pass)
     bool onepass = false;  // replay form in one pass (k3_onepass.cu): no summary launches, the walk is the fused kernel
 };
 
@@ -50,7 +51,7 @@ ScanKey make_key(const mq_scan_cfg *cfg, const double *A, const double *S)
 }
 
 int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const double *S, ScanRun &run, const char *who,
-                 bool will_walk = false)
+                 bool will_walk = false, bool allow_spec = false)
 {
     if (!ctx || !cfg) return fail(MQ_E_INVALID, "%s: NULL argument", who);
     if (cfg->jobs < 1 || cfg->job0 < 0) return fail(MQ_E_INVALID, "%s: jobs must be >= 1 and job0 >= 0", who);
@@ -114,6 +115,25 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
         const size_t have = ctx->in_a.cap + ctx->in_s.cap;  // buffers that would be reused
         stash = need <= have || need < (free_b + have) / 2;
     }
+    // Speculative mode: the walk is done inside the summary pass (every segment from its in-tile prefix) and k3_repair
+    // re-draws the few segments that depended on the carry -- no stash, no walk pass, 1 B/job of HBM instead of 8.  On a
+    // chain whose stash fits it is 5 % SLOWER than summary + walk (the summary pass is issue bound and the fp32 -> fp64
+    // conversions of the walk share the MUFU pipe with the samplers), so it is used when the stash does not fit (chains
+    // beyond ~1e10 jobs per GPU, which would otherwise be drawn twice) or when MQ_SCAN_SPEC=1 asks for it.
+    const bool spec_wanted = !replay && will_walk && allow_spec && !want_p && !std::getenv("MQ_SCAN_NO_SPEC") &&
+                             (!stash || std::getenv("MQ_SCAN_SPEC"));
+    if (spec_wanted) {
+        stash = false;
+        // a stash left behind by an earlier, shorter chain is dead weight now: give its memory to the segment prefixes
+        if (ctx->in_a.cap + ctx->in_s.cap > ((size_t)1 << 30)) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (Buf *b : {&ctx->in_a, &ctx->in_s}) {
+                if (b->p) cudaFree(b->p);
+                b->p = nullptr;
+                b->cap = 0;
+            }
+        }
+    }
     if (stash) {
         // an allocation failure only costs the optimisation
         if (ensure(ctx->in_a, sizeof(float) * ((size_t)P.n + 32)) != MQ_OK ||
@@ -127,19 +147,22 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     }
     // the summary pass can keep every segment's exclusive prefix (4 KB per tile) so that the walk skips its own fold and
     // CTA scan; MQ_SCAN_NO_PREFIX=1 turns it off
-    if (will_walk && !run.onepass && !std::getenv("MQ_SCAN_NO_PREFIX")) {
+    if (will_walk && !run.onepass && (spec_wanted || !std::getenv("MQ_SCAN_NO_PREFIX"))) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t need = sizeof(MP) * (size_t)K3_THREADS * (size_t)P.ntiles;
-        if (need <= ctx->agg.cap || need < (free_b + ctx->agg.cap) / 4) {
+        // (the speculative mode lives on these prefixes and keeps nothing else of the chain: it may take most of the HBM)
+        if (need <= ctx->agg.cap || need < (free_b + ctx->agg.cap) / 4 * (spec_wanted ? 3 : 1)) {
             if (ensure(ctx->agg, need) == MQ_OK)
                 P.thread_ex = (MP *)ctx->agg.p;
             else
                 cudaGetLastError();
         }
     }
+    run.spec = spec_wanted && P.thread_ex != nullptr;  // (without room for the segment prefixes: draw twice, as before)
+    P.spec = run.spec ? 1 : 0;
     int occ_s = 0, occ_w = 0;
-    CU(k3_occupancy(replay, stash, want_p, P.src.kind, P.srv.kind, &occ_s, &occ_w));
+    CU(k3_occupancy(replay, run.spec ? 2 : (stash ? 1 : 0), want_p, P.src.kind, P.srv.kind, &occ_s, &occ_w));
     if (run.onepass) {
         occ_w = 1;  // one CTA per SM by design
         if (int rc = ensure(ctx->lookback, k3_onepass_scratch_bytes(P.ntiles))) return rc;
@@ -147,10 +170,12 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     if (occ_s < 1 || occ_w < 1) return fail(MQ_E_CUDA, "%s: kernel does not fit on an SM", who);
     run.grid_sum = (int)std::min<long long>(P.ntiles, (long long)occ_s * ctx->sms);
     run.grid_walk = (int)std::min<long long>(P.ntiles, (long long)occ_w * ctx->sms);
+    run.grid_rep = run.spec ? k3_repair_grid(P.ntiles, ctx->sms) : 0;
 
-    // scratch: tile_sum, tile_ex, total, tail, partial, stats
+    // scratch: tile_sum, tile_ex, total, tail, partial (speculative mode: the summary's blocks, then the repair's), stats
+    const size_t nblocks = run.spec ? (size_t)run.grid_sum + (size_t)run.grid_rep : (size_t)run.grid_walk;
     const size_t bytes = sizeof(MP) * (2 * (size_t)P.ntiles + 1 + 2 * K3_TOP) +
-                         sizeof(double) * (2 + (size_t)run.grid_walk * (K3_NSTAT + K3_NLEVEL) + K3_NSTAT + K3_NLEVEL);
+                         sizeof(double) * (2 + nblocks * (K3_NSTAT + K3_NLEVEL) + K3_NSTAT + K3_NLEVEL);
     if (int rc = ensure(ctx->rec, bytes)) return rc;
     char *base = (char *)ctx->rec.p;
     P.tile_sum = (MP *)base;
@@ -160,6 +185,7 @@ int scan_prepare(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const dou
     P.chunk_ex = P.chunk_f + K3_TOP;
     P.tail = (double *)(P.chunk_ex + K3_TOP);
     P.partial = P.tail + 2;
+    P.spec_partial = P.partial;
     P.level_partial = want_p ? P.partial + (size_t)run.grid_walk * K3_NSTAT + K3_NSTAT + K3_NLEVEL : nullptr;
     if (int rc = ensure_host_agg(ctx, sizeof(double) * 64)) return rc;
     return MQ_OK;
@@ -188,12 +214,19 @@ int scan_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, ScanRun &run, double w_in, d
         }
     }
     P.W = dW;
-    double *d_stats = P.partial + (size_t)run.grid_walk * K3_NSTAT;
-    if (run.onepass)
+    const int nblocks = run.spec ? run.grid_sum + run.grid_rep : run.grid_walk;
+    double *d_stats = P.partial + (size_t)nblocks * K3_NSTAT;
+    if (run.spec) {
+        if (W) return fail(MQ_E_INVALID, "mq_scan_gg1: per-job waits need the walk pass (internal: speculative run with W)");
+        K3Params R = P;  // the repair's blocks write their sums behind the summary's
+        R.partial = P.partial + (size_t)run.grid_sum * K3_NSTAT;
+        CU(k3_launch_repair(R, run.grid_rep, ctx->stream));
+    } else if (run.onepass) {
         CU(k3_launch_onepass(P, ctx->lookback.p, run.grid_walk, ctx->stream));
-    else
+    } else {
         CU(k3_launch_walk(P, run.grid_walk, ctx->stream));
-    CU(k3_launch_final(P.partial, P.level_partial, run.grid_walk, d_stats, ctx->stream));
+    }
+    CU(k3_launch_final(P.partial, P.level_partial, nblocks, d_stats, ctx->stream));
     ctx->launches += 2;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -250,7 +283,7 @@ int mq_scan_gg1_summary(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, co
     ScanRun run;
     // generator form only: a replayed range is read once by the summary and once by the (one-pass) apply either way
     const bool keep = cfg && (cfg->flags & MQ_SCAN_KEEP) != 0 && !A && !S;
-    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_summary", keep)) return rc;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_summary", keep, keep)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (int rc = scan_summary(ctx, run)) return rc;
@@ -279,8 +312,11 @@ int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, cons
     if (ctx && cfg && ctx->scan_valid) {
         // the previous call on this context was the summary of this very range with MQ_SCAN_KEEP: walk from what it left
         const ScanKey key = make_key(cfg, A, S);
-        if (std::memcmp(ctx->scan_key, &key, sizeof(key)) == 0) {
-            std::memcpy(&run, ctx->scan_cache, sizeof(run));
+        ScanRun cached;
+        std::memcpy(&cached, ctx->scan_cache, sizeof(cached));
+        // (a kept speculative run has no walk pass to take per-job waits from: redo the range then)
+        if (std::memcmp(ctx->scan_key, &key, sizeof(key)) == 0 && !(cached.spec && W)) {
+            run = cached;
             ctx->scan_valid = false;
             CU(cudaSetDevice(ctx->device));
             ctx->launches = 0;
@@ -288,7 +324,7 @@ int mq_scan_gg1_apply(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, cons
             return scan_apply(ctx, cfg, run, w_in, stats, W);
         }
     }
-    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_apply", true)) return rc;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1_apply", true, W == nullptr)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     // the tile prefixes are a function of the range only; recompute them (scratch is not kept between calls)
@@ -300,7 +336,7 @@ int mq_scan_gg1(mq_ctx *ctx, const mq_scan_cfg *cfg, const double *A, const doub
 {
     if (!stats) return fail(MQ_E_INVALID, "mq_scan_gg1: NULL output");
     ScanRun run;
-    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1", true)) return rc;
+    if (int rc = scan_prepare(ctx, cfg, A, S, run, "mq_scan_gg1", true, W == nullptr)) return rc;
     ctx->launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (int rc = scan_summary(ctx, run)) return rc;

@@ -54,6 +54,31 @@ def test_cfg3_chain_1e10_identities(L):
     assert np.array_equal(one, again)
 
 
+def test_chain_longer_than_the_draw_stash_3e10(L):
+    """3 x the BASELINE chain on one GPU: the fp32 draw stash (8 B per job = 275 GB) cannot exist, so the engine walks
+    inside the summary pass and repairs (speculative mode, 1 B per job) instead of drawing everything twice.  Same
+    identities as the 1e10-job chain, and the first 1e10 jobs' carry equals the carry the stash path computes."""
+    from most_queue_b200.random.distributions import GammaDistribution, ParetoDistribution
+
+    ctx = L.default_context()
+    gam = GammaDistribution.get_params_by_mean_and_cv(1.0, 0.56)
+    par = ParetoDistribution.get_params_by_mean_and_cv(0.7, 1.2)
+    src, srv = L.make_dist("Gamma", gam), L.make_dist("Pa", par)
+    N = 1 << 35
+    one, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=3, last_range=False)
+    assert ctx.last_timing()["launches"] == 6 and ctx.last_timing()["sim_ms"] < 1000.0
+    assert one[L.S_TAKED] == N and one[L.S_SERVED] == N
+    np.testing.assert_allclose(one[L.S_V], one[L.S_W] + one[L.S_SUMS], rtol=1e-11)
+    ttek = one[L.S_SUMA] + one[L.S_TAILV]
+    assert abs(one[L.S_SUMS] / ttek - 0.7) < 2e-4
+    # the same jobs as a 1e10-job range (stash path) followed by the rest (speculative path): sums add up, carries chain
+    a, _ = ctx.scan_apply(10_000_000_000, 0.0, src=src, srv=srv, seed=3, last_range=False)
+    b, _ = ctx.scan_apply(N - 10_000_000_000, a[L.S_WOUT], job0=10_000_000_000, src=src, srv=srv, seed=3, last_range=False)
+    assert b[L.S_WOUT] == pytest.approx(one[L.S_WOUT], rel=1e-9)
+    for row in (L.S_W, L.S_W + 1, L.S_V, L.S_V + 1, L.S_SUMA, L.S_SUMS):
+        np.testing.assert_allclose(a[row] + b[row], one[row], rtol=1e-10)
+
+
 @pytest.mark.parametrize("prty", ["NP", "PR"])
 def test_cfg4_priority_full_size(L, prty):
     from most_queue_b200.random.distributions import GammaDistribution

@@ -135,32 +135,70 @@ def test_generator_chain_sums_equal_the_sums_of_the_variates():
     N, seed = 30_000_000, 3
     S = ctx.variates(srv, seed, 0, 1, N).astype(np.float64)
     A = ctx.variates(src, seed, 0, 0, N).astype(np.float64)
-    one, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=seed, last_range=False)
-    os.environ["MQ_SCAN_NO_STASH"] = "1"
-    try:
-        two, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=seed, last_range=False)
-    finally:
-        del os.environ["MQ_SCAN_NO_STASH"]
+    def run(n=N, w_in=0.0, job0=0, **env):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            return ctx.scan_apply(n, w_in, job0=job0, src=src, srv=srv, seed=seed, last_range=False)[0]
+        finally:
+            for k in env:
+                del os.environ[k]
+
+    one = run(MQ_SCAN_SPEC="1")                                        # speculative walk in the summary pass + repair
+    stash = run()                                                      # summary with draw stash, walk pass (the default)
+    assert np.array_equal(stash, run(MQ_SCAN_NO_SPEC="1"))
+    nostash = run(MQ_SCAN_NO_STASH="1")                                # no room for a stash: speculative mode by itself
+    assert np.array_equal(nostash, one)
+    two = run(MQ_SCAN_NO_SPEC="1", MQ_SCAN_NO_STASH="1")               # everything drawn twice
+    three = run(MQ_SCAN_NO_SPEC="1", MQ_SCAN_NO_PREFIX="1")            # the walk folds and scans again
     h = N // 2 + 7
-    p1, _ = ctx.scan_apply(h, 0.0, src=src, srv=srv, seed=seed, last_range=False)
-    p2, _ = ctx.scan_apply(N - h, p1[L.S_WOUT], job0=h, src=src, srv=srv, seed=seed, last_range=False)
-    for st in (one, two):
+    p1 = run(h)
+    p2 = run(N - h, p1[L.S_WOUT], job0=h)
+    q1 = run(h, MQ_SCAN_SPEC="1")
+    q2 = run(N - h, q1[L.S_WOUT], job0=h, MQ_SCAN_SPEC="1")
+    assert q1[L.S_WOUT] == p1[L.S_WOUT] and q2[L.S_WOUT] == p2[L.S_WOUT]
+    for st in (one, stash, two):
         np.testing.assert_allclose(st[L.S_SUMS], S.sum(), rtol=1e-12)
         np.testing.assert_allclose(st[L.S_SUMA], A.sum(), rtol=1e-12)
     np.testing.assert_allclose(p1[L.S_SUMS] + p2[L.S_SUMS], S.sum(), rtol=1e-12)
     np.testing.assert_allclose(p1[L.S_SUMA], A[:h].sum(), rtol=1e-12)
     # the walk that reuses the summary pass's per-segment prefixes does the same arithmetic as the one that folds and
     # scans again: identical statistics
-    os.environ["MQ_SCAN_NO_PREFIX"] = "1"
+    assert np.array_equal(three, stash)
+    # the range summary, the carry out and the tail are the same bits on every path (one association tree)
+    for row in (L.S_A, L.S_B, L.S_WOUT, L.S_TAILRAW, L.S_TAILV, L.S_TAKED, L.S_SERVED):
+        assert one[row] == stash[row] == two[row], row
+    # the waits are functions of the same draws: all forms and both cuts agree to rounding (all four moments)
+    for row in list(range(L.S_W, L.S_W + 4)) + list(range(L.S_V, L.S_V + 4)):
+        np.testing.assert_allclose(one[row], stash[row], rtol=1e-11)
+        np.testing.assert_allclose(two[row], stash[row], rtol=1e-11)
+        np.testing.assert_allclose(p1[row] + p2[row], stash[row], rtol=1e-10)
+        np.testing.assert_allclose(q1[row] + q2[row], stash[row], rtol=1e-10)
+
+
+@pytest.mark.parametrize("rho", [0.9, 1.1])
+def test_speculative_generator_walk_near_and_above_saturation(rho):
+    """Generator form, speculative mode against the walk pass when the carry rarely (or never) dies: the repair then
+    re-walks most (all) segments; M/M/1 so that the run is cheap."""
+    import os
+
+    from most_queue_b200 import _lib as L
+
+    ctx = L.default_context()
+    src, srv = L.make_dist("M", 1.0), L.make_dist("M", 1.0 / rho)
+    N = 5_000_000 + 321
+    os.environ["MQ_SCAN_SPEC"] = "1"
     try:
-        three, _ = ctx.scan_apply(N, 0.0, src=src, srv=srv, seed=seed, last_range=False)
+        spec, _ = ctx.scan_apply(N, 0.5, src=src, srv=srv, seed=9, last_range=True)
+        assert ctx.last_timing()["launches"] == 6  # summary, 3 x tile scan, repair, reduction
     finally:
-        del os.environ["MQ_SCAN_NO_PREFIX"]
-    assert np.array_equal(three, one)
-    # the waits are functions of the same draws: both forms and both cuts agree to rounding
-    for row in (L.S_W, L.S_W + 1, L.S_V, L.S_V + 1):
-        np.testing.assert_allclose(two[row], one[row], rtol=1e-11)
-        np.testing.assert_allclose(p1[row] + p2[row], one[row], rtol=1e-10)
+        del os.environ["MQ_SCAN_SPEC"]
+    walk, W = ctx.scan_apply(N, 0.5, src=src, srv=srv, seed=9, last_range=True, want_w=True)
+    for row in (L.S_A, L.S_B, L.S_WOUT, L.S_TAILRAW, L.S_TAILV, L.S_TAKED, L.S_SERVED):
+        assert spec[row] == walk[row], row
+    for row in list(range(L.S_W, L.S_W + 4)) + list(range(L.S_V, L.S_V + 4)) + [L.S_SUMA, L.S_SUMS]:
+        np.testing.assert_allclose(spec[row], walk[row], rtol=1e-10)
+    assert W[0] == 0.5 and (rho < 1 or W[-1] > 1e3)
 
 
 def test_levels_of_ranges_equal_single_range_on_a_fresh_context():
@@ -193,12 +231,15 @@ def test_levels_of_ranges_equal_single_range_on_a_fresh_context():
     np.testing.assert_allclose(three["p"][:24], one["p"][:24], rtol=0, atol=1e-12)
 
 
-def test_summary_keep_then_apply_walks_from_the_kept_state():
+@pytest.mark.parametrize("spec", [False, True])
+def test_summary_keep_then_apply_walks_from_the_kept_state(spec, monkeypatch):
     """MQ_SCAN_KEEP (the multi-GPU sequence summary -> exchange -> apply on one context): the apply that follows the kept
     summary gives the statistics of the stand-alone apply bit for bit, and a call in between invalidates the kept state
     without changing the answer."""
     from most_queue_b200 import _lib
 
+    if spec:  # the speculative mode: the kept summary has already walked, the apply only repairs
+        monkeypatch.setenv("MQ_SCAN_SPEC", "1")
     ctx = _lib.default_context()
     src, srv = _lib.make_dist("Gamma", GAMMA), _lib.make_dist("Pa", PARETO)
     n, j0, ahead = 3_000_017, 1_000_000, 5_000
@@ -215,6 +256,11 @@ def test_summary_keep_then_apply_walks_from_the_kept_state():
     ctx.sim_fifo(2, None, _lib.make_dist("M", 1.0), _lib.make_dist("M", 0.8), 200, 64, 0, 1, p_bins=8)
     again, _ = ctx.scan_apply(n, 0.37, job0=j0, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead)
     assert np.array_equal(again, alone)
+    if spec:  # per-job waits need the walk pass: a kept speculative summary is set aside and the range redone
+        ctx.scan_summary(n, job0=j0, src=src, srv=srv, seed=9, keep=True, jobs_ahead=ahead)
+        st_w, W = ctx.scan_apply(n, 0.37, job0=j0, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead, want_w=True)
+        assert W[0] == 0.37 and st_w[_lib.S_WOUT] == alone[_lib.S_WOUT]
+        np.testing.assert_allclose(st_w[_lib.S_W], alone[_lib.S_W], rtol=1e-11)
     # a different range description does not match the key
     ctx.scan_summary(n, job0=j0, src=src, srv=srv, seed=9, keep=True, jobs_ahead=ahead)
     other, _ = ctx.scan_apply(n, 0.37, job0=j0 + 16, src=src, srv=srv, seed=9, last_range=False, jobs_ahead=ahead)
