@@ -925,27 +925,30 @@ bool k3_onepass_usable(const K3Params &P)
 // one int of mapped pinned host memory per process: written by op_give_up(), readable by the host even after a trap
 static int *error_word(bool device_side)
 {
-    static int *h = nullptr, *d = nullptr;
-    if (!h) {
-        if (cudaHostAlloc((void **)&h, 64 + 16 * 4 * 257, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
-            h = nullptr;
-            return nullptr;
+    struct Holder {  // (a function-local static: initialised once, thread-safe)
+        int *h = nullptr, *d = nullptr;
+        Holder()
+        {
+            if (cudaHostAlloc((void **)&h, 64 + 16 * 4 * 257, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+                h = nullptr;
+                cudaGetLastError();
+                return;
+            }
+            *h = 0;
+            if (cudaHostGetDevicePointer((void **)&d, h, 0) != cudaSuccess) d = h;  // unified addressing: same pointer
         }
-        *h = 0;
-        if (cudaHostGetDevicePointer((void **)&d, h, 0) != cudaSuccess) d = h;  // unified addressing: same pointer
-    }
-    return device_side ? d : h;
+    };
+    static Holder holder;
+    return device_side ? holder.d : holder.h;
 }
 
 // `scratch` = k3_onepass_scratch_bytes(ntiles) bytes of device memory; grid <= resident CTAs (one per SM)
 cudaError_t k3_launch_onepass(const K3Params &P, void *scratch, int grid, cudaStream_t st)
 {
-    static bool attr_set = false;
     const size_t smem = k3_onepass_smem();
-    if (!attr_set) {
+    {   // (per device, so on every launch: a process may hold contexts on several GPUs)
         cudaError_t e = cudaFuncSetAttribute(k3_onepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     K3OnePassParams Q;
     Q.P = P;
