@@ -15,12 +15,13 @@
 // At rho = 0.7 that holds for all but 1.2 of the 256 segments of a tile on average (6 at rho = 0.9, 24 at rho = 0.95).
 // So the compute warps walk every segment from a_s at once, while the tile is still in shared memory, and a look-back
 // warp -- when w_tile finally arrives -- tests max(a_s, w_tile + b_s) != a_s for all 256 segments and re-walks exactly
-// those (from global memory: a few hundred bytes, usually still in L2), adding (true - provisional) to the sums and
+// those (the first segment from a copy in shared memory, the others from global memory through L1), adding (true -
+// provisional) to the sums and
 // overwriting their stored waits.  The look-back latency is off the critical path altogether: nothing waits for it but a
 // 4 KB ring slot of segment prefixes.
 //
-// One CTA per SM, co-resident (cooperative launch), static tile order t = blockIdx.x + k * gridDim.x, 23 warps:
-//   producer    warp 22 (one lane) brings tile k from HBM into one of three 64 KB stages with two TMA tensor copies (S and
+// One CTA per SM, co-resident (cooperative launch), static tile order t = blockIdx.x + k * gridDim.x, 24 warps:
+//   producer    warp 23 (one lane; it also prefetches the NEXT tile into L2 while it waits for a stage) brings tile k from HBM into one of three 64 KB stages with two TMA tensor copies (S and
 //               A as [rows][16] fp64 boxes of 256 x 16 with the 128-byte swizzle: thread r reads ITS row -- its 16-job
 //               segment -- with conflict-free LDS.128) + one 16-byte bulk copy for the gap that follows the tile.
 //   compute     two groups of 8 warps (tile k goes to group k % 2): fold the rows (x = S - A'), scan the 256 segment
@@ -30,11 +31,13 @@
 //               the identity up to the tile (needs published summaries only), the exclusive prefix of a chunk (first tile
 //               of the chunk: Kogge-Stone over the earlier chunk folds of the group + the group carry) and the carry into
 //               the next group.
-//   look-back B warps 19-21 resolve the tile's own exclusive prefix (from the nearest predecessor that has published its
+//   look-back B warps 19-22 (tile k on warp 19 + k % 4) resolve the tile's own exclusive prefix (from the nearest predecessor that has published its
 //               inclusive prefix, else from the chunk's exclusive prefix; the sequential association makes every such
 //               route give the same bits), publish the inclusive one, and do the repair described above.  The last tile
 //               of the range (bounds checks, the tail sample of base.py:300-305) is walked here only.
 // Published words carry their own "ready" flag (see publish()): no fences anywhere on the look-back path.
+// Every mbarrier that is waited on by parity has the SAME waiter in every phase (see OpShared::full): try_wait.parity can
+// only tell the current phase from the preceding one.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -73,7 +76,7 @@ constexpr uint32_t OP_TX = 2u * OP_ARR_BYTES + 16u;
 #ifndef OP_V_SPIN_LIMIT
 #define OP_V_SPIN_LIMIT 4000000u
 #endif
-constexpr uint32_t OP_SPIN_LIMIT = OP_V_SPIN_LIMIT;     // wait iterations (each sleeps 20 ns .. 20 us) before a protocol bug traps instead of hanging
+constexpr uint32_t OP_SPIN_LIMIT = OP_V_SPIN_LIMIT;     // wait iterations before a wait gives up (op_give_up): a protocol bug traps with a code instead of hanging
 
 struct OpTrue {
     static constexpr bool value = true;
