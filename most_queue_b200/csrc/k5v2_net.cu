@@ -45,7 +45,9 @@ struct K5VLayout {
     }
 };
 
-template <int ST, bool REPLAY>
+// SRCK / SRVK: the law kinds of the external flow and of ALL nodes when they are known to be one kind (-1: switch on the
+// kind at run time)
+template <int ST, bool REPLAY, int SRCK = -1, int SRVK = -1>
 __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
 {
     using LY = K5VLayout<REPLAY>;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                 return P.A[(long long)i * R + rl];
             }
             uint2 w = philox2x32_10((uint32_t)i, rep, key_m);
-            return (double)sample<-1>(src_law, w.x, (uint32_t)i, rep, key_m, 0);
+            return (double)sample<SRCK>(src_law, w.x, (uint32_t)i, rep, key_m, 0);
         };
         auto next_uniform = [&]() -> double {
             const int i = u_idx++;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
                     if (more) {
                         const uint32_t j = (uint32_t)(IN(node, SIDX) + fill);
                         uint2 w = philox2x32_10(j, rep, key);
-                        smf[(node * K5V_SB + (int)(j & (K5V_SB - 1))) * K5V_BLOCK] = sample<-1>(d, w.y, j, rep, key, 1);
+                        smf[(node * K5V_SB + (int)(j & (K5V_SB - 1))) * K5V_BLOCK] = sample<SRVK>(d, w.y, j, rep, key, 1);
                         IN(node, SFILL) = fill + 1;
                     }
                 }
@@ -425,37 +427,38 @@ __global__ void __launch_bounds__(K5V_BLOCK) k5v2_net(const K5Params P)
 #undef IN
 }
 
+using K5Kernel = void (*)(const K5Params);
+// generator tier: own instantiations for networks whose nodes all serve with one law kind (M or H2) under Poisson arrivals
+template <int ST>
+static K5Kernel gen_kernel(const K5Params &P)
+{
+    int kind = P.srv[0].kind;
+    for (int i = 1; i < P.m; ++i)
+        if (P.srv[i].kind != kind) kind = -1;
+    if (P.src.kind == MQ_M && kind == MQ_H2) return k5v2_net<ST, false, MQ_M, MQ_H2>;
+    if (P.src.kind == MQ_M && kind == MQ_M) return k5v2_net<ST, false, MQ_M, MQ_M>;
+    return k5v2_net<ST, false, -1, -1>;
+}
+
 template <int ST>
 static cudaError_t launch_one(const K5Params &P, int grid, cudaStream_t st)
 {
-    cudaError_t e;
-    if (P.replay) {
-        const size_t smem = K5VLayout<true>::bytes(P.nserv, P.m);
-        e = cudaFuncSetAttribute(k5v2_net<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k5v2_net<ST, true><<<grid, K5V_BLOCK, smem, st>>>(P);
-    } else {
-        const size_t smem = K5VLayout<false>::bytes(P.nserv, P.m);
-        e = cudaFuncSetAttribute(k5v2_net<ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k5v2_net<ST, false><<<grid, K5V_BLOCK, smem, st>>>(P);
-    }
+    const K5Kernel kern = P.replay ? (K5Kernel)k5v2_net<ST, true> : gen_kernel<ST>(P);
+    const size_t smem = P.replay ? K5VLayout<true>::bytes(P.nserv, P.m) : K5VLayout<false>::bytes(P.nserv, P.m);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, K5V_BLOCK, smem, st>>>(P);
     return cudaGetLastError();
 }
 
 template <int ST>
 static cudaError_t occupancy_one(const K5Params &P, int *occ)
 {
-    if (P.replay) {
-        const size_t smem = K5VLayout<true>::bytes(P.nserv, P.m);
-        cudaError_t e = cudaFuncSetAttribute(k5v2_net<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k5v2_net<ST, true>, K5V_BLOCK, smem);
-    }
-    const size_t smem = K5VLayout<false>::bytes(P.nserv, P.m);
-    cudaError_t e = cudaFuncSetAttribute(k5v2_net<ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const K5Kernel kern = P.replay ? (K5Kernel)k5v2_net<ST, true> : gen_kernel<ST>(P);
+    const size_t smem = P.replay ? K5VLayout<true>::bytes(P.nserv, P.m) : K5VLayout<false>::bytes(P.nserv, P.m);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k5v2_net<ST, false>, K5V_BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, K5V_BLOCK, smem);
 }
 
 bool k5v2_supported(int m, int nserv) { return m >= 1 && m <= K5V_MAXN && nserv >= 1 && nserv <= 16; }
